@@ -1,0 +1,596 @@
+// elementwise.cu — see elementwise.cuh.  All kernels: fp16 NHWC, 16-byte vector accesses on the
+// channel axis, grid sized from the element count (multiples of full 256-thread blocks).
+#include "elementwise.cuh"
+
+#include <math.h>
+#include <stdio.h>
+
+namespace dcvc {
+
+#define DCVC_LAUNCH_CHECK()                                  \
+    do {                                                     \
+        cudaError_t e__ = cudaGetLastError();                \
+        if (e__ != cudaSuccess) {                            \
+            fprintf(stderr, "dcvc kernel launch failed at %s:%d: %s\n", __FILE__, __LINE__, \
+                    cudaGetErrorString(e__));                \
+            return 1;                                        \
+        }                                                    \
+    } while (0)
+
+static inline int blocks_for(long long n, int threads) { return static_cast<int>((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------- dw3x3
+__global__ void __launch_bounds__(256)
+dw3x3_kernel(const __half* __restrict__ in, int in_pitch, __half* __restrict__ out, int out_pitch,
+             const __half* __restrict__ w, int C, int W, int H)
+{
+    const int cg_n = C >> 3;
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(W) * H * cg_n;
+    if (tid >= total) return;
+    const int cg = static_cast<int>(tid % cg_n);
+    const long long pix = tid / cg_n;
+    const int x = static_cast<int>(pix % W);
+    const int y = static_cast<int>(pix / W);
+    const int c = cg << 3;
+
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xx = x + kx - 1;
+            if (xx < 0 || xx >= W) continue;
+            const uint4 v = *reinterpret_cast<const uint4*>(
+                in + (static_cast<long long>(yy) * W + xx) * in_pitch + c);
+            const uint4 k = __ldg(reinterpret_cast<const uint4*>(w + (ky * 3 + kx) * C + c));
+            const __half2* vh = reinterpret_cast<const __half2*>(&v);
+            const __half2* kh = reinterpret_cast<const __half2*>(&k);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 a = __half22float2(vh[i]);
+                const float2 b = __half22float2(kh[i]);
+                acc[2 * i] = fmaf(a.x, b.x, acc[2 * i]);
+                acc[2 * i + 1] = fmaf(a.y, b.y, acc[2 * i + 1]);
+            }
+        }
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
+    *reinterpret_cast<uint4*>(out + pix * out_pitch + c) = o;
+}
+
+int launch_dw3x3(const ActView& in, const ActView& out, const __half* w, cudaStream_t s)
+{
+    const long long total = static_cast<long long>(in.W) * in.H * (in.C / 8);
+    dw3x3_kernel<<<blocks_for(total, 256), 256, 0, s>>>(
+        static_cast<const __half*>(in.ptr), in.pitch,
+        static_cast<__half*>(const_cast<void*>(out.ptr)), out.pitch, w, in.C, in.W, in.H);
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- unshuffle8
+__global__ void __launch_bounds__(256)
+unshuffle8_pad_kernel(const __half* __restrict__ x, int Cs, int H, int W, long long sc,
+                      long long sh, long long sw, __half* __restrict__ out, int out_pitch, int W8,
+                      int H8)
+{
+    // one thread: 8 consecutive output channels = 8 horizontally adjacent source pixels
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int per_pix = Cs * 8;
+    const long long total = static_cast<long long>(W8) * H8 * per_pix;
+    if (tid >= total) return;
+    const int r = static_cast<int>(tid % per_pix);
+    const long long pix = tid / per_pix;
+    const int cs = r >> 3;
+    const int dy = r & 7;
+    const int w8 = static_cast<int>(pix % W8);
+    const int h8 = static_cast<int>(pix / W8);
+    const int sy = min(h8 * 8 + dy, H - 1);
+    __half v[8];
+#pragma unroll
+    for (int dx = 0; dx < 8; ++dx) {
+        const int sx = min(w8 * 8 + dx, W - 1);
+        v[dx] = x[cs * sc + sy * sh + sx * sw];
+    }
+    *reinterpret_cast<uint4*>(out + pix * out_pitch + cs * 64 + dy * 8) =
+        *reinterpret_cast<const uint4*>(v);
+}
+
+int launch_unshuffle8_pad(const __half* x, int Cs, int H, int W, long long sc, long long sh,
+                          long long sw, const ActView& out, cudaStream_t s)
+{
+    const long long total = static_cast<long long>(out.W) * out.H * Cs * 8;
+    unshuffle8_pad_kernel<<<blocks_for(total, 256), 256, 0, s>>>(
+        x, Cs, H, W, sc, sh, sw, static_cast<__half*>(const_cast<void*>(out.ptr)), out.pitch,
+        out.W, out.H);
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- shuffle8
+template <int CS>
+__global__ void __launch_bounds__(256)
+shuffle8_clamp_kernel(const __half* __restrict__ in, int in_pitch, int W8, int H8,
+                      __half* __restrict__ out, int clamp)
+{
+    // one thread: source pixel (h8, w8), row dy of its 8x8 block -> 8 px x CS channels, contiguous
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(W8) * H8 * 8;
+    if (tid >= total) return;
+    const int dy = static_cast<int>(tid & 7);
+    const long long pix = tid >> 3;
+    const int w8 = static_cast<int>(pix % W8);
+    const int h8 = static_cast<int>(pix / W8);
+    __half o[8 * CS];
+    const __half lo = __float2half(-0.5f);
+    const __half hi = __float2half(0.5f);
+#pragma unroll
+    for (int cs = 0; cs < CS; ++cs) {
+        const uint4 v = *reinterpret_cast<const uint4*>(in + pix * in_pitch + cs * 64 + dy * 8);
+        const __half* vh = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+        for (int dx = 0; dx < 8; ++dx) {
+            __half t = vh[dx];
+            if (clamp) t = __hmin(__hmax(t, lo), hi);
+            o[dx * CS + cs] = t;
+        }
+    }
+    const long long Wo = static_cast<long long>(W8) * 8;
+    __half* dst = out + ((static_cast<long long>(h8) * 8 + dy) * Wo + static_cast<long long>(w8) * 8) * CS;
+    if ((CS * 16) % 16 == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < CS; ++i) {
+            reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(o)[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8 * CS; ++i) dst[i] = o[i];
+    }
+}
+
+int launch_shuffle8_clamp(const ActView& in, __half* out, int Cs, int clamp, cudaStream_t s)
+{
+    const long long total = static_cast<long long>(in.W) * in.H * 8;
+    const __half* ip = static_cast<const __half*>(in.ptr);
+    if (Cs == 3) {
+        shuffle8_clamp_kernel<3><<<blocks_for(total, 256), 256, 0, s>>>(ip, in.pitch, in.W, in.H, out, clamp);
+    } else if (Cs == 1) {
+        shuffle8_clamp_kernel<1><<<blocks_for(total, 256), 256, 0, s>>>(ip, in.pitch, in.W, in.H, out, clamp);
+    } else {
+        fprintf(stderr, "shuffle8_clamp: unsupported Cs=%d\n", Cs);
+        return 1;
+    }
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- pad/crop, scale
+__global__ void __launch_bounds__(256)
+pad_crop_kernel(const __half* __restrict__ in, int in_pitch, int Wi, int Hi,
+                __half* __restrict__ out, int out_pitch, int Wo, int Ho, int C)
+{
+    const int cg_n = C >> 3;
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(Wo) * Ho * cg_n;
+    if (tid >= total) return;
+    const int cg = static_cast<int>(tid % cg_n);
+    const long long pix = tid / cg_n;
+    const int x = static_cast<int>(pix % Wo);
+    const int y = static_cast<int>(pix / Wo);
+    const int sx = min(x, Wi - 1);
+    const int sy = min(y, Hi - 1);
+    *reinterpret_cast<uint4*>(out + pix * out_pitch + cg * 8) = *reinterpret_cast<const uint4*>(
+        in + (static_cast<long long>(sy) * Wi + sx) * in_pitch + cg * 8);
+}
+
+int launch_pad_crop(const ActView& in, const ActView& out, cudaStream_t s)
+{
+    const long long total = static_cast<long long>(out.W) * out.H * (out.C / 8);
+    pad_crop_kernel<<<blocks_for(total, 256), 256, 0, s>>>(
+        static_cast<const __half*>(in.ptr), in.pitch, in.W, in.H,
+        static_cast<__half*>(const_cast<void*>(out.ptr)), out.pitch, out.W, out.H, out.C);
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+scale_channels_kernel(const __half* __restrict__ in, int in_pitch, const __half* __restrict__ q,
+                      __half* __restrict__ out, int out_pitch, long long npix, int C)
+{
+    const int cg_n = C >> 3;
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (tid >= npix * cg_n) return;
+    const int cg = static_cast<int>(tid % cg_n);
+    const long long pix = tid / cg_n;
+    const uint4 v = *reinterpret_cast<const uint4*>(in + pix * in_pitch + cg * 8);
+    const uint4 k = __ldg(reinterpret_cast<const uint4*>(q + cg * 8));
+    const __half2* vh = reinterpret_cast<const __half2*>(&v);
+    const __half2* kh = reinterpret_cast<const __half2*>(&k);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) oh[i] = __hmul2(vh[i], kh[i]);
+    *reinterpret_cast<uint4*>(out + pix * out_pitch + cg * 8) = o;
+}
+
+int launch_scale_channels(const ActView& in, const __half* q, const ActView& out, cudaStream_t s)
+{
+    const long long npix = static_cast<long long>(in.W) * in.H;
+    scale_channels_kernel<<<blocks_for(npix * (in.C / 8), 256), 256, 0, s>>>(
+        static_cast<const __half*>(in.ptr), in.pitch, q,
+        static_cast<__half*>(const_cast<void*>(out.ptr)), out.pitch, npix, in.C);
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- z path
+__device__ __forceinline__ float round_half_away(float v)
+{
+    // CUDA round(at::Half) == roundf: ties away from zero (stream.cu:587-588, 873-874)
+    return roundf(v);
+}
+
+__global__ void __launch_bounds__(256)
+round_z_kernel(const __half* __restrict__ z, __half* __restrict__ z_hat, int8_t* __restrict__ z_i8,
+               long long n)
+{
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = round_half_away(__half2float(z[i]));
+    v = fminf(fmaxf(v, -64.f), 63.f);
+    z_hat[i] = __float2half_rn(v);
+    z_i8[i] = static_cast<int8_t>(v);
+}
+
+int launch_round_z(const __half* z, __half* z_hat, int8_t* z_i8, long long n, cudaStream_t s)
+{
+    round_z_kernel<<<blocks_for(n, 256), 256, 0, s>>>(z, z_hat, z_i8, n);
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+int8_to_half_kernel(const int8_t* __restrict__ x, __half* __restrict__ out, long long n)
+{
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = __int2half_rn(static_cast<int>(x[i]));
+}
+
+int launch_int8_to_half(const int8_t* x, __half* out, long long n, cudaStream_t s)
+{
+    int8_to_half_kernel<<<blocks_for(n, 256), 256, 0, s>>>(x, out, n);
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- entropy path
+// One warp per latent pixel.  The active channel group of step k at 2x2 phase p = (h&1)*2+(w&1)
+// is p ^ {0,3,2,1}[k]  (get_mask_4x, common_model.py:174-195; dmci_proxy.cpp:678-699).
+__device__ __forceinline__ int active_group(int step, int h, int w)
+{
+    const int p = ((h & 1) << 1) | (w & 1);
+    const int x = (step == 0) ? 0 : (step == 1 ? 3 : (step == 2 ? 2 : 1));
+    return p ^ x;
+}
+
+struct EntropyDev {
+    int H, W, G, step;
+    const __half* y; int y_pitch;
+    const __half* q_enc;
+    const __half* scales; const __half* means; int p_pitch;
+    __half* acc; int acc_pitch;
+    __half thres;
+    const uint8_t* lut;
+    int16_t* sym_raw; uint8_t* idx_raw; int32_t* counts;
+};
+
+static EntropyDev to_dev(const EntropyStepArgs& a)
+{
+    EntropyDev d;
+    d.H = a.H; d.W = a.W; d.G = a.G; d.step = a.step;
+    d.y = a.y; d.y_pitch = a.y_pitch; d.q_enc = a.q_enc;
+    d.scales = a.scales; d.means = a.means; d.p_pitch = a.p_pitch;
+    d.acc = a.y_hat_acc; d.acc_pitch = a.acc_pitch;
+    d.thres = __float2half_rn(a.skip_thres);
+    d.lut = a.scale_lut;
+    d.sym_raw = a.sym_raw; d.idx_raw = a.idx_raw; d.counts = a.counts;
+    return d;
+}
+
+__global__ void __launch_bounds__(256)
+entropy_enc_step_kernel(const EntropyDev d)
+{
+    const int lane = threadIdx.x & 31;
+    const long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long npix = static_cast<long long>(d.H) * d.W;
+    if (pix >= npix) return;
+    const int w = static_cast<int>(pix % d.W);
+    const int h = static_cast<int>(pix / d.W);
+    const int g = active_group(d.step, h, w);
+    int count = 0;
+    for (int c = lane * 2; c < d.G; c += 64) {
+        const int ch = g * d.G + c;
+        __half2 yv = *reinterpret_cast<const __half2*>(d.y + pix * d.y_pitch + ch);
+        if (d.q_enc) yv = __hmul2(yv, *reinterpret_cast<const __half2*>(d.q_enc + ch));
+        const __half2 mv = *reinterpret_cast<const __half2*>(d.means + pix * d.p_pitch + ch);
+        const __half2 sv = *reinterpret_cast<const __half2*>(d.scales + pix * d.p_pitch + ch);
+        const __half2 res = __hsub2(yv, mv);
+        float q0 = round_half_away(__low2float(res));
+        float q1 = round_half_away(__high2float(res));
+        const bool c0 = __hgt(__low2half(sv), d.thres);
+        const bool c1 = __hgt(__high2half(sv), d.thres);
+        if (!c0) q0 = 0.f;
+        if (!c1) q1 = 0.f;
+        q0 = fminf(fmaxf(q0, -128.f), 127.f);
+        q1 = fminf(fmaxf(q1, -128.f), 127.f);
+        const __half2 yq = __floats2half2_rn(q0, q1);
+        const __half2 yh = __hadd2(yq, mv);
+        *reinterpret_cast<__half2*>(d.acc + pix * d.acc_pitch + ch) = yh;
+        const int i0 = d.lut[__half_as_ushort(__low2half(sv))];
+        const int i1 = d.lut[__half_as_ushort(__high2half(sv))];
+        short2 sym;
+        sym.x = static_cast<short>((static_cast<int>(q0) << 8) + i0);
+        sym.y = static_cast<short>((static_cast<int>(q1) << 8) + i1);
+        *reinterpret_cast<short2*>(d.sym_raw + pix * d.G + c) = sym;
+        count += (c0 ? 1 : 0) + (c1 ? 1 : 0);
+    }
+    if (d.step == 0) {
+        // y_hat_so_far.copy_(y_hat): the three inactive groups start at zero (dmci_proxy.cpp:344)
+        const __half2 z = __floats2half2_rn(0.f, 0.f);
+        for (int c = lane * 2; c < 4 * d.G; c += 64) {
+            if (c / d.G != g) *reinterpret_cast<__half2*>(d.acc + pix * d.acc_pitch + c) = z;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if (lane == 0) d.counts[pix] = count;
+}
+
+__global__ void __launch_bounds__(256)
+entropy_dec_index_kernel(const EntropyDev d)
+{
+    const int lane = threadIdx.x & 31;
+    const long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long npix = static_cast<long long>(d.H) * d.W;
+    if (pix >= npix) return;
+    const int w = static_cast<int>(pix % d.W);
+    const int h = static_cast<int>(pix / d.W);
+    const int g = active_group(d.step, h, w);
+    int count = 0;
+    for (int c = lane * 2; c < d.G; c += 64) {
+        const int ch = g * d.G + c;
+        const __half2 sv = *reinterpret_cast<const __half2*>(d.scales + pix * d.p_pitch + ch);
+        const bool c0 = __hgt(__low2half(sv), d.thres);
+        const bool c1 = __hgt(__high2half(sv), d.thres);
+        uchar2 idx;
+        idx.x = d.lut[__half_as_ushort(__low2half(sv))];
+        idx.y = d.lut[__half_as_ushort(__high2half(sv))];
+        *reinterpret_cast<uchar2*>(d.idx_raw + pix * d.G + c) = idx;
+        count += (c0 ? 1 : 0) + (c1 ? 1 : 0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if (lane == 0) d.counts[pix] = count;
+}
+
+// rank of this lane's two adjacent entries (2*lane, 2*lane+1) among the kept entries of the warp
+__device__ __forceinline__ void pair_ranks(bool c0, bool c1, int lane, int& r0, int& r1, int& tot)
+{
+    const unsigned b0 = __ballot_sync(0xffffffffu, c0);
+    const unsigned b1 = __ballot_sync(0xffffffffu, c1);
+    const unsigned lt = (1u << lane) - 1u;
+    r0 = __popc(b0 & lt) + __popc(b1 & lt);
+    r1 = r0 + (c0 ? 1 : 0);
+    tot = __popc(b0) + __popc(b1);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+compact_kernel(const EntropyDev d, const T* __restrict__ raw, const int32_t* __restrict__ offsets,
+               T* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long npix = static_cast<long long>(d.H) * d.W;
+    if (pix >= npix) return;
+    const int w = static_cast<int>(pix % d.W);
+    const int h = static_cast<int>(pix / d.W);
+    const int g = active_group(d.step, h, w);
+    int base = offsets[pix];
+    for (int c0i = 0; c0i < d.G; c0i += 64) {
+        const int c = c0i + lane * 2;
+        bool k0 = false, k1 = false;
+        T v0 = 0, v1 = 0;
+        if (c < d.G) {
+            const __half2 sv = *reinterpret_cast<const __half2*>(d.scales + pix * d.p_pitch + g * d.G + c);
+            k0 = __hgt(__low2half(sv), d.thres);
+            k1 = __hgt(__high2half(sv), d.thres);
+            v0 = raw[pix * d.G + c];
+            v1 = raw[pix * d.G + c + 1];
+        }
+        int r0, r1, tot;
+        pair_ranks(k0, k1, lane, r0, r1, tot);
+        if (k0) out[base + r0] = v0;
+        if (k1) out[base + r1] = v1;
+        base += tot;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+entropy_dec_restore_kernel(const EntropyDev d, const int32_t* __restrict__ offsets,
+                           const int8_t* __restrict__ decoded)
+{
+    const int lane = threadIdx.x & 31;
+    const long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long npix = static_cast<long long>(d.H) * d.W;
+    if (pix >= npix) return;
+    const int w = static_cast<int>(pix % d.W);
+    const int h = static_cast<int>(pix / d.W);
+    const int g = active_group(d.step, h, w);
+    int base = offsets[pix];
+    for (int c0i = 0; c0i < d.G; c0i += 64) {
+        const int c = c0i + lane * 2;
+        bool k0 = false, k1 = false;
+        __half2 mv = __floats2half2_rn(0.f, 0.f);
+        const int ch = g * d.G + c;
+        if (c < d.G) {
+            const __half2 sv = *reinterpret_cast<const __half2*>(d.scales + pix * d.p_pitch + ch);
+            k0 = __hgt(__low2half(sv), d.thres);
+            k1 = __hgt(__high2half(sv), d.thres);
+            mv = *reinterpret_cast<const __half2*>(d.means + pix * d.p_pitch + ch);
+        }
+        int r0, r1, tot;
+        pair_ranks(k0, k1, lane, r0, r1, tot);
+        if (c < d.G) {
+            const float q0 = k0 ? static_cast<float>(decoded[base + r0]) : 0.f;
+            const float q1 = k1 ? static_cast<float>(decoded[base + r1]) : 0.f;
+            const __half2 yh = __hadd2(__floats2half2_rn(q0, q1), mv);
+            *reinterpret_cast<__half2*>(d.acc + pix * d.acc_pitch + ch) = yh;
+        }
+        base += tot;
+    }
+    if (d.step == 0) {
+        const __half2 z = __floats2half2_rn(0.f, 0.f);
+        for (int c = lane * 2; c < 4 * d.G; c += 64) {
+            if (c / d.G != g) *reinterpret_cast<__half2*>(d.acc + pix * d.acc_pitch + c) = z;
+        }
+    }
+}
+
+static inline int warp_grid(long long npix) { return static_cast<int>((npix * 32 + 255) / 256); }
+
+int launch_entropy_enc_step(const EntropyStepArgs& a, cudaStream_t s)
+{
+    const long long npix = static_cast<long long>(a.H) * a.W;
+    entropy_enc_step_kernel<<<warp_grid(npix), 256, 0, s>>>(to_dev(a));
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_entropy_dec_index(const EntropyStepArgs& a, cudaStream_t s)
+{
+    const long long npix = static_cast<long long>(a.H) * a.W;
+    entropy_dec_index_kernel<<<warp_grid(npix), 256, 0, s>>>(to_dev(a));
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_compact_i16(const EntropyStepArgs& a, const int32_t* offsets, int16_t* out, cudaStream_t s)
+{
+    const long long npix = static_cast<long long>(a.H) * a.W;
+    compact_kernel<int16_t><<<warp_grid(npix), 256, 0, s>>>(to_dev(a), a.sym_raw, offsets, out);
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_compact_u8(const EntropyStepArgs& a, const int32_t* offsets, uint8_t* out, cudaStream_t s)
+{
+    const long long npix = static_cast<long long>(a.H) * a.W;
+    compact_kernel<uint8_t><<<warp_grid(npix), 256, 0, s>>>(to_dev(a), a.idx_raw, offsets, out);
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_entropy_dec_restore(const EntropyStepArgs& a, const int32_t* offsets,
+                               const int8_t* decoded, cudaStream_t s)
+{
+    const long long npix = static_cast<long long>(a.H) * a.W;
+    entropy_dec_restore_kernel<<<warp_grid(npix), 256, 0, s>>>(to_dev(a), offsets, decoded);
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+// single-CTA exclusive scan (n <= 1024 * 64)
+__global__ void __launch_bounds__(1024)
+scan_counts_kernel(const int32_t* __restrict__ counts, int32_t* __restrict__ offsets,
+                   int32_t* __restrict__ total, int n)
+{
+    __shared__ int warp_sums[32];
+    const int tid = threadIdx.x;
+    const int per = (n + 1023) / 1024;
+    const int begin = tid * per;
+    const int end = min(begin + per, n);
+    int local = 0;
+    for (int i = begin; i < end; ++i) local += counts[i];
+    // inclusive warp scan
+    int v = local;
+    const int lane = tid & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) warp_sums[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+        int ws = warp_sums[tid];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, ws, o);
+            if (tid >= o) ws += t;
+        }
+        warp_sums[tid] = ws;
+    }
+    __syncthreads();
+    int run = v - local + ((tid >> 5) > 0 ? warp_sums[(tid >> 5) - 1] : 0);
+    for (int i = begin; i < end; ++i) {
+        offsets[i] = run;
+        run += counts[i];
+    }
+    if (tid == 1023) {
+        offsets[n] = warp_sums[31];
+        *total = warp_sums[31];
+    }
+}
+
+int launch_scan_counts(const int32_t* counts, int32_t* offsets, int32_t* total, int n, cudaStream_t s)
+{
+    if (n > 1024 * 64) {
+        fprintf(stderr, "scan_counts: n=%d too large\n", n);
+        return 1;
+    }
+    scan_counts_kernel<<<1, 1024, 0, s>>>(counts, offsets, total, n);
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- host LUT
+void build_scale_lut(uint8_t* lut)
+{
+    // Reference (stream.cu:77-87) in half arithmetic:
+    //   s = min(max(s, 0.11), 16); s = hlog(s) - LOG_SCALE_MIN; s = s * LOG_SCALE_STEP_RECIP;
+    //   idx = __half2uint_rd(s)
+    const float log_min_f = -2.2073f;
+    const float log_max_f = 2.7726f;
+    const float recip_f = 1.f / ((log_max_f - log_min_f) / 127.f);
+    const __half h_min = __float2half_rn(0.11f);
+    const __half h_max = __float2half_rn(16.f);
+    const __half h_logmin = __float2half_rn(log_min_f);
+    const __half h_recip = __float2half_rn(recip_f);
+    for (int b = 0; b < 65536; ++b) {
+        const __half_raw raw = { static_cast<unsigned short>(b) };
+        float s = __half2float(__half(raw));
+        const float fmin_ = __half2float(h_min);
+        const float fmax_ = __half2float(h_max);
+        if (!(s >= fmin_)) s = fmin_;  // also maps NaN / negatives to the minimum
+        if (s > fmax_) s = fmax_;
+        const __half l = __float2half_rn(logf(s));
+        const __half d = __float2half_rn(__half2float(l) - __half2float(h_logmin));
+        const __half m = __float2half_rn(__half2float(d) * __half2float(h_recip));
+        float f = floorf(__half2float(m));
+        if (f < 0.f) f = 0.f;
+        if (f > 127.f) f = 127.f;
+        lut[b] = static_cast<uint8_t>(f);
+    }
+}
+
+}  // namespace dcvc

@@ -1,0 +1,174 @@
+/*
+ * dcvc_b200.h — C ABI of libdcvc_b200.so: the B200-native drop-in for the DCVC-UF per-frame
+ * inference hot path.  Plain pointers and sizes only; no torch / ATen types cross this boundary.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * microsoft/DCVC tree; the pybind11 module `inference_extensions_cuda` is defined in
+ * src/layers/extensions/inference/bind.cpp:11-38).
+ *
+ * Conventions: all functions return 0 on success, non-zero on failure; the message is available
+ * through dcvc_last_error() (thread-local for op-level calls, per-handle for codec calls).
+ * Activations are fp16, NHWC ("channels_last"), batch 1, with an explicit channel pitch so that
+ * channel slices of concatenated buffers can be passed without copies.  `stream` is a
+ * cudaStream_t passed as void*.
+ */
+#ifndef DCVC_B200_H
+#define DCVC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* dcvc_last_error(void);
+/* compiled-for architecture string ("sm_100a") and ABI version */
+const char* dcvc_build_info(void);
+int dcvc_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Op-level ABI — one entry per kernel family of SURVEY.md §2.2.
+ * ------------------------------------------------------------------------------------------- */
+
+/* NHWC view: element (y,x,c) = ptr[(y*W + x)*pitch + c] */
+typedef struct dcvc_view {
+    const void* ptr;
+    int32_t C, pitch, W, H;
+} dcvc_view;
+
+enum { DCVC_GEMM_PW = 0, DCVC_GEMM_CONV3X3_S2 = 1, DCVC_GEMM_CONV2X2_S2 = 2, DCVC_GEMM_TCONV2X2 = 3 };
+enum { DCVC_ACT_NONE = 0, DCVC_ACT_WSILU = 1 };
+
+/*
+ * Dense contraction with fused epilogue: out = [chunk_add4]( act( in (*) W + bias ) ) [+ res1] [+ res2] [* qscale]
+ * Replaces conv1x1_bias / _wsilu / _shortcut / _shortcut2 / _with_quant / _shortcut_with_quant /
+ * _wsilu_chunk_add (cutlass/conv1x1_*.cu), conv_bias (cutlass/conv_bias.cu:131-150, 3x3/s2 and
+ * 2x2/s2) and transposed_conv (cutlass/transposed_conv.cu:101-119).
+ * `weight` is the packed [N][taps*Cin] K-major matrix produced by dcvc_pack_weight().
+ */
+typedef struct dcvc_gemm_desc {
+    int32_t kind;          /* DCVC_GEMM_* */
+    dcvc_view in, out, res1, res2; /* res*.ptr == NULL: absent */
+    const void* weight;    /* fp16 packed */
+    const void* bias;      /* fp16 [N] or NULL */
+    const void* qscale;    /* fp16 [out.C] or NULL */
+    int32_t N;             /* GEMM columns */
+    int32_t act;           /* DCVC_ACT_* */
+    int32_t chunk_add;     /* 1: N -> N/4 by summing groups of 4 consecutive columns after act */
+} dcvc_gemm_desc;
+
+int dcvc_op_gemm(const dcvc_gemm_desc* d, void* stream);
+
+/* Host helper: re-lay a PyTorch conv weight (fp16, contiguous [Cout][Cin][kh][kw] on the HOST)
+ * into the packed layout of `kind` (layers_proxy.cpp:260-266, 314-323).  dst holds N*Ktot halves. */
+int dcvc_pack_weight(int32_t kind, const void* w_host, int32_t cout, int32_t cin, int32_t kh,
+                     int32_t kw, void* dst_host);
+
+/* depthwise 3x3, pad 1, no bias; w = [9][C] fp16 tap-major (cutlass/d3x3.cu:443-446) */
+int dcvc_op_dw3x3(const dcvc_view* in, const dcvc_view* out, const void* w, void* stream);
+
+/* pad_and_unshuffle_8_cuda (elementwise/cat_and_pad.cu:7-51): x is [1,Cs,H,W] with element
+ * strides (sc,sh,sw); replicate-pads to the size of `out` * 8 */
+int dcvc_op_unshuffle8_pad(const void* x, int32_t Cs, int32_t H, int32_t W, int64_t sc, int64_t sh,
+                           int64_t sw, const dcvc_view* out, void* stream);
+/* pixel_shuffle_8_cuda(clamp) (elementwise/shuffle.cu:123-137): out is NHWC [in.H*8][in.W*8][Cs] */
+int dcvc_op_shuffle8_clamp(const dcvc_view* in, void* out, int32_t Cs, int32_t clamp, void* stream);
+/* replicate_pad_cuda / slice_cuda (elementwise/cat_and_pad.cu:53-110) */
+int dcvc_op_pad_crop(const dcvc_view* in, const dcvc_view* out, void* stream);
+/* multiply_with_broadcast_cuda (elementwise/stream.cu:484-546) */
+int dcvc_op_scale_channels(const dcvc_view* in, const void* q, const dcvc_view* out, void* stream);
+/* round_z_cuda / int8_to_dtype_cuda (elementwise/stream.cu:862-894, 454-482) */
+int dcvc_op_round_z(const void* z, void* z_hat, void* z_i8, int64_t n, void* stream);
+int dcvc_op_int8_to_half(const void* x, void* out, int64_t n, void* stream);
+
+/* Entropy-parameter path, one 4x-mask step (elementwise/stream.cu:77-173, 175-420, 548-630,
+ * 756-818, 896-949).  Buffers: see dcvc_entropy_step. */
+typedef struct dcvc_entropy_step {
+    int32_t H, W, G, step;
+    const void* y; int32_t y_pitch;
+    const void* q_enc;
+    const void* scales; const void* means; int32_t p_pitch;
+    void* y_hat_acc; int32_t acc_pitch;
+    float skip_thres;
+    void* sym_raw;   /* int16 [H*W][G]  (encoder) */
+    void* idx_raw;   /* uint8 [H*W][G]  (decoder) */
+    void* counts;    /* int32 [H*W] */
+    void* offsets;   /* int32 [H*W+1] */
+    void* total;     /* int32 [1] */
+    void* compact;   /* int16 (enc) or uint8 (dec) [H*W*G] */
+    const void* decoded; /* int8 compacted decoded symbols (decoder restore) */
+} dcvc_entropy_step;
+
+/* process_with_mask + fold + build_index_enc + compaction */
+int dcvc_op_entropy_enc_step(const dcvc_entropy_step* a, void* stream);
+/* fold + build_index_dec + compaction */
+int dcvc_op_entropy_dec_index(const dcvc_entropy_step* a, void* stream);
+/* conditional_recover + restore_y_4x */
+int dcvc_op_entropy_dec_restore(const dcvc_entropy_step* a, void* stream);
+/* 65536-entry fp16-bits -> scale-table index LUT (host) */
+int dcvc_scale_index_lut(uint8_t* lut65536);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host rANS coder (stays on the CPU).  Replaces MLCodec_extensions_cpp RansEncoder/RansDecoder/
+ * pmf_to_quantized_cdf (src/cpp/py_rans/bind.cpp:14-40) with bit-identical streams.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dcvc_rans dcvc_rans;
+int dcvc_rans_create(dcvc_rans** out);
+void dcvc_rans_destroy(dcvc_rans* r);
+/* index 0: z (factorised) tables, 1: y (Gaussian) tables; cdf is [rows][width] int32 */
+int dcvc_rans_set_cdf(dcvc_rans* r, const int32_t* cdf, const int32_t* cdf_sizes, int32_t rows,
+                      int32_t width, int32_t index);
+/* encoder: queue jobs in coding order, then finish() -> merged stream */
+int dcvc_rans_enc_reset(dcvc_rans* r);
+int dcvc_rans_enc_y(dcvc_rans* r, const int16_t* symbols, int32_t n);
+int dcvc_rans_enc_z(dcvc_rans* r, const int8_t* symbols, int32_t n, int32_t cdf_offset, int32_t ch);
+int dcvc_rans_enc_finish(dcvc_rans* r, int32_t n_parallel, const uint8_t** data, int32_t* size);
+/* decoder */
+int dcvc_rans_dec_set_stream(dcvc_rans* r, const uint8_t* data, int32_t size, int32_t n_parallel);
+int dcvc_rans_dec_z(dcvc_rans* r, int8_t* out, int32_t n, int32_t cdf_offset, int32_t ch);
+int dcvc_rans_dec_y(dcvc_rans* r, int8_t* out, const uint8_t* cdf_rows, int32_t n);
+int dcvc_pmf_to_quantized_cdf(const float* pmf, int32_t n, uint32_t* cdf_out /* n+1 */);
+
+/* ---------------------------------------------------------------------------------------------
+ * Codec-level ABI — what the pybind classes DMCIProxy / DMCHTSProxy bind (bind.cpp:13-31).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dcvc_codec dcvc_codec;
+enum { DCVC_KIND_INTRA = 0, DCVC_KIND_HTS = 1, DCVC_KIND_HTL = 2, DCVC_KIND_LD = 3 };
+enum { DCVC_DTYPE_F16 = 0, DCVC_DTYPE_I32 = 1, DCVC_DTYPE_F32 = 2 };
+
+/* DMCIProxy() / DMCHTSProxy() constructors (dmci_proxy.cpp:269-276) */
+int dcvc_create(int32_t kind, int32_t device, dcvc_codec** out);
+int dcvc_destroy(dcvc_codec* h);
+const char* dcvc_codec_error(dcvc_codec* h);
+
+/* set_param(state_dict, skip_thres) (dmci_proxy.cpp:604-652), one tensor at a time: `data` is a
+ * device pointer for fp16 params, a host pointer for the int32 CDF tables; contiguous in `shape`. */
+int dcvc_set_param(dcvc_codec* h, const char* name, const void* data, int32_t dtype, int32_t ndim,
+                   const int64_t* shape, int32_t on_device);
+int dcvc_finalize_params(dcvc_codec* h, float skip_thres);
+
+/* DMCIProxy::compress (dmci_proxy.cpp:296-421): x = fp16 [1,3,H,W] device tensor with element
+ * strides (sc,sh,sw); x_hat_out = caller-owned fp16 NHWC [H16*16][W16*16][3] device buffer.
+ * The bitstream stays valid until the next call on this handle. */
+int dcvc_compress(dcvc_codec* h, const void* x, int32_t H, int32_t W, int64_t sc, int64_t sh,
+                  int64_t sw, int32_t qp, int32_t pad_b, int32_t pad_r, void* stream,
+                  const uint8_t** bit_stream, int32_t* bit_stream_len, int32_t* ec_parallel,
+                  void* x_hat_out);
+/* DMCIProxy::decompress (dmci_proxy.cpp:423-602) */
+int dcvc_decompress(dcvc_codec* h, const uint8_t* bit_stream, int32_t len, int32_t qp,
+                    int32_t height, int32_t width, int32_t ec_parallel, void* stream,
+                    void* x_hat_out);
+
+/* instrumentation for bench.py: kernels launched by this handle since creation, and the GPU-only
+ * duration (ms) of the segments of the last compress/decompress (CUDA events on `stream`). */
+int64_t dcvc_kernel_launches(dcvc_codec* h);
+int dcvc_last_gpu_ms(dcvc_codec* h, float* ms);
+/* debug taps for parity tests: copy a named internal buffer (fp16) to host. */
+int dcvc_debug_fetch(dcvc_codec* h, const char* name, void* host_dst, int64_t max_bytes,
+                     int64_t* bytes_written);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCVC_B200_H */
