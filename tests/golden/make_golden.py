@@ -1,0 +1,124 @@
+"""Generates tests/golden/*.npz|json by importing the REFERENCE itself (python modules from
+/root/reference, rANS built from its sources into oracle/_ref).  Run in the authoring container:
+
+    python tests/golden/make_golden.py
+
+The reference ships no golden vectors of its own, so these fixtures are what pins
+the oracle (oracle/dmci_oracle.py, oracle/ops_ref.py) and the host-side mirrors (dcvc_b200/spec.py,
+dcvc_b200/entropy.py, the product rANS coder).  Weights are never stored: they are regenerated from
+dcvc_b200.spec.synth_state_dict(seed).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+from oracle.build_ref import build_ref, OUT_DIR  # noqa: E402
+
+build_ref()
+sys.path.insert(0, OUT_DIR)
+
+from src.models.image_model import DMCI  # noqa: E402  (reference)
+from src.models.entropy_models import BitEstimator, EntropyCoder, GaussianEncoder  # noqa: E402
+import MLCodec_extensions_cpp as ref_rans  # noqa: E402
+
+from dcvc_b200.spec import dmci_spec, synth_state_dict  # noqa: E402
+
+
+def synth_frame(h, w, seed):
+    """band-limited noise frame in [-0.5, 0.5], fp16-representable (SURVEY.md §8d recipe, 4:4:4)"""
+    rng = np.random.default_rng(seed)
+    x = rng.random((1, 3, h + 4, w + 4)).astype(np.float32)
+    t = torch.from_numpy(x)
+    t = torch.nn.functional.avg_pool2d(t, 5, 1)
+    t = (t - t.mean()) / t.std() * 0.18
+    return t.clamp(-0.5, 0.5).half().float()
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    # 1. state_dict layout of the reference model
+    m = DMCI()
+    layout = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(HERE, "dmci_state_dict_layout.json"), "w") as f:
+        json.dump(layout, f, indent=0, sort_keys=True)
+
+    # 2. Gaussian CDF table (deterministic) and a seeded factorised-z table
+    ec = EntropyCoder()
+    ge = GaussianEncoder()
+    ge.update(ec, skip_thres=0.15)
+    q, l = ge.get_cdf_info()
+    np.savez_compressed(os.path.join(HERE, "gaussian_cdf.npz"), quantized_cdf=q, cdf_length=l)
+    be = BitEstimator(4, 16)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        be.h.copy_(torch.randn(be.h.shape, generator=g) * 0.6 + 0.4)
+        be.b.copy_(torch.randn(be.b.shape, generator=g) * 0.5)
+        be.a.copy_(torch.randn(be.a.shape, generator=g) * 0.5)
+    be.update(ec)
+    q, l = be.get_cdf_info()
+    np.savez_compressed(os.path.join(HERE, "bitest_cdf.npz"), h=be.h.detach().numpy(), b=be.b.detach().numpy(),
+                        a=be.a.detach().numpy(), quantized_cdf=q, cdf_length=l)
+
+    # 3. reference forward_one_frame on synthetic weights (seed 0), 64x64 and 128x64
+    sd = synth_state_dict(dmci_spec(), 0)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    for (h, w, qp) in [(64, 64, 0), (64, 64, 32), (128, 64, 63)]:
+        x = synth_frame(h, w, 1234 + qp)
+        with torch.inference_mode():
+            # replicate the internals we want to pin in addition to x_hat
+            res = m.forward_one_frame(x, torch.tensor([qp]))
+            q_enc = m.index_select_dim0(m.q_scale_enc, torch.tensor([qp]))
+            y = m.enc(x, q_enc)
+            z = m.hyper_enc(y)
+        np.savez_compressed(os.path.join(HERE, f"dmci_forward_{h}x{w}_qp{qp}.npz"),
+                            x=x.numpy(), x_hat=res["x_hat"].numpy(), y=y.numpy(), z=z.numpy(),
+                            bits_y=res["bits_y"].numpy(), bits_z=res["bits_z"].numpy())
+
+    # 4. reference rANS streams for seeded symbols
+    m.update(0.15)
+    zc, zl = m.bit_estimator_z.get_cdf_info()
+    yc, yl = m.gaussian_encoder.get_cdf_info()
+    enc = ref_rans.RansEncoder()
+    enc.set_cdf(zc, zl, 0)
+    enc.set_cdf(yc, yl, 1)
+    out = {}
+    rng = np.random.default_rng(77)
+    for n_par, n_y, n_z in [(1, 5000, 640), (2, 70000, 1280), (3, 100001, 2560), (4, 40000, 128 * 7), (5, 170000, 1280),
+                            (8, 270000, 65280), (1, 0, 128), (2, 3, 128)]:
+        # symbols: mostly small, a few escapes; rows random
+        def make_y(n):
+            sym = np.rint(rng.standard_normal(n) * rng.choice([0.3, 1.5, 6.0, 40.0], n, p=[0.5, 0.3, 0.15, 0.05]))
+            sym = np.clip(sym, -128, 127).astype(np.int32)
+            row = rng.integers(0, 128, n).astype(np.int32)
+            return ((sym << 8) + row).astype(np.int16)
+        ys = [make_y(n_y // (k + 1)) for k in range(4)]
+        z = np.clip(np.rint(rng.standard_normal(n_z) * 3), -64, 63).astype(np.int8)
+        qp = int(rng.integers(0, 64))
+        enc.reset()
+        enc.set_entropy_coder_parallel(n_par)
+        for k in (3, 2, 1, 0):
+            enc.encode_y(ys[k])
+        enc.encode_z(z, qp * 128, 128)
+        enc.flush()
+        stream = np.asarray(enc.get_encoded_stream()).copy()
+        key = f"p{n_par}_y{n_y}_z{n_z}"
+        for k in range(4):
+            out[f"{key}_y{k}"] = ys[k]
+        out[f"{key}_z"] = z
+        out[f"{key}_qp"] = np.int32(qp)
+        out[f"{key}_stream"] = stream
+    np.savez_compressed(os.path.join(HERE, "rans_streams.npz"), **out)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

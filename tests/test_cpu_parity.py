@@ -1,0 +1,229 @@
+"""CPU-side checks (no GPU): the oracle against the golden vectors minted from the reference,
+the host-side mirrors (spec, CDF tables, rANS coder) against the same goldens, and the C-ABI
+library loading with every symbol include/dcvc_b200.h declares."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from dcvc_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from dcvc_b200.build import build
+        build()
+    return _lib.load()
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    from dcvc_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "dcvc_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(dcvc_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) > 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in dcvc_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.dcvc_abi_version() == 1
+    assert b"sm_100a" in lib.dcvc_build_info()
+
+
+def test_spec_matches_reference_layout():
+    from dcvc_b200.spec import dmci_spec
+    gold = json.load(open(os.path.join(GOLD, "dmci_state_dict_layout.json")))
+    mine = {k: list(v) for k, v in dmci_spec().items()}
+    assert mine == gold
+
+
+def test_gaussian_cdf_tables(lib):
+    from dcvc_b200.entropy import gaussian_cdf_tables
+    g = np.load(os.path.join(GOLD, "gaussian_cdf.npz"))
+    cdf, length = gaussian_cdf_tables()
+    assert np.array_equal(cdf, g["quantized_cdf"])
+    assert np.array_equal(length, g["cdf_length"])
+
+
+def test_bit_estimator_cdf_tables(lib):
+    from dcvc_b200.entropy import bit_estimator_cdf_tables
+    g = np.load(os.path.join(GOLD, "bitest_cdf.npz"))
+    cdf, length = bit_estimator_cdf_tables(torch.from_numpy(g["h"]), torch.from_numpy(g["b"]), torch.from_numpy(g["a"]))
+    assert np.array_equal(cdf, g["quantized_cdf"])
+    assert np.array_equal(length, g["cdf_length"])
+
+
+def test_scale_lut_product_equals_oracle(lib):
+    from dcvc_b200 import ops
+    from oracle import ops_ref
+    lut = ops.scale_index_lut()
+    assert np.array_equal(lut, ops_ref.scale_index_lut())
+    # monotone in the scale, spans the table
+    vals = np.arange(0x2000, 0x5000, dtype=np.uint16)
+    assert np.all(np.diff(lut[vals].astype(int)) >= 0) and lut[vals].max() == 127 and lut[vals].min() == 0
+
+
+class _Rans:
+    def __init__(self, lib, zc, zl, yc, yl):
+        self.lib = lib
+        self.h = C.c_void_p()
+        assert lib.dcvc_rans_create(C.byref(self.h)) == 0
+        for idx, (c, l) in enumerate(((zc, zl), (yc, yl))):
+            c = np.ascontiguousarray(c, dtype=np.int32)
+            l = np.ascontiguousarray(l, dtype=np.int32)
+            assert lib.dcvc_rans_set_cdf(self.h, c.ctypes.data, l.ctypes.data, c.shape[0], c.shape[1], idx) == 0
+
+    def encode(self, ys, z, qp, n_par):
+        lib = self.lib
+        lib.dcvc_rans_enc_reset(self.h)
+        keep = []
+        for k in (3, 2, 1, 0):
+            a = np.ascontiguousarray(ys[k], dtype=np.int16)
+            keep.append(a)
+            lib.dcvc_rans_enc_y(self.h, a.ctypes.data, a.size)
+        zz = np.ascontiguousarray(z, dtype=np.int8)
+        lib.dcvc_rans_enc_z(self.h, zz.ctypes.data, zz.size, qp * 128, 128)
+        data, size = C.c_void_p(), C.c_int32()
+        assert lib.dcvc_rans_enc_finish(self.h, n_par, C.byref(data), C.byref(size)) == 0
+        return np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_uint8)), (size.value,)).copy()
+
+    def decode(self, stream, ys, n_z, qp, n_par):
+        lib = self.lib
+        s = np.ascontiguousarray(stream, dtype=np.uint8)
+        assert lib.dcvc_rans_dec_set_stream(self.h, s.ctypes.data, s.size, n_par) == 0
+        z = np.zeros(n_z, dtype=np.int8)
+        assert lib.dcvc_rans_dec_z(self.h, z.ctypes.data, n_z, qp * 128, 128) == 0
+        outs = []
+        for k in range(4):
+            rows = np.ascontiguousarray((ys[k] & 0xff).astype(np.uint8))
+            o = np.zeros(rows.size, dtype=np.int8)
+            assert lib.dcvc_rans_dec_y(self.h, o.ctypes.data, rows.ctypes.data, rows.size) == 0
+            outs.append(o)
+        return z, outs
+
+    def __del__(self):
+        self.lib.dcvc_rans_destroy(self.h)
+
+
+@pytest.fixture(scope="module")
+def tables(lib):
+    from dcvc_b200.entropy import bit_estimator_cdf_tables, gaussian_cdf_tables
+    from dcvc_b200.spec import dmci_spec, synth_state_dict
+    sd = synth_state_dict({k: v for k, v in dmci_spec().items() if k.startswith("bit_estimator_z.")}, 0)
+    # NB: the generator consumes random numbers in spec order, bit_estimator_z.* come first
+    zc, zl = bit_estimator_cdf_tables(sd["bit_estimator_z.h"], sd["bit_estimator_z.b"], sd["bit_estimator_z.a"])
+    yc, yl = gaussian_cdf_tables()
+    return zc, zl, yc, yl
+
+
+def test_rans_streams_bit_identical_to_reference(lib, tables):
+    """product coder vs byte streams produced by the reference's own coder (golden)"""
+    g = np.load(os.path.join(GOLD, "rans_streams.npz"))
+    r = _Rans(lib, *tables)
+    keys = sorted({k.rsplit("_", 1)[0] for k in g.files})
+    assert len(keys) >= 8
+    for key in keys:
+        n_par = int(key.split("_")[0][1:])
+        ys = [g[f"{key}_y{k}"] for k in range(4)]
+        z, qp, ref_stream = g[f"{key}_z"], int(g[f"{key}_qp"]), g[f"{key}_stream"]
+        mine = r.encode(ys, z, qp, n_par)
+        assert mine.size == ref_stream.size and np.array_equal(mine, ref_stream), f"stream differs for {key}"
+        dz, dys = r.decode(ref_stream, ys, z.size, qp, n_par)
+        assert np.array_equal(dz, z)
+        for k in range(4):
+            assert np.array_equal(dys[k], (ys[k] >> 8).astype(np.int8)), f"decode differs {key} step {k}"
+
+
+def test_rans_live_against_reference_build(lib, tables):
+    """same check against the reference coder built into oracle/_ref, on fresh random symbols"""
+    from oracle.build_ref import import_ref_shim
+    ref = import_ref_shim()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    zc, zl, yc, yl = tables
+    enc, dec = ref.RansEncoder(), ref.RansDecoder()
+    for c in (enc, dec):
+        c.set_cdf(zc, zl, 0)
+        c.set_cdf(yc, yl, 1)
+    r = _Rans(lib, *tables)
+    rng = np.random.default_rng(3)
+    for n_par in (1, 2, 3, 4, 6, 7, 8):
+        n = int(rng.integers(1000, 60000))
+        sym = np.clip(np.rint(rng.standard_normal(n) * rng.choice([0.5, 3, 30], n)), -128, 127).astype(np.int32)
+        ys = [((sym[: n // (k + 1)] << 8) + rng.integers(0, 128, n // (k + 1))).astype(np.int16) for k in range(4)]
+        z = np.clip(np.rint(rng.standard_normal(128 * 9) * 5), -64, 63).astype(np.int8)
+        qp = int(rng.integers(0, 64))
+        enc.reset()
+        enc.set_entropy_coder_parallel(n_par)
+        for k in (3, 2, 1, 0):
+            enc.encode_y(ys[k])
+        enc.encode_z(z, qp * 128, 128)
+        enc.flush()
+        ref_stream = np.asarray(enc.get_encoded_stream()).copy()
+        assert np.array_equal(r.encode(ys, z, qp, n_par), ref_stream)
+        # reference decoder on the product's stream
+        dec.set_entropy_coder_parallel(n_par)
+        dec.set_stream(ref_stream)
+        dec.decode_z(z.size, qp * 128, 128)
+        assert np.array_equal(dec.get_decoded(z.size), z)
+        dz, dys = r.decode(ref_stream, ys, z.size, qp, n_par)
+        assert np.array_equal(dz, z)
+
+
+def test_pmf_to_quantized_cdf_against_reference(lib):
+    from oracle.build_ref import import_ref_shim
+    from dcvc_b200.entropy import pmf_to_quantized_cdf
+    ref = import_ref_shim()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(9)
+    for _ in range(200):
+        n = int(rng.integers(2, 19))
+        p = rng.random(n).astype(np.float32) ** 6
+        p[rng.integers(0, n)] += 1e-9
+        p = (p / p.sum()).astype(np.float32)
+        assert list(ref.pmf_to_quantized_cdf(p.tolist())) == pmf_to_quantized_cdf(p).tolist()
+
+
+@pytest.mark.parametrize("name", ["dmci_forward_64x64_qp0", "dmci_forward_64x64_qp32", "dmci_forward_128x64_qp63"])
+def test_oracle_forward_pinned_to_reference(name):
+    """oracle.forward_one_frame (fp32) vs outputs of the reference's own nn.Modules"""
+    from dcvc_b200.spec import dmci_spec, synth_state_dict
+    from oracle.dmci_oracle import DmciOracle
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    qp = int(name.split("qp")[1])
+    o = DmciOracle(synth_state_dict(dmci_spec(), 0), emulate_fp16=False, threads=8)
+    x = torch.from_numpy(g["x"])
+    y = o.encoder(torch.nn.functional.pixel_unshuffle(x, 8), qp)
+    assert np.allclose(y.numpy(), g["y"], atol=2e-4, rtol=1e-4)
+    assert np.allclose(o.hyper_enc(y).numpy(), g["z"], atol=2e-4, rtol=1e-4)
+    res = o.forward_one_frame(x, qp)
+    # quantisation can flip on fp32 reassociation noise at exact ties; bound the damage
+    diff = np.abs(res["x_hat"].numpy() - g["x_hat"])
+    assert np.mean(diff > 1e-3) < 2e-3, f"x_hat mismatch fraction {np.mean(diff > 1e-3)}"
+
+
+def test_oracle_compress_decompress_consistency():
+    """proxy restatement: decoder reproduces the encoder's reconstruction bit for bit, through the
+    reference's own rANS coder"""
+    from oracle.build_ref import import_ref_shim
+    if import_ref_shim() is None:
+        pytest.skip("oracle/_ref not built")
+    from dcvc_b200.spec import dmci_spec, synth_state_dict
+    from oracle.dmci_oracle import DmciOracle
+    g = np.load(os.path.join(GOLD, "dmci_forward_64x64_qp32.npz"))
+    x = torch.from_numpy(g["x"])[:, :, :56, :60].contiguous()   # ragged: exercises padding
+    o = DmciOracle(synth_state_dict(dmci_spec(), 0), skip_thres=0.15, emulate_fp16=True, threads=8)
+    enc = o.compress(x, 40, 8, 4)
+    dec = o.decompress(enc["bit_stream"], 40, 56, 60, enc["ec_parallel"])
+    assert np.array_equal(enc["y_hat"].view(np.uint16), dec["y_hat"].view(np.uint16))
+    assert torch.equal(enc["x_hat"], dec["x_hat"])
+    assert enc["x_hat"].shape == (1, 3, 64, 64)
+    total = sum(len(s) for s in enc["symbols"])
+    assert 0 < total < 4 * 4 * 256 * 4 and len(enc["bit_stream"]) > 8
