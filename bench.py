@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — DCVC-UF-Intra 1080p decode/encode throughput on N x B200 (BASELINE.json configs[1]).
+
+A "step" is one pass of the hot path over one synthetic 1080p 4:4:4 frame: `DMCI.decompress` of a
+bitstream produced beforehand by `DMCI.compress` (neural synthesis + entropy-parameter path on the
+GPU, rANS on the host CPU, exactly the reference's FPS protocol: test_video.py:295-325).  `value`
+keeps the reconstruction in HBM; `e2e` additionally copies the reconstruction to pinned host memory
+inside the timed region.  Encode FPS, GPU-only segment time, the per-kernel-family roofline and the
+CPU baseline (oracle port on the host cores) ride along in the same JSON line.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference        # the reference's CPU path (oracle port + reference rANS)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+H, W = 1080, 1920
+QP = 32
+SKIP = 0.15  # test_compress_time.py:41
+METRIC = "1080p_yuv_decode_fps"
+# algorithmic bytes of the Intra decode side at the reference's fusion granularity
+ALG_BYTES_DECODE = 5.89e9
+ALG_GMAC_DECODE = 701.2
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+
+
+def make_model(device, world, rank):
+    """rank 0 generates the synthetic checkpoint; it is broadcast once over NCCL."""
+    import torch.distributed as dist
+    from dcvc_b200.model import DMCI
+    from dcvc_b200.spec import dmci_spec, synth_state_dict
+    spec = dmci_spec()
+    if world == 1:
+        sd = synth_state_dict(spec, 0)
+    else:
+        numel = sum(int(np.prod(s)) for s in spec.values())
+        blob = torch.empty(numel, dtype=torch.float32, device=device)
+        if rank == 0:
+            sd0 = synth_state_dict(spec, 0)
+            blob.copy_(torch.cat([sd0[k].reshape(-1) for k in spec]))
+        dist.broadcast(blob, 0)
+        sd, off = {}, 0
+        host = blob.cpu()
+        for k, s in spec.items():
+            n = int(np.prod(s))
+            sd[k] = host[off:off + n].view(s).clone()
+            off += n
+    m = DMCI()
+    m.load_state_dict(sd)
+    m.update(SKIP)
+    return m.half().to(device)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from util_frames import psnr, synth_frame
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the product has no CPU path)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    model = make_model(device, world, rank)
+    stream = torch.cuda.Stream(device)
+    torch.cuda.set_stream(stream)  # a non-default stream, like test_video.py:423-425
+
+    x = synth_frame(H, W, 1234 + rank).half().to(device).contiguous(memory_format=torch.channels_last)
+    pad_r, pad_b = model.get_padding_size(H, W, 16)
+    sps = {"height": H, "width": W}
+    enc = model.compress(x, QP, pad_b, pad_r)
+    x_hat_enc = enc["x_hat"].clone()
+    bs = enc["bit_stream"]
+    dec = model.decompress(bs, sps, QP, enc["ec_parallel"])
+    torch.cuda.synchronize()
+    assert torch.equal(x_hat_enc, dec["x_hat"]), "decode does not match encode"
+    totals = model.proxy.debug_fetch("totals", np.int32)
+    n_sym = int(totals.sum())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    host_out = torch.empty(dec["x_hat"].shape, dtype=torch.float16).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for e0, e1 in evs:
+            flush.zero_()            # evict L2 between timed iterations (outside the timed interval)
+            e0.record()
+            fn()
+            e1.record()
+        barrier()
+        return [e0.elapsed_time(e1) for e0, e1 in evs]
+
+    def step_dec():
+        model.decompress(bs, sps, QP, enc["ec_parallel"])
+
+    def step_dec_e2e():
+        out = model.decompress(bs, sps, QP, enc["ec_parallel"])["x_hat"]
+        host_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller owns the host copy when the step ends
+
+    def step_enc():
+        model.compress(x, QP, pad_b, pad_r)
+
+    for _ in range(args.warmup):
+        step_dec(); step_dec_e2e(); step_enc()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = model.proxy.kernel_launches()
+    t_dec = timed(step_dec, args.steps)
+    l1 = model.proxy.kernel_launches()
+    gpu_only_ms = model.proxy.last_gpu_ms()
+    t_e2e = timed(step_dec_e2e, args.steps)
+    t_enc = timed(step_enc, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    def reduce_max(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    tot_dec = reduce_max(sum(t_dec))
+    tot_e2e = reduce_max(sum(t_e2e))
+    tot_enc = reduce_max(sum(t_enc))
+
+    # ---- per-kernel-family roofline (CUDA events around every launch, graphs off)
+    hbm_peak, tf_peak, peak_src = _peaks()
+    model.proxy.profile_enable(True)
+    for _ in range(3):
+        step_dec()
+    torch.cuda.synchronize()
+    prof = model.proxy.profile_get()
+    model.proxy.profile_enable(False)
+    g = prof["pw_gemm"]
+    roofline = None
+    if g["launches"]:
+        gbs = g["alg_bytes"] / (g["ms"] * 1e-3) / 1e9
+        tfs = g["flops"] / (g["ms"] * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_pw_gemm.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "kernel": "pw_gemm_kernel", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
+                    "frac": round(gbs / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
+                    "launches_per_step": g["launches"] // 3,
+                    "avg_launch_us": round(g["ms"] * 1e3 / g["launches"], 2),
+                    "alg_bytes_per_launch": round(g["alg_bytes"] / g["launches"]),
+                    "tensor_tflops": round(tfs, 1), "tensor_frac": round(tfs / tf_peak, 4),
+                    "share_of_gpu_time": round(g["ms"] / max(1e-9, sum(v["ms"] for v in prof.values())), 3),
+                    "families_ms_per_step": {k: round(v["ms"] / 3, 3) for k, v in prof.items()},
+                    "whole_decode_alg_gbs": round(ALG_BYTES_DECODE / (gpu_only_ms * 1e-3) / 1e9, 1),
+                    "whole_decode_frac": round(ALG_BYTES_DECODE / (gpu_only_ms * 1e-3) / 1e9 / hbm_peak, 4)}
+
+    # ---- CPU baseline: the oracle port on the host cores (rank 0, N=1 only), bounded sample
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_reference_sample(steps=1, sample_hw=(544, 960))
+
+    if rank == 0:
+        fps = world * args.steps / (tot_dec * 1e-3)
+        out = {
+            "metric": METRIC, "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(tot_dec / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "DCVC-UF-Intra 1080p single-frame decode (configs[1]), q_index 32, skip_thres 0.15, "
+                                   "one independent frame per GPU", "resolution": [H, W], "qp": QP,
+                       "l2": "flushed between timed steps (256 MiB memset outside the timed interval)",
+                       "weights": "seeded synthetic checkpoint (no checkpoints offline)"},
+            "e2e": {"value": round(world * args.steps / (tot_e2e * 1e-3), 2), "unit": "frames/s",
+                    "h2d_bytes_per_step": int(65280 + n_sym), "d2h_bytes_per_step": int(n_sym + 16 + host_out.numel() * 2),
+                    "bitstream_bytes": len(bs)},
+            "encode_fps": round(world * args.steps / (tot_enc * 1e-3), 2),
+            "gpu_only_ms_per_decode": round(gpu_only_ms, 4),
+            "gpu_launches": int(l1 - l0),
+            "bpp": round(len(bs) * 8 / (H * W), 4),
+            "psnr_db": round(psnr(dec["x_hat"].float().cpu()[:, :, :H, :W], x.float().cpu()), 3),
+            "clocks": sampler.summary(),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference_sample(steps, sample_hw, threads=None):
+    """The reference's CPU path = oracle port (PyTorch fp32-accumulate restatement of the proxy control
+    flow + the reference's own rANS coder from oracle/_ref), timed on the host cores on a bounded
+    sample; FPS is scaled to 1080p by pixel count."""
+    from util_frames import synth_frame
+    from dcvc_b200.spec import dmci_spec, synth_state_dict
+    from oracle.dmci_oracle import DmciOracle
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    h, w = sample_hw
+    o = DmciOracle(synth_state_dict(dmci_spec(), 0), skip_thres=SKIP, emulate_fp16=True, threads=cores)
+    x = synth_frame(h, w, 1234)
+    pad_b, pad_r = (16 - h % 16) % 16, (16 - w % 16) % 16
+    enc = o.compress(x, QP, pad_b, pad_r)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.decompress(enc["bit_stream"], QP, h, w, enc["ec_parallel"])
+    dt = (time.perf_counter() - t0) / steps
+    scale = (h * w) / float(H * W)
+    return {"value": round(scale / dt, 4), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} decode(s) of a {h}x{w} crop-sized frame ({scale:.3f} of 1080p area), "
+                      f"{dt:.2f} s each, FPS scaled by area", "seconds_per_sample": round(dt, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.steps + args.warmup
+    t0 = time.time()
+    # each step = one decode of a 272x480 sample (1/16 of the 1080p area) on all host cores
+    from util_frames import synth_frame
+    from dcvc_b200.spec import dmci_spec, synth_state_dict
+    from oracle.dmci_oracle import DmciOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    h, w = 272, 480
+    o = DmciOracle(synth_state_dict(dmci_spec(), 0), skip_thres=SKIP, emulate_fp16=True, threads=cores)
+    x = synth_frame(h, w, 1234)
+    enc = o.compress(x, QP, 0, 0)
+    for _ in range(args.warmup):
+        o.decompress(enc["bit_stream"], QP, h, w, enc["ec_parallel"])
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        o.decompress(enc["bit_stream"], QP, h, w, enc["ec_parallel"])
+    dt = time.perf_counter() - t1
+    scale = (h * w) / float(H * W)
+    fps = args.steps / dt * scale
+    out = {"impl": "reference", "metric": METRIC, "value": round(fps, 4), "unit": "frames/s",
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "DCVC-UF-Intra 1080p single-frame decode (configs[1]), q_index 32, skip_thres 0.15",
+                      "resolution": [H, W], "qp": QP},
+           "cpu_baseline": {"value": round(fps, 4), "unit": "frames/s", "cores": cores, "kind": "port",
+                            "sample": f"each step decodes a {h}x{w} frame ({scale:.4f} of the 1080p area) with the oracle "
+                                      f"port + the reference's own rANS coder; FPS scaled by area"},
+           "e2e": {"value": round(fps, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": round(time.time() - t0, 1)}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

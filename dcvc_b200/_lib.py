@@ -83,6 +83,9 @@ SIGNATURES = {
     "dcvc_decompress": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "dcvc_kernel_launches": (C.c_int64, [_P]),
     "dcvc_last_gpu_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "dcvc_profile_enable": (C.c_int, [_P, _I]),
+    "dcvc_profile_get": (C.c_int, [_P, _I, C.POINTER(C.c_double), C.POINTER(_L), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_double)]),
     "dcvc_debug_fetch": (C.c_int, [_P, C.c_char_p, _P, _L, C.POINTER(_L)]),
 }
 

@@ -1,14 +1,1120 @@
-// temporary stubs (codec runtime lands next)
+// codec.cu — codec-level runtime behind the C ABI (dcvc_create / set_param / compress / decompress).
+//
+// B200-native counterpart of the reference's proxy runtime for DCVC-UF-Intra
+// (src/layers/extensions/inference/dmci_proxy.{h,cpp}, layers_proxy.{h,cpp}, dmc_common.{h,cpp},
+// memory_pool.h), re-designed rather than translated:
+//   * weights are re-laid out once on the host (dw bias folded into the next 1x1, stride-2 /
+//     transposed-conv weights packed per tap / phase) and live in one device arena;
+//   * activations live in a per-resolution arena; every DepthConvBlock ping-pongs between the
+//     same four buffers of its pyramid level so the working set stays inside the 126 MB L2;
+//   * the QP only selects four per-channel scale vectors: they are staged into fixed device
+//     buffers before each call, so ONE CUDA graph per segment serves all 64 QPs (the reference
+//     captures 64 graphs per segment, dmc_common.cpp:95-106);
+//   * host rANS stays on the CPU (north_star); symbol counts/streams cross PCIe in two small
+//     copies per step; the synthesis transform overlaps the CPU encode.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
 #include "../../include/dcvc_b200.h"
-extern "C" {
-int dcvc_create(int32_t, int32_t, dcvc_codec**) { return 1; }
-int dcvc_destroy(dcvc_codec*) { return 1; }
-const char* dcvc_codec_error(dcvc_codec*) { return "not implemented"; }
-int dcvc_set_param(dcvc_codec*, const char*, const void*, int32_t, int32_t, const int64_t*, int32_t) { return 1; }
-int dcvc_finalize_params(dcvc_codec*, float) { return 1; }
-int dcvc_compress(dcvc_codec*, const void*, int32_t, int32_t, int64_t, int64_t, int64_t, int32_t, int32_t, int32_t, void*, const uint8_t**, int32_t*, int32_t*, void*) { return 1; }
-int dcvc_decompress(dcvc_codec*, const uint8_t*, int32_t, int32_t, int32_t, int32_t, int32_t, void*, void*) { return 1; }
-int64_t dcvc_kernel_launches(dcvc_codec*) { return 0; }
-int dcvc_last_gpu_ms(dcvc_codec*, float*) { return 1; }
-int dcvc_debug_fetch(dcvc_codec*, const char*, void*, int64_t, int64_t*) { return 1; }
+#include "elementwise.cuh"
+#include "pw_gemm.cuh"
+#include "rans_host.h"
+
+namespace dcvc {
+
+namespace {
+
+constexpr int kQpNum = 64;
+constexpr int kChSrc = 192, kChEncDec = 384, kChY = 256, kChZ = 128;
+
+#define CK(expr)                                                                           \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+        }                                                                                  \
+    } while (0)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct HostTensor {
+    int dtype = DCVC_DTYPE_F16;
+    std::vector<int64_t> shape;
+    std::vector<uint8_t> bytes;
+    int64_t numel() const
+    {
+        int64_t n = 1;
+        for (auto s : shape) n *= s;
+        return n;
+    }
+};
+
+// bump allocator over one cudaMalloc block
+class Arena {
+public:
+    ~Arena() { release(); }
+    void release()
+    {
+        if (base_) cudaFree(base_);
+        base_ = nullptr;
+        cap_ = used_ = 0;
+    }
+    void reserve(size_t bytes)
+    {
+        release();
+        CK(cudaMalloc(&base_, bytes));
+        cap_ = bytes;
+        used_ = 0;
+    }
+    void* alloc(size_t bytes)
+    {
+        const size_t off = (used_ + 1023) & ~static_cast<size_t>(1023);
+        if (off + bytes > cap_) throw std::runtime_error("device arena exhausted");
+        used_ = off + bytes;
+        return static_cast<uint8_t*>(base_) + off;
+    }
+    size_t used() const { return used_; }
+
+private:
+    void* base_ = nullptr;
+    size_t cap_ = 0, used_ = 0;
+};
+
+struct DcbW {
+    bool adaptor = false;
+    int cin = 0, c = 0, inner = 0;
+    const __half *wa = nullptr, *ba = nullptr;
+    const __half *w0 = nullptr, *b0 = nullptr;
+    const __half* wdw = nullptr;  // [9][inner]
+    const __half *w3 = nullptr, *b3 = nullptr;  // b3: dc.3 bias + W3 . dw-bias
+    const __half *wf0 = nullptr, *bf0 = nullptr;
+    const __half *wf2 = nullptr, *bf2 = nullptr;
+};
+
+struct ConvW {
+    const __half* w = nullptr;
+    const __half* b = nullptr;
+    int cout = 0, cin = 0;
+};
+
+struct Level {  // one pyramid level: two ping-pong buffers + two scratch buffers
+    int H = 0, W = 0;
+    __half *A = nullptr, *B = nullptr, *T1 = nullptr, *T2 = nullptr;
+};
+
+using OpFn = std::function<int(cudaStream_t)>;
+
+enum OpKind { OP_GEMM = 0, OP_DW = 1, OP_ELEM = 2, OP_KINDS = 3 };
+
+struct Segment {
+    std::vector<OpFn> ops;
+    std::vector<int> kinds;        // OpKind per op (kept in step with `ops`)
+    std::vector<double> alg_bytes; // algorithmic bytes per op (activations in + residuals in + out)
+    std::vector<double> flops;
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+    void annotate(int kind, double bytes, double fl)
+    {
+        while (kinds.size() < ops.size()) {
+            kinds.push_back(kind);
+            alg_bytes.push_back(bytes);
+            flops.push_back(fl);
+        }
+    }
+};
+
+struct ProfileAcc {
+    double ms = 0, bytes = 0, flops = 0;
+    long long launches = 0;
+};
+
+inline ActView make_view(const void* p, int C, int pitch, int W, int H)
+{
+    ActView v;
+    v.ptr = p; v.C = C; v.pitch = pitch; v.W = W; v.H = H;
+    return v;
 }
+
+}  // namespace
+
+class IntraCodec {
+public:
+    explicit IntraCodec(int device) : device_(device) {}
+    ~IntraCodec();
+
+    void set_param(const char* name, const void* data, int dtype, int ndim, const int64_t* shape,
+                   int on_device);
+    void finalize(float skip_thres);
+    void compress(const void* x, int H, int W, int64_t sc, int64_t sh, int64_t sw, int qp, int pad_b,
+                  int pad_r, cudaStream_t stream, const uint8_t** bs, int32_t* bs_len,
+                  int32_t* ec_parallel, void* x_hat_out);
+    void decompress(const uint8_t* bs, int len, int qp, int height, int width, int ec_parallel,
+                    cudaStream_t stream, void* x_hat_out);
+    int debug_fetch(const char* name, void* dst, int64_t max_bytes, int64_t* written);
+
+    float gpu_ms();
+    bool profile_ = false;
+    ProfileAcc prof_[OP_KINDS];
+
+    std::string err;
+    int64_t launches = 0;
+
+private:
+    // ---- parameters
+    const HostTensor& param(const std::string& k) const;
+    std::vector<__half> param_f16(const std::string& k) const;
+    const __half* upload(const std::vector<__half>& v);
+    DcbW load_dcb(const std::string& p);
+    ConvW load_conv(const std::string& p, int kind);
+
+    // ---- plan
+    void plan(int height, int width);
+    void clear_plan();
+    ActView dcb(Segment& s, Level& L, const ActView& in, const DcbW& w, bool shortcut,
+                const __half* qscale, const ActView* out);
+    void add_gemm(Segment& s, int kind, const ActView& in, const ActView& out, const __half* w,
+                  const __half* bias, int N, int act, int chunk, const ActView* r1, const ActView* r2,
+                  const __half* q);
+    void build_hyper_tail(Segment& s);  // z_hat -> params, reduced
+    void build_spatial_prior(Segment& s, int k);
+    void build_synthesis(Segment& s);
+    void run(Segment& s, cudaStream_t stream);
+    void stage_qp(int qp, cudaStream_t stream);
+
+    int device_;
+    bool finalized_ = false;
+    bool use_graphs_ = true;
+    float skip_thres_ = 0.f;
+    std::map<std::string, HostTensor> params_;
+    Arena warena_;
+    std::vector<std::pair<const std::vector<__half>*, const __half**>> pending_;  // unused
+    std::vector<std::vector<__half>> host_weights_;                             // staged before upload
+    std::vector<const __half**> host_weight_slots_;
+
+    // weights on device
+    DcbW enc1_, enc2_[6], henc0_, henc1_, henc2_, hdec0_, hdec1_, hdec2_, pf_[3], spa_[3], sp_[3],
+        dec1_[13], dec2_;
+    ConvW enc_down_, henc1_down_, henc2_down_, hdec0_up_, hdec1_up_, dec_up_, pf3_, sp3_, red_;
+    const __half *q_enc_all_ = nullptr, *q_dec_all_ = nullptr, *q_y_enc_all_ = nullptr,
+                 *q_y_dec_all_ = nullptr;
+    uint8_t* lut_ = nullptr;
+    RansCodec rans_;
+
+    // plan state
+    int H8_ = 0, W8_ = 0, H16_ = 0, W16_ = 0, H16p_ = 0, W16p_ = 0, H64_ = 0, W64_ = 0;
+    Arena arena_;
+    Level l8_, l16_, l32_, l64_;
+    __half *in8_ = nullptr, *y_ = nullptr, *ypad_ = nullptr, *hyp_ = nullptr, *params_p_ = nullptr,
+           *params_c_ = nullptr, *cat_ = nullptr, *sp_out_ = nullptr, *yhat_ = nullptr,
+           *zhat_ = nullptr, *dec_out_ = nullptr;
+    int8_t* z_i8_ = nullptr;
+    __half *q_enc_ = nullptr, *q_dec_ = nullptr, *q_y_enc_ = nullptr, *q_y_dec_ = nullptr;
+    int16_t* sym_raw_ = nullptr;
+    uint8_t* idx_raw_ = nullptr;
+    int32_t *counts_ = nullptr, *offsets_[4] = { nullptr, nullptr, nullptr, nullptr }, *totals_ = nullptr;
+    int16_t* sym_c_[4] = { nullptr, nullptr, nullptr, nullptr };
+    uint8_t* idx_c_ = nullptr;
+    int8_t* decoded_ = nullptr;
+    // pinned host mirrors
+    int32_t* h_totals_ = nullptr;
+    int16_t* h_sym_[4] = { nullptr, nullptr, nullptr, nullptr };
+    uint8_t* h_idx_ = nullptr;
+    int8_t* h_decoded_ = nullptr;
+    int8_t* h_z_ = nullptr;
+    size_t quarter_ = 0;
+
+    Segment enc0_, enc1_seg_, dec0_, dec_step_[4];  // dec_step_[k]: k = 1..3 prior steps, [0] unused
+    Segment dec4_;
+    cudaStream_t copy_stream_ = nullptr;
+    // CUDA graphs cannot be captured on the legacy default stream: calls made on it hop onto an
+    // internal stream and hand the result back with an event (the reference instead requires the
+    // caller to set a non-default stream, test_video.py:423-425).
+    cudaStream_t own_stream_ = nullptr;
+    cudaEvent_t ev_hop_ = nullptr;
+    struct StreamHop {
+        IntraCodec* c;
+        cudaStream_t user, run;
+        bool hop;
+        StreamHop(IntraCodec* codec, cudaStream_t u) : c(codec), user(u), run(u)
+        {
+            hop = (u == nullptr || u == cudaStreamLegacy || u == cudaStreamPerThread);
+            if (hop) {
+                if (cudaEventRecord(c->ev_hop_, user) != cudaSuccess ||
+                    cudaStreamWaitEvent(c->own_stream_, c->ev_hop_, 0) != cudaSuccess)
+                    throw std::runtime_error("stream hop failed");
+                run = c->own_stream_;
+            }
+        }
+        ~StreamHop()
+        {
+            if (hop) {
+                cudaEventRecord(c->ev_hop_, run);
+                cudaStreamWaitEvent(user, c->ev_hop_, 0);
+            }
+        }
+    };
+    cudaEvent_t ev_y_ = nullptr, ev_copy_ = nullptr;
+    // GPU-only timing: one (begin, end) event pair around every stretch of device work of a call
+    std::vector<cudaEvent_t> tev_;
+    int tev_n_ = 0;
+    void tick(cudaStream_t st);
+    void tock(cudaStream_t st);
+    std::vector<uint8_t> bitstream_;
+    const __half* params_cur_ = nullptr;  // params of step 0 (cropped)
+};
+
+// =============================================================================== parameters
+void IntraCodec::set_param(const char* name, const void* data, int dtype, int ndim,
+                           const int64_t* shape, int on_device)
+{
+    HostTensor t;
+    t.dtype = dtype;
+    t.shape.assign(shape, shape + ndim);
+    const size_t esz = (dtype == DCVC_DTYPE_F16) ? 2 : 4;
+    t.bytes.resize(static_cast<size_t>(t.numel()) * esz);
+    if (on_device) {
+        CK(cudaMemcpy(t.bytes.data(), data, t.bytes.size(), cudaMemcpyDeviceToHost));
+    } else {
+        memcpy(t.bytes.data(), data, t.bytes.size());
+    }
+    params_[name] = std::move(t);
+    finalized_ = false;
+}
+
+const HostTensor& IntraCodec::param(const std::string& k) const
+{
+    auto it = params_.find(k);
+    if (it == params_.end()) throw std::runtime_error("missing parameter '" + k + "'");
+    return it->second;
+}
+
+std::vector<__half> IntraCodec::param_f16(const std::string& k) const
+{
+    const HostTensor& t = param(k);
+    std::vector<__half> v(static_cast<size_t>(t.numel()));
+    if (t.dtype == DCVC_DTYPE_F16) {
+        memcpy(v.data(), t.bytes.data(), t.bytes.size());
+    } else if (t.dtype == DCVC_DTYPE_F32) {
+        const float* f = reinterpret_cast<const float*>(t.bytes.data());
+        for (size_t i = 0; i < v.size(); ++i) v[i] = __float2half_rn(f[i]);
+    } else {
+        throw std::runtime_error("parameter '" + k + "' is not floating point");
+    }
+    return v;
+}
+
+const __half* IntraCodec::upload(const std::vector<__half>& v)
+{
+    void* d = warena_.alloc(v.size() * sizeof(__half));
+    CK(cudaMemcpy(d, v.data(), v.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    return static_cast<const __half*>(d);
+}
+
+DcbW IntraCodec::load_dcb(const std::string& p)
+{
+    DcbW w;
+    if (params_.count(p + "adaptor.weight")) {
+        w.adaptor = true;
+        w.cin = static_cast<int>(param(p + "adaptor.weight").shape[1]);
+        w.wa = upload(param_f16(p + "adaptor.weight"));
+        w.ba = upload(param_f16(p + "adaptor.bias"));
+    }
+    const HostTensor& w0 = param(p + "dc.0.weight");
+    w.inner = static_cast<int>(w0.shape[0]);
+    w.c = static_cast<int>(w0.shape[1]);
+    if (!w.adaptor) w.cin = w.c;
+    w.w0 = upload(param_f16(p + "dc.0.weight"));
+    w.b0 = upload(param_f16(p + "dc.0.bias"));
+    {   // depthwise weight [inner][1][3][3] -> [9][inner]   (layers_proxy.cpp:171-173)
+        std::vector<__half> dw = param_f16(p + "dc.2.weight");
+        std::vector<__half> t(dw.size());
+        for (int c = 0; c < w.inner; ++c)
+            for (int k = 0; k < 9; ++k) t[static_cast<size_t>(k) * w.inner + c] = dw[static_cast<size_t>(c) * 9 + k];
+        w.wdw = upload(t);
+    }
+    {   // fold the depthwise bias into the bias of dc.3 (layers_proxy.cpp:175-178), fp32 then one rounding
+        std::vector<__half> w3 = param_f16(p + "dc.3.weight");
+        std::vector<__half> bdw = param_f16(p + "dc.2.bias");
+        std::vector<__half> b3 = param_f16(p + "dc.3.bias");
+        std::vector<__half> folded(b3.size());
+        for (int n = 0; n < w.c; ++n) {
+            float acc = 0.f;
+            for (int c = 0; c < w.inner; ++c)
+                acc += __half2float(w3[static_cast<size_t>(n) * w.inner + c]) * __half2float(bdw[c]);
+            folded[n] = __float2half_rn(acc + __half2float(b3[n]));
+        }
+        w.w3 = upload(w3);
+        w.b3 = upload(folded);
+    }
+    w.wf0 = upload(param_f16(p + "ffn.0.weight"));
+    w.bf0 = upload(param_f16(p + "ffn.0.bias"));
+    w.wf2 = upload(param_f16(p + "ffn.2.weight"));
+    w.bf2 = upload(param_f16(p + "ffn.2.bias"));
+    return w;
+}
+
+ConvW IntraCodec::load_conv(const std::string& p, int kind)
+{
+    ConvW c;
+    const HostTensor& wt = param(p + "weight");
+    const int cout = static_cast<int>(wt.shape[0]), cin = static_cast<int>(wt.shape[1]);
+    const int kh = static_cast<int>(wt.shape[2]), kw = static_cast<int>(wt.shape[3]);
+    std::vector<__half> src = param_f16(p + "weight");
+    std::vector<__half> dst(src.size());
+    if (dcvc_pack_weight(kind, src.data(), cout, cin, kh, kw, dst.data()))
+        throw std::runtime_error("pack_weight failed for " + p);
+    c.w = upload(dst);
+    if (params_.count(p + "bias")) c.b = upload(param_f16(p + "bias"));
+    c.cout = cout;
+    c.cin = cin;
+    return c;
+}
+
+void IntraCodec::finalize(float skip_thres)
+{
+    CK(cudaSetDevice(device_));
+    clear_plan();
+    skip_thres_ = skip_thres;
+    size_t total = 0;
+    for (auto& kv : params_) total += static_cast<size_t>(kv.second.numel()) * 2 + 2048;
+    warena_.reserve(total * 2 + (8u << 20));
+
+    enc1_ = load_dcb("enc.enc_1.");
+    for (int i = 0; i < 6; ++i) enc2_[i] = load_dcb("enc.enc_2." + std::to_string(i) + ".");
+    enc_down_ = load_conv("enc.enc_2.6.", DCVC_GEMM_CONV3X3_S2);
+    henc0_ = load_dcb("hyper_enc.conv.0.");
+    henc1_down_ = load_conv("hyper_enc.conv.1.down.", DCVC_GEMM_CONV2X2_S2);
+    henc1_ = load_dcb("hyper_enc.conv.1.conv.");
+    henc2_down_ = load_conv("hyper_enc.conv.2.down.", DCVC_GEMM_CONV2X2_S2);
+    henc2_ = load_dcb("hyper_enc.conv.2.conv.");
+    hdec0_up_ = load_conv("hyper_dec.conv.0.up.conv.0.", DCVC_GEMM_TCONV2X2);
+    hdec0_ = load_dcb("hyper_dec.conv.0.conv.");
+    hdec1_up_ = load_conv("hyper_dec.conv.1.up.conv.0.", DCVC_GEMM_TCONV2X2);
+    hdec1_ = load_dcb("hyper_dec.conv.1.conv.");
+    hdec2_ = load_dcb("hyper_dec.conv.2.");
+    for (int i = 0; i < 3; ++i) pf_[i] = load_dcb("y_prior_fusion.conv." + std::to_string(i) + ".");
+    pf3_ = load_conv("y_prior_fusion.conv.3.", DCVC_GEMM_PW);
+    red_ = load_conv("y_spatial_prior_reduction.", DCVC_GEMM_PW);
+    for (int i = 0; i < 3; ++i) spa_[i] = load_dcb("y_spatial_prior_adaptor_" + std::to_string(i + 1) + ".");
+    for (int i = 0; i < 3; ++i) sp_[i] = load_dcb("y_spatial_prior.conv." + std::to_string(i) + ".");
+    sp3_ = load_conv("y_spatial_prior.conv.3.", DCVC_GEMM_PW);
+    dec_up_ = load_conv("dec.dec_1.0.up.conv.0.", DCVC_GEMM_TCONV2X2);
+    dec1_[0] = load_dcb("dec.dec_1.0.conv.");
+    for (int i = 1; i < 13; ++i) dec1_[i] = load_dcb("dec.dec_1." + std::to_string(i) + ".");
+    dec2_ = load_dcb("dec.dec_2.");
+    q_enc_all_ = upload(param_f16("q_scale_enc"));
+    q_dec_all_ = upload(param_f16("q_scale_dec"));
+    q_y_enc_all_ = upload(param_f16("q_scale_y_enc"));
+    q_y_dec_all_ = upload(param_f16("q_scale_y_dec"));
+
+    {
+        std::vector<uint8_t> h(65536);
+        build_scale_lut(h.data());
+        lut_ = static_cast<uint8_t*>(warena_.alloc(65536));
+        CK(cudaMemcpy(lut_, h.data(), 65536, cudaMemcpyHostToDevice));
+    }
+    // CDF tables (common_model.py:64-70; dmci_proxy.cpp:639-651)
+    const char* names[2] = { "bit_estimator_z.", "gaussian_encoder." };
+    for (int i = 0; i < 2; ++i) {
+        const HostTensor& c = param(std::string(names[i]) + "quantized_cdf");
+        const HostTensor& l = param(std::string(names[i]) + "cdf_length");
+        if (c.dtype != DCVC_DTYPE_I32 || l.dtype != DCVC_DTYPE_I32 || c.shape.size() != 2)
+            throw std::runtime_error("CDF tables must be int32 [rows][width]");
+        rans_.set_cdf(reinterpret_cast<const int32_t*>(c.bytes.data()),
+                      reinterpret_cast<const int32_t*>(l.bytes.data()), static_cast<int>(c.shape[0]),
+                      static_cast<int>(c.shape[1]), i);
+    }
+    if (!copy_stream_) {
+        int lo, hi;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&copy_stream_, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ev_hop_, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_y_, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_copy_, cudaEventDisableTiming));
+        tev_.resize(32);
+        for (auto& e : tev_) CK(cudaEventCreate(&e));
+    }
+    gemm_init();
+    const char* g = getenv("DCVC_B200_GRAPHS");
+    use_graphs_ = !(g && g[0] == '0');
+    finalized_ = true;
+}
+
+IntraCodec::~IntraCodec()
+{
+    clear_plan();
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
+    if (own_stream_) cudaStreamDestroy(own_stream_);
+    if (ev_hop_) cudaEventDestroy(ev_hop_);
+    if (ev_y_) cudaEventDestroy(ev_y_);
+    if (ev_copy_) cudaEventDestroy(ev_copy_);
+    for (auto& e : tev_) cudaEventDestroy(e);
+}
+
+void IntraCodec::tick(cudaStream_t st)
+{
+    if (tev_n_ + 2 <= static_cast<int>(tev_.size())) CK(cudaEventRecord(tev_[tev_n_], st));
+}
+
+void IntraCodec::tock(cudaStream_t st)
+{
+    if (tev_n_ + 2 <= static_cast<int>(tev_.size())) {
+        CK(cudaEventRecord(tev_[tev_n_ + 1], st));
+        tev_n_ += 2;
+    }
+}
+
+float IntraCodec::gpu_ms()
+{
+    float total = 0.f;
+    for (int i = 0; i + 1 < tev_n_; i += 2) {
+        CK(cudaEventSynchronize(tev_[i + 1]));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, tev_[i], tev_[i + 1]));
+        total += ms;
+    }
+    return total;
+}
+
+// =============================================================================== plan
+void IntraCodec::clear_plan()
+{
+    Segment* segs[] = { &enc0_, &enc1_seg_, &dec0_, &dec_step_[0], &dec_step_[1], &dec_step_[2], &dec_step_[3], &dec4_ };
+    for (Segment* s : segs) {
+        if (s->exec) cudaGraphExecDestroy(s->exec);
+        s->exec = nullptr;
+        s->ops.clear();
+        s->launches = 0;
+    }
+    if (h_totals_) { cudaFreeHost(h_totals_); h_totals_ = nullptr; }
+    for (int k = 0; k < 4; ++k) if (h_sym_[k]) { cudaFreeHost(h_sym_[k]); h_sym_[k] = nullptr; }
+    if (h_idx_) { cudaFreeHost(h_idx_); h_idx_ = nullptr; }
+    if (h_decoded_) { cudaFreeHost(h_decoded_); h_decoded_ = nullptr; }
+    if (h_z_) { cudaFreeHost(h_z_); h_z_ = nullptr; }
+    arena_.release();
+    H8_ = W8_ = 0;
+}
+
+void IntraCodec::add_gemm(Segment& s, int kind, const ActView& in, const ActView& out, const __half* w,
+                          const __half* bias, int N, int act, int chunk, const ActView* r1,
+                          const ActView* r2, const __half* q)
+{
+    auto op = std::make_shared<GemmOp>();
+    op->kind = kind;
+    op->in = in;
+    op->out = out;
+    if (r1) op->res1 = *r1;
+    if (r2) op->res2 = *r2;
+    op->weight = w;
+    op->bias = bias;
+    op->qscale = q;
+    op->N = N;
+    op->act = act;
+    op->chunk_add = chunk;
+    if (gemm_plan(*op)) throw std::runtime_error(std::string("gemm_plan: ") + gemm_last_error());
+    s.annotate(OP_ELEM, 0, 0);  // anything pushed without annotation so far is elementwise
+    s.ops.push_back([op](cudaStream_t st) { return gemm_launch(*op, st); });
+    const double px_in = static_cast<double>(in.W) * in.H, px_out = static_cast<double>(out.W) * out.H;
+    const int taps = (kind == GEMM_CONV3X3_S2) ? 9 : (kind == GEMM_CONV2X2_S2 ? 4 : 1);
+    double bytes = px_in * in.C * 2 + px_out * out.C * 2;
+    if (r1) bytes += px_out * out.C * 2;
+    if (r2) bytes += px_out * out.C * 2;
+    const double m_px = (kind == GEMM_TCONV2X2) ? px_in : px_out;
+    s.annotate(OP_GEMM, bytes, 2.0 * m_px * N * taps * in.C);
+}
+
+// DepthConvBlock (layers.py:152-159): returns the view holding the block output.
+ActView IntraCodec::dcb(Segment& s, Level& L, const ActView& in, const DcbW& w, bool shortcut,
+                        const __half* qscale, const ActView* out)
+{
+    const int H = in.H, W = in.W;
+    __half* bufX;
+    ActView x;
+    if (w.adaptor) {
+        bufX = (in.ptr == L.A) ? L.B : L.A;
+        x = make_view(bufX, w.c, w.c, W, H);
+        add_gemm(s, GEMM_PW, in, x, w.wa, w.ba, w.c, ACT_NONE, 0, nullptr, nullptr, nullptr);
+    } else {
+        x = in;
+        bufX = static_cast<__half*>(const_cast<void*>(in.ptr));
+    }
+    __half* bufO = (bufX == L.A) ? L.B : L.A;
+    const ActView t1 = make_view(L.T1, w.inner, w.inner, W, H);
+    const ActView t2 = make_view(L.T2, w.inner, w.inner, W, H);
+    const ActView o = make_view(bufO, w.c, w.c, W, H);
+    add_gemm(s, GEMM_PW, x, t1, w.w0, w.b0, w.inner, ACT_WSILU, 0, nullptr, nullptr, nullptr);
+    {
+        const __half* wdw = w.wdw;
+        s.annotate(OP_ELEM, 0, 0);
+        s.ops.push_back([t1, t2, wdw](cudaStream_t st) { return launch_dw3x3(t1, t2, wdw, st); });
+        s.annotate(OP_DW, 2.0 * 2 * W * H * w.inner, 2.0 * 9 * W * H * w.inner);
+    }
+    add_gemm(s, GEMM_PW, t2, o, w.w3, w.b3, w.c, ACT_NONE, 0, &x, nullptr, nullptr);
+    add_gemm(s, GEMM_PW, o, t1, w.wf0, w.bf0, 4 * w.inner, ACT_WSILU, 1, nullptr, nullptr, nullptr);
+    const ActView dst = out ? *out : x;  // in place over the block input unless redirected
+    add_gemm(s, GEMM_PW, t1, dst, w.wf2, w.bf2, w.c, ACT_NONE, 0, &o, shortcut ? &x : nullptr, qscale);
+    return dst;
+}
+
+void IntraCodec::plan(int height, int width)
+{
+    const int H = round_up(height, 16), W = round_up(width, 16);
+    const int H8 = H / 8, W8 = W / 8;
+    if (H8 == H8_ && W8 == W8_) return;
+    if (!finalized_) throw std::runtime_error("set_param/finalize_params must be called first");
+    clear_plan();
+    H8_ = H8; W8_ = W8;
+    H16_ = H8 / 2; W16_ = W8 / 2;
+    H16p_ = round_up(H16_, 4); W16p_ = round_up(W16_, 4);
+    const int H32 = H16p_ / 2, W32 = W16p_ / 2;
+    H64_ = H16p_ / 4; W64_ = W16p_ / 4;
+    const size_t p8 = static_cast<size_t>(H8) * W8, p16p = static_cast<size_t>(H16p_) * W16p_;
+    const size_t p16 = static_cast<size_t>(H16_) * W16_, p32 = static_cast<size_t>(H32) * W32;
+    const size_t p64 = static_cast<size_t>(H64_) * W64_;
+    quarter_ = p16 * (kChY / 4);
+
+    size_t bytes = 0;
+    bytes += 4 * p8 * kChEncDec * 2 + p8 * kChSrc * 2 * 2;          // level 8 + in8 + dec_out
+    bytes += 4 * p16p * 512 * 2 + 8 * p16p * 512 * 2;                // level 16 + named P16 buffers
+    bytes += 4 * p32 * 128 * 2 + 6 * p64 * 128 * 2;
+    bytes += quarter_ * (2 + 1 + 4 * 2 + 1 + 1) + p16 * 4 * 6 + (1u << 20);
+    bytes += 64 * 1024;  // alignment slack per allocation
+    arena_.reserve(bytes + (4u << 20));
+    auto half_buf = [&](size_t n) { return static_cast<__half*>(arena_.alloc(n * 2)); };
+
+    l8_.H = H8; l8_.W = W8;
+    l8_.A = half_buf(p8 * kChEncDec); l8_.B = half_buf(p8 * kChEncDec);
+    l8_.T1 = half_buf(p8 * kChEncDec); l8_.T2 = half_buf(p8 * kChEncDec);
+    in8_ = half_buf(p8 * kChSrc);
+    dec_out_ = half_buf(p8 * kChSrc);
+    l16_.H = H16p_; l16_.W = W16p_;
+    l16_.A = half_buf(p16p * 512); l16_.B = half_buf(p16p * 512);
+    l16_.T1 = half_buf(p16p * 512); l16_.T2 = half_buf(p16p * 512);
+    l32_.H = H32; l32_.W = W32;
+    l32_.A = half_buf(p32 * 128); l32_.B = half_buf(p32 * 128);
+    l32_.T1 = half_buf(p32 * 128); l32_.T2 = half_buf(p32 * 128);
+    l64_.H = H64_; l64_.W = W64_;
+    l64_.A = half_buf(p64 * 128); l64_.B = half_buf(p64 * 128);
+    l64_.T1 = half_buf(p64 * 128); l64_.T2 = half_buf(p64 * 128);
+    y_ = half_buf(p16 * kChY);
+    const bool padded = (H16p_ != H16_) || (W16p_ != W16_);
+    ypad_ = padded ? half_buf(p16p * kChY) : y_;
+    hyp_ = half_buf(p16p * kChY);
+    params_p_ = half_buf(p16p * 512);
+    params_c_ = padded ? half_buf(p16 * 512) : params_p_;
+    cat_ = half_buf(p16 * 512);
+    sp_out_ = half_buf(p16 * 512);
+    yhat_ = half_buf(p16 * kChY);
+    zhat_ = half_buf(p64 * kChZ);
+    z_i8_ = static_cast<int8_t*>(arena_.alloc(p64 * kChZ));
+    q_enc_ = half_buf(kChEncDec); q_dec_ = half_buf(kChEncDec);
+    q_y_enc_ = half_buf(kChY); q_y_dec_ = half_buf(kChY);
+    sym_raw_ = static_cast<int16_t*>(arena_.alloc(quarter_ * 2));
+    idx_raw_ = static_cast<uint8_t*>(arena_.alloc(quarter_));
+    counts_ = static_cast<int32_t*>(arena_.alloc(p16 * 4));
+    totals_ = static_cast<int32_t*>(arena_.alloc(64));
+    for (int k = 0; k < 4; ++k) {
+        offsets_[k] = static_cast<int32_t*>(arena_.alloc((p16 + 1) * 4));
+        sym_c_[k] = static_cast<int16_t*>(arena_.alloc(quarter_ * 2));
+    }
+    idx_c_ = static_cast<uint8_t*>(arena_.alloc(quarter_));
+    decoded_ = static_cast<int8_t*>(arena_.alloc(quarter_));
+    CK(cudaMallocHost(&h_totals_, 64));
+    for (int k = 0; k < 4; ++k) CK(cudaMallocHost(&h_sym_[k], quarter_ * 2));
+    CK(cudaMallocHost(&h_idx_, quarter_));
+    CK(cudaMallocHost(&h_decoded_, quarter_));
+    CK(cudaMallocHost(&h_z_, p64 * kChZ));
+
+    const ActView v_in8 = make_view(in8_, kChSrc, kChSrc, W8, H8);
+    const ActView v_y = make_view(y_, kChY, kChY, W16_, H16_);
+    const ActView v_ypad = make_view(ypad_, kChY, kChY, W16p_, H16p_);
+    const ActView v_scales0 = make_view(params_c_, kChY, 512, W16_, H16_);
+
+    // ------------------------------------------------------------------ enc_0 (dmci_proxy.cpp:308-394)
+    {
+        Segment& s = enc0_;
+        ActView t = dcb(s, l8_, v_in8, enc1_, false, q_enc_, nullptr);     // enc_1, then * q_enc
+        for (int i = 0; i < 6; ++i) t = dcb(s, l8_, t, enc2_[i], false, nullptr, nullptr);
+        add_gemm(s, GEMM_CONV3X3_S2, t, v_y, enc_down_.w, enc_down_.b, kChY, ACT_NONE, 0, nullptr, nullptr, nullptr);
+        if (padded) s.ops.push_back([v_y, v_ypad](cudaStream_t st) { return launch_pad_crop(v_y, v_ypad, st); });
+        // hyper encoder
+        ActView h = dcb(s, l16_, v_ypad, henc0_, false, nullptr, nullptr);
+        ActView d32 = make_view(l32_.A, kChZ, kChZ, W32, H32);
+        add_gemm(s, GEMM_CONV2X2_S2, h, d32, henc1_down_.w, henc1_down_.b, kChZ, ACT_NONE, 0, nullptr, nullptr, nullptr);
+        d32 = dcb(s, l32_, d32, henc1_, true, nullptr, nullptr);
+        ActView d64 = make_view(l64_.A, kChZ, kChZ, W64_, H64_);
+        add_gemm(s, GEMM_CONV2X2_S2, d32, d64, henc2_down_.w, henc2_down_.b, kChZ, ACT_NONE, 0, nullptr, nullptr, nullptr);
+        d64 = dcb(s, l64_, d64, henc2_, true, nullptr, nullptr);
+        {
+            const __half* z = static_cast<const __half*>(d64.ptr);
+            __half* zh = zhat_;
+            int8_t* zi = z_i8_;
+            const long long n = static_cast<long long>(p64) * kChZ;
+            s.ops.push_back([z, zh, zi, n](cudaStream_t st) { return launch_round_z(z, zh, zi, n, st); });
+        }
+        build_hyper_tail(s);
+        for (int k = 0; k < 4; ++k) {
+            if (k > 0) build_spatial_prior(s, k);
+            EntropyStepArgs a;
+            a.H = H16_; a.W = W16_; a.G = kChY / 4; a.step = k;
+            a.y = y_; a.y_pitch = kChY; a.q_enc = q_y_enc_;
+            const __half* pbase = (k == 0) ? params_c_ : sp_out_;
+            a.scales = pbase; a.means = pbase + kChY; a.p_pitch = 512;
+            a.y_hat_acc = cat_; a.acc_pitch = 512;
+            a.skip_thres = skip_thres_; a.scale_lut = lut_;
+            a.sym_raw = sym_raw_; a.counts = counts_;
+            int32_t* offs = offsets_[k];
+            int32_t* tot = totals_ + k;
+            int16_t* dst = sym_c_[k];
+            const int n = static_cast<int>(p16);
+            s.ops.push_back([a](cudaStream_t st) { return launch_entropy_enc_step(a, st); });
+            s.ops.push_back([a, offs, tot, n](cudaStream_t st) { return launch_scan_counts(a.counts, offs, tot, n, st); });
+            s.ops.push_back([a, offs, dst](cudaStream_t st) { return launch_compact_i16(a, offs, dst, st); });
+        }
+        const ActView acc = make_view(cat_, kChY, 512, W16_, H16_);
+        const ActView yh = make_view(yhat_, kChY, kChY, W16_, H16_);
+        const __half* qd = q_y_dec_;
+        s.ops.push_back([acc, qd, yh](cudaStream_t st) { return launch_scale_channels(acc, qd, yh, st); });
+    }
+    (void)v_scales0;
+    // ------------------------------------------------------------------ enc_1 = synthesis
+    build_synthesis(enc1_seg_);
+
+    // ------------------------------------------------------------------ decoder segments (dmci_proxy.cpp:461-599)
+    {
+        Segment& s = dec0_;
+        const int8_t* zi = z_i8_;
+        __half* zh = zhat_;
+        const long long n = static_cast<long long>(p64) * kChZ;
+        s.ops.push_back([zi, zh, n](cudaStream_t st) { return launch_int8_to_half(zi, zh, n, st); });
+        build_hyper_tail(s);
+    }
+    for (int k = 0; k < 4; ++k) {
+        // segment producing the indexes of step k; for k > 0 it first restores step k-1
+        Segment& s = (k == 0) ? dec0_ : dec_step_[k];
+        if (k > 0) {
+            EntropyStepArgs r;
+            r.H = H16_; r.W = W16_; r.G = kChY / 4; r.step = k - 1;
+            const __half* pb = (k - 1 == 0) ? params_c_ : sp_out_;
+            r.scales = pb; r.means = pb + kChY; r.p_pitch = 512;
+            r.y_hat_acc = cat_; r.acc_pitch = 512; r.skip_thres = skip_thres_; r.scale_lut = lut_;
+            const int32_t* offs = offsets_[k - 1];
+            const int8_t* dec = decoded_;
+            s.ops.push_back([r, offs, dec](cudaStream_t st) { return launch_entropy_dec_restore(r, offs, dec, st); });
+            build_spatial_prior(s, k);
+        }
+        EntropyStepArgs a;
+        a.H = H16_; a.W = W16_; a.G = kChY / 4; a.step = k;
+        const __half* pbase = (k == 0) ? params_c_ : sp_out_;
+        a.scales = pbase; a.means = pbase + kChY; a.p_pitch = 512;
+        a.skip_thres = skip_thres_; a.scale_lut = lut_;
+        a.idx_raw = idx_raw_; a.counts = counts_;
+        int32_t* offs = offsets_[k];
+        int32_t* tot = totals_ + k;
+        uint8_t* dst = idx_c_;
+        const int n = static_cast<int>(p16);
+        s.ops.push_back([a](cudaStream_t st) { return launch_entropy_dec_index(a, st); });
+        s.ops.push_back([a, offs, tot, n](cudaStream_t st) { return launch_scan_counts(a.counts, offs, tot, n, st); });
+        s.ops.push_back([a, offs, dst](cudaStream_t st) { return launch_compact_u8(a, offs, dst, st); });
+    }
+    {
+        Segment& s = dec4_;
+        EntropyStepArgs r;
+        r.H = H16_; r.W = W16_; r.G = kChY / 4; r.step = 3;
+        r.scales = sp_out_; r.means = sp_out_ + kChY; r.p_pitch = 512;
+        r.y_hat_acc = cat_; r.acc_pitch = 512; r.skip_thres = skip_thres_; r.scale_lut = lut_;
+        const int32_t* offs = offsets_[3];
+        const int8_t* dec = decoded_;
+        s.ops.push_back([r, offs, dec](cudaStream_t st) { return launch_entropy_dec_restore(r, offs, dec, st); });
+        const ActView acc = make_view(cat_, kChY, 512, W16_, H16_);
+        const ActView yh = make_view(yhat_, kChY, kChY, W16_, H16_);
+        const __half* qd = q_y_dec_;
+        s.ops.push_back([acc, qd, yh](cudaStream_t st) { return launch_scale_channels(acc, qd, yh, st); });
+        build_synthesis(s);
+    }
+    Segment* segs[] = { &enc0_, &enc1_seg_, &dec0_, &dec_step_[1], &dec_step_[2], &dec_step_[3], &dec4_ };
+    for (Segment* s : segs) {
+        s->annotate(OP_ELEM, 0, 0);
+        s->launches = static_cast<int>(s->ops.size());
+    }
+}
+
+// z_hat -> hyper decoder -> prior fusion -> crop -> (scales, means) + reduced params into the cat buffer
+void IntraCodec::build_hyper_tail(Segment& s)
+{
+    const int H32 = l32_.H, W32 = l32_.W;
+    const ActView zh = make_view(zhat_, kChZ, kChZ, W64_, H64_);
+    ActView u32 = make_view(l32_.A, kChZ, kChZ, W32, H32);
+    add_gemm(s, GEMM_TCONV2X2, zh, u32, hdec0_up_.w, nullptr, 4 * kChZ, ACT_NONE, 0, nullptr, nullptr, nullptr);
+    u32 = dcb(s, l32_, u32, hdec0_, true, nullptr, nullptr);
+    ActView u16 = make_view(l16_.A, kChZ, kChZ, W16p_, H16p_);
+    add_gemm(s, GEMM_TCONV2X2, u32, u16, hdec1_up_.w, nullptr, 4 * kChZ, ACT_NONE, 0, nullptr, nullptr, nullptr);
+    u16 = dcb(s, l16_, u16, hdec1_, true, nullptr, nullptr);
+    const ActView hyp = make_view(hyp_, kChY, kChY, W16p_, H16p_);
+    dcb(s, l16_, u16, hdec2_, false, nullptr, &hyp);
+    ActView t = dcb(s, l16_, hyp, pf_[0], false, nullptr, nullptr);
+    t = dcb(s, l16_, t, pf_[1], false, nullptr, nullptr);
+    t = dcb(s, l16_, t, pf_[2], false, nullptr, nullptr);
+    const ActView pp = make_view(params_p_, 512, 512, W16p_, H16p_);
+    add_gemm(s, GEMM_PW, t, pp, pf3_.w, pf3_.b, 512, ACT_NONE, 0, nullptr, nullptr, nullptr);
+    const ActView pc = make_view(params_c_, 512, 512, W16_, H16_);
+    if (params_c_ != params_p_) s.ops.push_back([pp, pc](cudaStream_t st) { return launch_pad_crop(pp, pc, st); });
+    const ActView red = make_view(cat_ + kChY, kChY, 512, W16_, H16_);
+    add_gemm(s, GEMM_PW, pc, red, red_.w, red_.b, kChY, ACT_NONE, 0, nullptr, nullptr, nullptr);
+}
+
+// adaptor_k + 3 blocks + 1x1 on cat(y_hat_so_far, reduced) -> sp_out (dmci_proxy.cpp:347-349)
+void IntraCodec::build_spatial_prior(Segment& s, int k)
+{
+    // the spatial prior works on the unpadded latent grid
+    Level L = l16_;
+    const ActView cat = make_view(cat_, 512, 512, W16_, H16_);
+    ActView t = dcb(s, L, cat, spa_[k - 1], false, nullptr, nullptr);
+    for (int i = 0; i < 3; ++i) t = dcb(s, L, t, sp_[i], false, nullptr, nullptr);
+    const ActView out = make_view(sp_out_, 512, 512, W16_, H16_);
+    add_gemm(s, GEMM_PW, t, out, sp3_.w, sp3_.b, 512, ACT_NONE, 0, nullptr, nullptr, nullptr);
+}
+
+// y_hat -> x_hat features (dmci_proxy.cpp:14-33); the final shuffle+clamp writes to the caller's buffer
+void IntraCodec::build_synthesis(Segment& s)
+{
+    const ActView yh = make_view(yhat_, kChY, kChY, W16_, H16_);
+    ActView t = make_view(l8_.A, kChEncDec, kChEncDec, W8_, H8_);
+    add_gemm(s, GEMM_TCONV2X2, yh, t, dec_up_.w, nullptr, 4 * kChEncDec, ACT_NONE, 0, nullptr, nullptr, nullptr);
+    t = dcb(s, l8_, t, dec1_[0], true, nullptr, nullptr);
+    for (int i = 1; i < 13; ++i) t = dcb(s, l8_, t, dec1_[i], false, (i == 12) ? q_dec_ : nullptr, nullptr);
+    const ActView out = make_view(dec_out_, kChSrc, kChSrc, W8_, H8_);
+    dcb(s, l8_, t, dec2_, false, nullptr, &out);
+}
+
+void IntraCodec::run(Segment& s, cudaStream_t stream)
+{
+    if (profile_) {
+        // per-op CUDA-event timing (no graphs): feeds the roofline numbers of bench.py
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        for (size_t i = 0; i < s.ops.size(); ++i) {
+            CK(cudaEventRecord(e0, stream));
+            if (s.ops[i](stream)) throw std::runtime_error(std::string("kernel launch failed: ") + gemm_last_error());
+            CK(cudaEventRecord(e1, stream));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            ProfileAcc& a = prof_[s.kinds[i]];
+            a.ms += ms; a.bytes += s.alg_bytes[i]; a.flops += s.flops[i]; a.launches += 1;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        launches += s.launches;
+        return;
+    }
+    if (use_graphs_) {
+        if (!s.exec) {
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            int rc = 0;
+            for (auto& op : s.ops) {
+                rc = op(stream);
+                if (rc) break;
+            }
+            cudaError_t e = cudaStreamEndCapture(stream, &graph);
+            if (rc || e != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                throw std::runtime_error(std::string("graph capture failed: ") +
+                                         (rc ? gemm_last_error() : cudaGetErrorString(e)));
+            }
+            e = cudaGraphInstantiate(&s.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        }
+        CK(cudaGraphLaunch(s.exec, stream));
+    } else {
+        for (auto& op : s.ops) {
+            if (op(stream)) throw std::runtime_error(std::string("kernel launch failed: ") + gemm_last_error());
+        }
+    }
+    launches += s.launches;
+}
+
+void IntraCodec::stage_qp(int qp, cudaStream_t stream)
+{
+    if (qp < 0 || qp >= kQpNum) throw std::runtime_error("qp out of range");
+    CK(cudaMemcpyAsync(q_enc_, q_enc_all_ + static_cast<size_t>(qp) * kChEncDec, kChEncDec * 2, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemcpyAsync(q_dec_, q_dec_all_ + static_cast<size_t>(qp) * kChEncDec, kChEncDec * 2, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemcpyAsync(q_y_enc_, q_y_enc_all_ + static_cast<size_t>(qp) * kChY, kChY * 2, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemcpyAsync(q_y_dec_, q_y_dec_all_ + static_cast<size_t>(qp) * kChY, kChY * 2, cudaMemcpyDeviceToDevice, stream));
+}
+
+// =============================================================================== compress
+void IntraCodec::compress(const void* x, int H, int W, int64_t sc, int64_t sh, int64_t sw, int qp,
+                          int pad_b, int pad_r, cudaStream_t stream, const uint8_t** bs,
+                          int32_t* bs_len, int32_t* ec_parallel, void* x_hat_out)
+{
+    CK(cudaSetDevice(device_));
+    if ((H + pad_b) % 16 || (W + pad_r) % 16) throw std::runtime_error("padded size must be a multiple of 16");
+    plan(H + pad_b, W + pad_r);
+    StreamHop hop(this, stream);
+    stream = hop.run;
+    stage_qp(qp, stream);
+    tev_n_ = 0;
+    tick(stream);
+    // pad + unshuffle (outside the graph: the input pointer changes per call, dmci_proxy.cpp:304-305)
+    if (launch_unshuffle8_pad(static_cast<const __half*>(x), 3, H, W, sc, sh, sw,
+                              make_view(in8_, kChSrc, kChSrc, W8_, H8_), stream))
+        throw std::runtime_error("unshuffle8_pad launch failed");
+    ++launches;
+    run(enc0_, stream);
+    CK(cudaEventRecord(ev_y_, stream));
+
+    // symbols -> host on the copy stream while the synthesis transform runs on `stream`
+    CK(cudaStreamWaitEvent(copy_stream_, ev_y_, 0));
+    const size_t nz = static_cast<size_t>(H64_) * W64_ * kChZ;
+    CK(cudaMemcpyAsync(h_totals_, totals_, 16, cudaMemcpyDeviceToHost, copy_stream_));
+    CK(cudaMemcpyAsync(h_z_, z_i8_, nz, cudaMemcpyDeviceToHost, copy_stream_));
+
+    run(enc1_seg_, stream);
+    if (launch_shuffle8_clamp(make_view(dec_out_, kChSrc, kChSrc, W8_, H8_),
+                              static_cast<__half*>(x_hat_out), 3, 1, stream))
+        throw std::runtime_error("shuffle8_clamp launch failed");
+    ++launches;
+    tock(stream);
+
+    CK(cudaStreamSynchronize(copy_stream_));
+    int total = 0;
+    for (int k = 0; k < 4; ++k) {
+        const int n = h_totals_[k];
+        if (n < 0 || static_cast<size_t>(n) > quarter_) throw std::runtime_error("corrupt symbol count");
+        total += n;
+        if (n) CK(cudaMemcpyAsync(h_sym_[k], sym_c_[k], static_cast<size_t>(n) * 2, cudaMemcpyDeviceToHost, copy_stream_));
+    }
+    CK(cudaStreamSynchronize(copy_stream_));
+    const int n_par = RansCodec::ec_parallel_for(total);
+    std::vector<EncodeJob> jobs;
+    for (int k = 3; k >= 0; --k) {  // dmci_proxy.cpp:839-841
+        EncodeJob j;
+        j.kind = EncodeJob::Y; j.y = h_sym_[k]; j.size = h_totals_[k];
+        jobs.push_back(j);
+    }
+    EncodeJob jz;
+    jz.kind = EncodeJob::Z; jz.z = h_z_; jz.size = static_cast<int>(nz);
+    jz.cdf_offset = qp * kChZ; jz.ch = kChZ;   // dmci_proxy.cpp:843-844
+    jobs.push_back(jz);
+    rans_.encode(jobs, n_par, bitstream_);
+    *bs = bitstream_.data();
+    *bs_len = static_cast<int32_t>(bitstream_.size());
+    *ec_parallel = n_par;
+}
+
+// =============================================================================== decompress
+void IntraCodec::decompress(const uint8_t* bs, int len, int qp, int height, int width,
+                            int ec_parallel, cudaStream_t stream, void* x_hat_out)
+{
+    CK(cudaSetDevice(device_));
+    plan(height, width);
+    StreamHop hop(this, stream);
+    stream = hop.run;
+    stage_qp(qp, stream);
+    const int zh = (height + 63) / 64, zw = (width + 63) / 64;  // dmci_proxy.cpp:432-433
+    if (zh != H64_ || zw != W64_) throw std::runtime_error("z geometry mismatch");
+    const int nz = kChZ * zh * zw;
+    rans_.set_stream(bs, len, ec_parallel);
+    rans_.decode_z(h_z_, nz, qp * kChZ, kChZ);
+    tev_n_ = 0;
+    CK(cudaMemcpyAsync(z_i8_, h_z_, nz, cudaMemcpyHostToDevice, stream));
+    for (int k = 0; k < 4; ++k) {
+        tick(stream);
+        run(k == 0 ? dec0_ : dec_step_[k], stream);
+        tock(stream);
+        CK(cudaMemcpyAsync(h_totals_ + k, totals_ + k, 4, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        const int n = h_totals_[k];
+        if (n < 0 || static_cast<size_t>(n) > quarter_) throw std::runtime_error("corrupt index count");
+        if (n) {
+            CK(cudaMemcpyAsync(h_idx_, idx_c_, n, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            rans_.decode_y(h_decoded_, h_idx_, n);
+            CK(cudaMemcpyAsync(decoded_, h_decoded_, n, cudaMemcpyHostToDevice, stream));
+        }
+    }
+    tick(stream);
+    run(dec4_, stream);
+    if (launch_shuffle8_clamp(make_view(dec_out_, kChSrc, kChSrc, W8_, H8_),
+                              static_cast<__half*>(x_hat_out), 3, 1, stream))
+        throw std::runtime_error("shuffle8_clamp launch failed");
+    ++launches;
+    tock(stream);
+}
+
+int IntraCodec::debug_fetch(const char* name, void* dst, int64_t max_bytes, int64_t* written)
+{
+    struct Tap { const char* n; const void* p; size_t bytes; };
+    const size_t p16 = static_cast<size_t>(H16_) * W16_;
+    const Tap taps[] = {
+        { "y", y_, p16 * kChY * 2 },
+        { "y_hat", yhat_, p16 * kChY * 2 },
+        { "params", params_c_, p16 * 512 * 2 },
+        { "cat", cat_, p16 * 512 * 2 },
+        { "sp_out", sp_out_, p16 * 512 * 2 },
+        { "z_i8", z_i8_, static_cast<size_t>(H64_) * W64_ * kChZ },
+        { "dec_out", dec_out_, static_cast<size_t>(H8_) * W8_ * kChSrc * 2 },
+        { "in8", in8_, static_cast<size_t>(H8_) * W8_ * kChSrc * 2 },
+        { "totals", totals_, 16 },
+        { "sym0", sym_c_[0], quarter_ * 2 },
+        { "sym1", sym_c_[1], quarter_ * 2 },
+        { "sym2", sym_c_[2], quarter_ * 2 },
+        { "sym3", sym_c_[3], quarter_ * 2 },
+    };
+    for (const Tap& t : taps) {
+        if (strcmp(t.n, name) == 0) {
+            if (!t.p) throw std::runtime_error("debug_fetch: buffer not allocated yet");
+            const size_t n = std::min<size_t>(t.bytes, static_cast<size_t>(max_bytes));
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(dst, t.p, n, cudaMemcpyDeviceToHost));
+            *written = static_cast<int64_t>(n);
+            return 0;
+        }
+    }
+    throw std::runtime_error(std::string("debug_fetch: unknown buffer '") + name + "'");
+}
+
+}  // namespace dcvc
+
+// =================================================================================== C ABI
+using dcvc::IntraCodec;
+
+struct dcvc_codec {
+    int kind;
+    std::unique_ptr<IntraCodec> intra;
+    std::string err;
+};
+
+namespace dcvc { void set_api_error(const std::string& s); }
+
+#define CODEC_TRY(h) try {
+#define CODEC_CATCH(h)                              \
+    }                                               \
+    catch (const std::exception& e) {               \
+        (h)->err = e.what();                        \
+        dcvc::set_api_error(e.what());              \
+        return 1;                                   \
+    }                                               \
+    catch (...) {                                   \
+        (h)->err = "unknown C++ exception";         \
+        dcvc::set_api_error((h)->err);              \
+        return 1;                                   \
+    }
+
+extern "C" {
+
+int dcvc_create(int32_t kind, int32_t device, dcvc_codec** out)
+{
+    if (kind != DCVC_KIND_INTRA) {
+        dcvc::set_api_error("dcvc_create: only DCVC_KIND_INTRA is implemented in this build");
+        return 1;
+    }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+        dcvc::set_api_error("dcvc_create: no such CUDA device (this library has no CPU fallback)");
+        return 1;
+    }
+    dcvc_codec* h = new dcvc_codec();
+    h->kind = kind;
+    h->intra.reset(new IntraCodec(device));
+    *out = h;
+    return 0;
+}
+
+int dcvc_destroy(dcvc_codec* h)
+{
+    delete h;
+    return 0;
+}
+
+const char* dcvc_codec_error(dcvc_codec* h) { return h ? h->err.c_str() : "null handle"; }
+
+int dcvc_set_param(dcvc_codec* h, const char* name, const void* data, int32_t dtype, int32_t ndim,
+                   const int64_t* shape, int32_t on_device)
+{
+    CODEC_TRY(h)
+    h->intra->set_param(name, data, dtype, ndim, shape, on_device);
+    return 0;
+    CODEC_CATCH(h)
+}
+
+int dcvc_finalize_params(dcvc_codec* h, float skip_thres)
+{
+    CODEC_TRY(h)
+    h->intra->finalize(skip_thres);
+    return 0;
+    CODEC_CATCH(h)
+}
+
+int dcvc_compress(dcvc_codec* h, const void* x, int32_t H, int32_t W, int64_t sc, int64_t sh,
+                  int64_t sw, int32_t qp, int32_t pad_b, int32_t pad_r, void* stream,
+                  const uint8_t** bit_stream, int32_t* bit_stream_len, int32_t* ec_parallel,
+                  void* x_hat_out)
+{
+    CODEC_TRY(h)
+    h->intra->compress(x, H, W, sc, sh, sw, qp, pad_b, pad_r, static_cast<cudaStream_t>(stream),
+                       bit_stream, bit_stream_len, ec_parallel, x_hat_out);
+    return 0;
+    CODEC_CATCH(h)
+}
+
+int dcvc_decompress(dcvc_codec* h, const uint8_t* bit_stream, int32_t len, int32_t qp,
+                    int32_t height, int32_t width, int32_t ec_parallel, void* stream, void* x_hat_out)
+{
+    CODEC_TRY(h)
+    h->intra->decompress(bit_stream, len, qp, height, width, ec_parallel,
+                         static_cast<cudaStream_t>(stream), x_hat_out);
+    return 0;
+    CODEC_CATCH(h)
+}
+
+int64_t dcvc_kernel_launches(dcvc_codec* h) { return h->intra->launches; }
+
+int dcvc_last_gpu_ms(dcvc_codec* h, float* ms)
+{
+    CODEC_TRY(h)
+    *ms = h->intra->gpu_ms();
+    return 0;
+    CODEC_CATCH(h)
+}
+
+int dcvc_profile_enable(dcvc_codec* h, int32_t on)
+{
+    h->intra->profile_ = on != 0;
+    if (on) for (auto& a : h->intra->prof_) a = dcvc::ProfileAcc();
+    return 0;
+}
+
+int dcvc_profile_get(dcvc_codec* h, int32_t kind, double* ms, int64_t* launches, double* alg_bytes,
+                     double* flops)
+{
+    if (kind < 0 || kind >= dcvc::OP_KINDS) return 1;
+    const dcvc::ProfileAcc& a = h->intra->prof_[kind];
+    *ms = a.ms; *launches = a.launches; *alg_bytes = a.bytes; *flops = a.flops;
+    return 0;
+}
+
+int dcvc_debug_fetch(dcvc_codec* h, const char* name, void* host_dst, int64_t max_bytes,
+                     int64_t* bytes_written)
+{
+    CODEC_TRY(h)
+    return h->intra->debug_fetch(name, host_dst, max_bytes, bytes_written);
+    CODEC_CATCH(h)
+}
+
+}  // extern "C"

@@ -532,16 +532,31 @@ int gemm_plan(GemmOp& op)
 }
 
 template <int BN>
+static cudaError_t set_attr()
+{
+    return cudaFuncSetAttribute(pw_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                TileCfg<BN>::SMEM_BYTES);
+}
+
+int gemm_init()
+{
+    static bool done = false;
+    if (done) return 0;
+    cudaError_t e = set_attr<64>();
+    if (e == cudaSuccess) e = set_attr<128>();
+    if (e == cudaSuccess) e = set_attr<192>();
+    if (e == cudaSuccess) e = set_attr<256>();
+    if (e != cudaSuccess) {
+        g_err = std::string("cudaFuncSetAttribute(pw_gemm): ") + cudaGetErrorString(e);
+        return 1;
+    }
+    done = true;
+    return 0;
+}
+
+template <int BN>
 static cudaError_t launch_bn(const GemmOp& op, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(pw_gemm_kernel<BN>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             TileCfg<BN>::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     pw_gemm_kernel<BN><<<op.grid, NUM_THREADS, op.smem, stream>>>(op.p);
     return cudaGetLastError();
 }
@@ -549,6 +564,7 @@ static cudaError_t launch_bn(const GemmOp& op, cudaStream_t stream)
 int gemm_launch(const GemmOp& op, cudaStream_t stream)
 {
     if (!op.planned) { g_err = "gemm_launch: op not planned"; return 1; }
+    if (gemm_init()) return 1;
     cudaError_t e;
     switch (op.block_n) {
     case 64: e = launch_bn<64>(op, stream); break;

@@ -76,5 +76,7 @@ struct GemmOp {
 int gemm_plan(GemmOp& op);
 int gemm_launch(const GemmOp& op, cudaStream_t stream);
 const char* gemm_last_error();
+// one-time kernel attribute setup (dynamic smem opt-in); call outside stream capture
+int gemm_init();
 
 }  // namespace dcvc

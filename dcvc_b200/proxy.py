@@ -1,0 +1,128 @@
+"""Python face of the codec-level C ABI: drop-in for the reference's pybind11 classes
+(src/layers/extensions/inference/bind.cpp:11-38).  Same class names, method names, argument order
+and return values; torch is used only for device memory and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class _CodecHandle:
+    def __init__(self, kind: int):
+        if not torch.cuda.is_available():
+            raise RuntimeError("inference_extensions_cuda (dcvc_b200) needs a CUDA device: there is no CPU path")
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        self.device = torch.cuda.current_device()
+        rc = self.lib.dcvc_create(kind, self.device, C.byref(self.h))
+        if rc:
+            raise RuntimeError("dcvc_create failed: " + self.lib.dcvc_last_error().decode())
+
+    def check(self, rc, what):
+        if rc:
+            raise RuntimeError(f"{what}: " + self.lib.dcvc_codec_error(self.h).decode(errors="replace"))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.dcvc_destroy(self.h)
+        except Exception:
+            pass
+
+
+def _push_state_dict(hd: _CodecHandle, state_dict, skip_threshold: float):
+    for name, t in state_dict.items():
+        if not isinstance(t, torch.Tensor):
+            continue
+        if t.dtype in (torch.int32, torch.int64):
+            tt = t.detach().to("cpu", torch.int32).contiguous()
+            dtype, on_dev = _lib.DTYPE_I32, 0
+        elif t.is_floating_point():
+            # logical (row-major) order, whatever the memory_format of the module was
+            tt = t.detach().contiguous(memory_format=torch.contiguous_format)
+            if tt.dtype == torch.float16:
+                dtype = _lib.DTYPE_F16
+            else:
+                tt = tt.float()
+                dtype = _lib.DTYPE_F32
+            on_dev = 1 if tt.is_cuda else 0
+        else:
+            continue
+        shape = (C.c_int64 * max(1, tt.dim()))(*tt.shape)
+        hd.check(hd.lib.dcvc_set_param(hd.h, name.encode(), C.c_void_p(tt.data_ptr()), dtype, tt.dim(), shape, on_dev),
+                 f"set_param({name})")
+    hd.check(hd.lib.dcvc_finalize_params(hd.h, C.c_float(float(skip_threshold))), "finalize_params")
+
+
+class DMCIProxy:
+    """DCVC-UF-Intra proxy (reference: DMCIProxy, dmci_proxy.h:142-144)."""
+
+    def __init__(self):
+        self._hd = _CodecHandle(_lib.KIND_INTRA)
+        self._x_hat = None
+
+    def set_param(self, state_dict, skip_threshold: float):
+        _push_state_dict(self._hd, state_dict, skip_threshold)
+
+    def _out(self, hp, wp, device):
+        if self._x_hat is None or self._x_hat.shape[2] != hp or self._x_hat.shape[3] != wp:
+            self._x_hat = torch.empty((1, 3, hp, wp), dtype=torch.float16, device=device,
+                                      memory_format=torch.channels_last)
+        return self._x_hat
+
+    def compress(self, x: torch.Tensor, qp: int, padding_b: int, padding_r: int):
+        """-> (bit_stream: np.ndarray[uint8], x_hat: fp16 channels_last [1,3,H16p,W16p], ec_parallel)"""
+        hd = self._hd
+        assert x.is_cuda and x.dtype == torch.float16 and x.dim() == 4 and x.shape[0] == 1 and x.shape[1] == 3
+        _, _, H, W = x.shape
+        out = self._out(H + padding_b, W + padding_r, x.device)
+        bs, n, ec = C.c_void_p(), C.c_int32(), C.c_int32()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        hd.check(hd.lib.dcvc_compress(hd.h, C.c_void_p(x.data_ptr()), H, W, x.stride(1), x.stride(2), x.stride(3),
+                                      int(qp), int(padding_b), int(padding_r), stream, C.byref(bs), C.byref(n),
+                                      C.byref(ec), C.c_void_p(out.data_ptr())), "compress")
+        stream_np = np.ctypeslib.as_array(C.cast(bs, C.POINTER(C.c_uint8)), (n.value,)).copy()
+        return stream_np, out, ec.value
+
+    def decompress(self, bit_stream: np.ndarray, qp: int, height: int, width: int, ec_parallel: int):
+        hd = self._hd
+        bs = np.ascontiguousarray(bit_stream, dtype=np.uint8)
+        hp, wp = (height + 15) // 16 * 16, (width + 15) // 16 * 16
+        out = self._out(hp, wp, torch.device("cuda", hd.device))
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        hd.check(hd.lib.dcvc_decompress(hd.h, C.c_void_p(bs.ctypes.data), bs.size, int(qp), int(height), int(width),
+                                        int(ec_parallel), stream, C.c_void_p(out.data_ptr())), "decompress")
+        return out
+
+    # ---- instrumentation (not part of the reference surface)
+    def kernel_launches(self) -> int:
+        return int(self._hd.lib.dcvc_kernel_launches(self._hd.h))
+
+    def last_gpu_ms(self) -> float:
+        ms = C.c_float()
+        self._hd.check(self._hd.lib.dcvc_last_gpu_ms(self._hd.h, C.byref(ms)), "last_gpu_ms")
+        return ms.value
+
+    def profile_enable(self, on: bool):
+        self._hd.lib.dcvc_profile_enable(self._hd.h, 1 if on else 0)
+
+    def profile_get(self):
+        """{family: dict(ms, launches, alg_bytes, flops)} accumulated since profile_enable(True)"""
+        out = {}
+        for kind, name in enumerate(("pw_gemm", "dw3x3", "elementwise")):
+            ms, n, b, f = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+            self._hd.lib.dcvc_profile_get(self._hd.h, kind, C.byref(ms), C.byref(n), C.byref(b), C.byref(f))
+            out[name] = {"ms": ms.value, "launches": n.value, "alg_bytes": b.value, "flops": f.value}
+        return out
+
+    def debug_fetch(self, name: str, dtype=np.float16) -> np.ndarray:
+        buf = np.zeros(64 << 20, dtype=np.uint8)
+        n = C.c_int64()
+        self._hd.check(self._hd.lib.dcvc_debug_fetch(self._hd.h, name.encode(), C.c_void_p(buf.ctypes.data), buf.size,
+                                                     C.byref(n)), "debug_fetch")
+        return buf[: n.value].view(dtype).copy()
