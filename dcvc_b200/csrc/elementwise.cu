@@ -20,55 +20,87 @@ namespace dcvc {
 static inline int blocks_for(long long n, int threads) { return static_cast<int>((n + threads - 1) / threads); }
 
 // ------------------------------------------------------------------------------- dw3x3
-__global__ void __launch_bounds__(256)
+// One thread = 8 channels x a vertical strip of DW_TY output rows: every input row of the strip is
+// loaded once per thread (3 x 16 B, the x-1 / x+1 neighbours hit L1 because adjacent threads of the
+// CTA load them as their centre) and scattered into the <= 3 output rows it contributes to.  HBM/L2
+// traffic per output drops from ~3 input rows to (DW_TY + 2) / DW_TY.
+static constexpr int DW_TY = 8;
+
+__global__ void __launch_bounds__(256, 2)
 dw3x3_kernel(const __half* __restrict__ in, int in_pitch, __half* __restrict__ out, int out_pitch,
              const __half* __restrict__ w, int C, int W, int H)
 {
     const int cg_n = C >> 3;
+    const int row_items = W * cg_n;  // (x, channel-group) pairs of one row
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long total = static_cast<long long>(W) * H * cg_n;
-    if (tid >= total) return;
-    const int cg = static_cast<int>(tid % cg_n);
-    const long long pix = tid / cg_n;
-    const int x = static_cast<int>(pix % W);
-    const int y = static_cast<int>(pix / W);
+    const int strips = (H + DW_TY - 1) / DW_TY;
+    if (tid >= static_cast<long long>(row_items) * strips) return;
+    const int item = static_cast<int>(tid % row_items);
+    const int strip = static_cast<int>(tid / row_items);
+    const int cg = item % cg_n;
+    const int x = item / cg_n;
     const int c = cg << 3;
+    const int y0 = strip * DW_TY;
 
-    float acc[8];
+    uint4 wk[9];  // packed fp16 taps (converted on use: keeps the register count low enough for 2 CTAs/SM)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int k = 0; k < 9; ++k) wk[k] = __ldg(reinterpret_cast<const uint4*>(w + k * C + c));
+    float acc[DW_TY][8];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        const int yy = y + ky - 1;
+    for (int r = 0; r < DW_TY; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
+
+#pragma unroll
+    for (int ry = -1; ry <= DW_TY; ++ry) {
+        const int yy = y0 + ry;
         if (yy < 0 || yy >= H) continue;
+        const __half* rowp = in + (static_cast<long long>(yy) * W + x) * in_pitch + c;
+        float v[3][8];
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
             const int xx = x + kx - 1;
-            if (xx < 0 || xx >= W) continue;
-            const uint4 v = *reinterpret_cast<const uint4*>(
-                in + (static_cast<long long>(yy) * W + xx) * in_pitch + c);
-            const uint4 k = __ldg(reinterpret_cast<const uint4*>(w + (ky * 3 + kx) * C + c));
-            const __half2* vh = reinterpret_cast<const __half2*>(&v);
-            const __half2* kh = reinterpret_cast<const __half2*>(&k);
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (xx >= 0 && xx < W) q = *reinterpret_cast<const uint4*>(rowp + static_cast<long long>(kx - 1) * in_pitch);
+            const __half2* qh = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float2 a = __half22float2(vh[i]);
-                const float2 b = __half22float2(kh[i]);
-                acc[2 * i] = fmaf(a.x, b.x, acc[2 * i]);
-                acc[2 * i + 1] = fmaf(a.y, b.y, acc[2 * i + 1]);
+                const float2 f = __half22float2(qh[i]);
+                v[kx][2 * i] = f.x;
+                v[kx][2 * i + 1] = f.y;
+            }
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int r = ry - ky + 1;  // output row (inside the strip) this input row feeds through tap ky
+            if (r < 0 || r >= DW_TY) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const __half2* kh = reinterpret_cast<const __half2*>(&wk[ky * 3 + kx]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 wf = __half22float2(kh[i]);
+                    acc[r][2 * i] = fmaf(v[kx][2 * i], wf.x, acc[r][2 * i]);
+                    acc[r][2 * i + 1] = fmaf(v[kx][2 * i + 1], wf.y, acc[r][2 * i + 1]);
+                }
             }
         }
     }
-    uint4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
-    *reinterpret_cast<uint4*>(out + pix * out_pitch + c) = o;
+    for (int r = 0; r < DW_TY; ++r) {
+        const int y = y0 + r;
+        if (y >= H) break;
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(acc[r][2 * i], acc[r][2 * i + 1]);
+        *reinterpret_cast<uint4*>(out + (static_cast<long long>(y) * W + x) * out_pitch + c) = o;
+    }
 }
 
 int launch_dw3x3(const ActView& in, const ActView& out, const __half* w, cudaStream_t s)
 {
-    const long long total = static_cast<long long>(in.W) * in.H * (in.C / 8);
+    const long long total = static_cast<long long>(in.W) * (in.C / 8) * ((in.H + DW_TY - 1) / DW_TY);
     dw3x3_kernel<<<blocks_for(total, 256), 256, 0, s>>>(
         static_cast<const __half*>(in.ptr), in.pitch,
         static_cast<__half*>(const_cast<void*>(out.ptr)), out.pitch, w, in.C, in.W, in.H);

@@ -127,9 +127,10 @@ __device__ __forceinline__ void tma_store_commit()
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-__device__ __forceinline__ void tma_store_wait_read0()
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read()
 {
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
 __device__ __forceinline__ void tma_store_wait0()

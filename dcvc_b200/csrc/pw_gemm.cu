@@ -15,6 +15,7 @@
 #include "pw_gemm.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -28,83 +29,130 @@ static constexpr int BLOCK_K = 64;
 static constexpr int UMMA_K = 16;
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 static constexpr int SUB_TILE_BYTES = BLOCK_M * 64 * 2;      // one [128][64] fp16 store box
-static constexpr int NUM_THREADS = 192;
+static constexpr int EPI_GROUPS = 2;                          // one per TMEM accumulator buffer
+static constexpr int NUM_THREADS = 64 + EPI_GROUPS * 128;     // TMA warp + MMA warp + 2 x 4 epilogue warps
+
+static constexpr int MAX_STAGES = 8;
+static constexpr int SMEM_TOTAL = 232448;   // 227 KB: the whole SM, one persistent CTA per SM
+// control block at the end of the carve-up: barriers, tmem pointer, bias tiles of both groups
+static constexpr int CTRL_BYTES = 512 + EPI_GROUPS * 256 * 2;
+static constexpr int SMEM_USABLE = SMEM_TOTAL - 1024 /*alignment slack*/ - CTRL_BYTES;
 
 template <int BLOCK_N>
 struct TileCfg {
     static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (BLOCK_N >= 192) ? 2 : (BLOCK_N == 128 ? 3 : 4);
-    static constexpr int TMEM_COLS = (BLOCK_N <= 64) ? 64 : (BLOCK_N <= 128 ? 128 : 256);
-    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-    // + barriers (2*STAGES + 2) * 8, tmem ptr, bias tile, 1 KB alignment slack
-    static constexpr int SMEM_BYTES = PIPE_BYTES + 256 + BLOCK_N * 2 + 1024;
+    static constexpr int ACC_COLS = (BLOCK_N <= 64) ? 64 : (BLOCK_N <= 128 ? 128 : 256);
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;  // double-buffered accumulator
 };
 
 __device__ __forceinline__ float wsilu_f(float x)
 {
-    // x * sigmoid(4x)  (reference: src/layers/layers.py:106-111)
-    return __fdividef(x, 1.f + __expf(-4.f * x));
+    // x * sigmoid(4x) = 0.5 x (1 + tanh(2x))   (reference: src/layers/layers.py:106-111); one MUFU op
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(2.f * x));
+    return 0.5f * x * (1.f + t);
 }
 
+__device__ __forceinline__ void add_half8(float (&o)[8], const uint4& r)
+{
+    const __half2* rh = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(rh[j]);
+        o[2 * j] += f.x;
+        o[2 * j + 1] += f.y;
+    }
+}
+
+struct TileCoord {
+    int n0, ox0, oy0, oc0, opx, opy;
+};
+
+template <int BLOCK_N>
+__device__ __forceinline__ TileCoord tile_coord(const PwGemmParams& p, int tile)
+{
+    TileCoord t;
+    const int nt = tile % p.n_tiles;
+    const int mt = tile / p.n_tiles;
+    t.n0 = nt * BLOCK_N;
+    t.ox0 = (mt % p.tiles_x) * p.bw;
+    t.oy0 = (mt / p.tiles_x) * p.bh;
+    t.oc0 = p.chunk_add ? t.n0 / 4 : t.n0;
+    t.opx = 0;
+    t.opy = 0;
+    if (p.phase_c > 0) {  // tconv: this N tile is one 2x2 phase of the upsampled image
+        const int phase = t.n0 / p.phase_c;
+        t.oc0 = t.n0 - phase * p.phase_c;
+        t.opx = phase & 1;
+        t.opy = phase >> 1;
+    }
+    return t;
+}
+
+// Persistent kernel: grid = min(#tiles, #SMs), one CTA per SM, tiles assigned round-robin with the
+// N tile fastest so that concurrently running CTAs share the same activation tile in L2.
 template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
 {
     using Cfg = TileCfg<BLOCK_N>;
-    constexpr int STAGES = Cfg::STAGES;
+    const int STAGES = p.num_stages;
 
+    // run-time carve-up of the 227 KB:
+    //   streaming : [STAGES x (A 16 KB | B BLOCK_N*128 B)] [staging] [control]
+    //   b_resident: [weight slab: num_kblocks x B] [STAGES x A 16 KB] [staging] [control]
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint64_t* res_full_bar = tmem_full_bar + 1;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_full_bar + 1);
-    __half* bias_s = reinterpret_cast<__half*>(smem + Cfg::PIPE_BYTES + 256);
+    const int slab_bytes = p.b_resident ? p.num_kblocks * Cfg::B_STAGE_BYTES : 0;
+    const int a_stride = p.b_resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES;
+    uint8_t* a_base = smem + slab_bytes;
+    uint8_t* staging = a_base + STAGES * a_stride;
+    uint8_t* ctrl = smem + SMEM_USABLE;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);   // [MAX_STAGES]
+    uint64_t* empty_bar = full_bar + MAX_STAGES;              // [MAX_STAGES]
+    uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;         // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;             // [2]
+    uint64_t* slab_bar = tmem_empty_bar + 2;                  // [1]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ctrl + 256);
+    __half* bias_all = reinterpret_cast<__half*>(ctrl + 512);
+
+    // tile schedule: streaming -> round-robin over (m, n) with n fastest; b_resident -> the CTA is
+    // pinned to N tile (blockIdx % n_tiles) and strides over the M tiles of that column.
+    const int my_nt = blockIdx.x % p.n_tiles;
+    const int my_j = blockIdx.x / p.n_tiles;
+    const int col_ctas = (static_cast<int>(gridDim.x) - my_nt + p.n_tiles - 1) / p.n_tiles;
+    auto tile_of = [&](int i) -> int {  // global tile id of this CTA's i-th tile, or -1
+        if (p.b_resident) {
+            const int mt = my_j + i * col_ctas;
+            return mt < p.m_tiles ? mt * p.n_tiles + my_nt : -1;
+        }
+        const int t = blockIdx.x + i * static_cast<int>(gridDim.x);
+        return t < p.total_tiles ? t : -1;
+    };
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    const int nt = blockIdx.x;          // N tile
-    const int ox0 = blockIdx.y * p.bw;  // pixel tile origin
-    const int oy0 = blockIdx.z * p.bh;
-    const int n0 = nt * BLOCK_N;
-
-    const int out_cols = p.chunk_add ? BLOCK_N / 4 : BLOCK_N;
-    const int n_sub = (out_cols + 63) / 64;
-    // output channel origin / 2x2 phase (tconv stores phase (opy, opx) of the upsampled image)
-    int oc0 = p.chunk_add ? n0 / 4 : n0;
-    int opx = 0, opy = 0;
-    if (p.phase_c > 0) {
-        const int phase = n0 / p.phase_c;
-        oc0 = n0 - phase * p.phase_c;
-        opx = phase & 1;
-        opy = phase >> 1;
-    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tm_a);
         tma_prefetch_desc(&p.tm_b);
         tma_prefetch_desc(&p.tm_c);
-        if (p.n_res > 0) tma_prefetch_desc(&p.tm_r1);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(tmem_full_bar, 1);
-        mbar_init(res_full_bar, 1);
+        mbar_init(slab_bar, 1);
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&tmem_full_bar[g], 1);
+            mbar_init(&tmem_empty_bar[g], 4);  // one arrival per epilogue warp of the group
+        }
         mbar_fence_init();
     }
     if (warp == 1) {
         tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
         tmem_relinquish();
-    }
-    if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
-            bias_s[i] = p.bias ? p.bias[n0 + i] : __float2half(0.f);
-        }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -114,26 +162,31 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------------------------------------ TMA producer
-            for (int kb = 0; kb < p.num_kblocks; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                const int tap = kb / p.kblk_per_tap;
-                const int kc = kb - tap * p.kblk_per_tap;
-                uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
-                uint8_t* b_dst = a_dst + A_STAGE_BYTES;
-                mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                tma_load_5d(a_dst, &p.tm_a, &full_bar[s], kc * BLOCK_K, p.tap_px[tap],
-                            ox0 + p.tap_dx[tap], p.tap_py[tap], oy0 + p.tap_dy[tap]);
-                tma_load_2d(b_dst, &p.tm_b, &full_bar[s], kb * BLOCK_K, n0);
+            if (p.b_resident) {
+                // the weight slab of this CTA's N tile: loaded once, reused by every M tile
+                mbar_expect_tx(slab_bar, slab_bytes);
+                for (int kb = 0; kb < p.num_kblocks; ++kb) {
+                    tma_load_2d(smem + kb * Cfg::B_STAGE_BYTES, &p.tm_b, slab_bar, kb * BLOCK_K, my_nt * BLOCK_N);
+                }
             }
-            if (p.n_res > 0) {
-                // staging tile aliases the pipeline stages: wait until every MMA has drained
-                mbar_wait(tmem_full_bar, 0);
-                mbar_expect_tx(res_full_bar, n_sub * SUB_TILE_BYTES);
-                for (int j = 0; j < n_sub; ++j) {
-                    tma_load_5d(smem + j * SUB_TILE_BYTES, &p.tm_r1, res_full_bar, oc0 + j * 64,
-                                opx, ox0, opy, oy0);
+            uint32_t it = 0;
+            for (int i = 0;; ++i) {
+                const int tile = tile_of(i);
+                if (tile < 0) break;
+                const TileCoord tc = tile_coord<BLOCK_N>(p, tile);
+                for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    const int tap = kb / p.kblk_per_tap;
+                    const int kc = kb - tap * p.kblk_per_tap;
+                    uint8_t* a_dst = a_base + s * a_stride;
+                    mbar_expect_tx(&full_bar[s], p.b_resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES);
+                    tma_load_5d(a_dst, &p.tm_a, &full_bar[s], kc * BLOCK_K, p.tap_px[tap],
+                                tc.ox0 + p.tap_dx[tap], p.tap_py[tap], tc.oy0 + p.tap_dy[tap]);
+                    if (!p.b_resident) {
+                        tma_load_2d(a_dst + A_STAGE_BYTES, &p.tm_b, &full_bar[s], kb * BLOCK_K, tc.n0);
+                    }
                 }
             }
         }
@@ -142,152 +195,168 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
         if (lane == 0) {
             // ------------------------------------------------------------ MMA issuer
             constexpr uint32_t idesc = make_idesc_f16_f32(BLOCK_M, BLOCK_N);
-            for (int kb = 0; kb < p.num_kblocks; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+            uint32_t it = 0;
+            if (p.b_resident) {
+                mbar_wait(slab_bar, 0);
                 tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint64_t a_desc = make_kmajor_sw128_desc(a_addr);
-                const uint64_t b_desc = make_kmajor_sw128_desc(a_addr + A_STAGE_BYTES);
-#pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    // advance 16 fp16 = 32 B inside the 128 B swizzle span: +2 in 16 B units
-                    umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                                (kb | k) != 0 ? 1u : 0u);
-                }
-                umma_commit(&empty_bar[s]);
             }
-            umma_commit(tmem_full_bar);
+            for (int i = 0; tile_of(i) >= 0; ++i) {
+                const int g = i & 1;
+                const uint32_t u = static_cast<uint32_t>(i >> 1);
+                mbar_wait(&tmem_empty_bar[g], (u & 1) ^ 1);  // epilogue drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t acc = tmem_base + g * Cfg::ACC_COLS;
+                for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(a_base + s * a_stride);
+                    const uint32_t b_addr = p.b_resident ? smem_u32(smem + kb * Cfg::B_STAGE_BYTES)
+                                                         : a_addr + A_STAGE_BYTES;
+                    const uint64_t a_desc = make_kmajor_sw128_desc(a_addr);
+                    const uint64_t b_desc = make_kmajor_sw128_desc(b_addr);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 16 fp16 = 32 B inside the 128 B swizzle span: +2 in 16 B units
+                        umma_f16_ss(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tmem_full_bar[g]);
+            }
         }
         __syncwarp();
     } else {
-        // ---------------------------------------------------------------- epilogue
-        const int q = warp & 3;  // TMEM lane quarter this warp may touch
+        // ---------------------------------------------------------------- epilogue (2 groups x 4 warps)
+        const int g = (warp - 2) >> 2;       // group <-> accumulator buffer
+        const int q = warp & 3;              // TMEM lane quarter this warp may touch
         const int row = q * 32 + lane;
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
-        if (p.n_res > 0) mbar_wait(res_full_bar, 0);
-
+        const int tg = (warp - 2 - 4 * g) * 32 + lane;  // thread index inside the group
+        const bool issuer = (tg == 0);
+        const uint32_t bar_id = 1 + g;
+        uint8_t* stage_g = staging + g * p.staging_bufs * SUB_TILE_BYTES;
+        __half* bias_s = bias_all + g * BLOCK_N;
         const __half* qs = p.qscale;
-        // second residual: read straight from global (rare: ResidualBlock* with shortcut)
-        const __half* r2_row = nullptr;
-        if (p.n_res > 1) {
-            // tm_r2 is unused by TMA; its first 16 bytes carry {ptr, pitch, W, H} (see gemm_plan)
-            const uint64_t* raw = reinterpret_cast<const uint64_t*>(&p.tm_r2);
-            const __half* base = reinterpret_cast<const __half*>(raw[0]);
-            const int pitch = static_cast<int>(raw[1] & 0xffffffffu);
-            const int W = static_cast<int>(raw[2] & 0xffffffffu);
-            const int H = static_cast<int>(raw[2] >> 32);
-            const int bx = row % p.bw;
-            const int by = row / p.bw;
-            const long long x = ox0 + bx;
-            const long long y = oy0 + by;
-            if (x < W && y < H) r2_row = base + (y * W + x) * pitch;
-        }
+        const int n_sub = p.chunk_add ? 1 : BLOCK_N / 64;
+        uint32_t cnt = 0;  // store-buffer counter of this group
 
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-            tmem_ld_wait();
-            float x[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float t = __uint_as_float(v[j]) + __half2float(bias_s[c0 + j]);
-                x[j] = (p.act == ACT_WSILU) ? wsilu_f(t) : t;
+        for (int i = g;; i += 2) {
+            const int tile = tile_of(i);
+            if (tile < 0) break;
+            const TileCoord tc = tile_coord<BLOCK_N>(p, tile);
+            const uint32_t u = static_cast<uint32_t>(i >> 1);
+            for (int c = tg; c < BLOCK_N; c += 128) {
+                bias_s[c] = p.bias ? p.bias[tc.n0 + c] : __float2half(0.f);
             }
-            if (p.chunk_add) {
-                float o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    o[j] = (x[4 * j] + x[4 * j + 1]) + (x[4 * j + 2] + x[4 * j + 3]);
+            // residual rows of this thread (same pixel grid as the output)
+            const __half* r1_row = nullptr;
+            const __half* r2_row = nullptr;
+            if (p.n_res > 0) {
+                const long long x = tc.ox0 + (row % p.bw);
+                const long long y = tc.oy0 + (row / p.bw);
+                if (x < p.res_w && y < p.res_h) {
+                    r1_row = p.r1 + (y * p.res_w + x) * p.r1_pitch + tc.oc0;
+                    if (p.n_res > 1) r2_row = p.r2 + (y * p.res_w + x) * p.r2_pitch + tc.oc0;
                 }
-                const int oc = c0 >> 2;  // output column inside the tile
-                const int sub = oc >> 6;
-                const int chunk = (oc & 63) >> 3;
-                uint8_t* dst = smem + sub * SUB_TILE_BYTES + sw128_offset(row, chunk);
-                if (p.n_res > 0) {
-                    const uint4 r = *reinterpret_cast<const uint4*>(dst);
-                    const __half2* rh = reinterpret_cast<const __half2*>(&r);
+            }
+            mbar_wait(&tmem_full_bar[g], u & 1);
+            tcgen05_fence_after();
+            const uint32_t acc = tmem_base + g * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+
+            for (int sub = 0; sub < n_sub; ++sub, ++cnt) {
+                uint8_t* sbuf = stage_g + ((p.staging_bufs == 2) ? (cnt & 1) : 0) * SUB_TILE_BYTES;
+                // residual prefetch for the 64 output columns of this sub-tile
+                uint4 r1v[8], r2v[8];
+                if (r1_row) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = __half22float2(rh[j]);
-                        o[2 * j] += f.x;
-                        o[2 * j + 1] += f.y;
-                    }
+                    for (int j = 0; j < 8; ++j) r1v[j] = *reinterpret_cast<const uint4*>(r1_row + sub * 64 + j * 8);
                 }
                 if (r2_row) {
-                    const uint4 r = *reinterpret_cast<const uint4*>(r2_row + oc0 + oc);
-                    const __half2* rh = reinterpret_cast<const __half2*>(&r);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = __half22float2(rh[j]);
-                        o[2 * j] += f.x;
-                        o[2 * j + 1] += f.y;
+                    for (int j = 0; j < 8; ++j) r2v[j] = *reinterpret_cast<const uint4*>(r2_row + sub * 64 + j * 8);
+                }
+                // the store that used this buffer two sub-tiles ago must have drained
+                if (issuer) {
+                    if (p.staging_bufs == 2) tma_store_wait_read<1>();
+                    else tma_store_wait_read<0>();
+                }
+                named_bar_sync(bar_id, 128);
+
+                if (p.chunk_add) {
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) {  // 8 x 32 accumulator columns -> 8 x 8 outputs
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(acc + a * 32, v);
+                        tmem_ld_wait();
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float s4 = 0.f;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float t = __uint_as_float(v[4 * j + e]) + __half2float(bias_s[a * 32 + 4 * j + e]);
+                                s4 += (p.act == ACT_WSILU) ? wsilu_f(t) : t;
+                            }
+                            o[j] = s4;
+                        }
+                        if (r1_row) add_half8(o, r1v[a]);
+                        if (r2_row) add_half8(o, r2v[a]);
+                        if (qs) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] *= __half2float(qs[tc.oc0 + a * 8 + j]);
+                        }
+                        uint4 w;
+                        __half2* wh = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) wh[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+                        *reinterpret_cast<uint4*>(sbuf + sw128_offset(row, a)) = w;
                     }
-                }
-                if (qs) {
+                } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] *= __half2float(qs[oc0 + oc + j]);
-                }
-                uint4 w;
-                __half2* wh = reinterpret_cast<__half2*>(&w);
+                    for (int a = 0; a < 2; ++a) {  // 2 x 32 accumulator columns = 64 outputs
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(acc + sub * 64 + a * 32, v);
+                        tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 4; ++j) wh[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
-                *reinterpret_cast<uint4*>(dst) = w;
-            } else {
+                        for (int gq = 0; gq < 4; ++gq) {
+                            const int oc = a * 4 + gq;  // 16-byte chunk inside the sub-tile
+                            float o[8];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int oc = c0 + g * 8;
-                    const int sub = oc >> 6;
-                    const int chunk = (oc & 63) >> 3;
-                    uint8_t* dst = smem + sub * SUB_TILE_BYTES + sw128_offset(row, chunk);
-                    float o[8];
+                            for (int j = 0; j < 8; ++j) {
+                                const float t = __uint_as_float(v[gq * 8 + j]) +
+                                                __half2float(bias_s[sub * 64 + oc * 8 + j]);
+                                o[j] = (p.act == ACT_WSILU) ? wsilu_f(t) : t;
+                            }
+                            if (r1_row) add_half8(o, r1v[oc]);
+                            if (r2_row) add_half8(o, r2v[oc]);
+                            if (qs) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = x[g * 8 + j];
-                    if (p.n_res > 0) {
-                        const uint4 r = *reinterpret_cast<const uint4*>(dst);
-                        const __half2* rh = reinterpret_cast<const __half2*>(&r);
+                                for (int j = 0; j < 8; ++j) o[j] *= __half2float(qs[tc.oc0 + sub * 64 + oc * 8 + j]);
+                            }
+                            uint4 w;
+                            __half2* wh = reinterpret_cast<__half2*>(&w);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 f = __half22float2(rh[j]);
-                            o[2 * j] += f.x;
-                            o[2 * j + 1] += f.y;
+                            for (int j = 0; j < 4; ++j) wh[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+                            *reinterpret_cast<uint4*>(sbuf + sw128_offset(row, oc)) = w;
                         }
                     }
-                    if (r2_row) {
-                        const uint4 r = *reinterpret_cast<const uint4*>(r2_row + oc0 + oc);
-                        const __half2* rh = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 f = __half22float2(rh[j]);
-                            o[2 * j] += f.x;
-                            o[2 * j + 1] += f.y;
-                        }
-                    }
-                    if (qs) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] *= __half2float(qs[oc0 + oc + j]);
-                    }
-                    uint4 w;
-                    __half2* wh = reinterpret_cast<__half2*>(&w);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) wh[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
-                    *reinterpret_cast<uint4*>(dst) = w;
+                }
+                if (sub == n_sub - 1) {
+                    // every tcgen05.ld of this tile has completed: hand the accumulator back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(bar_id, 128);
+                if (issuer) {
+                    tma_store_5d(&p.tm_c, sbuf, tc.oc0 + sub * 64, tc.opx, tc.ox0, tc.opy, tc.oy0);
+                    tma_store_commit();
                 }
             }
         }
-        tcgen05_fence_before();
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (warp == 2 && lane == 0) {
-            for (int j = 0; j < n_sub; ++j) {
-                tma_store_5d(&p.tm_c, smem + j * SUB_TILE_BYTES, oc0 + j * 64, opx, ox0, opy, oy0);
-            }
-            tma_store_commit();
-            tma_store_wait_read0();
-        }
+        if (issuer) tma_store_wait_read<0>();
         __syncwarp();
     }
 
@@ -389,7 +458,7 @@ static int pick_block_n(int n_unit, bool chunk_add, long long m_tiles)
     else if (n_unit % 128 == 0) bn = 128;
     else if (n_unit % 64 == 0) bn = 64;
     else return 0;
-    // small problems: prefer more CTAs over wider tiles (148 SMs x 2 resident CTAs)
+    // small problems: prefer more tiles (one persistent CTA per SM, 148 SMs) over wider tiles
     while (bn > 64 && m_tiles * (n_unit / bn) < 148 && (bn % 2 == 0) && (n_unit % (bn / 2) == 0) &&
            ((bn / 2) % 64 == 0)) {
         bn /= 2;
@@ -500,33 +569,73 @@ int gemm_plan(GemmOp& op)
     const bool out_split = (op.kind == GEMM_TCONV2X2);
     if (encode_act_map(&p.tm_c, op.out, out_split, linear, p.bw, p.bh)) return 1;
     if (op.res1.ptr) {
-        if (op.res1.W != op.out.W || op.res1.H != op.out.H || op.res1.C != op.out.C) {
-            g_err = "gemm_plan: residual geometry mismatch";
-            return 1;
+        if (op.kind == GEMM_TCONV2X2) { g_err = "gemm_plan: tconv takes no residual"; return 1; }
+        const ActView* rs[2] = { &op.res1, &op.res2 };
+        for (int i = 0; i < p.n_res; ++i) {
+            if (rs[i]->W != op.out.W || rs[i]->H != op.out.H || rs[i]->C != op.out.C || (rs[i]->pitch % 8) ||
+                (reinterpret_cast<uintptr_t>(rs[i]->ptr) & 15)) {
+                g_err = "gemm_plan: residual geometry mismatch";
+                return 1;
+            }
         }
-        if (encode_act_map(&p.tm_r1, op.res1, out_split, linear, p.bw, p.bh)) return 1;
+        p.r1 = static_cast<const __half*>(op.res1.ptr);
+        p.r1_pitch = op.res1.pitch;
+        if (op.res2.ptr) {
+            p.r2 = static_cast<const __half*>(op.res2.ptr);
+            p.r2_pitch = op.res2.pitch;
+        }
+        if (linear) {
+            p.res_w = static_cast<int>(static_cast<long long>(op.out.W) * op.out.H);
+            p.res_h = 1;
+        } else {
+            p.res_w = op.out.W;
+            p.res_h = op.out.H;
+        }
     }
-    if (op.res2.ptr) {
-        if (op.kind != GEMM_PW) { g_err = "gemm_plan: res2 only for 1x1"; return 1; }
-        uint64_t* raw = reinterpret_cast<uint64_t*>(&p.tm_r2);
-        raw[0] = reinterpret_cast<uint64_t>(op.res2.ptr);
-        raw[1] = static_cast<uint64_t>(op.res2.pitch);
-        // linear tiling: the epilogue sees a (W = M, H = 1) strip
-        const uint64_t M = static_cast<uint64_t>(op.res2.W) * op.res2.H;
-        raw[2] = M | (1ull << 32);
+    p.n_tiles = op.N / bn;
+    p.tiles_x = tiles_x;
+    p.total_tiles = static_cast<int>(m_tiles) * p.n_tiles;
+    int num_sms = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) {
+            int v = 0;
+            if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) num_sms = v;
+        }
     }
-
-    op.grid = dim3(op.N / bn, tiles_x, tiles_y);
-    switch (bn) {
-    case 64: op.smem = TileCfg<64>::SMEM_BYTES; op.stages = TileCfg<64>::STAGES; break;
-    case 128: op.smem = TileCfg<128>::SMEM_BYTES; op.stages = TileCfg<128>::STAGES; break;
-    case 192: op.smem = TileCfg<192>::SMEM_BYTES; op.stages = TileCfg<192>::STAGES; break;
-    case 256: op.smem = TileCfg<256>::SMEM_BYTES; op.stages = TileCfg<256>::STAGES; break;
+    p.m_tiles = static_cast<int>(m_tiles);
+    op.grid = dim3(p.total_tiles < num_sms ? p.total_tiles : num_sms, 1, 1);
+    op.smem = SMEM_TOTAL;
+    {
+        // carve-up of the 227 KB (see the kernel): weights resident when the CTA reuses its slab for
+        // >= 2 M tiles and >= 3 activation stages still fit; otherwise stream A+B stages.
+        const int b_stage = bn * BLOCK_K * 2;
+        const int slab = p.num_kblocks * b_stage;
+        const int grid_n = static_cast<int>(op.grid.x);
+        const bool reuse = grid_n >= p.n_tiles && (m_tiles * p.n_tiles) >= 2LL * grid_n;
+        int staging_bufs = 2;
+        int a_stages = (SMEM_USABLE - slab - EPI_GROUPS * 2 * SUB_TILE_BYTES) / A_STAGE_BYTES;
+        if (reuse && a_stages < 3) {
+            staging_bufs = 1;
+            a_stages = (SMEM_USABLE - slab - EPI_GROUPS * 1 * SUB_TILE_BYTES) / A_STAGE_BYTES;
+        }
+        const char* force = getenv("DCVC_B200_GEMM_MODE");  // "stream" | "resident" (debug / A-B tests)
+        bool resident = reuse && slab < SMEM_USABLE && a_stages >= 3;
+        if (force && force[0] == 's') resident = false;
+        if (resident) {
+            p.b_resident = 1;
+            p.num_stages = a_stages > MAX_STAGES ? MAX_STAGES : a_stages;
+            p.staging_bufs = staging_bufs;
+        } else {
+            p.b_resident = 0;
+            int st = (SMEM_USABLE - EPI_GROUPS * 2 * SUB_TILE_BYTES) / (A_STAGE_BYTES + b_stage);
+            p.num_stages = st > MAX_STAGES ? MAX_STAGES : st;
+            p.staging_bufs = 2;
+        }
+        op.stages = p.num_stages;
+        if (p.num_stages < 2) { g_err = "gemm_plan: pipeline does not fit"; return 1; }
     }
-    // staging tile (aliased over the pipeline stages) must fit
-    const int out_cols = op.chunk_add ? bn / 4 : bn;
-    const size_t staging = static_cast<size_t>((out_cols + 63) / 64) * SUB_TILE_BYTES;
-    if (staging > op.smem - 1024 - 256 - bn * 2) { g_err = "gemm_plan: staging does not fit"; return 1; }
+    if (!op.chunk_add && bn % 64 != 0) { g_err = "gemm_plan: BLOCK_N must be a multiple of 64"; return 1; }
     op.planned = true;
     return 0;
 }
@@ -534,8 +643,7 @@ int gemm_plan(GemmOp& op)
 template <int BN>
 static cudaError_t set_attr()
 {
-    return cudaFuncSetAttribute(pw_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                TileCfg<BN>::SMEM_BYTES);
+    return cudaFuncSetAttribute(pw_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
 }
 
 int gemm_init()

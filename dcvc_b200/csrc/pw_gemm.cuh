@@ -37,10 +37,19 @@ struct alignas(64) PwGemmParams {
     CUtensorMap tm_a;
     CUtensorMap tm_b;
     CUtensorMap tm_c;
-    CUtensorMap tm_r1;
-    CUtensorMap tm_r2;
     const __half* bias;    // [N] (GEMM columns, i.e. before chunk-add) or nullptr
     const __half* qscale;  // [N_out] per-output-channel multiplier or nullptr
+    const __half* r1;      // residual operands: same pixel grid as the output, own channel pitch
+    const __half* r2;
+    int r1_pitch, r2_pitch;
+    int res_w, res_h;      // output pixel grid seen by the tile scheduler (linear tiling: W = M, H = 1)
+    int n_tiles;           // N tiles
+    int tiles_x;           // pixel tiles along x
+    int total_tiles;       // n_tiles * tiles_x * tiles_y
+    int m_tiles;           // tiles_x * tiles_y
+    int b_resident;        // 1: the CTA keeps the whole [BLOCK_N][K] weight slab of its N tile in smem
+    int num_stages;        // pipeline depth (A+B stages when streaming, A-only stages when b_resident)
+    int staging_bufs;      // store staging buffers per epilogue group (1 or 2)
     int num_kblocks;       // taps * C / 64
     int kblk_per_tap;      // C / 64
     int bw, bh;            // pixel tile, bw*bh == 128

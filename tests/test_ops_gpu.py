@@ -230,7 +230,12 @@ def test_entropy_steps_bit_exact(H, W, skip):
         sym = ops.entropy_enc_step(b, step, yt, torch.from_numpy(q_enc).cuda(), scales_t, means_t, acc, skip)
         y_hat, sym_ref, y_q = ops_ref.entropy_enc_step_np(step, y, q_enc, params[..., :C_], params[..., C_:], skip, lut)
         acc_ref = (acc_ref.astype(np.float32) + y_hat.astype(np.float32)).astype(np.float16)
-        assert np.array_equal(sym.cpu().numpy(), sym_ref), f"symbols differ at step {step}"
+        got = sym.cpu().numpy()
+        if not np.array_equal(got, sym_ref):
+            n = min(len(got), len(sym_ref))
+            bad = np.flatnonzero(got[:n] != sym_ref[:n])
+            raise AssertionError(f"symbols differ at step {step}: len {len(got)} vs {len(sym_ref)}, {len(bad)} mismatches, "
+                                 f"first {bad[:6]}, got {got[bad[:6]]}, ref {sym_ref[bad[:6]]}")
         if step == 3:
             assert np.array_equal(acc.cpu().numpy().view(np.uint16), acc_ref.view(np.uint16))
         # decoder side of the same step
