@@ -14,6 +14,7 @@
 //     copies per step; the synthesis transform overlaps the CPU encode.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -814,6 +815,12 @@ void IntraCodec::run(Segment& s, cudaStream_t stream)
             CK(cudaEventElapsedTime(&ms, e0, e1));
             ProfileAcc& a = prof_[s.kinds[i]];
             a.ms += ms; a.bytes += s.alg_bytes[i]; a.flops += s.flops[i]; a.launches += 1;
+            if (const char* path = getenv("DCVC_B200_PROFILE_CSV")) {
+                if (FILE* f = fopen(path, "a")) {
+                    fprintf(f, "%d,%zu,%.3f,%.0f,%.0f\n", s.kinds[i], i, ms * 1e3, s.alg_bytes[i], s.flops[i]);
+                    fclose(f);
+                }
+            }
         }
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);

@@ -24,9 +24,20 @@ static inline int blocks_for(long long n, int threads) { return static_cast<int>
 // loaded once per thread (3 x 16 B, the x-1 / x+1 neighbours hit L1 because adjacent threads of the
 // CTA load them as their centre) and scattered into the <= 3 output rows it contributes to.  HBM/L2
 // traffic per output drops from ~3 input rows to (DW_TY + 2) / DW_TY.
-static constexpr int DW_TY = 8;
+static constexpr int DW_TY = 4;
 
-__global__ void __launch_bounds__(256, 2)
+__device__ __forceinline__ void dw_load_row(const __half* in, int in_pitch, int W, int H, int x, int yy, int c,
+                                            uint4 (&q)[3])
+{
+    q[0] = q[1] = q[2] = make_uint4(0, 0, 0, 0);
+    if (yy < 0 || yy >= H) return;
+    const __half* rowp = in + (static_cast<long long>(yy) * W + x) * in_pitch + c;
+    if (x > 0) q[0] = *reinterpret_cast<const uint4*>(rowp - in_pitch);
+    q[1] = *reinterpret_cast<const uint4*>(rowp);
+    if (x + 1 < W) q[2] = *reinterpret_cast<const uint4*>(rowp + in_pitch);
+}
+
+__global__ void __launch_bounds__(128)
 dw3x3_kernel(const __half* __restrict__ in, int in_pitch, __half* __restrict__ out, int out_pitch,
              const __half* __restrict__ w, int C, int W, int H)
 {
@@ -42,58 +53,40 @@ dw3x3_kernel(const __half* __restrict__ in, int in_pitch, __half* __restrict__ o
     const int c = cg << 3;
     const int y0 = strip * DW_TY;
 
-    uint4 wk[9];  // packed fp16 taps (converted on use: keeps the register count low enough for 2 CTAs/SM)
+    // all DW_TY + 2 input rows are requested up front (18 independent 16-byte loads in flight per thread)
+    uint4 rows[DW_TY + 2][3];
+#pragma unroll
+    for (int r = 0; r < DW_TY + 2; ++r) dw_load_row(in, in_pitch, W, H, x, y0 + r - 1, c, rows[r]);
+    uint4 wk[9];  // packed fp16 taps, converted on use
 #pragma unroll
     for (int k = 0; k < 9; ++k) wk[k] = __ldg(reinterpret_cast<const uint4*>(w + k * C + c));
-    float acc[DW_TY][8];
-#pragma unroll
-    for (int r = 0; r < DW_TY; ++r)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
 
-#pragma unroll
-    for (int ry = -1; ry <= DW_TY; ++ry) {
-        const int yy = y0 + ry;
-        if (yy < 0 || yy >= H) continue;
-        const __half* rowp = in + (static_cast<long long>(yy) * W + x) * in_pitch + c;
-        float v[3][8];
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int xx = x + kx - 1;
-            uint4 q = make_uint4(0, 0, 0, 0);
-            if (xx >= 0 && xx < W) q = *reinterpret_cast<const uint4*>(rowp + static_cast<long long>(kx - 1) * in_pitch);
-            const __half2* qh = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(qh[i]);
-                v[kx][2 * i] = f.x;
-                v[kx][2 * i + 1] = f.y;
-            }
-        }
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int r = ry - ky + 1;  // output row (inside the strip) this input row feeds through tap ky
-            if (r < 0 || r >= DW_TY) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const __half2* kh = reinterpret_cast<const __half2*>(&wk[ky * 3 + kx]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 wf = __half22float2(kh[i]);
-                    acc[r][2 * i] = fmaf(v[kx][2 * i], wf.x, acc[r][2 * i]);
-                    acc[r][2 * i + 1] = fmaf(v[kx][2 * i + 1], wf.y, acc[r][2 * i + 1]);
-                }
-            }
-        }
-    }
 #pragma unroll
     for (int r = 0; r < DW_TY; ++r) {
         const int y = y0 + r;
         if (y >= H) break;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const __half2* vh = reinterpret_cast<const __half2*>(&rows[r + ky][kx]);
+                const __half2* kh = reinterpret_cast<const __half2*>(&wk[ky * 3 + kx]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 vf = __half22float2(vh[i]);
+                    const float2 wf = __half22float2(kh[i]);
+                    acc[2 * i] = fmaf(vf.x, wf.x, acc[2 * i]);
+                    acc[2 * i + 1] = fmaf(vf.y, wf.y, acc[2 * i + 1]);
+                }
+            }
+        }
         uint4 o;
         __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(acc[r][2 * i], acc[r][2 * i + 1]);
+        for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
         *reinterpret_cast<uint4*>(out + (static_cast<long long>(y) * W + x) * out_pitch + c) = o;
     }
 }
@@ -101,7 +94,7 @@ dw3x3_kernel(const __half* __restrict__ in, int in_pitch, __half* __restrict__ o
 int launch_dw3x3(const ActView& in, const ActView& out, const __half* w, cudaStream_t s)
 {
     const long long total = static_cast<long long>(in.W) * (in.C / 8) * ((in.H + DW_TY - 1) / DW_TY);
-    dw3x3_kernel<<<blocks_for(total, 256), 256, 0, s>>>(
+    dw3x3_kernel<<<blocks_for(total, 128), 128, 0, s>>>(
         static_cast<const __half*>(in.ptr), in.pitch,
         static_cast<__half*>(const_cast<void*>(out.ptr)), out.pitch, w, in.C, in.W, in.H);
     DCVC_LAUNCH_CHECK();
@@ -352,10 +345,10 @@ entropy_enc_step_kernel(const EntropyDev d)
     for (int c = lane * 2; c < d.G; c += 64) {
         const int ch = g * d.G + c;
         __half2 yv = *reinterpret_cast<const __half2*>(d.y + pix * d.y_pitch + ch);
-        if (d.q_enc) yv = __hmul2(yv, *reinterpret_cast<const __half2*>(d.q_enc + ch));
+        if (d.q_enc) yv = __hmul2_rn(yv, *reinterpret_cast<const __half2*>(d.q_enc + ch));
         const __half2 mv = *reinterpret_cast<const __half2*>(d.means + pix * d.p_pitch + ch);
         const __half2 sv = *reinterpret_cast<const __half2*>(d.scales + pix * d.p_pitch + ch);
-        const __half2 res = __hsub2(yv, mv);
+        const __half2 res = __hsub2_rn(yv, mv);  // _rn: never contracted into an fma with the multiply above
         float q0 = round_half_away(__low2float(res));
         float q1 = round_half_away(__high2float(res));
         const bool c0 = __hgt(__low2half(sv), d.thres);
@@ -365,7 +358,7 @@ entropy_enc_step_kernel(const EntropyDev d)
         q0 = fminf(fmaxf(q0, -128.f), 127.f);
         q1 = fminf(fmaxf(q1, -128.f), 127.f);
         const __half2 yq = __floats2half2_rn(q0, q1);
-        const __half2 yh = __hadd2(yq, mv);
+        const __half2 yh = __hadd2_rn(yq, mv);
         *reinterpret_cast<__half2*>(d.acc + pix * d.acc_pitch + ch) = yh;
         const int i0 = d.lut[__half_as_ushort(__low2half(sv))];
         const int i1 = d.lut[__half_as_ushort(__high2half(sv))];
@@ -485,7 +478,7 @@ entropy_dec_restore_kernel(const EntropyDev d, const int32_t* __restrict__ offse
         if (c < d.G) {
             const float q0 = k0 ? static_cast<float>(decoded[base + r0]) : 0.f;
             const float q1 = k1 ? static_cast<float>(decoded[base + r1]) : 0.f;
-            const __half2 yh = __hadd2(__floats2half2_rn(q0, q1), mv);
+            const __half2 yh = __hadd2_rn(__floats2half2_rn(q0, q1), mv);
             *reinterpret_cast<__half2*>(d.acc + pix * d.acc_pitch + ch) = yh;
         }
         base += tot;

@@ -267,11 +267,7 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
             for (int sub = 0; sub < n_sub; ++sub, ++cnt) {
                 uint8_t* sbuf = stage_g + ((p.staging_bufs == 2) ? (cnt & 1) : 0) * SUB_TILE_BYTES;
                 // residual prefetch for the 64 output columns of this sub-tile
-                uint4 r1v[8], r2v[8];
-                if (r1_row) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) r1v[j] = *reinterpret_cast<const uint4*>(r1_row + sub * 64 + j * 8);
-                }
+                uint4 r2v[8];
                 if (r2_row) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) r2v[j] = *reinterpret_cast<const uint4*>(r2_row + sub * 64 + j * 8);
@@ -282,6 +278,14 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
                     else tma_store_wait_read<0>();
                 }
                 named_bar_sync(bar_id, 128);
+                // first residual: asynchronous copy of this thread's 128-byte row segment into its own
+                // slots of the staging tile (L2 latency overlaps the TMEM loads and the activation math)
+                if (r1_row) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) cp_async_16(sbuf + sw128_offset(row, j), r1_row + sub * 64 + j * 8);
+                }
+                cp_async_commit();
+                bool res_ready = false;
 
                 if (p.chunk_add) {
 #pragma unroll
@@ -300,7 +304,10 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
                             }
                             o[j] = s4;
                         }
-                        if (r1_row) add_half8(o, r1v[a]);
+                        if (r1_row) {
+                            if (!res_ready) { cp_async_wait_all(); res_ready = true; }
+                            add_half8(o, *reinterpret_cast<const uint4*>(sbuf + sw128_offset(row, a)));
+                        }
                         if (r2_row) add_half8(o, r2v[a]);
                         if (qs) {
 #pragma unroll
@@ -328,7 +335,10 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
                                                 __half2float(bias_s[sub * 64 + oc * 8 + j]);
                                 o[j] = (p.act == ACT_WSILU) ? wsilu_f(t) : t;
                             }
-                            if (r1_row) add_half8(o, r1v[oc]);
+                            if (r1_row) {
+                                if (!res_ready) { cp_async_wait_all(); res_ready = true; }
+                                add_half8(o, *reinterpret_cast<const uint4*>(sbuf + sw128_offset(row, oc)));
+                            }
                             if (r2_row) add_half8(o, r2v[oc]);
                             if (qs) {
 #pragma unroll

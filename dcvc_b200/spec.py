@@ -95,6 +95,70 @@ def dmci_spec() -> "OrderedDict[str, tuple]":
     return s
 
 
+G_FRAME_DELAY = 8                      # video_model_ht.py:16
+G_CH_SRC_D = G_CH_SRC * G_FRAME_DELAY  # 1536
+G_CH_D = 512                           # video_model_ht.py:21
+G_CH_M = 512                           # video_model_ht.py:22
+G_CH_RECON = 256                       # video_model_ht.py:23
+
+
+def hts_spec() -> "OrderedDict[str, tuple]":
+    """state_dict layout of DMC(ModelStructure.HTS) (src/models/video_model_ht.py:26-345)."""
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    s["bit_estimator_z.h"] = (QP_NUM, G_CH_Z, 4)
+    s["bit_estimator_z.b"] = (QP_NUM, G_CH_Z, 4)
+    s["bit_estimator_z.a"] = (QP_NUM, G_CH_Z, 3)
+    s["q_encoder"] = (QP_NUM, G_CH_D)
+    s["q_decoder"] = (QP_NUM, G_CH_D)
+    s["q_feature"] = (QP_NUM, G_CH_D)
+    # FeatureAdaptorI / FeatureAdaptorM / FeatureExtractor (video_model_ht.py:95-164)
+    depth_conv_block(s, "feature_adaptor_i.conv.0.", G_CH_SRC, G_CH_M, dcb2=True)
+    for i in range(1, 4):
+        depth_conv_block(s, f"feature_adaptor_i.conv.{i}.", G_CH_M, G_CH_M, dcb2=True)
+    depth_conv_block(s, "feature_adaptor_m.conv.0.", G_CH_M + G_CH_D, G_CH_M, dcb2=True)
+    for i in range(1, 6):
+        depth_conv_block(s, f"feature_adaptor_m.conv.{i}.", G_CH_M, G_CH_M, dcb2=True)
+    for i in range(5):
+        depth_conv_block(s, f"feature_extractor.conv.{i}.", G_CH_D, G_CH_D, dcb2=True)
+    # Encoder (:63-92)
+    depth_conv_block(s, "encoder.conv1.0.", G_CH_SRC_D + G_CH_D, G_CH_D, dcb2=True)
+    for i in range(1, 6):
+        depth_conv_block(s, f"encoder.conv1.{i}.", G_CH_D, G_CH_D, dcb2=True)
+    _conv(s, "encoder.down.", G_CH_Y, G_CH_D, k=3)
+    # HyperEncoder / HyperDecoder (:167-198)
+    depth_conv_block(s, "hyper_encoder.conv.0.", G_CH_Y, G_CH_Y)
+    residual_block_stride2(s, "hyper_encoder.conv.1.", G_CH_Y, G_CH_Y)
+    residual_block_stride2(s, "hyper_encoder.conv.2.", G_CH_Y, G_CH_Z)
+    residual_block_upsample(s, "hyper_decoder.conv.0.", G_CH_Z, G_CH_Y)
+    residual_block_upsample(s, "hyper_decoder.conv.1.", G_CH_Y, G_CH_Y)
+    depth_conv_block(s, "hyper_decoder.conv.2.", G_CH_Y, G_CH_Y)
+    # TemporalPriorEncoder (:307-317), PriorFusion (:201-212)
+    residual_block_stride2(s, "temporal_prior_encoder.conv.", G_CH_D, G_CH_Y * 2)
+    for i in range(3):
+        depth_conv_block(s, f"y_prior_fusion.conv.{i}.", G_CH_Y * 3, G_CH_Y * 3)
+    _conv(s, "y_prior_fusion.conv.3.", G_CH_Y * 3, G_CH_Y * 3)
+    _conv(s, "y_spatial_prior_reduction.", G_CH_Y, G_CH_Y * 3)
+    for i in (1, 2, 3):
+        depth_conv_block(s, f"y_spatial_prior_adaptor_{i}.", G_CH_Y * 2, G_CH_Y * 2, force_adaptor=True)
+    for i in range(3):
+        depth_conv_block(s, f"y_spatial_prior.conv.{i}.", G_CH_Y * 2, G_CH_Y * 2)
+    _conv(s, "y_spatial_prior.conv.3.", G_CH_Y, G_CH_Y * 2)
+    # Decoder (:26-60)
+    _conv(s, "decoder.up.conv.0.", G_CH_D * 4, G_CH_Y, bias=False)
+    depth_conv_block(s, "decoder.conv1.0.", G_CH_D * 2, G_CH_D, dcb2=True)
+    for i in range(1, 7):
+        depth_conv_block(s, f"decoder.conv1.{i}.", G_CH_D, G_CH_D, dcb2=True)
+    # ReconHead (:215-275)
+    for i in range(G_FRAME_DELAY // 2):
+        depth_conv_block(s, f"recon_head.conv1.{i}.0.", G_CH_D, G_CH_D)
+    for i in range(G_FRAME_DELAY):
+        depth_conv_block(s, f"recon_head.conv2.{i}.0.", G_CH_D, G_CH_RECON)
+        depth_conv_block(s, f"recon_head.conv2.{i}.1.", G_CH_RECON, G_CH_RECON)
+        depth_conv_block(s, f"recon_head.conv2.{i}.2.", G_CH_RECON, G_CH_RECON)
+        _conv(s, f"recon_head.conv2.{i}.3.", G_CH_SRC, G_CH_RECON)
+    return s
+
+
 # hand-calibrated gains (checked with the reference modules on random inputs): keep z within a few
 # levels, the predicted (scale, mean) noise around the hand-set biases small, x_hat inside [-0.5, 0.5]
 _WEIGHT_GAIN = {
@@ -104,7 +168,13 @@ _WEIGHT_GAIN = {
     "dec.dec_2.adaptor.weight": 0.08,
     "dec.dec_2.dc.3.weight": 0.3,
     "dec.dec_2.ffn.2.weight": 0.3,
+    # HT-S
+    "decoder.conv1.0.adaptor.weight": 0.35,          # keep the memory/context recurrence contractive
+    "feature_adaptor_m.conv.0.adaptor.weight": 0.35,
+    "feature_adaptor_i.conv.0.adaptor.weight": 0.5,
 }
+for _i in range(G_FRAME_DELAY):
+    _WEIGHT_GAIN[f"recon_head.conv2.{_i}.3.weight"] = 0.5
 
 
 def synth_state_dict(spec, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
@@ -117,11 +187,13 @@ def synth_state_dict(spec, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
             leaf = name.rsplit(".", 1)[1]
             mean = {"h": 0.5, "b": 0.0, "a": 0.0}[leaf]
             t = torch.randn(shape, generator=g) * 0.2 + mean
-        elif name.startswith("q_scale"):
+        elif name.startswith("q_scale") or name in ("q_encoder", "q_decoder", "q_feature"):
             jitter = 1.0 + 0.05 * torch.randn(shape, generator=g)
-            if name == "q_scale_enc":
+            if name in ("q_scale_enc", "q_encoder"):
                 t = (0.6 + 0.8 * qp)[:, None] * jitter
-            elif name == "q_scale_dec":
+            elif name == "q_feature":
+                t = (0.8 + 0.4 * qp)[:, None] * jitter
+            elif name in ("q_scale_dec", "q_decoder"):
                 t = (1.0 / (0.6 + 0.8 * qp))[:, None] * jitter
             elif name == "q_scale_y_enc":
                 t = (0.4 + 1.2 * qp)[:, None] * jitter
@@ -136,12 +208,20 @@ def synth_state_dict(spec, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
             t = torch.randn(shape, generator=g) * std
             if ".dc.3." in name or ".ffn.2." in name:
                 t = t * 0.3  # damp the residual branches
-            if name == "enc.enc_2.6.weight":
+            if name in ("enc.enc_2.6.weight", "encoder.down.weight"):
                 t = t * 1.5  # latent spread: a few quantisation levels
             t = t * _WEIGHT_GAIN.get(name, 1.0)
         elif name.endswith(".bias"):
             t = torch.randn(shape, generator=g) * 0.02
-            if name in ("y_prior_fusion.conv.3.bias", "y_spatial_prior.conv.3.bias"):
+            if name == "y_prior_fusion.conv.3.bias" and shape[0] == 3 * G_CH_Y:   # HT: (q_dec, scales, means)
+                third = G_CH_Y
+                perm = torch.randperm(third, generator=g)
+                t[:third] = torch.rand(third, generator=g) * 1.0 + 0.6
+                t[third:2 * third] = torch.exp(torch.linspace(math.log(0.02), math.log(1.5), third))[perm]
+                t[2 * third:] = torch.randn(third, generator=g) * 0.3
+            elif name == "y_spatial_prior.conv.3.bias" and shape[0] == G_CH_Y:    # HT-S: means only
+                t = torch.randn(shape, generator=g) * 0.3
+            elif name in ("y_prior_fusion.conv.3.bias", "y_spatial_prior.conv.3.bias"):
                 half = shape[0] // 2
                 perm = torch.randperm(half, generator=g)
                 t[:half] = torch.exp(torch.linspace(math.log(0.02), math.log(1.5), half))[perm]  # scales

@@ -31,10 +31,10 @@ import MLCodec_extensions_cpp as ref_rans  # noqa: E402
 from dcvc_b200.spec import dmci_spec, synth_state_dict  # noqa: E402
 
 
-def synth_frame(h, w, seed):
+def synth_frame(h, w, seed, channels=3):
     """band-limited noise frame in [-0.5, 0.5], fp16-representable (SURVEY.md §8d recipe, 4:4:4)"""
     rng = np.random.default_rng(seed)
-    x = rng.random((1, 3, h + 4, w + 4)).astype(np.float32)
+    x = rng.random((1, channels, h + 4, w + 4)).astype(np.float32)
     t = torch.from_numpy(x)
     t = torch.nn.functional.avg_pool2d(t, 5, 1)
     t = (t - t.mean()) / t.std() * 0.18
@@ -117,6 +117,28 @@ def main():
         out[f"{key}_qp"] = np.int32(qp)
         out[f"{key}_stream"] = stream
     np.savez_compressed(os.path.join(HERE, "rans_streams.npz"), **out)
+
+    # 5. HT-S: layout + a 3-chunk forward sequence (state carried, reset on chunk 1) on synthetic weights (seed 1)
+    from src.models.video_model_ht import DMC
+    from src.utils.common import ModelStructure
+    from dcvc_b200.spec import hts_spec
+    p = DMC(ModelStructure.HTS)
+    with open(os.path.join(HERE, "hts_state_dict_layout.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in p.state_dict().items()}, f, indent=0, sort_keys=True)
+    p.load_state_dict(synth_state_dict(hts_spec(), 1), strict=True)
+    p.eval()
+    ref0 = synth_frame(64, 64, 500)
+    out = {"ref_frame": ref0.numpy()}
+    with torch.inference_mode():
+        p.clear_dpb()
+        p.ref_feature = torch.nn.functional.pixel_unshuffle(ref0, 8)
+        for c, reset in enumerate([False, True, False]):
+            x = synth_frame(64, 64, 600 + c, channels=24)
+            r = p.forward_one_frame(x, torch.tensor([20 + c]), reset_feature_memory=reset)
+            out[f"x{c}"] = x.numpy()
+            out[f"x_hat{c}"] = torch.cat(r["x_hat"], 1).numpy()
+            out[f"ref_feature{c}"] = p.ref_feature.numpy()
+    np.savez_compressed(os.path.join(HERE, "hts_forward_64x64.npz"), **out)
     print("golden fixtures written to", HERE)
 
 

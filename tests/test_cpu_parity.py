@@ -227,3 +227,46 @@ def test_oracle_compress_decompress_consistency():
     assert enc["x_hat"].shape == (1, 3, 64, 64)
     total = sum(len(s) for s in enc["symbols"])
     assert 0 < total < 4 * 4 * 256 * 4 and len(enc["bit_stream"]) > 8
+
+
+def test_hts_spec_matches_reference_layout():
+    from dcvc_b200.spec import hts_spec
+    gold = json.load(open(os.path.join(GOLD, "hts_state_dict_layout.json")))
+    assert {k: list(v) for k, v in hts_spec().items()} == gold
+
+
+def test_hts_oracle_forward_pinned_to_reference():
+    """3 chunks with carried state (reset on the 2nd) vs the reference's DMC(HTS).forward_one_frame"""
+    from dcvc_b200.spec import hts_spec, synth_state_dict
+    from oracle.hts_oracle import HtsOracle
+    g = np.load(os.path.join(GOLD, "hts_forward_64x64.npz"))
+    o = HtsOracle(synth_state_dict(hts_spec(), 1), emulate_fp16=False, threads=8)
+    o.feature_p = torch.nn.functional.pixel_unshuffle(torch.from_numpy(g["ref_frame"]), 8)
+    for c, reset in enumerate([False, True, False]):
+        res = o.forward_one_frame(torch.from_numpy(g[f"x{c}"]), 20 + c, reset_feature_memory=reset)
+        x_hat = torch.cat(res["x_hat"], 1).numpy()
+        d = np.abs(x_hat - g[f"x_hat{c}"])
+        assert np.mean(d > 1e-3) < 5e-3, (c, np.mean(d > 1e-3), d.max())
+        df = np.abs(o.feature_p.numpy() - g[f"ref_feature{c}"])
+        assert np.mean(df > 2e-3) < 5e-3, (c, np.mean(df > 2e-3), df.max())
+
+
+def test_hts_oracle_compress_decompress_consistency():
+    from oracle.build_ref import import_ref_shim
+    if import_ref_shim() is None:
+        pytest.skip("oracle/_ref not built")
+    from dcvc_b200.spec import hts_spec, synth_state_dict
+    from oracle.hts_oracle import HtsOracle
+    g = np.load(os.path.join(GOLD, "hts_forward_64x64.npz"))
+    sd = synth_state_dict(hts_spec(), 1)
+    enc, dec = HtsOracle(sd, 0.15, True, threads=8), HtsOracle(sd, 0.15, True, threads=8)
+    ref = torch.from_numpy(g["ref_frame"])
+    enc.add_ref_feature_from_frame(ref, True)        # encoder side of test_video.py:228-229
+    dec.add_ref_feature_from_frame(ref, False)       # decoder side of test_video.py:314-315
+    for c, reset in enumerate([False, True, False]):
+        x = torch.from_numpy(g[f"x{c}"])[:, :, :56, :60].contiguous()
+        e = enc.compress(x, 30 + c, reset, 8, 4)
+        d = dec.decompress(e["bit_stream"], 30 + c, 56, 60, e["ec_parallel"], reset)
+        assert np.array_equal(e["y_hat"].view(np.uint16), d["y_hat"].view(np.uint16)), f"chunk {c}"
+        assert torch.equal(enc.feature_p, dec.feature_p), f"decoder state drifted at chunk {c}"
+        assert len(d["x_hat"]) == 8 and d["x_hat"][0].shape == (1, 3, 64, 64)
