@@ -81,6 +81,10 @@ SIGNATURES = {
     "dcvc_compress": (C.c_int, [_P, _P, _I, _I, _L, _L, _L, _I, _I, _I, _P, C.POINTER(_P),
                                 C.POINTER(_I), C.POINTER(_I), _P]),
     "dcvc_decompress": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "dcvc_add_ref_feature_from_frame": (C.c_int, [_P, _P, _I, _I, _L, _L, _L, _I, _P]),
+    "dcvc_compress_chunk": (C.c_int, [_P, _P, _I, _I, _L, _L, _L, _I, _I, _I, _I, _P, C.POINTER(_P),
+                                      C.POINTER(_I), C.POINTER(_I)]),
+    "dcvc_decompress_chunk": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, C.POINTER(_P)]),
     "dcvc_kernel_launches": (C.c_int64, [_P]),
     "dcvc_last_gpu_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "dcvc_profile_enable": (C.c_int, [_P, _I]),

@@ -24,6 +24,7 @@ SOURCES = [
     "rans_host.cpp",
     "c_api_ops.cu",
     "codec.cu",
+    "codec_hts.cu",
 ]
 
 NVCC_FLAGS = [

@@ -12,195 +12,37 @@
 //     captures 64 graphs per segment, dmc_common.cpp:95-106);
 //   * host rANS stays on the CPU (north_star); symbol counts/streams cross PCIe in two small
 //     copies per step; the synthesis transform overlaps the CPU encode.
-#include <cuda_fp16.h>
-#include <cuda_runtime.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include <algorithm>
-#include <functional>
-#include <map>
-#include <memory>
-#include <stdexcept>
-#include <string>
-#include <vector>
-
-#include "../../include/dcvc_b200.h"
-#include "elementwise.cuh"
-#include "pw_gemm.cuh"
-#include "rans_host.h"
+#include "codec_common.cuh"
 
 namespace dcvc {
 
 namespace {
-
-constexpr int kQpNum = 64;
 constexpr int kChSrc = 192, kChEncDec = 384, kChY = 256, kChZ = 128;
-
-#define CK(expr)                                                                           \
-    do {                                                                                   \
-        cudaError_t e__ = (expr);                                                          \
-        if (e__ != cudaSuccess) {                                                          \
-            throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e__)); \
-        }                                                                                  \
-    } while (0)
-
-inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
-struct HostTensor {
-    int dtype = DCVC_DTYPE_F16;
-    std::vector<int64_t> shape;
-    std::vector<uint8_t> bytes;
-    int64_t numel() const
-    {
-        int64_t n = 1;
-        for (auto s : shape) n *= s;
-        return n;
-    }
-};
-
-// bump allocator over one cudaMalloc block
-class Arena {
-public:
-    ~Arena() { release(); }
-    void release()
-    {
-        if (base_) cudaFree(base_);
-        base_ = nullptr;
-        cap_ = used_ = 0;
-    }
-    void reserve(size_t bytes)
-    {
-        release();
-        CK(cudaMalloc(&base_, bytes));
-        cap_ = bytes;
-        used_ = 0;
-    }
-    void* alloc(size_t bytes)
-    {
-        const size_t off = (used_ + 1023) & ~static_cast<size_t>(1023);
-        if (off + bytes > cap_) throw std::runtime_error("device arena exhausted");
-        used_ = off + bytes;
-        return static_cast<uint8_t*>(base_) + off;
-    }
-    size_t used() const { return used_; }
-
-private:
-    void* base_ = nullptr;
-    size_t cap_ = 0, used_ = 0;
-};
-
-struct DcbW {
-    bool adaptor = false;
-    int cin = 0, c = 0, inner = 0;
-    const __half *wa = nullptr, *ba = nullptr;
-    const __half *w0 = nullptr, *b0 = nullptr;
-    const __half* wdw = nullptr;  // [9][inner]
-    const __half *w3 = nullptr, *b3 = nullptr;  // b3: dc.3 bias + W3 . dw-bias
-    const __half *wf0 = nullptr, *bf0 = nullptr;
-    const __half *wf2 = nullptr, *bf2 = nullptr;
-};
-
-struct ConvW {
-    const __half* w = nullptr;
-    const __half* b = nullptr;
-    int cout = 0, cin = 0;
-};
-
-struct Level {  // one pyramid level: two ping-pong buffers + two scratch buffers
-    int H = 0, W = 0;
-    __half *A = nullptr, *B = nullptr, *T1 = nullptr, *T2 = nullptr;
-};
-
-using OpFn = std::function<int(cudaStream_t)>;
-
-enum OpKind { OP_GEMM = 0, OP_DW = 1, OP_ELEM = 2, OP_KINDS = 3 };
-
-struct Segment {
-    std::vector<OpFn> ops;
-    std::vector<int> kinds;        // OpKind per op (kept in step with `ops`)
-    std::vector<double> alg_bytes; // algorithmic bytes per op (activations in + residuals in + out)
-    std::vector<double> flops;
-    cudaGraphExec_t exec = nullptr;
-    int launches = 0;
-    void annotate(int kind, double bytes, double fl)
-    {
-        while (kinds.size() < ops.size()) {
-            kinds.push_back(kind);
-            alg_bytes.push_back(bytes);
-            flops.push_back(fl);
-        }
-    }
-};
-
-struct ProfileAcc {
-    double ms = 0, bytes = 0, flops = 0;
-    long long launches = 0;
-};
-
-inline ActView make_view(const void* p, int C, int pitch, int W, int H)
-{
-    ActView v;
-    v.ptr = p; v.C = C; v.pitch = pitch; v.W = W; v.H = H;
-    return v;
-}
-
 }  // namespace
 
-class IntraCodec {
+class IntraCodec : public CodecBase {
 public:
-    explicit IntraCodec(int device) : device_(device) {}
-    ~IntraCodec();
+    explicit IntraCodec(int device) : CodecBase(device) {}
+    ~IntraCodec() override;
 
-    void set_param(const char* name, const void* data, int dtype, int ndim, const int64_t* shape,
-                   int on_device);
-    void finalize(float skip_thres);
+    void finalize(float skip_thres) override;
     void compress(const void* x, int H, int W, int64_t sc, int64_t sh, int64_t sw, int qp, int pad_b,
                   int pad_r, cudaStream_t stream, const uint8_t** bs, int32_t* bs_len,
                   int32_t* ec_parallel, void* x_hat_out);
     void decompress(const uint8_t* bs, int len, int qp, int height, int width, int ec_parallel,
                     cudaStream_t stream, void* x_hat_out);
-    int debug_fetch(const char* name, void* dst, int64_t max_bytes, int64_t* written);
-
-    float gpu_ms();
-    bool profile_ = false;
-    ProfileAcc prof_[OP_KINDS];
-
-    std::string err;
-    int64_t launches = 0;
+    int debug_fetch(const char* name, void* dst, int64_t max_bytes, int64_t* written) override;
 
 private:
-    // ---- parameters
-    const HostTensor& param(const std::string& k) const;
-    std::vector<__half> param_f16(const std::string& k) const;
-    const __half* upload(const std::vector<__half>& v);
-    DcbW load_dcb(const std::string& p);
-    ConvW load_conv(const std::string& p, int kind);
 
     // ---- plan
     void plan(int height, int width);
     void clear_plan();
-    ActView dcb(Segment& s, Level& L, const ActView& in, const DcbW& w, bool shortcut,
-                const __half* qscale, const ActView* out);
-    void add_gemm(Segment& s, int kind, const ActView& in, const ActView& out, const __half* w,
-                  const __half* bias, int N, int act, int chunk, const ActView* r1, const ActView* r2,
-                  const __half* q);
     void build_hyper_tail(Segment& s);  // z_hat -> params, reduced
     void build_spatial_prior(Segment& s, int k);
     void build_synthesis(Segment& s);
-    void run(Segment& s, cudaStream_t stream);
     void stage_qp(int qp, cudaStream_t stream);
 
-    int device_;
-    bool finalized_ = false;
-    bool use_graphs_ = true;
-    float skip_thres_ = 0.f;
-    std::map<std::string, HostTensor> params_;
-    Arena warena_;
-    std::vector<std::pair<const std::vector<__half>*, const __half**>> pending_;  // unused
-    std::vector<std::vector<__half>> host_weights_;                             // staged before upload
-    std::vector<const __half**> host_weight_slots_;
 
     // weights on device
     DcbW enc1_, enc2_[6], henc0_, henc1_, henc2_, hdec0_, hdec1_, hdec2_, pf_[3], spa_[3], sp_[3],
@@ -208,8 +50,6 @@ private:
     ConvW enc_down_, henc1_down_, henc2_down_, hdec0_up_, hdec1_up_, dec_up_, pf3_, sp3_, red_;
     const __half *q_enc_all_ = nullptr, *q_dec_all_ = nullptr, *q_y_enc_all_ = nullptr,
                  *q_y_dec_all_ = nullptr;
-    uint8_t* lut_ = nullptr;
-    RansCodec rans_;
 
     // plan state
     int H8_ = 0, W8_ = 0, H16_ = 0, W16_ = 0, H16p_ = 0, W16p_ = 0, H64_ = 0, W64_ = 0;
@@ -236,160 +76,13 @@ private:
 
     Segment enc0_, enc1_seg_, dec0_, dec_step_[4];  // dec_step_[k]: k = 1..3 prior steps, [0] unused
     Segment dec4_;
-    cudaStream_t copy_stream_ = nullptr;
-    // CUDA graphs cannot be captured on the legacy default stream: calls made on it hop onto an
-    // internal stream and hand the result back with an event (the reference instead requires the
-    // caller to set a non-default stream, test_video.py:423-425).
-    cudaStream_t own_stream_ = nullptr;
-    cudaEvent_t ev_hop_ = nullptr;
-    struct StreamHop {
-        IntraCodec* c;
-        cudaStream_t user, run;
-        bool hop;
-        StreamHop(IntraCodec* codec, cudaStream_t u) : c(codec), user(u), run(u)
-        {
-            hop = (u == nullptr || u == cudaStreamLegacy || u == cudaStreamPerThread);
-            if (hop) {
-                if (cudaEventRecord(c->ev_hop_, user) != cudaSuccess ||
-                    cudaStreamWaitEvent(c->own_stream_, c->ev_hop_, 0) != cudaSuccess)
-                    throw std::runtime_error("stream hop failed");
-                run = c->own_stream_;
-            }
-        }
-        ~StreamHop()
-        {
-            if (hop) {
-                cudaEventRecord(c->ev_hop_, run);
-                cudaStreamWaitEvent(user, c->ev_hop_, 0);
-            }
-        }
-    };
-    cudaEvent_t ev_y_ = nullptr, ev_copy_ = nullptr;
-    // GPU-only timing: one (begin, end) event pair around every stretch of device work of a call
-    std::vector<cudaEvent_t> tev_;
-    int tev_n_ = 0;
-    void tick(cudaStream_t st);
-    void tock(cudaStream_t st);
-    std::vector<uint8_t> bitstream_;
     const __half* params_cur_ = nullptr;  // params of step 0 (cropped)
 };
 
-// =============================================================================== parameters
-void IntraCodec::set_param(const char* name, const void* data, int dtype, int ndim,
-                           const int64_t* shape, int on_device)
-{
-    HostTensor t;
-    t.dtype = dtype;
-    t.shape.assign(shape, shape + ndim);
-    const size_t esz = (dtype == DCVC_DTYPE_F16) ? 2 : 4;
-    t.bytes.resize(static_cast<size_t>(t.numel()) * esz);
-    if (on_device) {
-        CK(cudaMemcpy(t.bytes.data(), data, t.bytes.size(), cudaMemcpyDeviceToHost));
-    } else {
-        memcpy(t.bytes.data(), data, t.bytes.size());
-    }
-    params_[name] = std::move(t);
-    finalized_ = false;
-}
-
-const HostTensor& IntraCodec::param(const std::string& k) const
-{
-    auto it = params_.find(k);
-    if (it == params_.end()) throw std::runtime_error("missing parameter '" + k + "'");
-    return it->second;
-}
-
-std::vector<__half> IntraCodec::param_f16(const std::string& k) const
-{
-    const HostTensor& t = param(k);
-    std::vector<__half> v(static_cast<size_t>(t.numel()));
-    if (t.dtype == DCVC_DTYPE_F16) {
-        memcpy(v.data(), t.bytes.data(), t.bytes.size());
-    } else if (t.dtype == DCVC_DTYPE_F32) {
-        const float* f = reinterpret_cast<const float*>(t.bytes.data());
-        for (size_t i = 0; i < v.size(); ++i) v[i] = __float2half_rn(f[i]);
-    } else {
-        throw std::runtime_error("parameter '" + k + "' is not floating point");
-    }
-    return v;
-}
-
-const __half* IntraCodec::upload(const std::vector<__half>& v)
-{
-    void* d = warena_.alloc(v.size() * sizeof(__half));
-    CK(cudaMemcpy(d, v.data(), v.size() * sizeof(__half), cudaMemcpyHostToDevice));
-    return static_cast<const __half*>(d);
-}
-
-DcbW IntraCodec::load_dcb(const std::string& p)
-{
-    DcbW w;
-    if (params_.count(p + "adaptor.weight")) {
-        w.adaptor = true;
-        w.cin = static_cast<int>(param(p + "adaptor.weight").shape[1]);
-        w.wa = upload(param_f16(p + "adaptor.weight"));
-        w.ba = upload(param_f16(p + "adaptor.bias"));
-    }
-    const HostTensor& w0 = param(p + "dc.0.weight");
-    w.inner = static_cast<int>(w0.shape[0]);
-    w.c = static_cast<int>(w0.shape[1]);
-    if (!w.adaptor) w.cin = w.c;
-    w.w0 = upload(param_f16(p + "dc.0.weight"));
-    w.b0 = upload(param_f16(p + "dc.0.bias"));
-    {   // depthwise weight [inner][1][3][3] -> [9][inner]   (layers_proxy.cpp:171-173)
-        std::vector<__half> dw = param_f16(p + "dc.2.weight");
-        std::vector<__half> t(dw.size());
-        for (int c = 0; c < w.inner; ++c)
-            for (int k = 0; k < 9; ++k) t[static_cast<size_t>(k) * w.inner + c] = dw[static_cast<size_t>(c) * 9 + k];
-        w.wdw = upload(t);
-    }
-    {   // fold the depthwise bias into the bias of dc.3 (layers_proxy.cpp:175-178), fp32 then one rounding
-        std::vector<__half> w3 = param_f16(p + "dc.3.weight");
-        std::vector<__half> bdw = param_f16(p + "dc.2.bias");
-        std::vector<__half> b3 = param_f16(p + "dc.3.bias");
-        std::vector<__half> folded(b3.size());
-        for (int n = 0; n < w.c; ++n) {
-            float acc = 0.f;
-            for (int c = 0; c < w.inner; ++c)
-                acc += __half2float(w3[static_cast<size_t>(n) * w.inner + c]) * __half2float(bdw[c]);
-            folded[n] = __float2half_rn(acc + __half2float(b3[n]));
-        }
-        w.w3 = upload(w3);
-        w.b3 = upload(folded);
-    }
-    w.wf0 = upload(param_f16(p + "ffn.0.weight"));
-    w.bf0 = upload(param_f16(p + "ffn.0.bias"));
-    w.wf2 = upload(param_f16(p + "ffn.2.weight"));
-    w.bf2 = upload(param_f16(p + "ffn.2.bias"));
-    return w;
-}
-
-ConvW IntraCodec::load_conv(const std::string& p, int kind)
-{
-    ConvW c;
-    const HostTensor& wt = param(p + "weight");
-    const int cout = static_cast<int>(wt.shape[0]), cin = static_cast<int>(wt.shape[1]);
-    const int kh = static_cast<int>(wt.shape[2]), kw = static_cast<int>(wt.shape[3]);
-    std::vector<__half> src = param_f16(p + "weight");
-    std::vector<__half> dst(src.size());
-    if (dcvc_pack_weight(kind, src.data(), cout, cin, kh, kw, dst.data()))
-        throw std::runtime_error("pack_weight failed for " + p);
-    c.w = upload(dst);
-    if (params_.count(p + "bias")) c.b = upload(param_f16(p + "bias"));
-    c.cout = cout;
-    c.cin = cin;
-    return c;
-}
-
 void IntraCodec::finalize(float skip_thres)
 {
-    CK(cudaSetDevice(device_));
+    finalize_begin(skip_thres);
     clear_plan();
-    skip_thres_ = skip_thres;
-    size_t total = 0;
-    for (auto& kv : params_) total += static_cast<size_t>(kv.second.numel()) * 2 + 2048;
-    warena_.reserve(total * 2 + (8u << 20));
-
     enc1_ = load_dcb("enc.enc_1.");
     for (int i = 0; i < 6; ++i) enc2_[i] = load_dcb("enc.enc_2." + std::to_string(i) + ".");
     enc_down_ = load_conv("enc.enc_2.6.", DCVC_GEMM_CONV3X3_S2);
@@ -418,86 +111,16 @@ void IntraCodec::finalize(float skip_thres)
     q_y_enc_all_ = upload(param_f16("q_scale_y_enc"));
     q_y_dec_all_ = upload(param_f16("q_scale_y_dec"));
 
-    {
-        std::vector<uint8_t> h(65536);
-        build_scale_lut(h.data());
-        lut_ = static_cast<uint8_t*>(warena_.alloc(65536));
-        CK(cudaMemcpy(lut_, h.data(), 65536, cudaMemcpyHostToDevice));
-    }
-    // CDF tables (common_model.py:64-70; dmci_proxy.cpp:639-651)
-    const char* names[2] = { "bit_estimator_z.", "gaussian_encoder." };
-    for (int i = 0; i < 2; ++i) {
-        const HostTensor& c = param(std::string(names[i]) + "quantized_cdf");
-        const HostTensor& l = param(std::string(names[i]) + "cdf_length");
-        if (c.dtype != DCVC_DTYPE_I32 || l.dtype != DCVC_DTYPE_I32 || c.shape.size() != 2)
-            throw std::runtime_error("CDF tables must be int32 [rows][width]");
-        rans_.set_cdf(reinterpret_cast<const int32_t*>(c.bytes.data()),
-                      reinterpret_cast<const int32_t*>(l.bytes.data()), static_cast<int>(c.shape[0]),
-                      static_cast<int>(c.shape[1]), i);
-    }
-    if (!copy_stream_) {
-        int lo, hi;
-        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CK(cudaStreamCreateWithPriority(&copy_stream_, cudaStreamNonBlocking, hi));
-        CK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&ev_hop_, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_y_, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_copy_, cudaEventDisableTiming));
-        tev_.resize(32);
-        for (auto& e : tev_) CK(cudaEventCreate(&e));
-    }
-    gemm_init();
-    const char* g = getenv("DCVC_B200_GRAPHS");
-    use_graphs_ = !(g && g[0] == '0');
-    finalized_ = true;
+    finalize_end();
 }
 
-IntraCodec::~IntraCodec()
-{
-    clear_plan();
-    if (copy_stream_) cudaStreamDestroy(copy_stream_);
-    if (own_stream_) cudaStreamDestroy(own_stream_);
-    if (ev_hop_) cudaEventDestroy(ev_hop_);
-    if (ev_y_) cudaEventDestroy(ev_y_);
-    if (ev_copy_) cudaEventDestroy(ev_copy_);
-    for (auto& e : tev_) cudaEventDestroy(e);
-}
-
-void IntraCodec::tick(cudaStream_t st)
-{
-    if (tev_n_ + 2 <= static_cast<int>(tev_.size())) CK(cudaEventRecord(tev_[tev_n_], st));
-}
-
-void IntraCodec::tock(cudaStream_t st)
-{
-    if (tev_n_ + 2 <= static_cast<int>(tev_.size())) {
-        CK(cudaEventRecord(tev_[tev_n_ + 1], st));
-        tev_n_ += 2;
-    }
-}
-
-float IntraCodec::gpu_ms()
-{
-    float total = 0.f;
-    for (int i = 0; i + 1 < tev_n_; i += 2) {
-        CK(cudaEventSynchronize(tev_[i + 1]));
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, tev_[i], tev_[i + 1]));
-        total += ms;
-    }
-    return total;
-}
+IntraCodec::~IntraCodec() { clear_plan(); }
 
 // =============================================================================== plan
 void IntraCodec::clear_plan()
 {
     Segment* segs[] = { &enc0_, &enc1_seg_, &dec0_, &dec_step_[0], &dec_step_[1], &dec_step_[2], &dec_step_[3], &dec4_ };
-    for (Segment* s : segs) {
-        if (s->exec) cudaGraphExecDestroy(s->exec);
-        s->exec = nullptr;
-        s->ops.clear();
-        s->launches = 0;
-    }
+    for (Segment* s : segs) s->reset();
     if (h_totals_) { cudaFreeHost(h_totals_); h_totals_ = nullptr; }
     for (int k = 0; k < 4; ++k) if (h_sym_[k]) { cudaFreeHost(h_sym_[k]); h_sym_[k] = nullptr; }
     if (h_idx_) { cudaFreeHost(h_idx_); h_idx_ = nullptr; }
@@ -505,67 +128,6 @@ void IntraCodec::clear_plan()
     if (h_z_) { cudaFreeHost(h_z_); h_z_ = nullptr; }
     arena_.release();
     H8_ = W8_ = 0;
-}
-
-void IntraCodec::add_gemm(Segment& s, int kind, const ActView& in, const ActView& out, const __half* w,
-                          const __half* bias, int N, int act, int chunk, const ActView* r1,
-                          const ActView* r2, const __half* q)
-{
-    auto op = std::make_shared<GemmOp>();
-    op->kind = kind;
-    op->in = in;
-    op->out = out;
-    if (r1) op->res1 = *r1;
-    if (r2) op->res2 = *r2;
-    op->weight = w;
-    op->bias = bias;
-    op->qscale = q;
-    op->N = N;
-    op->act = act;
-    op->chunk_add = chunk;
-    if (gemm_plan(*op)) throw std::runtime_error(std::string("gemm_plan: ") + gemm_last_error());
-    s.annotate(OP_ELEM, 0, 0);  // anything pushed without annotation so far is elementwise
-    s.ops.push_back([op](cudaStream_t st) { return gemm_launch(*op, st); });
-    const double px_in = static_cast<double>(in.W) * in.H, px_out = static_cast<double>(out.W) * out.H;
-    const int taps = (kind == GEMM_CONV3X3_S2) ? 9 : (kind == GEMM_CONV2X2_S2 ? 4 : 1);
-    double bytes = px_in * in.C * 2 + px_out * out.C * 2;
-    if (r1) bytes += px_out * out.C * 2;
-    if (r2) bytes += px_out * out.C * 2;
-    const double m_px = (kind == GEMM_TCONV2X2) ? px_in : px_out;
-    s.annotate(OP_GEMM, bytes, 2.0 * m_px * N * taps * in.C);
-}
-
-// DepthConvBlock (layers.py:152-159): returns the view holding the block output.
-ActView IntraCodec::dcb(Segment& s, Level& L, const ActView& in, const DcbW& w, bool shortcut,
-                        const __half* qscale, const ActView* out)
-{
-    const int H = in.H, W = in.W;
-    __half* bufX;
-    ActView x;
-    if (w.adaptor) {
-        bufX = (in.ptr == L.A) ? L.B : L.A;
-        x = make_view(bufX, w.c, w.c, W, H);
-        add_gemm(s, GEMM_PW, in, x, w.wa, w.ba, w.c, ACT_NONE, 0, nullptr, nullptr, nullptr);
-    } else {
-        x = in;
-        bufX = static_cast<__half*>(const_cast<void*>(in.ptr));
-    }
-    __half* bufO = (bufX == L.A) ? L.B : L.A;
-    const ActView t1 = make_view(L.T1, w.inner, w.inner, W, H);
-    const ActView t2 = make_view(L.T2, w.inner, w.inner, W, H);
-    const ActView o = make_view(bufO, w.c, w.c, W, H);
-    add_gemm(s, GEMM_PW, x, t1, w.w0, w.b0, w.inner, ACT_WSILU, 0, nullptr, nullptr, nullptr);
-    {
-        const __half* wdw = w.wdw;
-        s.annotate(OP_ELEM, 0, 0);
-        s.ops.push_back([t1, t2, wdw](cudaStream_t st) { return launch_dw3x3(t1, t2, wdw, st); });
-        s.annotate(OP_DW, 2.0 * 2 * W * H * w.inner, 2.0 * 9 * W * H * w.inner);
-    }
-    add_gemm(s, GEMM_PW, t2, o, w.w3, w.b3, w.c, ACT_NONE, 0, &x, nullptr, nullptr);
-    add_gemm(s, GEMM_PW, o, t1, w.wf0, w.bf0, 4 * w.inner, ACT_WSILU, 1, nullptr, nullptr, nullptr);
-    const ActView dst = out ? *out : x;  // in place over the block input unless redirected
-    add_gemm(s, GEMM_PW, t1, dst, w.wf2, w.bf2, w.c, ACT_NONE, 0, &o, shortcut ? &x : nullptr, qscale);
-    return dst;
 }
 
 void IntraCodec::plan(int height, int width)
@@ -745,10 +307,7 @@ void IntraCodec::plan(int height, int width)
         build_synthesis(s);
     }
     Segment* segs[] = { &enc0_, &enc1_seg_, &dec0_, &dec_step_[1], &dec_step_[2], &dec_step_[3], &dec4_ };
-    for (Segment* s : segs) {
-        s->annotate(OP_ELEM, 0, 0);
-        s->launches = static_cast<int>(s->ops.size());
-    }
+    for (Segment* s : segs) s->seal();
 }
 
 // z_hat -> hyper decoder -> prior fusion -> crop -> (scales, means) + reduced params into the cat buffer
@@ -797,62 +356,6 @@ void IntraCodec::build_synthesis(Segment& s)
     for (int i = 1; i < 13; ++i) t = dcb(s, l8_, t, dec1_[i], false, (i == 12) ? q_dec_ : nullptr, nullptr);
     const ActView out = make_view(dec_out_, kChSrc, kChSrc, W8_, H8_);
     dcb(s, l8_, t, dec2_, false, nullptr, &out);
-}
-
-void IntraCodec::run(Segment& s, cudaStream_t stream)
-{
-    if (profile_) {
-        // per-op CUDA-event timing (no graphs): feeds the roofline numbers of bench.py
-        cudaEvent_t e0, e1;
-        CK(cudaEventCreate(&e0));
-        CK(cudaEventCreate(&e1));
-        for (size_t i = 0; i < s.ops.size(); ++i) {
-            CK(cudaEventRecord(e0, stream));
-            if (s.ops[i](stream)) throw std::runtime_error(std::string("kernel launch failed: ") + gemm_last_error());
-            CK(cudaEventRecord(e1, stream));
-            CK(cudaEventSynchronize(e1));
-            float ms = 0.f;
-            CK(cudaEventElapsedTime(&ms, e0, e1));
-            ProfileAcc& a = prof_[s.kinds[i]];
-            a.ms += ms; a.bytes += s.alg_bytes[i]; a.flops += s.flops[i]; a.launches += 1;
-            if (const char* path = getenv("DCVC_B200_PROFILE_CSV")) {
-                if (FILE* f = fopen(path, "a")) {
-                    fprintf(f, "%d,%zu,%.3f,%.0f,%.0f\n", s.kinds[i], i, ms * 1e3, s.alg_bytes[i], s.flops[i]);
-                    fclose(f);
-                }
-            }
-        }
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-        launches += s.launches;
-        return;
-    }
-    if (use_graphs_) {
-        if (!s.exec) {
-            cudaGraph_t graph = nullptr;
-            CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-            int rc = 0;
-            for (auto& op : s.ops) {
-                rc = op(stream);
-                if (rc) break;
-            }
-            cudaError_t e = cudaStreamEndCapture(stream, &graph);
-            if (rc || e != cudaSuccess) {
-                if (graph) cudaGraphDestroy(graph);
-                throw std::runtime_error(std::string("graph capture failed: ") +
-                                         (rc ? gemm_last_error() : cudaGetErrorString(e)));
-            }
-            e = cudaGraphInstantiate(&s.exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (e != cudaSuccess) throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-        }
-        CK(cudaGraphLaunch(s.exec, stream));
-    } else {
-        for (auto& op : s.ops) {
-            if (op(stream)) throw std::runtime_error(std::string("kernel launch failed: ") + gemm_last_error());
-        }
-    }
-    launches += s.launches;
 }
 
 void IntraCodec::stage_qp(int qp, cudaStream_t stream)
@@ -999,11 +502,24 @@ int IntraCodec::debug_fetch(const char* name, void* dst, int64_t max_bytes, int6
 }  // namespace dcvc
 
 // =================================================================================== C ABI
+using dcvc::CodecBase;
 using dcvc::IntraCodec;
+
+namespace dcvc {
+// codec_hts.cu
+CodecBase* make_hts_codec(int device);
+int hts_add_ref(CodecBase* c, const void* frame, int H, int W, int64_t sc, int64_t sh, int64_t sw, int apply,
+                cudaStream_t stream);
+int hts_compress(CodecBase* c, const void* x, int H, int W, int64_t sc, int64_t sh, int64_t sw, int qp, int reset,
+                 int pad_b, int pad_r, cudaStream_t stream, const uint8_t** bs, int32_t* len, int32_t* ec);
+int hts_decompress(CodecBase* c, const uint8_t* bs, int len, int qp, int height, int width, int ec, int reset,
+                   cudaStream_t stream, void* const* x_hat_out);
+}  // namespace dcvc
 
 struct dcvc_codec {
     int kind;
-    std::unique_ptr<IntraCodec> intra;
+    std::unique_ptr<CodecBase> base;
+    IntraCodec* intra = nullptr;
     std::string err;
 };
 
@@ -1027,8 +543,8 @@ extern "C" {
 
 int dcvc_create(int32_t kind, int32_t device, dcvc_codec** out)
 {
-    if (kind != DCVC_KIND_INTRA) {
-        dcvc::set_api_error("dcvc_create: only DCVC_KIND_INTRA is implemented in this build");
+    if (kind != DCVC_KIND_INTRA && kind != DCVC_KIND_HTS) {
+        dcvc::set_api_error("dcvc_create: only DCVC_KIND_INTRA and DCVC_KIND_HTS are implemented in this build");
         return 1;
     }
     int n = 0;
@@ -1038,7 +554,12 @@ int dcvc_create(int32_t kind, int32_t device, dcvc_codec** out)
     }
     dcvc_codec* h = new dcvc_codec();
     h->kind = kind;
-    h->intra.reset(new IntraCodec(device));
+    if (kind == DCVC_KIND_INTRA) {
+        h->intra = new IntraCodec(device);
+        h->base.reset(h->intra);
+    } else {
+        h->base.reset(dcvc::make_hts_codec(device));
+    }
     *out = h;
     return 0;
 }
@@ -1055,7 +576,7 @@ int dcvc_set_param(dcvc_codec* h, const char* name, const void* data, int32_t dt
                    const int64_t* shape, int32_t on_device)
 {
     CODEC_TRY(h)
-    h->intra->set_param(name, data, dtype, ndim, shape, on_device);
+    h->base->set_param(name, data, dtype, ndim, shape, on_device);
     return 0;
     CODEC_CATCH(h)
 }
@@ -1063,7 +584,7 @@ int dcvc_set_param(dcvc_codec* h, const char* name, const void* data, int32_t dt
 int dcvc_finalize_params(dcvc_codec* h, float skip_thres)
 {
     CODEC_TRY(h)
-    h->intra->finalize(skip_thres);
+    h->base->finalize(skip_thres);
     return 0;
     CODEC_CATCH(h)
 }
@@ -1074,6 +595,7 @@ int dcvc_compress(dcvc_codec* h, const void* x, int32_t H, int32_t W, int64_t sc
                   void* x_hat_out)
 {
     CODEC_TRY(h)
+    if (!h->intra) throw std::runtime_error("dcvc_compress is the intra entry point; use dcvc_compress_chunk");
     h->intra->compress(x, H, W, sc, sh, sw, qp, pad_b, pad_r, static_cast<cudaStream_t>(stream),
                        bit_stream, bit_stream_len, ec_parallel, x_hat_out);
     return 0;
@@ -1084,26 +606,27 @@ int dcvc_decompress(dcvc_codec* h, const uint8_t* bit_stream, int32_t len, int32
                     int32_t height, int32_t width, int32_t ec_parallel, void* stream, void* x_hat_out)
 {
     CODEC_TRY(h)
+    if (!h->intra) throw std::runtime_error("dcvc_decompress is the intra entry point; use dcvc_decompress_chunk");
     h->intra->decompress(bit_stream, len, qp, height, width, ec_parallel,
                          static_cast<cudaStream_t>(stream), x_hat_out);
     return 0;
     CODEC_CATCH(h)
 }
 
-int64_t dcvc_kernel_launches(dcvc_codec* h) { return h->intra->launches; }
+int64_t dcvc_kernel_launches(dcvc_codec* h) { return h->base->launches; }
 
 int dcvc_last_gpu_ms(dcvc_codec* h, float* ms)
 {
     CODEC_TRY(h)
-    *ms = h->intra->gpu_ms();
+    *ms = h->base->gpu_ms();
     return 0;
     CODEC_CATCH(h)
 }
 
 int dcvc_profile_enable(dcvc_codec* h, int32_t on)
 {
-    h->intra->profile_ = on != 0;
-    if (on) for (auto& a : h->intra->prof_) a = dcvc::ProfileAcc();
+    h->base->profile_ = on != 0;
+    if (on) for (auto& a : h->base->prof_) a = dcvc::ProfileAcc();
     return 0;
 }
 
@@ -1111,16 +634,47 @@ int dcvc_profile_get(dcvc_codec* h, int32_t kind, double* ms, int64_t* launches,
                      double* flops)
 {
     if (kind < 0 || kind >= dcvc::OP_KINDS) return 1;
-    const dcvc::ProfileAcc& a = h->intra->prof_[kind];
+    const dcvc::ProfileAcc& a = h->base->prof_[kind];
     *ms = a.ms; *launches = a.launches; *alg_bytes = a.bytes; *flops = a.flops;
     return 0;
+}
+
+int dcvc_add_ref_feature_from_frame(dcvc_codec* h, const void* frame, int32_t H, int32_t W, int64_t sc, int64_t sh,
+                                    int64_t sw, int32_t apply_adaptor, void* stream)
+{
+    CODEC_TRY(h)
+    if (h->kind != DCVC_KIND_HTS) throw std::runtime_error("add_ref_feature_from_frame needs a chunk codec handle");
+    return dcvc::hts_add_ref(h->base.get(), frame, H, W, sc, sh, sw, apply_adaptor, static_cast<cudaStream_t>(stream));
+    CODEC_CATCH(h)
+}
+
+int dcvc_compress_chunk(dcvc_codec* h, const void* x, int32_t H, int32_t W, int64_t sc, int64_t sh, int64_t sw,
+                        int32_t qp, int32_t reset_feature_memory, int32_t pad_b, int32_t pad_r, void* stream,
+                        const uint8_t** bit_stream, int32_t* bit_stream_len, int32_t* ec_parallel)
+{
+    CODEC_TRY(h)
+    if (h->kind != DCVC_KIND_HTS) throw std::runtime_error("compress_chunk needs a chunk codec handle");
+    return dcvc::hts_compress(h->base.get(), x, H, W, sc, sh, sw, qp, reset_feature_memory, pad_b, pad_r,
+                              static_cast<cudaStream_t>(stream), bit_stream, bit_stream_len, ec_parallel);
+    CODEC_CATCH(h)
+}
+
+int dcvc_decompress_chunk(dcvc_codec* h, const uint8_t* bit_stream, int32_t len, int32_t qp, int32_t height,
+                          int32_t width, int32_t ec_parallel, int32_t reset_feature_memory, void* stream,
+                          void* const* x_hat_out)
+{
+    CODEC_TRY(h)
+    if (h->kind != DCVC_KIND_HTS) throw std::runtime_error("decompress_chunk needs a chunk codec handle");
+    return dcvc::hts_decompress(h->base.get(), bit_stream, len, qp, height, width, ec_parallel, reset_feature_memory,
+                                static_cast<cudaStream_t>(stream), x_hat_out);
+    CODEC_CATCH(h)
 }
 
 int dcvc_debug_fetch(dcvc_codec* h, const char* name, void* host_dst, int64_t max_bytes,
                      int64_t* bytes_written)
 {
     CODEC_TRY(h)
-    return h->intra->debug_fetch(name, host_dst, max_bytes, bytes_written);
+    return h->base->debug_fetch(name, host_dst, max_bytes, bytes_written);
     CODEC_CATCH(h)
 }
 

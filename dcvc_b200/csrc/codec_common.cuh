@@ -1,0 +1,520 @@
+// codec_common.cuh — shared runtime of the codec-level C ABI (Intra + HT-S): parameter store, weight
+// re-layout, device arenas, the DepthConvBlock op builder, CUDA-graph segments, GPU-only timing and
+// per-kernel-family profiling.  See codec.cu (DCVC-UF-Intra) and codec_hts.cu (DCVC-UF HT-S).
+//
+// Reference counterparts: src/layers/extensions/inference/layers_proxy.{h,cpp} (block proxies, weight
+// folding), dmc_common.{h,cpp} (graph capture / run), memory_pool.h (buffer pool).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/dcvc_b200.h"
+#include "elementwise.cuh"
+#include "pw_gemm.cuh"
+#include "rans_host.h"
+
+namespace dcvc {
+
+constexpr int kQpNum = 64;
+
+#define CK(expr)                                                                           \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+        }                                                                                  \
+    } while (0)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct HostTensor {
+    int dtype = DCVC_DTYPE_F16;
+    std::vector<int64_t> shape;
+    std::vector<uint8_t> bytes;
+    int64_t numel() const
+    {
+        int64_t n = 1;
+        for (auto s : shape) n *= s;
+        return n;
+    }
+};
+
+// bump allocator over one cudaMalloc block
+class Arena {
+public:
+    ~Arena() { release(); }
+    void release()
+    {
+        if (base_) cudaFree(base_);
+        base_ = nullptr;
+        cap_ = used_ = 0;
+    }
+    void reserve(size_t bytes)
+    {
+        release();
+        CK(cudaMalloc(&base_, bytes));
+        cap_ = bytes;
+        used_ = 0;
+    }
+    void* alloc(size_t bytes)
+    {
+        const size_t off = (used_ + 1023) & ~static_cast<size_t>(1023);
+        if (off + bytes > cap_) throw std::runtime_error("device arena exhausted");
+        used_ = off + bytes;
+        return static_cast<uint8_t*>(base_) + off;
+    }
+    __half* halves(size_t n) { return static_cast<__half*>(alloc(n * 2)); }
+    size_t used() const { return used_; }
+
+private:
+    void* base_ = nullptr;
+    size_t cap_ = 0, used_ = 0;
+};
+
+struct DcbW {
+    bool adaptor = false;
+    int cin = 0, c = 0, inner = 0;
+    const __half *wa = nullptr, *ba = nullptr;
+    const __half *w0 = nullptr, *b0 = nullptr;
+    const __half* wdw = nullptr;                // [9][inner]
+    const __half *w3 = nullptr, *b3 = nullptr;  // b3: dc.3 bias + W3 . dw-bias
+    const __half *wf0 = nullptr, *bf0 = nullptr;
+    const __half *wf2 = nullptr, *bf2 = nullptr;
+};
+
+struct ConvW {
+    const __half* w = nullptr;
+    const __half* b = nullptr;
+    int cout = 0, cin = 0;
+};
+
+struct Level {  // one pyramid level: two ping-pong buffers + two scratch buffers
+    int H = 0, W = 0;
+    __half *A = nullptr, *B = nullptr, *T1 = nullptr, *T2 = nullptr;
+};
+
+using OpFn = std::function<int(cudaStream_t)>;
+
+enum OpKind { OP_GEMM = 0, OP_DW = 1, OP_ELEM = 2, OP_KINDS = 3 };
+
+struct Segment {
+    std::vector<OpFn> ops;
+    std::vector<int> kinds;         // OpKind per op (kept in step with `ops`)
+    std::vector<double> alg_bytes;  // algorithmic bytes per op (activations in + residuals in + out)
+    std::vector<double> flops;
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+    void annotate(int kind, double bytes, double fl)
+    {
+        while (kinds.size() < ops.size()) {
+            kinds.push_back(kind);
+            alg_bytes.push_back(bytes);
+            flops.push_back(fl);
+        }
+    }
+    void elem(OpFn f)
+    {
+        annotate(OP_ELEM, 0, 0);
+        ops.push_back(std::move(f));
+        annotate(OP_ELEM, 0, 0);
+    }
+    void seal()
+    {
+        annotate(OP_ELEM, 0, 0);
+        launches = static_cast<int>(ops.size());
+    }
+    void reset()
+    {
+        if (exec) cudaGraphExecDestroy(exec);
+        exec = nullptr;
+        ops.clear(); kinds.clear(); alg_bytes.clear(); flops.clear();
+        launches = 0;
+    }
+};
+
+struct ProfileAcc {
+    double ms = 0, bytes = 0, flops = 0;
+    long long launches = 0;
+};
+
+inline ActView make_view(const void* p, int C, int pitch, int W, int H)
+{
+    ActView v;
+    v.ptr = p; v.C = C; v.pitch = pitch; v.W = W; v.H = H;
+    return v;
+}
+
+class CodecBase {
+public:
+    explicit CodecBase(int device) : device_(device) {}
+    virtual ~CodecBase()
+    {
+        if (copy_stream_) cudaStreamDestroy(copy_stream_);
+        if (own_stream_) cudaStreamDestroy(own_stream_);
+        if (ev_hop_) cudaEventDestroy(ev_hop_);
+        if (ev_y_) cudaEventDestroy(ev_y_);
+        for (auto& e : tev_) cudaEventDestroy(e);
+    }
+
+    virtual void finalize(float skip_thres) = 0;
+    virtual int debug_fetch(const char* name, void* dst, int64_t max_bytes, int64_t* written) = 0;
+
+    void set_param(const char* name, const void* data, int dtype, int ndim, const int64_t* shape, int on_device)
+    {
+        HostTensor t;
+        t.dtype = dtype;
+        t.shape.assign(shape, shape + ndim);
+        const size_t esz = (dtype == DCVC_DTYPE_F16) ? 2 : 4;
+        t.bytes.resize(static_cast<size_t>(t.numel()) * esz);
+        if (on_device) {
+            CK(cudaMemcpy(t.bytes.data(), data, t.bytes.size(), cudaMemcpyDeviceToHost));
+        } else {
+            memcpy(t.bytes.data(), data, t.bytes.size());
+        }
+        params_[name] = std::move(t);
+        finalized_ = false;
+    }
+
+    float gpu_ms()
+    {
+        float total = 0.f;
+        for (int i = 0; i + 1 < tev_n_; i += 2) {
+            CK(cudaEventSynchronize(tev_[i + 1]));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, tev_[i], tev_[i + 1]));
+            total += ms;
+        }
+        return total;
+    }
+
+    bool profile_ = false;
+    ProfileAcc prof_[OP_KINDS];
+    std::string err;
+    int64_t launches = 0;
+
+protected:
+    // ------------------------------------------------------------------ parameters
+    bool has_param(const std::string& k) const { return params_.count(k) != 0; }
+    const HostTensor& param(const std::string& k) const
+    {
+        auto it = params_.find(k);
+        if (it == params_.end()) throw std::runtime_error("missing parameter '" + k + "'");
+        return it->second;
+    }
+    std::vector<__half> param_f16(const std::string& k) const
+    {
+        const HostTensor& t = param(k);
+        std::vector<__half> v(static_cast<size_t>(t.numel()));
+        if (t.dtype == DCVC_DTYPE_F16) {
+            memcpy(v.data(), t.bytes.data(), t.bytes.size());
+        } else if (t.dtype == DCVC_DTYPE_F32) {
+            const float* f = reinterpret_cast<const float*>(t.bytes.data());
+            for (size_t i = 0; i < v.size(); ++i) v[i] = __float2half_rn(f[i]);
+        } else {
+            throw std::runtime_error("parameter '" + k + "' is not floating point");
+        }
+        return v;
+    }
+    const __half* upload(const std::vector<__half>& v)
+    {
+        void* d = warena_.alloc(v.size() * sizeof(__half));
+        CK(cudaMemcpy(d, v.data(), v.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        return static_cast<const __half*>(d);
+    }
+    const __half* upload_param(const std::string& k) { return upload(param_f16(k)); }
+
+    // DepthConvBlock weights (layers_proxy.cpp:160-206): dw weight -> [9][C'], dw bias folded into dc.3
+    DcbW load_dcb(const std::string& p)
+    {
+        DcbW w;
+        if (has_param(p + "adaptor.weight")) {
+            w.adaptor = true;
+            w.cin = static_cast<int>(param(p + "adaptor.weight").shape[1]);
+            w.wa = upload_param(p + "adaptor.weight");
+            w.ba = upload_param(p + "adaptor.bias");
+        }
+        const HostTensor& w0 = param(p + "dc.0.weight");
+        w.inner = static_cast<int>(w0.shape[0]);
+        w.c = static_cast<int>(w0.shape[1]);
+        if (!w.adaptor) w.cin = w.c;
+        w.w0 = upload_param(p + "dc.0.weight");
+        w.b0 = upload_param(p + "dc.0.bias");
+        {
+            std::vector<__half> dw = param_f16(p + "dc.2.weight");
+            std::vector<__half> t(dw.size());
+            for (int c = 0; c < w.inner; ++c)
+                for (int k = 0; k < 9; ++k) t[static_cast<size_t>(k) * w.inner + c] = dw[static_cast<size_t>(c) * 9 + k];
+            w.wdw = upload(t);
+        }
+        {
+            // fold the depthwise bias into the bias of dc.3 (layers_proxy.cpp:175-178), fp32 then one rounding
+            std::vector<__half> w3 = param_f16(p + "dc.3.weight");
+            std::vector<__half> bdw = param_f16(p + "dc.2.bias");
+            std::vector<__half> b3 = param_f16(p + "dc.3.bias");
+            std::vector<__half> folded(b3.size());
+            for (int n = 0; n < w.c; ++n) {
+                float acc = 0.f;
+                for (int c = 0; c < w.inner; ++c)
+                    acc += __half2float(w3[static_cast<size_t>(n) * w.inner + c]) * __half2float(bdw[c]);
+                folded[n] = __float2half_rn(acc + __half2float(b3[n]));
+            }
+            w.w3 = upload(w3);
+            w.b3 = upload(folded);
+        }
+        w.wf0 = upload_param(p + "ffn.0.weight");
+        w.bf0 = upload_param(p + "ffn.0.bias");
+        w.wf2 = upload_param(p + "ffn.2.weight");
+        w.bf2 = upload_param(p + "ffn.2.bias");
+        return w;
+    }
+
+    ConvW load_conv(const std::string& p, int kind)
+    {
+        ConvW c;
+        const HostTensor& wt = param(p + "weight");
+        const int cout = static_cast<int>(wt.shape[0]), cin = static_cast<int>(wt.shape[1]);
+        const int kh = static_cast<int>(wt.shape[2]), kw = static_cast<int>(wt.shape[3]);
+        std::vector<__half> src = param_f16(p + "weight");
+        std::vector<__half> dst(src.size());
+        if (dcvc_pack_weight(kind, src.data(), cout, cin, kh, kw, dst.data()))
+            throw std::runtime_error("pack_weight failed for " + p);
+        c.w = upload(dst);
+        if (has_param(p + "bias")) c.b = upload_param(p + "bias");
+        c.cout = cout;
+        c.cin = cin;
+        return c;
+    }
+
+    // reserve the weight arena, then (after the model-specific loads) finish with LUT/CDF/streams
+    void finalize_begin(float skip_thres)
+    {
+        CK(cudaSetDevice(device_));
+        skip_thres_ = skip_thres;
+        size_t total = 0;
+        for (auto& kv : params_) total += static_cast<size_t>(kv.second.numel()) * 2 + 2048;
+        warena_.reserve(total * 2 + (8u << 20));
+    }
+    void finalize_end()
+    {
+        std::vector<uint8_t> h(65536);
+        build_scale_lut(h.data());
+        lut_ = static_cast<uint8_t*>(warena_.alloc(65536));
+        CK(cudaMemcpy(lut_, h.data(), 65536, cudaMemcpyHostToDevice));
+        // CDF tables (common_model.py:64-70; dmci_proxy.cpp:639-651)
+        const char* names[2] = { "bit_estimator_z.", "gaussian_encoder." };
+        for (int i = 0; i < 2; ++i) {
+            const HostTensor& c = param(std::string(names[i]) + "quantized_cdf");
+            const HostTensor& l = param(std::string(names[i]) + "cdf_length");
+            if (c.dtype != DCVC_DTYPE_I32 || l.dtype != DCVC_DTYPE_I32 || c.shape.size() != 2)
+                throw std::runtime_error("CDF tables must be int32 [rows][width]");
+            rans_.set_cdf(reinterpret_cast<const int32_t*>(c.bytes.data()), reinterpret_cast<const int32_t*>(l.bytes.data()),
+                          static_cast<int>(c.shape[0]), static_cast<int>(c.shape[1]), i);
+        }
+        if (!copy_stream_) {
+            int lo, hi;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&copy_stream_, cudaStreamNonBlocking, hi));
+            CK(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ev_hop_, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ev_y_, cudaEventDisableTiming));
+            tev_.resize(48);
+            for (auto& e : tev_) CK(cudaEventCreate(&e));
+        }
+        if (gemm_init()) throw std::runtime_error(gemm_last_error());
+        const char* g = getenv("DCVC_B200_GRAPHS");
+        use_graphs_ = !(g && g[0] == '0');
+        finalized_ = true;
+    }
+
+    // ------------------------------------------------------------------ op builders
+    void add_gemm(Segment& s, int kind, const ActView& in, const ActView& out, const __half* w, const __half* bias,
+                  int N, int act, int chunk, const ActView* r1, const ActView* r2, const __half* q)
+    {
+        auto op = std::make_shared<GemmOp>();
+        op->kind = kind;
+        op->in = in;
+        op->out = out;
+        if (r1) op->res1 = *r1;
+        if (r2) op->res2 = *r2;
+        op->weight = w;
+        op->bias = bias;
+        op->qscale = q;
+        op->N = N;
+        op->act = act;
+        op->chunk_add = chunk;
+        if (gemm_plan(*op)) throw std::runtime_error(std::string("gemm_plan: ") + gemm_last_error());
+        s.annotate(OP_ELEM, 0, 0);
+        s.ops.push_back([op](cudaStream_t st) { return gemm_launch(*op, st); });
+        const double px_in = static_cast<double>(in.W) * in.H, px_out = static_cast<double>(out.W) * out.H;
+        const int taps = (kind == GEMM_CONV3X3_S2) ? 9 : (kind == GEMM_CONV2X2_S2 ? 4 : 1);
+        double bytes = px_in * in.C * 2 + px_out * out.C * 2;
+        if (r1) bytes += px_out * out.C * 2;
+        if (r2) bytes += px_out * out.C * 2;
+        const double m_px = (kind == GEMM_TCONV2X2) ? px_in : px_out;
+        s.annotate(OP_GEMM, bytes, 2.0 * m_px * N * taps * in.C);
+    }
+    void conv1x1(Segment& s, const ActView& in, const ActView& out, const ConvW& c)
+    {
+        add_gemm(s, GEMM_PW, in, out, c.w, c.b, c.cout, ACT_NONE, 0, nullptr, nullptr, nullptr);
+    }
+
+    // DepthConvBlock (layers.py:152-159 == layers_proxy.cpp:71-101): returns the view holding the output.
+    // The block input is overwritten in place unless `out` redirects the last GEMM.  `in` may live in one
+    // of the level's ping-pong buffers or outside of it (then, without an adaptor, `out` is mandatory
+    // and must not be L.A, which holds the dc.3 output).
+    ActView dcb(Segment& s, Level& L, const ActView& in, const DcbW& w, bool shortcut, const __half* qscale,
+                const ActView* out)
+    {
+        const int H = in.H, W = in.W;
+        __half* bufX;
+        ActView x;
+        if (w.adaptor) {
+            bufX = (in.ptr == L.A) ? L.B : L.A;
+            x = make_view(bufX, w.c, w.c, W, H);
+            add_gemm(s, GEMM_PW, in, x, w.wa, w.ba, w.c, ACT_NONE, 0, nullptr, nullptr, nullptr);
+        } else {
+            x = in;
+            bufX = static_cast<__half*>(const_cast<void*>(in.ptr));
+            const bool internal = (bufX == L.A || bufX == L.B);
+            if (!internal && (!out || out->ptr == L.A))
+                throw std::runtime_error("dcb: external input without adaptor needs an output outside L.A");
+        }
+        __half* bufO = (bufX == L.A) ? L.B : L.A;
+        const ActView t1 = make_view(L.T1, w.inner, w.inner, W, H);
+        const ActView t2 = make_view(L.T2, w.inner, w.inner, W, H);
+        const ActView o = make_view(bufO, w.c, w.c, W, H);
+        add_gemm(s, GEMM_PW, x, t1, w.w0, w.b0, w.inner, ACT_WSILU, 0, nullptr, nullptr, nullptr);
+        {
+            const __half* wdw = w.wdw;
+            s.annotate(OP_ELEM, 0, 0);
+            s.ops.push_back([t1, t2, wdw](cudaStream_t st) { return launch_dw3x3(t1, t2, wdw, st); });
+            s.annotate(OP_DW, 2.0 * 2 * W * H * w.inner, 2.0 * 9 * W * H * w.inner);
+        }
+        add_gemm(s, GEMM_PW, t2, o, w.w3, w.b3, w.c, ACT_NONE, 0, &x, nullptr, nullptr);
+        add_gemm(s, GEMM_PW, o, t1, w.wf0, w.bf0, 4 * w.inner, ACT_WSILU, 1, nullptr, nullptr, nullptr);
+        const ActView dst = out ? *out : x;
+        add_gemm(s, GEMM_PW, t1, dst, w.wf2, w.bf2, w.c, ACT_NONE, 0, &o, shortcut ? &x : nullptr, qscale);
+        return dst;
+    }
+
+    // ------------------------------------------------------------------ execution
+    void run(Segment& s, cudaStream_t stream)
+    {
+        if (s.ops.empty()) return;
+        if (profile_) {
+            cudaEvent_t e0, e1;
+            CK(cudaEventCreate(&e0));
+            CK(cudaEventCreate(&e1));
+            for (size_t i = 0; i < s.ops.size(); ++i) {
+                CK(cudaEventRecord(e0, stream));
+                if (s.ops[i](stream)) throw std::runtime_error(std::string("kernel launch failed: ") + gemm_last_error());
+                CK(cudaEventRecord(e1, stream));
+                CK(cudaEventSynchronize(e1));
+                float ms = 0.f;
+                CK(cudaEventElapsedTime(&ms, e0, e1));
+                ProfileAcc& a = prof_[s.kinds[i]];
+                a.ms += ms; a.bytes += s.alg_bytes[i]; a.flops += s.flops[i]; a.launches += 1;
+                if (const char* path = getenv("DCVC_B200_PROFILE_CSV")) {
+                    if (FILE* f = fopen(path, "a")) {
+                        fprintf(f, "%d,%zu,%.3f,%.0f,%.0f\n", s.kinds[i], i, ms * 1e3, s.alg_bytes[i], s.flops[i]);
+                        fclose(f);
+                    }
+                }
+            }
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            launches += s.launches;
+            return;
+        }
+        if (use_graphs_) {
+            if (!s.exec) {
+                cudaGraph_t graph = nullptr;
+                CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                int rc = 0;
+                for (auto& op : s.ops) {
+                    rc = op(stream);
+                    if (rc) break;
+                }
+                cudaError_t e = cudaStreamEndCapture(stream, &graph);
+                if (rc || e != cudaSuccess) {
+                    if (graph) cudaGraphDestroy(graph);
+                    throw std::runtime_error(std::string("graph capture failed: ") + (rc ? gemm_last_error() : cudaGetErrorString(e)));
+                }
+                e = cudaGraphInstantiate(&s.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (e != cudaSuccess) throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+            }
+            CK(cudaGraphLaunch(s.exec, stream));
+        } else {
+            for (auto& op : s.ops) {
+                if (op(stream)) throw std::runtime_error(std::string("kernel launch failed: ") + gemm_last_error());
+            }
+        }
+        launches += s.launches;
+    }
+
+    void tick(cudaStream_t st)
+    {
+        if (tev_n_ + 2 <= static_cast<int>(tev_.size())) CK(cudaEventRecord(tev_[tev_n_], st));
+    }
+    void tock(cudaStream_t st)
+    {
+        if (tev_n_ + 2 <= static_cast<int>(tev_.size())) {
+            CK(cudaEventRecord(tev_[tev_n_ + 1], st));
+            tev_n_ += 2;
+        }
+    }
+
+    // CUDA graphs cannot be captured on the legacy default stream: calls made on it hop onto an internal
+    // stream and hand the result back with an event (the reference instead requires the caller to set a
+    // non-default stream, test_video.py:423-425).
+    struct StreamHop {
+        CodecBase* c;
+        cudaStream_t user, run;
+        bool hop;
+        StreamHop(CodecBase* codec, cudaStream_t u) : c(codec), user(u), run(u)
+        {
+            hop = (u == nullptr || u == cudaStreamLegacy || u == cudaStreamPerThread);
+            if (hop) {
+                if (cudaEventRecord(c->ev_hop_, user) != cudaSuccess ||
+                    cudaStreamWaitEvent(c->own_stream_, c->ev_hop_, 0) != cudaSuccess)
+                    throw std::runtime_error("stream hop failed");
+                run = c->own_stream_;
+            }
+        }
+        ~StreamHop()
+        {
+            if (hop) {
+                cudaEventRecord(c->ev_hop_, run);
+                cudaStreamWaitEvent(user, c->ev_hop_, 0);
+            }
+        }
+    };
+
+    int device_;
+    bool finalized_ = false;
+    bool use_graphs_ = true;
+    float skip_thres_ = 0.f;
+    std::map<std::string, HostTensor> params_;
+    Arena warena_;
+    uint8_t* lut_ = nullptr;
+    RansCodec rans_;
+    cudaStream_t copy_stream_ = nullptr, own_stream_ = nullptr;
+    cudaEvent_t ev_hop_ = nullptr, ev_y_ = nullptr;
+    std::vector<cudaEvent_t> tev_;
+    int tev_n_ = 0;
+    std::vector<uint8_t> bitstream_;
+};
+
+}  // namespace dcvc

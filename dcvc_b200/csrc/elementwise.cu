@@ -308,6 +308,7 @@ __device__ __forceinline__ int active_group(int step, int h, int w)
 }
 
 struct EntropyDev {
+    const __half* qdiv; int q_pitch; int m_pitch; int8_t* yq; int full;
     int H, W, G, step;
     const __half* y; int y_pitch;
     const __half* q_enc;
@@ -321,6 +322,8 @@ struct EntropyDev {
 static EntropyDev to_dev(const EntropyStepArgs& a)
 {
     EntropyDev d;
+    d.qdiv = a.q_div; d.q_pitch = a.q_pitch; d.m_pitch = a.m_pitch ? a.m_pitch : a.p_pitch;
+    d.yq = a.yq_dense; d.full = a.full;
     d.H = a.H; d.W = a.W; d.G = a.G; d.step = a.step;
     d.y = a.y; d.y_pitch = a.y_pitch; d.q_enc = a.q_enc;
     d.scales = a.scales; d.means = a.means; d.p_pitch = a.p_pitch;
@@ -346,7 +349,13 @@ entropy_enc_step_kernel(const EntropyDev d)
         const int ch = g * d.G + c;
         __half2 yv = *reinterpret_cast<const __half2*>(d.y + pix * d.y_pitch + ch);
         if (d.q_enc) yv = __hmul2_rn(yv, *reinterpret_cast<const __half2*>(d.q_enc + ch));
-        const __half2 mv = *reinterpret_cast<const __half2*>(d.means + pix * d.p_pitch + ch);
+        if (d.qdiv) {
+            // y * hrcp(max(q, 0.5)): reciprocal rounded to half, then a half multiply (stream.cu:437-440)
+            const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(d.qdiv + pix * d.q_pitch + ch));
+            const __half2 rc = __floats2half2_rn(1.0f / fmaxf(qf.x, 0.5f), 1.0f / fmaxf(qf.y, 0.5f));
+            yv = __hmul2_rn(yv, rc);
+        }
+        const __half2 mv = *reinterpret_cast<const __half2*>(d.means + pix * d.m_pitch + ch);
         const __half2 sv = *reinterpret_cast<const __half2*>(d.scales + pix * d.p_pitch + ch);
         const __half2 res = __hsub2_rn(yv, mv);  // _rn: never contracted into an fma with the multiply above
         float q0 = round_half_away(__low2float(res));
@@ -360,12 +369,20 @@ entropy_enc_step_kernel(const EntropyDev d)
         const __half2 yq = __floats2half2_rn(q0, q1);
         const __half2 yh = __hadd2_rn(yq, mv);
         *reinterpret_cast<__half2*>(d.acc + pix * d.acc_pitch + ch) = yh;
-        const int i0 = d.lut[__half_as_ushort(__low2half(sv))];
-        const int i1 = d.lut[__half_as_ushort(__high2half(sv))];
-        short2 sym;
-        sym.x = static_cast<short>((static_cast<int>(q0) << 8) + i0);
-        sym.y = static_cast<short>((static_cast<int>(q1) << 8) + i1);
-        *reinterpret_cast<short2*>(d.sym_raw + pix * d.G + c) = sym;
+        if (d.yq) {
+            char2 qq;
+            qq.x = static_cast<signed char>(q0);
+            qq.y = static_cast<signed char>(q1);
+            *reinterpret_cast<char2*>(d.yq + pix * (4 * d.G) + ch) = qq;
+        }
+        if (d.sym_raw) {
+            const int i0 = d.lut[__half_as_ushort(__low2half(sv))];
+            const int i1 = d.lut[__half_as_ushort(__high2half(sv))];
+            short2 sym;
+            sym.x = static_cast<short>((static_cast<int>(q0) << 8) + i0);
+            sym.y = static_cast<short>((static_cast<int>(q1) << 8) + i1);
+            *reinterpret_cast<short2*>(d.sym_raw + pix * d.G + c) = sym;
+        }
         count += (c0 ? 1 : 0) + (c1 ? 1 : 0);
     }
     if (d.step == 0) {
@@ -377,7 +394,7 @@ entropy_enc_step_kernel(const EntropyDev d)
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
-    if (lane == 0) d.counts[pix] = count;
+    if (lane == 0 && d.counts) d.counts[pix] = count;
 }
 
 __global__ void __launch_bounds__(256)
@@ -389,7 +406,7 @@ entropy_dec_index_kernel(const EntropyDev d)
     if (pix >= npix) return;
     const int w = static_cast<int>(pix % d.W);
     const int h = static_cast<int>(pix / d.W);
-    const int g = active_group(d.step, h, w);
+    const int g = d.full ? 0 : active_group(d.step, h, w);
     int count = 0;
     for (int c = lane * 2; c < d.G; c += 64) {
         const int ch = g * d.G + c;
@@ -429,7 +446,7 @@ compact_kernel(const EntropyDev d, const T* __restrict__ raw, const int32_t* __r
     if (pix >= npix) return;
     const int w = static_cast<int>(pix % d.W);
     const int h = static_cast<int>(pix / d.W);
-    const int g = active_group(d.step, h, w);
+    const int g = d.full ? 0 : active_group(d.step, h, w);
     int base = offsets[pix];
     for (int c0i = 0; c0i < d.G; c0i += 64) {
         const int c = c0i + lane * 2;
@@ -491,6 +508,103 @@ entropy_dec_restore_kernel(const EntropyDev d, const int32_t* __restrict__ offse
     }
 }
 
+// ---- chunk-codec kernels: symbols over the whole latent, dense y_q
+__global__ void __launch_bounds__(256)
+entropy_build_symbols_full_kernel(const EntropyDev d)
+{
+    const int lane = threadIdx.x & 31;
+    const long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (pix >= static_cast<long long>(d.H) * d.W) return;
+    int count = 0;
+    for (int c = lane * 2; c < d.G; c += 64) {
+        const __half2 sv = *reinterpret_cast<const __half2*>(d.scales + pix * d.p_pitch + c);
+        const char2 qq = *reinterpret_cast<const char2*>(d.yq + pix * d.G + c);
+        const int i0 = d.lut[__half_as_ushort(__low2half(sv))];
+        const int i1 = d.lut[__half_as_ushort(__high2half(sv))];
+        short2 sym;
+        sym.x = static_cast<short>((static_cast<int>(qq.x) << 8) + i0);
+        sym.y = static_cast<short>((static_cast<int>(qq.y) << 8) + i1);
+        *reinterpret_cast<short2*>(d.sym_raw + pix * d.G + c) = sym;
+        count += (__hgt(__low2half(sv), d.thres) ? 1 : 0) + (__hgt(__high2half(sv), d.thres) ? 1 : 0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if (lane == 0) d.counts[pix] = count;
+}
+
+__global__ void __launch_bounds__(256)
+entropy_recover_dense_kernel(const EntropyDev d, const int32_t* __restrict__ offsets,
+                             const int8_t* __restrict__ decoded)
+{
+    const int lane = threadIdx.x & 31;
+    const long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (pix >= static_cast<long long>(d.H) * d.W) return;
+    int base = offsets[pix];
+    for (int c0i = 0; c0i < d.G; c0i += 64) {
+        const int c = c0i + lane * 2;
+        bool k0 = false, k1 = false;
+        if (c < d.G) {
+            const __half2 sv = *reinterpret_cast<const __half2*>(d.scales + pix * d.p_pitch + c);
+            k0 = __hgt(__low2half(sv), d.thres);
+            k1 = __hgt(__high2half(sv), d.thres);
+        }
+        int r0, r1, tot;
+        pair_ranks(k0, k1, lane, r0, r1, tot);
+        if (c < d.G) {
+            char2 qq;
+            qq.x = k0 ? decoded[base + r0] : 0;
+            qq.y = k1 ? decoded[base + r1] : 0;
+            *reinterpret_cast<char2*>(d.yq + pix * d.G + c) = qq;
+        }
+        base += tot;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+entropy_restore_dense_kernel(const EntropyDev d)
+{
+    const int lane = threadIdx.x & 31;
+    const long long pix = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (pix >= static_cast<long long>(d.H) * d.W) return;
+    const int w = static_cast<int>(pix % d.W);
+    const int h = static_cast<int>(pix / d.W);
+    const int g = active_group(d.step, h, w);
+    for (int c = lane * 2; c < d.G; c += 64) {
+        const int ch = g * d.G + c;
+        const char2 qq = *reinterpret_cast<const char2*>(d.yq + pix * (4 * d.G) + ch);
+        const __half2 mv = *reinterpret_cast<const __half2*>(d.means + pix * d.m_pitch + ch);
+        const __half2 yh = __hadd2_rn(__floats2half2_rn(static_cast<float>(qq.x), static_cast<float>(qq.y)), mv);
+        *reinterpret_cast<__half2*>(d.acc + pix * d.acc_pitch + ch) = yh;
+    }
+    if (d.step == 0) {
+        const __half2 z = __floats2half2_rn(0.f, 0.f);
+        for (int c = lane * 2; c < 4 * d.G; c += 64) {
+            if (c / d.G != g) *reinterpret_cast<__half2*>(d.acc + pix * d.acc_pitch + c) = z;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mul_clamp_min_kernel(const __half* __restrict__ in, int in_pitch, const __half* __restrict__ q, int q_pitch,
+                     __half* __restrict__ out, int out_pitch, long long npix, int C)
+{
+    const int cg_n = C >> 3;
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (tid >= npix * cg_n) return;
+    const int cg = static_cast<int>(tid % cg_n);
+    const long long pix = tid / cg_n;
+    const uint4 v = *reinterpret_cast<const uint4*>(in + pix * in_pitch + cg * 8);
+    const uint4 k = *reinterpret_cast<const uint4*>(q + pix * q_pitch + cg * 8);
+    const __half2* vh = reinterpret_cast<const __half2*>(&v);
+    const __half2* kh = reinterpret_cast<const __half2*>(&k);
+    const __half2 half_ = __floats2half2_rn(0.5f, 0.5f);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) oh[i] = __hmul2_rn(vh[i], __hmax2(kh[i], half_));
+    *reinterpret_cast<uint4*>(out + pix * out_pitch + cg * 8) = o;
+}
+
 static inline int warp_grid(long long npix) { return static_cast<int>((npix * 32 + 255) / 256); }
 
 int launch_entropy_enc_step(const EntropyStepArgs& a, cudaStream_t s)
@@ -530,6 +644,40 @@ int launch_entropy_dec_restore(const EntropyStepArgs& a, const int32_t* offsets,
 {
     const long long npix = static_cast<long long>(a.H) * a.W;
     entropy_dec_restore_kernel<<<warp_grid(npix), 256, 0, s>>>(to_dev(a), offsets, decoded);
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_entropy_build_symbols_full(const EntropyStepArgs& a, cudaStream_t s)
+{
+    const long long npix = static_cast<long long>(a.H) * a.W;
+    entropy_build_symbols_full_kernel<<<warp_grid(npix), 256, 0, s>>>(to_dev(a));
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_entropy_recover_dense(const EntropyStepArgs& a, const int32_t* offsets, const int8_t* decoded, cudaStream_t s)
+{
+    const long long npix = static_cast<long long>(a.H) * a.W;
+    entropy_recover_dense_kernel<<<warp_grid(npix), 256, 0, s>>>(to_dev(a), offsets, decoded);
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_entropy_restore_dense(const EntropyStepArgs& a, cudaStream_t s)
+{
+    const long long npix = static_cast<long long>(a.H) * a.W;
+    entropy_restore_dense_kernel<<<warp_grid(npix), 256, 0, s>>>(to_dev(a));
+    DCVC_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_mul_clamp_min(const ActView& in, const ActView& q, const ActView& out, cudaStream_t s)
+{
+    const long long npix = static_cast<long long>(in.W) * in.H;
+    mul_clamp_min_kernel<<<blocks_for(npix * (in.C / 8), 256), 256, 0, s>>>(
+        static_cast<const __half*>(in.ptr), in.pitch, static_cast<const __half*>(q.ptr), q.pitch,
+        static_cast<__half*>(const_cast<void*>(out.ptr)), out.pitch, npix, in.C);
     DCVC_LAUNCH_CHECK();
     return 0;
 }

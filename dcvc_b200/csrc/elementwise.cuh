@@ -47,6 +47,13 @@ struct EntropyStepArgs {
     int acc_pitch = 0;
     float skip_thres = 0.f;
     const uint8_t* scale_lut = nullptr;  // 65536-entry fp16-bits -> table index LUT
+    // --- chunk-codec (HT-S / LD) variants: per-element quantiser step, means in their own buffer,
+    //     symbols built once over all 4*G channels after the four means-refinement steps
+    const __half* q_div = nullptr;    // [H][W][q_pitch]: y *= 1 / max(q_div, 0.5) first (stream.cu:422-443)
+    int q_pitch = 0;
+    int m_pitch = 0;                  // pitch of `means` (0: same as p_pitch)
+    int8_t* yq_dense = nullptr;       // [H*W][4G] quantised latents, written (enc) / read (dec restore)
+    int full = 0;                     // 1: index/compaction kernels run over all 4*G channels of a pixel
     // outputs, per pixel row of G entries
     int16_t* sym_raw = nullptr;       // encoder: (sym << 8) + idx, uncompacted [H*W][G]
     uint8_t* idx_raw = nullptr;       // decoder: idx, uncompacted [H*W][G]
@@ -66,6 +73,16 @@ int launch_compact_u8(const EntropyStepArgs& a, const int32_t* offsets, uint8_t*
 // decoder step part 2: scatter decoded symbols + restore y_hat (stream.cu:359-383, 756-818)
 int launch_entropy_dec_restore(const EntropyStepArgs& a, const int32_t* offsets,
                                const int8_t* decoded, cudaStream_t s);
+
+// chunk codecs: symbols of the whole latent from the dense y_q (build_index_enc_cuda on the full tensor,
+// dmc_hts_proxy.cpp:559-562): a.full = 1, a.G = channels per pixel
+int launch_entropy_build_symbols_full(const EntropyStepArgs& a, cudaStream_t s);
+// conditional_recover_with_type_conversion (stream.cu:359-383) into the dense int8 y_q
+int launch_entropy_recover_dense(const EntropyStepArgs& a, const int32_t* offsets, const int8_t* decoded, cudaStream_t s);
+// restore_y / restore_y_and_add_inplace from the dense y_q (stream.cu:685-754)
+int launch_entropy_restore_dense(const EntropyStepArgs& a, cudaStream_t s);
+// out = half(in * max(q, 0.5)) elementwise (the final multiply of stream.cu:605-616 / :717-725)
+int launch_mul_clamp_min(const ActView& in, const ActView& q, const ActView& out, cudaStream_t s);
 
 // Host: fp16-bits -> Gaussian scale-table index, built with the reference's half arithmetic
 // (scale_to_index, stream.cu:77-87 + def_const.h:6-12).

@@ -105,3 +105,49 @@ class DMCI:
         x_hat = self.proxy.decompress(np.frombuffer(bit_stream, dtype=np.uint8), qp, sps["height"], sps["width"],
                                       ec_part)
         return {"x_hat": x_hat}
+
+
+class DMC(DMCI):
+    """Host-side mirror of the reference's HT-S video model API (src/models/video_model_ht.py:320-450):
+    clear_dpb / add_ref_feature_from_frame / compress / decompress, chunk = 8 frames stacked on the channel axis."""
+
+    def __init__(self):
+        from .spec import hts_spec
+        self._spec = hts_spec()
+        self._sd = OrderedDict((k, torch.zeros(v)) for k, v in self._spec.items())
+        self.proxy = None
+        self.skip_thres = 0.0
+        self._cdf = None
+
+    @classmethod
+    def synthetic(cls, seed: int = 1) -> "DMC":
+        m = cls()
+        m.load_state_dict(synth_state_dict(m._spec, seed))
+        return m
+
+    def clear_dpb(self):
+        # the reference forgets ref_feature/memory/ctx; the proxy state is rebuilt by the next
+        # add_ref_feature_from_frame (video_model_ht.py:364-367)
+        pass
+
+    def _ensure_proxy(self):
+        if self.proxy is None:
+            from inference_extensions_cuda import DMCHTSProxy
+            sd = self.add_cdf_to_state_dict(self.state_dict())
+            self.proxy = DMCHTSProxy()
+            self.proxy.set_param(sd, self.skip_thres)
+
+    def add_ref_feature_from_frame(self, frame, apply_feature_adaptor=True):
+        self._ensure_proxy()
+        return self.proxy.add_ref_feature_from_frame(frame, apply_feature_adaptor)
+
+    def compress(self, x, qp, reset_feature_memory, padding_b, padding_r):
+        self._ensure_proxy()
+        bit_stream, ec_parallel = self.proxy.compress(x, qp, reset_feature_memory, padding_b, padding_r)
+        return {"bit_stream": bit_stream.tobytes(), "ec_parallel": ec_parallel}
+
+    def decompress(self, bit_stream, sps, qp, ec_part, reset_feature_memory):
+        self._ensure_proxy()
+        x_hat = self.proxy.decompress(np.frombuffer(bit_stream, dtype=np.uint8), qp, sps["height"], sps["width"],
+                                      ec_part, reset_feature_memory)
+        return {"x_hat": x_hat}

@@ -126,3 +126,60 @@ class DMCIProxy:
         self._hd.check(self._hd.lib.dcvc_debug_fetch(self._hd.h, name.encode(), C.c_void_p(buf.ctypes.data), buf.size,
                                                      C.byref(n)), "debug_fetch")
         return buf[: n.value].view(dtype).copy()
+
+
+class DMCHTSProxy:
+    """DCVC-UF HT-S chunk codec proxy (reference: DMCHTSProxy, dmc_hts_proxy.h:229-233; bind.cpp:24-31)."""
+
+    FRAMES = 8
+
+    def __init__(self):
+        self._hd = _CodecHandle(_lib.KIND_HTS)
+        self._x_hat = None
+
+    def set_param(self, state_dict, skip_threshold: float):
+        _push_state_dict(self._hd, state_dict, skip_threshold)
+
+    def add_ref_feature_from_frame(self, frame: torch.Tensor, apply_adaptor: bool):
+        hd = self._hd
+        assert frame.is_cuda and frame.dtype == torch.float16 and frame.dim() == 4 and frame.shape[1] == 3
+        _, _, H, W = frame.shape
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        hd.check(hd.lib.dcvc_add_ref_feature_from_frame(hd.h, C.c_void_p(frame.data_ptr()), H, W, frame.stride(1),
+                                                        frame.stride(2), frame.stride(3), 1 if apply_adaptor else 0,
+                                                        stream), "add_ref_feature_from_frame")
+
+    def compress(self, x: torch.Tensor, qp: int, reset_feature_memory: bool, padding_b: int, padding_r: int):
+        """x: fp16 [1, 24, H, W] -> (bit_stream np.ndarray[uint8], ec_parallel)"""
+        hd = self._hd
+        assert x.is_cuda and x.dtype == torch.float16 and x.dim() == 4 and x.shape[1] == 3 * self.FRAMES
+        _, _, H, W = x.shape
+        bs, n, ec = C.c_void_p(), C.c_int32(), C.c_int32()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        hd.check(hd.lib.dcvc_compress_chunk(hd.h, C.c_void_p(x.data_ptr()), H, W, x.stride(1), x.stride(2), x.stride(3),
+                                            int(qp), 1 if reset_feature_memory else 0, int(padding_b), int(padding_r),
+                                            stream, C.byref(bs), C.byref(n), C.byref(ec)), "compress")
+        return np.ctypeslib.as_array(C.cast(bs, C.POINTER(C.c_uint8)), (n.value,)).copy(), ec.value
+
+    def decompress(self, bit_stream: np.ndarray, qp: int, height: int, width: int, ec_parallel: int,
+                   reset_feature_memory: bool):
+        """-> list of 8 fp16 channels_last tensors [1,3,H16p,W16p] (proxy-owned, reused by the next call)"""
+        hd = self._hd
+        bs = np.ascontiguousarray(bit_stream, dtype=np.uint8)
+        hp, wp = (height + 15) // 16 * 16, (width + 15) // 16 * 16
+        if self._x_hat is None or self._x_hat[0].shape[2] != hp or self._x_hat[0].shape[3] != wp:
+            dev = torch.device("cuda", hd.device)
+            self._x_hat = [torch.empty((1, 3, hp, wp), dtype=torch.float16, device=dev,
+                                       memory_format=torch.channels_last) for _ in range(self.FRAMES)]
+        ptrs = (C.c_void_p * self.FRAMES)(*[t.data_ptr() for t in self._x_hat])
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        hd.check(hd.lib.dcvc_decompress_chunk(hd.h, C.c_void_p(bs.ctypes.data), bs.size, int(qp), int(height), int(width),
+                                              int(ec_parallel), 1 if reset_feature_memory else 0, stream, ptrs),
+                 "decompress")
+        return self._x_hat
+
+    kernel_launches = DMCIProxy.kernel_launches
+    last_gpu_ms = DMCIProxy.last_gpu_ms
+    profile_enable = DMCIProxy.profile_enable
+    profile_get = DMCIProxy.profile_get
+    debug_fetch = DMCIProxy.debug_fetch

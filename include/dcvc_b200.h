@@ -160,6 +160,20 @@ int dcvc_decompress(dcvc_codec* h, const uint8_t* bit_stream, int32_t len, int32
                     int32_t height, int32_t width, int32_t ec_parallel, void* stream,
                     void* x_hat_out);
 
+/* Chunk codecs (DCVC_KIND_HTS): DMCHTSProxy::add_ref_feature_from_frame / compress / decompress
+ * (dmc_hts_proxy.cpp:492-502, 504-585, 587-710; bind.cpp:24-31).
+ * frame: fp16 [1,3,Hp,Wp] reconstruction (already padded to x16) with element strides;
+ * x: fp16 [1,24,H,W] = 8 stacked YUV444 frames; x_hat_out: 8 caller-owned fp16 NHWC [Hp][Wp][3] buffers. */
+int dcvc_add_ref_feature_from_frame(dcvc_codec* h, const void* frame, int32_t H, int32_t W, int64_t sc,
+                                    int64_t sh, int64_t sw, int32_t apply_adaptor, void* stream);
+int dcvc_compress_chunk(dcvc_codec* h, const void* x, int32_t H, int32_t W, int64_t sc, int64_t sh,
+                        int64_t sw, int32_t qp, int32_t reset_feature_memory, int32_t pad_b,
+                        int32_t pad_r, void* stream, const uint8_t** bit_stream,
+                        int32_t* bit_stream_len, int32_t* ec_parallel);
+int dcvc_decompress_chunk(dcvc_codec* h, const uint8_t* bit_stream, int32_t len, int32_t qp,
+                          int32_t height, int32_t width, int32_t ec_parallel,
+                          int32_t reset_feature_memory, void* stream, void* const* x_hat_out);
+
 /* instrumentation for bench.py: kernels launched by this handle since creation, and the GPU-only
  * duration (ms) of the segments of the last compress/decompress (CUDA events on `stream`). */
 int64_t dcvc_kernel_launches(dcvc_codec* h);

@@ -2,8 +2,11 @@
 (src/layers/extensions/inference/bind.cpp:11-38), backed by libdcvc_b200.so.
 
 Put the repository root on PYTHONPATH and the reference's own
-`from inference_extensions_cuda import DMCIProxy` (src/models/image_model.py:197) resolves here.
+`from inference_extensions_cuda import DMCIProxy` (src/models/image_model.py:197) /
+`from inference_extensions_cuda import DMCHTSProxy` (src/models/video_model_ht.py:420) resolve here.
+DMCHTLProxy / DMCLDProxy are not provided yet: importing them raises ImportError, which the reference
+turns into its NotImplementedError (video_model_ht.py:424-428, video_model_ld.py:280-284).
 """
-from dcvc_b200.proxy import DMCIProxy  # noqa: F401
+from dcvc_b200.proxy import DMCHTSProxy, DMCIProxy  # noqa: F401
 
-__all__ = ["DMCIProxy"]
+__all__ = ["DMCIProxy", "DMCHTSProxy"]
