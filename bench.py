@@ -81,22 +81,12 @@ def make_model(device, world, rank):
     import torch.distributed as dist
     from dcvc_b200.model import DMCI
     from dcvc_b200.spec import dmci_spec, synth_state_dict
+    from dcvc_b200.shard import broadcast_state_dict
     spec = dmci_spec()
     if world == 1:
         sd = synth_state_dict(spec, 0)
     else:
-        numel = sum(int(np.prod(s)) for s in spec.values())
-        blob = torch.empty(numel, dtype=torch.float32, device=device)
-        if rank == 0:
-            sd0 = synth_state_dict(spec, 0)
-            blob.copy_(torch.cat([sd0[k].reshape(-1) for k in spec]))
-        dist.broadcast(blob, 0)
-        sd, off = {}, 0
-        host = blob.cpu()
-        for k, s in spec.items():
-            n = int(np.prod(s))
-            sd[k] = host[off:off + n].view(s).clone()
-            off += n
+        sd = broadcast_state_dict(synth_state_dict(spec, 0) if rank == 0 else None, spec, 0, device)
     m = DMCI()
     m.load_state_dict(sd)
     m.update(SKIP)
@@ -211,6 +201,11 @@ def run_ours(args):
                     "whole_decode_alg_gbs": round(ALG_BYTES_DECODE / (gpu_only_ms * 1e-3) / 1e9, 1),
                     "whole_decode_frac": round(ALG_BYTES_DECODE / (gpu_only_ms * 1e-3) / 1e9 / hbm_peak, 4)}
 
+    # ---- HT-S chunk codec (configs[2]: the reference's published B200 headline) rides along
+    hts = None
+    if not args.no_hts:
+        hts = bench_hts(model, device, world, rank, args, timed, reduce_max)
+
     # ---- CPU baseline: the oracle port on the host cores (rank 0, N=1 only), bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -237,10 +232,83 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "hts": hts,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_hts(i_net, device, world, rank, args, timed, reduce_max):
+    """DCVC-UF HT-S 1080p chunk (8 frames) encode / decode after one intra frame (configs[2]); published B200
+    numbers of the reference's CUTLASS build: 1415.1 / 945.8 FPS."""
+    import torch.distributed as dist
+    from util_frames import psnr, synth_frame
+    from dcvc_b200.model import DMC
+    from dcvc_b200.shard import broadcast_state_dict
+    from dcvc_b200.spec import hts_spec, synth_state_dict
+    spec = hts_spec()
+    if world == 1:
+        sd = synth_state_dict(spec, 1)
+    else:
+        sd = broadcast_state_dict(synth_state_dict(spec, 1) if rank == 0 else None, spec, 0, device)
+    p_net = DMC()
+    p_net.load_state_dict(sd)
+    p_net.update(SKIP)
+    p_net = p_net.half().to(device)
+    pad_r, pad_b = i_net.get_padding_size(H, W, 16)
+    sps = {"height": H, "width": W}
+    x0 = synth_frame(H, W, 4000 + rank).half().to(device).contiguous(memory_format=torch.channels_last)
+    n_chunks = args.steps + args.warmup
+    chunks = [synth_frame(H, W, 4100 + 10 * rank + (c % 3), channels=24).half().to(device)
+              .contiguous(memory_format=torch.channels_last) for c in range(min(n_chunks, 3))]
+    enc = i_net.compress(x0, QP, pad_b, pad_r)
+    p_net.add_ref_feature_from_frame(enc["x_hat"])
+    state = {"c": 0, "streams": []}
+
+    def step_enc():
+        c = state["c"]
+        e = p_net.compress(chunks[c % len(chunks)], QP, 0, pad_b, pad_r)
+        state["streams"].append((e["bit_stream"], e["ec_parallel"]))
+        state["c"] += 1
+
+    for _ in range(args.warmup):
+        step_enc()
+    t_enc = timed(step_enc, args.steps)
+    streams = state["streams"]
+    d = i_net.decompress(enc["bit_stream"], sps, QP, enc["ec_parallel"])
+    p_net.add_ref_feature_from_frame(d["x_hat"], False)
+    state["c"] = 0
+
+    def step_dec():
+        bs, ec = streams[state["c"]]
+        state["x_hat"] = p_net.decompress(bs, sps, QP, ec, 0)["x_hat"]
+        state["c"] += 1
+
+    for _ in range(args.warmup):
+        step_dec()
+    l0 = p_net.proxy.kernel_launches()
+    t_dec = timed(step_dec, args.steps)
+    l1 = p_net.proxy.kernel_launches()
+    gpu_ms = p_net.proxy.last_gpu_ms()
+    tot_enc, tot_dec = reduce_max(sum(t_enc)), reduce_max(sum(t_dec))
+    last = (args.warmup + args.steps - 1) % len(chunks)
+    src = chunks[last][:, 0:3].float().cpu()
+    out = {
+        "workload": "DCVC-UF HT-S 1080p, 8-frame chunks after one intra frame, q_index 32, skip_thres 0.15 (configs[2])",
+        "decode_fps": round(world * 8 * args.steps / (tot_dec * 1e-3), 1),
+        "encode_fps": round(world * 8 * args.steps / (tot_enc * 1e-3), 1),
+        "ms_per_chunk_decode": round(tot_dec / args.steps, 3), "ms_per_chunk_encode": round(tot_enc / args.steps, 3),
+        "gpu_only_ms_per_chunk_decode": round(gpu_ms, 3),
+        "gpu_launches_per_chunk_decode": int((l1 - l0) // args.steps),
+        "bytes_per_chunk": int(np.mean([len(s[0]) for s in streams])),
+        "psnr_db_frame0": round(psnr(state["x_hat"][0].float().cpu()[:, :, :H, :W], src), 3),
+        "published_b200_reference_fps": {"encode": 1415.1, "decode": 945.8, "source": "BASELINE.md (assets/complexity.png)"},
+        "decode_vs_published": round(world * 8 * args.steps / (tot_dec * 1e-3) / 945.8, 3),
+        "alg_gbs_decode": round(14.09e9 / (gpu_ms * 1e-3) / 1e9, 1),
+    }
+    del p_net
+    return out
 
 
 def cpu_reference_sample(steps, sample_hw, threads=None):
@@ -250,7 +318,8 @@ def cpu_reference_sample(steps, sample_hw, threads=None):
     from util_frames import synth_frame
     from dcvc_b200.spec import dmci_spec, synth_state_dict
     from oracle.dmci_oracle import DmciOracle
-    cores = threads or os.cpu_count() or 1
+    # more than ~32 threads slows the small CPU convolutions of this model down (measured on the 128-core box)
+    cores = threads or min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     h, w = sample_hw
     o = DmciOracle(synth_state_dict(dmci_spec(), 0), skip_thres=SKIP, emulate_fp16=True, threads=cores)
@@ -277,7 +346,7 @@ def run_reference(args):
     from util_frames import synth_frame
     from dcvc_b200.spec import dmci_spec, synth_state_dict
     from oracle.dmci_oracle import DmciOracle
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     h, w = 272, 480
     o = DmciOracle(synth_state_dict(dmci_spec(), 0), skip_thres=SKIP, emulate_fp16=True, threads=cores)
@@ -312,6 +381,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hts", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -165,6 +165,7 @@ public:
         if (ev_hop_) cudaEventDestroy(ev_hop_);
         if (ev_y_) cudaEventDestroy(ev_y_);
         for (auto& e : tev_) cudaEventDestroy(e);
+        for (auto& e : prof_events_) cudaEventDestroy(e);
     }
 
     virtual void finalize(float skip_thres) = 0;
@@ -413,27 +414,31 @@ protected:
     {
         if (s.ops.empty()) return;
         if (profile_) {
-            cudaEvent_t e0, e1;
-            CK(cudaEventCreate(&e0));
-            CK(cudaEventCreate(&e1));
-            for (size_t i = 0; i < s.ops.size(); ++i) {
-                CK(cudaEventRecord(e0, stream));
+            // per-op CUDA-event timing (graphs off).  All ops of the segment are enqueued back to back with an
+            // event before and after each, and read only after the last one: the CPU runs ahead of the GPU, so an
+            // interval is the kernel's own duration (plus the inter-kernel gap), not the CPU launch latency.
+            const size_t n = s.ops.size();
+            while (prof_events_.size() < 2 * n) {
+                cudaEvent_t e;
+                CK(cudaEventCreate(&e));
+                prof_events_.push_back(e);
+            }
+            for (size_t i = 0; i < n; ++i) {
+                CK(cudaEventRecord(prof_events_[2 * i], stream));
                 if (s.ops[i](stream)) throw std::runtime_error(std::string("kernel launch failed: ") + gemm_last_error());
-                CK(cudaEventRecord(e1, stream));
-                CK(cudaEventSynchronize(e1));
+                CK(cudaEventRecord(prof_events_[2 * i + 1], stream));
+            }
+            CK(cudaEventSynchronize(prof_events_[2 * n - 1]));
+            const char* path = getenv("DCVC_B200_PROFILE_CSV");
+            FILE* f = path ? fopen(path, "a") : nullptr;
+            for (size_t i = 0; i < n; ++i) {
                 float ms = 0.f;
-                CK(cudaEventElapsedTime(&ms, e0, e1));
+                CK(cudaEventElapsedTime(&ms, prof_events_[2 * i], prof_events_[2 * i + 1]));
                 ProfileAcc& a = prof_[s.kinds[i]];
                 a.ms += ms; a.bytes += s.alg_bytes[i]; a.flops += s.flops[i]; a.launches += 1;
-                if (const char* path = getenv("DCVC_B200_PROFILE_CSV")) {
-                    if (FILE* f = fopen(path, "a")) {
-                        fprintf(f, "%d,%zu,%.3f,%.0f,%.0f\n", s.kinds[i], i, ms * 1e3, s.alg_bytes[i], s.flops[i]);
-                        fclose(f);
-                    }
-                }
+                if (f) fprintf(f, "%d,%zu,%.3f,%.0f,%.0f\n", s.kinds[i], i, ms * 1e3, s.alg_bytes[i], s.flops[i]);
             }
-            cudaEventDestroy(e0);
-            cudaEventDestroy(e1);
+            if (f) fclose(f);
             launches += s.launches;
             return;
         }
@@ -513,6 +518,7 @@ protected:
     cudaStream_t copy_stream_ = nullptr, own_stream_ = nullptr;
     cudaEvent_t ev_hop_ = nullptr, ev_y_ = nullptr;
     std::vector<cudaEvent_t> tev_;
+    std::vector<cudaEvent_t> prof_events_;
     int tev_n_ = 0;
     std::vector<uint8_t> bitstream_;
 };
