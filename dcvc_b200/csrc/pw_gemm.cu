@@ -118,19 +118,22 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ctrl + 256);
     __half* bias_all = reinterpret_cast<__half*>(ctrl + 512);
 
-    // tile schedule: streaming -> round-robin over (m, n) with n fastest; b_resident -> the CTA is
-    // pinned to N tile (blockIdx % n_tiles) and strides over the M tiles of that column.
-    const int my_nt = blockIdx.x % p.n_tiles;
-    const int my_j = blockIdx.x / p.n_tiles;
-    const int col_ctas = (static_cast<int>(gridDim.x) - my_nt + p.n_tiles - 1) / p.n_tiles;
-    auto tile_of = [&](int i) -> int {  // global tile id of this CTA's i-th tile, or -1
-        if (p.b_resident) {
-            const int mt = my_j + i * col_ctas;
-            return mt < p.m_tiles ? mt * p.n_tiles + my_nt : -1;
-        }
-        const int t = blockIdx.x + i * static_cast<int>(gridDim.x);
-        return t < p.total_tiles ? t : -1;
+    // tile schedule: a cluster of CS CTAs owns CS consecutive N tiles of one pixel tile (the activation tile is
+    // TMA-multicast to all of them); work items (pixel tile, N group) are dealt round-robin to the clusters.
+    // With CS == 1 this degenerates to one CTA per (pixel tile, N tile), N fastest.
+    const int CS = p.cluster;
+    const int rank = (CS > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+    const int cid = blockIdx.x / CS;
+    const int items = p.m_tiles * p.n_groups;
+    auto tile_of = [&](int i) -> int {  // global tile id (mt * n_tiles + nt) of this CTA's i-th tile, or -1
+        const int w = cid + i * p.num_clusters;
+        if (w >= items) return -1;
+        const int mt = w / p.n_groups;
+        const int ng = w - mt * p.n_groups;
+        return mt * p.n_tiles + ng * CS + rank;
     };
+    const int my_nt = rank;  // b_resident requires n_groups == 1: the CTA is pinned to N tile `rank`
+    const uint16_t mc_mask = static_cast<uint16_t>((1u << CS) - 1u);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -141,7 +144,7 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
         tma_prefetch_desc(&p.tm_c);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CS);  // every CTA of the cluster releases the (multicast) stage
         }
         mbar_init(slab_bar, 1);
         for (int g = 0; g < 2; ++g) {
@@ -156,6 +159,7 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();  // barriers of every CTA are initialised before any remote arrive / multicast
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -182,8 +186,14 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
                     const int kc = kb - tap * p.kblk_per_tap;
                     uint8_t* a_dst = a_base + s * a_stride;
                     mbar_expect_tx(&full_bar[s], p.b_resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES);
-                    tma_load_5d(a_dst, &p.tm_a, &full_bar[s], kc * BLOCK_K, p.tap_px[tap],
-                                tc.ox0 + p.tap_dx[tap], p.tap_py[tap], tc.oy0 + p.tap_dy[tap]);
+                    if (CS == 1) {
+                        tma_load_5d(a_dst, &p.tm_a, &full_bar[s], kc * BLOCK_K, p.tap_px[tap],
+                                    tc.ox0 + p.tap_dx[tap], p.tap_py[tap], tc.oy0 + p.tap_dy[tap]);
+                    } else if (static_cast<int>(it % CS) == rank) {
+                        // this CTA fetches the k-block for the whole cluster (one L2 read instead of CS)
+                        tma_load_5d_mc(a_dst, &p.tm_a, &full_bar[s], kc * BLOCK_K, p.tap_px[tap],
+                                       tc.ox0 + p.tap_dx[tap], p.tap_py[tap], tc.oy0 + p.tap_dy[tap], mc_mask);
+                    }
                     if (!p.b_resident) {
                         tma_load_2d(a_dst + A_STAGE_BYTES, &p.tm_b, &full_bar[s], kb * BLOCK_K, tc.n0);
                     }
@@ -216,12 +226,15 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
                                                          : a_addr + A_STAGE_BYTES;
                     const uint64_t a_desc = make_kmajor_sw128_desc(a_addr);
                     const uint64_t b_desc = make_kmajor_sw128_desc(b_addr);
+                    if (!(p.dbg & 1)) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        // advance 16 fp16 = 32 B inside the 128 B swizzle span: +2 in 16 B units
-                        umma_f16_ss(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            // advance 16 fp16 = 32 B inside the 128 B swizzle span: +2 in 16 B units
+                            umma_f16_ss(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
-                    umma_commit(&empty_bar[s]);
+                    if (CS == 1) umma_commit(&empty_bar[s]);
+                    else umma_commit_mc(&empty_bar[s], mc_mask);
                 }
                 umma_commit(&tmem_full_bar[g]);
             }
@@ -235,11 +248,22 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
         const int tg = (warp - 2 - 4 * g) * 32 + lane;  // thread index inside the group
         const bool issuer = (tg == 0);
         const uint32_t bar_id = 1 + g;
-        uint8_t* stage_g = staging + g * p.staging_bufs * SUB_TILE_BYTES;
+        // output sub-tile = one TMA store box: 64 columns (SWIZZLE_128B rows) or, for the 128-wide chunk-add
+        // tile, 32 columns (SWIZZLE_64B rows)
+        const bool out32 = p.chunk_add && BLOCK_N == 128;
+        const int sub_bytes = out32 ? SUB_TILE_BYTES / 2 : SUB_TILE_BYTES;
+        uint8_t* stage_g = staging + g * p.staging_bufs * sub_bytes;
         __half* bias_s = bias_all + g * BLOCK_N;
         const __half* qs = p.qscale;
-        const int n_sub = p.chunk_add ? 1 : BLOCK_N / 64;
+        constexpr int NC = BLOCK_N / 32;                     // accumulator chunks of 32 columns per tile
+        const int chunks_per_sub = p.chunk_add ? NC : 2;     // accumulator chunks feeding one store box
+        const int out_chunks = out32 ? 4 : 8;                // 16-byte output chunks per store-box row
         uint32_t cnt = 0;  // store-buffer counter of this group
+
+        auto sw_off = [&](int chunk) -> uint32_t {
+            return out32 ? static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4))
+                         : sw128_offset(row, chunk);
+        };
 
         for (int i = g;; i += 2) {
             const int tile = tile_of(i);
@@ -263,106 +287,125 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
             mbar_wait(&tmem_full_bar[g], u & 1);
             tcgen05_fence_after();
             const uint32_t acc = tmem_base + g * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+            if (p.dbg & 2) {  // micro-benchmark: drain nothing, just hand the accumulator back
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
+                continue;
+            }
 
-            for (int sub = 0; sub < n_sub; ++sub, ++cnt) {
-                uint8_t* sbuf = stage_g + ((p.staging_bufs == 2) ? (cnt & 1) : 0) * SUB_TILE_BYTES;
-                // residual prefetch for the 64 output columns of this sub-tile
-                uint4 r2v[8];
-                if (r2_row) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) r2v[j] = *reinterpret_cast<const uint4*>(r2_row + sub * 64 + j * 8);
-                }
-                // the store that used this buffer two sub-tiles ago must have drained
-                if (issuer) {
-                    if (p.staging_bufs == 2) tma_store_wait_read<1>();
-                    else tma_store_wait_read<0>();
-                }
-                named_bar_sync(bar_id, 128);
-                // first residual: asynchronous copy of this thread's 128-byte row segment into its own
-                // slots of the staging tile (L2 latency overlaps the TMEM loads and the activation math)
-                if (r1_row) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) cp_async_16(sbuf + sw128_offset(row, j), r1_row + sub * 64 + j * 8);
-                }
-                cp_async_commit();
-                bool res_ready = false;
-
-                if (p.chunk_add) {
-#pragma unroll
-                    for (int a = 0; a < 8; ++a) {  // 8 x 32 accumulator columns -> 8 x 8 outputs
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(acc + a * 32, v);
-                        tmem_ld_wait();
-                        float o[8];
+            // software-pipelined TMEM reads: chunk a+1 is in flight while chunk a is processed
+            uint32_t vn[32];
+            tmem_ld_32x32b_x32(acc, vn);
+            uint8_t* sbuf = nullptr;
+            bool res_ready = false;
+            uint4 r2v[8];
+            // NOT unrolled: the body is ~0.5 K instructions; unrolling NC x made the kernel 50-150 KB of SASS and
+            // the persistent loop thrashed the instruction cache (every launch also started I$-cold)
+#pragma unroll 1
+            for (int a = 0; a < NC; ++a) {
+                const int sub = a / chunks_per_sub;
+                const int a_in = a - sub * chunks_per_sub;
+                if (a_in == 0) {
+                    // ---- enter a store box: its staging buffer must be free again
+                    sbuf = stage_g + ((p.staging_bufs == 2) ? (cnt & 1) : 0) * sub_bytes;
+                    if (r2_row) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            float s4 = 0.f;
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float t = __uint_as_float(v[4 * j + e]) + __half2float(bias_s[a * 32 + 4 * j + e]);
-                                s4 += (p.act == ACT_WSILU) ? wsilu_f(t) : t;
-                            }
-                            o[j] = s4;
-                        }
-                        if (r1_row) {
-                            if (!res_ready) { cp_async_wait_all(); res_ready = true; }
-                            add_half8(o, *reinterpret_cast<const uint4*>(sbuf + sw128_offset(row, a)));
-                        }
-                        if (r2_row) add_half8(o, r2v[a]);
-                        if (qs) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] *= __half2float(qs[tc.oc0 + a * 8 + j]);
-                        }
-                        uint4 w;
-                        __half2* wh = reinterpret_cast<__half2*>(&w);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) wh[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
-                        *reinterpret_cast<uint4*>(sbuf + sw128_offset(row, a)) = w;
-                    }
-                } else {
-#pragma unroll
-                    for (int a = 0; a < 2; ++a) {  // 2 x 32 accumulator columns = 64 outputs
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(acc + sub * 64 + a * 32, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int gq = 0; gq < 4; ++gq) {
-                            const int oc = a * 4 + gq;  // 16-byte chunk inside the sub-tile
-                            float o[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float t = __uint_as_float(v[gq * 8 + j]) +
-                                                __half2float(bias_s[sub * 64 + oc * 8 + j]);
-                                o[j] = (p.act == ACT_WSILU) ? wsilu_f(t) : t;
-                            }
-                            if (r1_row) {
-                                if (!res_ready) { cp_async_wait_all(); res_ready = true; }
-                                add_half8(o, *reinterpret_cast<const uint4*>(sbuf + sw128_offset(row, oc)));
-                            }
-                            if (r2_row) add_half8(o, r2v[oc]);
-                            if (qs) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) o[j] *= __half2float(qs[tc.oc0 + sub * 64 + oc * 8 + j]);
-                            }
-                            uint4 w;
-                            __half2* wh = reinterpret_cast<__half2*>(&w);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) wh[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
-                            *reinterpret_cast<uint4*>(sbuf + sw128_offset(row, oc)) = w;
+                            if (j < out_chunks) r2v[j] = *reinterpret_cast<const uint4*>(r2_row + sub * 64 + j * 8);
                         }
                     }
+                    if (issuer) {
+                        if (p.staging_bufs == 2) tma_store_wait_read<1>();
+                        else tma_store_wait_read<0>();
+                    }
+                    named_bar_sync(bar_id, 128);
+                    // first residual: asynchronous copy of this thread's row segment into its own slots of the
+                    // staging tile (L2 latency overlaps the TMEM loads and the activation math)
+                    if (r1_row) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (j < out_chunks) cp_async_16(sbuf + sw_off(j), r1_row + sub * 64 + j * 8);
+                        }
+                    }
+                    cp_async_commit();
+                    res_ready = false;
                 }
-                if (sub == n_sub - 1) {
+                uint32_t v[32];
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = vn[j];
+                if (a + 1 < NC) {
+                    tmem_ld_32x32b_x32(acc + (a + 1) * 32, vn);
+                } else {
                     // every tcgen05.ld of this tile has completed: hand the accumulator back to the MMA warp
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
                 }
-                fence_proxy_async_smem();
-                named_bar_sync(bar_id, 128);
-                if (issuer) {
-                    tma_store_5d(&p.tm_c, sbuf, tc.oc0 + sub * 64, tc.opx, tc.ox0, tc.opy, tc.oy0);
-                    tma_store_commit();
+                if (p.chunk_add) {
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float s4 = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float t = __uint_as_float(v[4 * j + e]) + __half2float(bias_s[a * 32 + 4 * j + e]);
+                            s4 += (p.act == ACT_WSILU) ? wsilu_f(t) : t;
+                        }
+                        o[j] = s4;
+                    }
+                    uint8_t* dst = sbuf + sw_off(a_in);
+                    if (r1_row) {
+                        if (!res_ready) { cp_async_wait_all(); res_ready = true; }
+                        add_half8(o, *reinterpret_cast<const uint4*>(dst));
+                    }
+                    if (r2_row) add_half8(o, r2v[a_in & 7]);
+                    if (qs) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] *= __half2float(qs[tc.oc0 + a * 8 + j]);
+                    }
+                    uint4 w;
+                    __half2* wh = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) wh[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+                    *reinterpret_cast<uint4*>(dst) = w;
+                } else {
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) {
+                        const int oc = a_in * 4 + gq;  // 16-byte chunk inside the store box
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float t = __uint_as_float(v[gq * 8 + j]) + __half2float(bias_s[a * 32 + gq * 8 + j]);
+                            o[j] = (p.act == ACT_WSILU) ? wsilu_f(t) : t;
+                        }
+                        uint8_t* dst = sbuf + sw128_offset(row, oc);
+                        if (r1_row) {
+                            if (!res_ready) { cp_async_wait_all(); res_ready = true; }
+                            add_half8(o, *reinterpret_cast<const uint4*>(dst));
+                        }
+                        if (r2_row) add_half8(o, r2v[oc & 7]);
+                        if (qs) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] *= __half2float(qs[tc.oc0 + a * 32 + gq * 8 + j]);
+                        }
+                        uint4 w;
+                        __half2* wh = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) wh[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+                        *reinterpret_cast<uint4*>(dst) = w;
+                    }
+                }
+                if (a_in == chunks_per_sub - 1) {
+                    // ---- leave the store box: publish it
+                    fence_proxy_async_smem();
+                    named_bar_sync(bar_id, 128);
+                    if (issuer) {
+                        tma_store_5d(&p.tm_c, sbuf, tc.oc0 + sub * 64, tc.opx, tc.ox0, tc.opy, tc.oy0);
+                        tma_store_commit();
+                    }
+                    ++cnt;
                 }
             }
         }
@@ -371,6 +414,7 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
     }
 
     __syncthreads();
+    if (CS > 1) cluster_sync_all();  // no CTA may exit while peers can still multicast into it / arrive on its barriers
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -401,7 +445,8 @@ static EncodeTiledFn get_encode_fn()
 }
 
 static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box)
+                      const uint64_t* strides_bytes, const uint32_t* box,
+                      CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
@@ -419,7 +464,7 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
     }
     for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx,
-                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[256];
@@ -436,12 +481,13 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
 }
 
 // 5-D map of an NHWC view.  split2: expose the 2x2 pixel phases as dims 1 and 3.
-static int encode_act_map(CUtensorMap* m, const ActView& v, bool split2, bool linear, int bw, int bh)
+static int encode_act_map(CUtensorMap* m, const ActView& v, bool split2, bool linear, int bw, int bh,
+                          int box_c = 64)
 {
     const uint64_t pb = static_cast<uint64_t>(v.pitch) * 2;
     uint64_t dims[5];
     uint64_t st[4];
-    uint32_t box[5] = { 64, 1, static_cast<uint32_t>(bw), 1, static_cast<uint32_t>(bh) };
+    uint32_t box[5] = { static_cast<uint32_t>(box_c), 1, static_cast<uint32_t>(bw), 1, static_cast<uint32_t>(bh) };
     if (linear) {
         const uint64_t M = static_cast<uint64_t>(v.W) * v.H;
         dims[0] = v.C; dims[1] = 1; dims[2] = M; dims[3] = 1; dims[4] = 1;
@@ -456,24 +502,135 @@ static int encode_act_map(CUtensorMap* m, const ActView& v, bool split2, bool li
         st[3] = static_cast<uint64_t>(v.W) * pb;
     }
     if (box[0] > dims[0]) box[0] = static_cast<uint32_t>(dims[0]);
-    return encode_map(m, v.ptr, 5, dims, st, box);
+    return encode_map(m, v.ptr, 5, dims, st, box,
+                      box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-static int pick_block_n(int n_unit, bool chunk_add, long long m_tiles)
+struct TilePlan {
+    int bn = 0;
+    bool resident = false;
+    int stages = 0;
+    int staging_bufs = 2;
+    int cluster = 1;
+};
+
+// Chooses the N tile, the cluster size and the smem carve-up.
+// Measured on B200 (tools/gemm_micro.py, DCVC_B200_GEMM_DBG=3): the activation stream out of L2/HBM tops out at
+// ~7 TB/s chip-wide, i.e. every re-read of the activation tensor by another N tile costs as much as reading it
+// from HBM.  So the CTAs that need the same pixel tile form a cluster and share ONE TMA-multicast copy of it
+// (cluster size = N tiles, <= 8); the [bn][K] weight slab stays resident in smem when the CTA is pinned to its
+// N tile and >= 4 activation stages still fit.
+static TilePlan pick_tile_plan(int n_unit, int n_total, bool chunk_add, long long m_tiles, int num_kblocks, int num_sms)
 {
-    if (chunk_add) return 256;
-    int bn;
-    if (n_unit % 256 == 0) bn = 256;
-    else if (n_unit % 192 == 0) bn = 192;
-    else if (n_unit % 128 == 0) bn = 128;
-    else if (n_unit % 64 == 0) bn = 64;
-    else return 0;
-    // small problems: prefer more tiles (one persistent CTA per SM, 148 SMs) over wider tiles
-    while (bn > 64 && m_tiles * (n_unit / bn) < 148 && (bn % 2 == 0) && (n_unit % (bn / 2) == 0) &&
-           ((bn / 2) % 64 == 0)) {
-        bn /= 2;
+    TilePlan best;
+    const int cand_all[4] = { 256, 192, 128, 64 };
+    int force_bn = 0, force_sb = 0, force_cs = -1;
+    if (const char* f = getenv("DCVC_B200_GEMM_BN")) force_bn = atoi(f);
+    if (const char* f = getenv("DCVC_B200_GEMM_STAGING")) force_sb = atoi(f);
+    if (const char* f = getenv("DCVC_B200_GEMM_CLUSTER")) force_cs = atoi(f);
+    const char* force_mode = getenv("DCVC_B200_GEMM_MODE");
+    double best_cost = 1e30;
+    for (int ci = 0; ci < 4; ++ci) {
+        const int bn = cand_all[ci];
+        if (n_unit % bn) continue;
+        if (chunk_add && bn < 128) continue;
+        if (force_bn && bn != force_bn) continue;
+        const int n_tiles = n_total / bn;
+        const int out_cols = chunk_add ? bn / 4 : bn;
+        const int sub_bytes = (out_cols == 32) ? SUB_TILE_BYTES / 2 : SUB_TILE_BYTES;
+        const int b_stage = bn * BLOCK_K * 2;
+        const int slab = num_kblocks * b_stage;
+        // cluster size: the largest divisor of n_tiles that is <= 8
+        int cs = 1;
+        for (int c = 8; c >= 1; --c) {
+            if (n_tiles % c == 0) { cs = c; break; }
+        }
+        if (force_cs >= 1 && n_tiles % force_cs == 0 && force_cs <= 8) cs = force_cs;
+        const int n_groups = n_tiles / cs;
+        const long long items = m_tiles * n_groups;
+        const int max_clusters = num_sms / cs;
+        const int clusters = static_cast<int>(items < max_clusters ? items : max_clusters);
+        if (clusters < 1) continue;
+        const long long per_cluster = (items + clusters - 1) / clusters;
+        for (int mode = 0; mode < 2; ++mode) {  // 0 = resident, 1 = streaming
+            TilePlan t;
+            t.bn = bn;
+            t.cluster = cs;
+            if (mode == 0) {
+                if (force_mode && force_mode[0] == 's') continue;
+                if (n_groups != 1 || per_cluster < 2) continue;  // pinned N tile + actual reuse
+                t.resident = true;
+                t.staging_bufs = force_sb ? force_sb : 1;
+                t.stages = (SMEM_USABLE - slab - EPI_GROUPS * t.staging_bufs * sub_bytes) / A_STAGE_BYTES;
+                if (t.stages < 4) continue;
+            } else {
+                if (force_mode && force_mode[0] == 'r') continue;
+                t.resident = false;
+                t.staging_bufs = force_sb ? force_sb : 2;
+                t.stages = (SMEM_USABLE - EPI_GROUPS * t.staging_bufs * sub_bytes) / (A_STAGE_BYTES + b_stage);
+                if (t.stages < 2) continue;
+            }
+            if (t.stages > MAX_STAGES) t.stages = MAX_STAGES;
+            // cost model (arbitrary time units per pixel tile of the whole problem):
+            //   activation stream: one 16 KB k-block per N group (multicast) at the ~7 TB/s chip-wide cap,
+            //   weight stream when not resident (hot in L2, ~3x cheaper per byte), tensor pipe, all scaled by the
+            //   wave quantisation of the persistent grid and a latency penalty for shallow pipelines
+            const double act = static_cast<double>(n_groups) * num_kblocks * A_STAGE_BYTES;
+            const double wgt = t.resident ? 0.0 : static_cast<double>(n_tiles) * num_kblocks * b_stage / 3.0;
+            const double mma = static_cast<double>(n_total) * num_kblocks * 64.0 * 128.0 / 1500.0;  // ~bytes-equivalent
+            const double quant = static_cast<double>(per_cluster) * clusters / static_cast<double>(items);
+            const double depth = 1.0 + 1.5 / t.stages;
+            const double cost = (act + wgt > mma ? act + wgt : mma) * quant * depth * (static_cast<double>(num_sms) / (clusters * cs));
+            if (cost < best_cost) {
+                best_cost = cost;
+                best = t;
+            }
+        }
     }
-    return bn;
+    return best;
+}
+
+template <int BN>
+static int max_clusters_for(int cluster)
+{
+    if (gemm_init()) return 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(cluster * 64, 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SMEM_TOTAL;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, pw_gemm_kernel<BN>, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// co-resident clusters of `cluster` CTAs (GPC boundaries strand some SMs); cached per (bn, cluster)
+static int max_active_clusters(int bn, int cluster, int num_sms)
+{
+    static int cache[4][9];
+    const int bi = bn == 64 ? 0 : bn == 128 ? 1 : bn == 192 ? 2 : 3;
+    if (cluster <= 1) return num_sms;
+    if (cache[bi][cluster] == 0) {
+        int n = 0;
+        switch (bn) {
+        case 64: n = max_clusters_for<64>(cluster); break;
+        case 128: n = max_clusters_for<128>(cluster); break;
+        case 192: n = max_clusters_for<192>(cluster); break;
+        default: n = max_clusters_for<256>(cluster); break;
+        }
+        cache[bi][cluster] = n > 0 ? n : num_sms / cluster;
+    }
+    return cache[bi][cluster];
 }
 
 int gemm_plan(GemmOp& op)
@@ -551,7 +708,16 @@ int gemm_plan(GemmOp& op)
     m_tiles = static_cast<long long>(tiles_x) * tiles_y;
 
     const int n_unit = (op.kind == GEMM_TCONV2X2) ? op.out.C : op.N;
-    const int bn = pick_block_n(n_unit, op.chunk_add != 0, m_tiles);
+    int num_sms = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) {
+            int v = 0;
+            if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) num_sms = v;
+        }
+    }
+    const TilePlan tp = pick_tile_plan(n_unit, op.N, op.chunk_add != 0, m_tiles, taps * C / 64, num_sms);
+    const int bn = tp.bn;
     if (bn == 0 || op.N % bn != 0) { g_err = "gemm_plan: unsupported N"; return 1; }
     const int out_c_expected = op.chunk_add ? op.N / 4 : (op.kind == GEMM_TCONV2X2 ? op.N / 4 : op.N);
     if (op.out.C != out_c_expected) { g_err = "gemm_plan: out.C does not match N"; return 1; }
@@ -577,7 +743,8 @@ int gemm_plan(GemmOp& op)
         if (encode_map(&p.tm_b, op.weight, 2, dims, st, box)) return 1;
     }
     const bool out_split = (op.kind == GEMM_TCONV2X2);
-    if (encode_act_map(&p.tm_c, op.out, out_split, linear, p.bw, p.bh)) return 1;
+    const int out_box_c = (op.chunk_add && bn == 128) ? 32 : 64;
+    if (encode_act_map(&p.tm_c, op.out, out_split, linear, p.bw, p.bh, out_box_c)) return 1;
     if (op.res1.ptr) {
         if (op.kind == GEMM_TCONV2X2) { g_err = "gemm_plan: tconv takes no residual"; return 1; }
         const ActView* rs[2] = { &op.res1, &op.res2 };
@@ -605,46 +772,22 @@ int gemm_plan(GemmOp& op)
     p.n_tiles = op.N / bn;
     p.tiles_x = tiles_x;
     p.total_tiles = static_cast<int>(m_tiles) * p.n_tiles;
-    int num_sms = 148;
+    p.cluster = tp.cluster;
+    p.n_groups = p.n_tiles / p.cluster;
     {
-        int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess) {
-            int v = 0;
-            if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) num_sms = v;
-        }
+        const long long items = m_tiles * p.n_groups;
+        const int max_clusters = max_active_clusters(bn, p.cluster, num_sms);
+        p.num_clusters = static_cast<int>(items < max_clusters ? items : max_clusters);
     }
     p.m_tiles = static_cast<int>(m_tiles);
-    op.grid = dim3(p.total_tiles < num_sms ? p.total_tiles : num_sms, 1, 1);
+    op.grid = dim3(p.num_clusters * p.cluster, 1, 1);
     op.smem = SMEM_TOTAL;
-    {
-        // carve-up of the 227 KB (see the kernel): weights resident when the CTA reuses its slab for
-        // >= 2 M tiles and >= 3 activation stages still fit; otherwise stream A+B stages.
-        const int b_stage = bn * BLOCK_K * 2;
-        const int slab = p.num_kblocks * b_stage;
-        const int grid_n = static_cast<int>(op.grid.x);
-        const bool reuse = grid_n >= p.n_tiles && (m_tiles * p.n_tiles) >= 2LL * grid_n;
-        int staging_bufs = 2;
-        int a_stages = (SMEM_USABLE - slab - EPI_GROUPS * 2 * SUB_TILE_BYTES) / A_STAGE_BYTES;
-        if (reuse && a_stages < 3) {
-            staging_bufs = 1;
-            a_stages = (SMEM_USABLE - slab - EPI_GROUPS * 1 * SUB_TILE_BYTES) / A_STAGE_BYTES;
-        }
-        const char* force = getenv("DCVC_B200_GEMM_MODE");  // "stream" | "resident" (debug / A-B tests)
-        bool resident = reuse && slab < SMEM_USABLE && a_stages >= 3;
-        if (force && force[0] == 's') resident = false;
-        if (resident) {
-            p.b_resident = 1;
-            p.num_stages = a_stages > MAX_STAGES ? MAX_STAGES : a_stages;
-            p.staging_bufs = staging_bufs;
-        } else {
-            p.b_resident = 0;
-            int st = (SMEM_USABLE - EPI_GROUPS * 2 * SUB_TILE_BYTES) / (A_STAGE_BYTES + b_stage);
-            p.num_stages = st > MAX_STAGES ? MAX_STAGES : st;
-            p.staging_bufs = 2;
-        }
-        op.stages = p.num_stages;
-        if (p.num_stages < 2) { g_err = "gemm_plan: pipeline does not fit"; return 1; }
-    }
+    p.b_resident = tp.resident ? 1 : 0;
+    p.num_stages = tp.stages;
+    p.staging_bufs = tp.staging_bufs;
+    if (const char* d = getenv("DCVC_B200_GEMM_DBG")) p.dbg = atoi(d);
+    op.stages = p.num_stages;
+    if (p.num_stages < 2) { g_err = "gemm_plan: pipeline does not fit"; return 1; }
     if (!op.chunk_add && bn % 64 != 0) { g_err = "gemm_plan: BLOCK_N must be a multiple of 64"; return 1; }
     op.planned = true;
     return 0;
@@ -675,8 +818,20 @@ int gemm_init()
 template <int BN>
 static cudaError_t launch_bn(const GemmOp& op, cudaStream_t stream)
 {
-    pw_gemm_kernel<BN><<<op.grid, NUM_THREADS, op.smem, stream>>>(op.p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = op.grid;
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = op.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = op.p.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, pw_gemm_kernel<BN>, op.p);
 }
 
 int gemm_launch(const GemmOp& op, cudaStream_t stream)

@@ -50,6 +50,10 @@ struct alignas(64) PwGemmParams {
     int b_resident;        // 1: the CTA keeps the whole [BLOCK_N][K] weight slab of its N tile in smem
     int num_stages;        // pipeline depth (A+B stages when streaming, A-only stages when b_resident)
     int staging_bufs;      // store staging buffers per epilogue group (1 or 2)
+    int cluster;           // CTAs per cluster = N tiles that share one multicast activation tile (1: no cluster)
+    int n_groups;          // n_tiles / cluster
+    int num_clusters;      // gridDim.x / cluster
+    int dbg;               // micro-benchmark switches (env DCVC_B200_GEMM_DBG): 1 = no MMA, 2 = no epilogue body
     int num_kblocks;       // taps * C / 64
     int kblk_per_tap;      // C / 64
     int bw, bh;            // pixel tile, bw*bh == 128
