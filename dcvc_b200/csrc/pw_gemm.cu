@@ -125,14 +125,23 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
     const int rank = (CS > 1) ? static_cast<int>(cluster_ctarank()) : 0;
     const int cid = blockIdx.x / CS;
     const int items = p.m_tiles * p.n_groups;
+    // weight-resident CTAs without a cluster are pinned to N tile (blockIdx % n_tiles) and stride over its pixel tiles
+    const bool pinned = p.b_resident && CS == 1;
+    const int pin_nt = blockIdx.x % p.n_tiles;
+    const int pin_j = blockIdx.x / p.n_tiles;
+    const int pin_ctas = (static_cast<int>(gridDim.x) - pin_nt + p.n_tiles - 1) / p.n_tiles;
     auto tile_of = [&](int i) -> int {  // global tile id (mt * n_tiles + nt) of this CTA's i-th tile, or -1
+        if (pinned) {
+            const int mt = pin_j + i * pin_ctas;
+            return mt < p.m_tiles ? mt * p.n_tiles + pin_nt : -1;
+        }
         const int w = cid + i * p.num_clusters;
         if (w >= items) return -1;
         const int mt = w / p.n_groups;
         const int ng = w - mt * p.n_groups;
         return mt * p.n_tiles + ng * CS + rank;
     };
-    const int my_nt = rank;  // b_resident requires n_groups == 1: the CTA is pinned to N tile `rank`
+    const int my_nt = pinned ? pin_nt : rank;  // N tile whose weight slab stays resident
     const uint16_t mc_mask = static_cast<uint16_t>((1u << CS) - 1u);
 
     const int warp = threadIdx.x >> 5;
@@ -540,11 +549,11 @@ static TilePlan pick_tile_plan(int n_unit, int n_total, bool chunk_add, long lon
         const int sub_bytes = (out_cols == 32) ? SUB_TILE_BYTES / 2 : SUB_TILE_BYTES;
         const int b_stage = bn * BLOCK_K * 2;
         const int slab = num_kblocks * b_stage;
-        // cluster size: the largest divisor of n_tiles that is <= 8
+        // cluster size.  Measured (tools/micro.sh, r1): with clusters of 3-6 CTAs the per-k-block cluster-wide
+        // stage release (tcgen05.commit multicast to every CTA) costs more than the multicast saves — 42 us vs
+        // 25 us for M=32640,N=K=384 — and B200's L2 already de-duplicates near-simultaneous unicast reads of a
+        // line.  Clusters therefore stay opt-in (DCVC_B200_GEMM_CLUSTER=n) until the release protocol is reworked.
         int cs = 1;
-        for (int c = 8; c >= 1; --c) {
-            if (n_tiles % c == 0) { cs = c; break; }
-        }
         if (force_cs >= 1 && n_tiles % force_cs == 0 && force_cs <= 8) cs = force_cs;
         const int n_groups = n_tiles / cs;
         const long long items = m_tiles * n_groups;
@@ -558,7 +567,9 @@ static TilePlan pick_tile_plan(int n_unit, int n_total, bool chunk_add, long lon
             t.cluster = cs;
             if (mode == 0) {
                 if (force_mode && force_mode[0] == 's') continue;
-                if (n_groups != 1 || per_cluster < 2) continue;  // pinned N tile + actual reuse
+                if (cs > 1 && n_groups != 1) continue;                                   // cluster CTAs: N tile = rank
+                if (cs == 1 && (clusters < n_tiles || m_tiles * n_tiles < 2LL * clusters)) continue;  // pinned + reuse
+                if (cs > 1 && per_cluster < 2) continue;
                 t.resident = true;
                 t.staging_bufs = force_sb ? force_sb : 1;
                 t.stages = (SMEM_USABLE - slab - EPI_GROUPS * t.staging_bufs * sub_bytes) / A_STAGE_BYTES;
@@ -778,6 +789,8 @@ int gemm_plan(GemmOp& op)
         const long long items = m_tiles * p.n_groups;
         const int max_clusters = max_active_clusters(bn, p.cluster, num_sms);
         p.num_clusters = static_cast<int>(items < max_clusters ? items : max_clusters);
+        // pinned weight-resident CTAs: the same number of CTAs for every N tile
+        if (tp.resident && p.cluster == 1) p.num_clusters -= p.num_clusters % p.n_tiles;
     }
     p.m_tiles = static_cast<int>(m_tiles);
     op.grid = dim3(p.num_clusters * p.cluster, 1, 1);
