@@ -154,6 +154,8 @@ void IntraCodec::plan(int height, int width)
     bytes += quarter_ * (2 + 1 + 4 * 2 + 1 + 1) + p16 * 4 * 6 + (1u << 20);
     bytes += 64 * 1024;  // alignment slack per allocation
     arena_.reserve(bytes + (4u << 20));
+    dbg_base_ = arena_.base();
+    dbg_bytes_ = bytes + (4u << 20);
     auto half_buf = [&](size_t n) { return static_cast<__half*>(arena_.alloc(n * 2)); };
 
     l8_.H = H8; l8_.W = W8;

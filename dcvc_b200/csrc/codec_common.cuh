@@ -50,6 +50,20 @@ struct HostTensor {
     }
 };
 
+// debugging aid (DCVC_B200_OPSUM): order-sensitive checksum of a device range
+static __global__ void view_checksum_kernel(const uint16_t* __restrict__ p, int Cc, int pitch, size_t n_elems,
+                                            unsigned long long* out)
+{
+    unsigned long long acc = 0;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_elems;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t px = i / Cc;
+        acc += static_cast<unsigned long long>(p[px * pitch + (i - px * Cc)]) * (2 * i + 1);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 // bump allocator over one cudaMalloc block
 class Arena {
 public:
@@ -76,6 +90,7 @@ public:
     }
     __half* halves(size_t n) { return static_cast<__half*>(alloc(n * 2)); }
     size_t used() const { return used_; }
+    void* base() const { return base_; }
 
 private:
     void* base_ = nullptr;
@@ -113,6 +128,8 @@ struct Segment {
     std::vector<int> kinds;         // OpKind per op (kept in step with `ops`)
     std::vector<double> alg_bytes;  // algorithmic bytes per op (activations in + residuals in + out)
     std::vector<double> flops;
+    std::vector<ActView> out_views; // output view per op where known (DCVC_B200_OPSUM debugging)
+    std::vector<std::string> notes;
     cudaGraphExec_t exec = nullptr;
     int launches = 0;
     void annotate(int kind, double bytes, double fl)
@@ -357,6 +374,17 @@ protected:
         if (gemm_plan(*op)) throw std::runtime_error(std::string("gemm_plan: ") + gemm_last_error());
         s.annotate(OP_ELEM, 0, 0);
         s.ops.push_back([op](cudaStream_t st) { return gemm_launch(*op, st); });
+        s.out_views.resize(s.ops.size());
+        s.out_views.back() = out;
+        {
+            char buf[256];
+            snprintf(buf, sizeof(buf), "gemm kind=%d in=%dx%dx%d/%d@%p out=%d/%d@%p N=%d act=%d chunk=%d res=%p,%p bn=%d st=%d resident=%d sb=%d grid=%u",
+                     kind, in.H, in.W, in.C, in.pitch, in.ptr, out.C, out.pitch, out.ptr, N, act, chunk,
+                     r1 ? r1->ptr : nullptr, r2 ? r2->ptr : nullptr, op->block_n, op->stages, op->p.b_resident,
+                     op->p.staging_bufs, op->grid.x);
+            s.notes.resize(s.ops.size());
+            s.notes.back() = buf;
+        }
         const double px_in = static_cast<double>(in.W) * in.H, px_out = static_cast<double>(out.W) * out.H;
         const int taps = (kind == GEMM_CONV3X3_S2) ? 9 : (kind == GEMM_CONV2X2_S2 ? 4 : 1);
         double bytes = px_in * in.C * 2 + px_out * out.C * 2;
@@ -400,6 +428,8 @@ protected:
             const __half* wdw = w.wdw;
             s.annotate(OP_ELEM, 0, 0);
             s.ops.push_back([t1, t2, wdw](cudaStream_t st) { return launch_dw3x3(t1, t2, wdw, st); });
+            s.out_views.resize(s.ops.size());
+            s.out_views.back() = t2;
             s.annotate(OP_DW, 2.0 * 2 * W * H * w.inner, 2.0 * 9 * W * H * w.inner);
         }
         add_gemm(s, GEMM_PW, t2, o, w.w3, w.b3, w.c, ACT_NONE, 0, &x, nullptr, nullptr);
@@ -437,6 +467,28 @@ protected:
                 ProfileAcc& a = prof_[s.kinds[i]];
                 a.ms += ms; a.bytes += s.alg_bytes[i]; a.flops += s.flops[i]; a.launches += 1;
                 if (f) fprintf(f, "%d,%zu,%.3f,%.0f,%.0f\n", s.kinds[i], i, ms * 1e3, s.alg_bytes[i], s.flops[i]);
+            }
+            if (f) fclose(f);
+            launches += s.launches;
+            return;
+        }
+        if (const char* path = getenv("DCVC_B200_OPSUM")) {
+            // debugging aid: run op by op and log a checksum of each op's output view (GEMMs, dw3x3), so two
+            // runs of the same input can be diffed down to the first op that disagrees
+            if (!opsum_dev_) CK(cudaMalloc(&opsum_dev_, 8));
+            FILE* f = fopen(path, "a");
+            for (size_t i = 0; i < s.ops.size(); ++i) {
+                if (s.ops[i](stream)) throw std::runtime_error(std::string("kernel launch failed: ") + gemm_last_error());
+                CK(cudaMemsetAsync(opsum_dev_, 0, 8, stream));
+                const ActView ov = i < s.out_views.size() ? s.out_views[i] : ActView();
+                if (ov.ptr)
+                    view_checksum_kernel<<<1184, 256, 0, stream>>>(static_cast<const uint16_t*>(ov.ptr), ov.C, ov.pitch,
+                                                                   static_cast<size_t>(ov.W) * ov.H * ov.C, opsum_dev_);
+                unsigned long long h = 0;
+                CK(cudaMemcpyAsync(&h, opsum_dev_, 8, cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+                if (f) fprintf(f, "%p %zu kind=%d %s %016llx\n", static_cast<void*>(&s), i, s.kinds[i],
+                               i < s.notes.size() ? s.notes[i].c_str() : "-", h);
             }
             if (f) fclose(f);
             launches += s.launches;
@@ -510,6 +562,9 @@ protected:
     int device_;
     bool finalized_ = false;
     bool use_graphs_ = true;
+    void* dbg_base_ = nullptr;      // activation arena (DCVC_B200_OPSUM)
+    size_t dbg_bytes_ = 0;
+    unsigned long long* opsum_dev_ = nullptr;
     float skip_thres_ = 0.f;
     std::map<std::string, HostTensor> params_;
     Arena warena_;

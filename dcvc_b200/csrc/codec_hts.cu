@@ -175,6 +175,8 @@ void HtsCodec::plan(int height, int width)
     bytes += p32 * 2 * 4 * 256 + p64 * 2 * 4 * 256 + p64 * kZ * 3;
     bytes += n_lat_ * (1 + 2 + 2 + 1 + 1 + 1) + p16 * 8 + (2u << 20) + 64 * 4096;
     arena_.reserve(bytes);
+    dbg_base_ = arena_.base();
+    dbg_bytes_ = bytes;
 
     cat_enc_ = arena_.halves(p8 * 2048);
     cat_fam_ = arena_.halves(p8 * 1024);

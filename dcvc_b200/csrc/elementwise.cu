@@ -26,6 +26,13 @@ static inline int blocks_for(long long n, int threads) { return static_cast<int>
 // traffic per output drops from ~3 input rows to (DW_TY + 2) / DW_TY.
 static constexpr int DW_TY = 4;
 
+// d = a * b + c with fp16 a, b and fp32 c, d in one instruction (FHFMA)
+__device__ __forceinline__ float fma_f32_f16(uint16_t a, uint16_t b, float c)
+{
+    asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(c) : "h"(a), "h"(b));
+    return c;
+}
+
 __device__ __forceinline__ void dw_load_row(const __half* in, int in_pitch, int W, int H, int x, int yy, int c,
                                             uint4 (&q)[3])
 {
@@ -61,33 +68,34 @@ dw3x3_kernel(const __half* __restrict__ in, int in_pitch, __half* __restrict__ o
 #pragma unroll
     for (int k = 0; k < 9; ++k) wk[k] = __ldg(reinterpret_cast<const uint4*>(w + k * C + c));
 
-    // The kernel was instruction-bound with per-element fp32 FMAs + conversions (~28 instr / output element).
-    // Now each kernel ROW (3 taps) is a packed HMUL2/HFMA2 chain in fp16 and the three row partials are summed in
-    // fp32: ~5 instr / output element, error of a 3-term fp16 sum (the reference accumulates all 9 taps in fp32).
+    // The kernel was instruction-bound with per-element conversions + fp32 FMAs (~28 instr / output element).
+    // sm_100 has a mixed-precision FMA (PTX fma.rn.f32.f16 -> SASS FHFMA, with .H0/.H1 operand selectors): fp16
+    // operands straight out of the packed registers, fp32 accumulate — 9 instructions per output element and
+    // bit-identical to fmaf(half2float(v), half2float(k), acc), i.e. the reference's fp32 accumulation.
 #pragma unroll
     for (int r = 0; r < DW_TY; ++r) {
         const int y = y0 + r;
         if (y >= H) break;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const uint32_t* vh = reinterpret_cast<const uint32_t*>(&rows[r + ky][kx]);
+                const uint32_t* kh = reinterpret_cast<const uint32_t*>(&wk[ky * 3 + kx]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[2 * i] = fma_f32_f16(static_cast<uint16_t>(vh[i] & 0xffffu), static_cast<uint16_t>(kh[i] & 0xffffu), acc[2 * i]);
+                    acc[2 * i + 1] = fma_f32_f16(static_cast<uint16_t>(vh[i] >> 16), static_cast<uint16_t>(kh[i] >> 16), acc[2 * i + 1]);
+                }
+            }
+        }
         uint4 o;
         __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const __half2 v0 = reinterpret_cast<const __half2*>(&rows[r + ky][0])[i];
-                const __half2 v1 = reinterpret_cast<const __half2*>(&rows[r + ky][1])[i];
-                const __half2 v2 = reinterpret_cast<const __half2*>(&rows[r + ky][2])[i];
-                const __half2 k0 = reinterpret_cast<const __half2*>(&wk[ky * 3 + 0])[i];
-                const __half2 k1 = reinterpret_cast<const __half2*>(&wk[ky * 3 + 1])[i];
-                const __half2 k2 = reinterpret_cast<const __half2*>(&wk[ky * 3 + 2])[i];
-                const __half2 part = __hfma2(v2, k2, __hfma2(v1, k1, __hmul2(v0, k0)));
-                const float2 pf = __half22float2(part);
-                acc.x += pf.x;
-                acc.y += pf.y;
-            }
-            oh[i] = __floats2half2_rn(acc.x, acc.y);
-        }
+        for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
         *reinterpret_cast<uint4*>(out + (static_cast<long long>(y) * W + x) * out_pitch + c) = o;
     }
 }

@@ -542,7 +542,7 @@ static TilePlan pick_tile_plan(int n_unit, int n_total, bool chunk_add, long lon
     for (int ci = 0; ci < 4; ++ci) {
         const int bn = cand_all[ci];
         if (n_unit % bn) continue;
-        if (chunk_add && bn < 128) continue;
+        if (chunk_add && bn != 128 && bn != 256) continue;  // 4->1 fold: the store box is 32 or 64 output columns
         if (force_bn && bn != force_bn) continue;
         const int n_tiles = n_total / bn;
         const int out_cols = chunk_add ? bn / 4 : bn;
@@ -566,7 +566,9 @@ static TilePlan pick_tile_plan(int n_unit, int n_total, bool chunk_add, long lon
             t.bn = bn;
             t.cluster = cs;
             if (mode == 0) {
-                if (force_mode && force_mode[0] == 's') continue;
+                // measured slower than streaming on every codec shape (tools/run14.sh: 26.9 vs 24.7 us, 77 vs 53 us):
+                // the smaller N tile it forces re-reads the activations more often.  Kept as an opt-in experiment.
+                if (!force_mode || force_mode[0] != 'r') continue;
                 if (cs > 1 && n_groups != 1) continue;                                   // cluster CTAs: N tile = rank
                 if (cs == 1 && (clusters < n_tiles || m_tiles * n_tiles < 2LL * clusters)) continue;  // pinned + reuse
                 if (cs > 1 && per_cluster < 2) continue;
@@ -802,6 +804,7 @@ int gemm_plan(GemmOp& op)
     op.stages = p.num_stages;
     if (p.num_stages < 2) { g_err = "gemm_plan: pipeline does not fit"; return 1; }
     if (!op.chunk_add && bn % 64 != 0) { g_err = "gemm_plan: BLOCK_N must be a multiple of 64"; return 1; }
+    if (op.chunk_add && bn != 128 && bn != 256) { g_err = "gemm_plan: chunk-add needs BLOCK_N 128 or 256"; return 1; }
     op.planned = true;
     return 0;
 }

@@ -85,6 +85,28 @@ def test_chunk_roundtrip_state_consistency(nets, h, w, n_chunks, reset_at):
     assert all(len(s[1]) > 4 for s in streams)
 
 
+def test_chunk_encode_is_deterministic(nets):
+    """the same chunk encoded twice from the same reference state gives the same bytes and the same carried state
+    (guards against tile-overlap races between GEMM CTAs: the transform path has no atomics)."""
+    i_net, p_net = nets
+    h, w = 544, 960
+    frames = _sequence(h, w, 1, 77)
+    pad_r, pad_b = i_net.get_padding_size(h, w, 16)
+    x0 = frames[0].half().cuda().contiguous(memory_format=torch.channels_last)
+    x1 = frames[1].half().cuda().contiguous(memory_format=torch.channels_last)
+    xh = i_net.compress(x0, 30, pad_b, pad_r)["x_hat"].clone()
+    outs = []
+    for _ in range(3):
+        p_net.clear_dpb()
+        p_net.add_ref_feature_from_frame(xh)
+        e = p_net.compress(x1, 25, 0, pad_b, pad_r)
+        torch.cuda.synchronize()
+        outs.append((bytes(e["bit_stream"]), p_net.proxy.debug_fetch("cat_fam", np.float16).copy()))
+    for bs, st in outs[1:]:
+        assert bs == outs[0][0]
+        assert np.array_equal(st.view(np.uint16), outs[0][1].view(np.uint16))
+
+
 def test_hts_against_cpu_oracle(nets):
     """64x64... 128x128 sequence vs the fp16-emulating CPU restatement of the reference proxy: rate within 2 %,
     PSNR of every decoded frame within 0.1 dB (fp16 tie flips), same state machine."""

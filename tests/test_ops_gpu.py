@@ -42,6 +42,8 @@ PW_CASES = [
     (16, 16, 512, 2048, True, True, 0, False),
     (68, 120, 512, 512, False, False, 1, False),    # P16 of 1080p
     (16, 16, 256, 1024, True, True, 1, False),      # chunk-add + residual (fused variant)
+    (68, 120, 768, 3072, True, True, 0, False),     # HT-S prior-fusion FFN: N divisible by 192 must not pick a 48-col fold
+    (34, 60, 768, 768, True, False, 0, False),
 ]
 
 

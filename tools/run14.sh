@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -5
 echo "--- auto"
 timeout 120 python tools/gemm_micro.py 136 240 384 384 2>&1 | tail -1
 timeout 120 python tools/gemm_micro.py 136 240 384 384 0 0 1 2>&1 | tail -1
