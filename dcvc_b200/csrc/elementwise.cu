@@ -2,6 +2,9 @@
 // channel axis, grid sized from the element count (multiples of full 256-thread blocks).
 #include "elementwise.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <math.h>
 #include <stdio.h>
 
@@ -48,6 +51,10 @@ __global__ void __launch_bounds__(128)
 dw3x3_kernel(const __half* __restrict__ in, int in_pitch, __half* __restrict__ out, int out_pitch,
              const __half* __restrict__ w, int C, int W, int H)
 {
+    // programmatic dependent launch (the kernel sits between two GEMMs of a block): the next kernel may start its
+    // prologue now; this one waits here for the GEMM whose output it reads
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int cg_n = C >> 3;
     const int row_items = W * cg_n;  // (x, channel-group) pairs of one row
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -103,9 +110,19 @@ dw3x3_kernel(const __half* __restrict__ in, int in_pitch, __half* __restrict__ o
 int launch_dw3x3(const ActView& in, const ActView& out, const __half* w, cudaStream_t s)
 {
     const long long total = static_cast<long long>(in.W) * (in.C / 8) * ((in.H + DW_TY - 1) / DW_TY);
-    dw3x3_kernel<<<blocks_for(total, 128), 128, 0, s>>>(
-        static_cast<const __half*>(in.ptr), in.pitch,
-        static_cast<__half*>(const_cast<void*>(out.ptr)), out.pitch, w, in.C, in.W, in.H);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(blocks_for(total, 128), 1, 1);
+    cfg.blockDim = dim3(128, 1, 1);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    const char* e = getenv("DCVC_B200_PDL");
+    cfg.numAttrs = (e && e[0] == '0') ? 0 : 1;
+    cudaLaunchKernelEx(&cfg, dw3x3_kernel, static_cast<const __half*>(in.ptr), in.pitch,
+                       static_cast<__half*>(const_cast<void*>(out.ptr)), out.pitch, w, in.C, in.W, in.H);
     DCVC_LAUNCH_CHECK();
     return 0;
 }

@@ -64,6 +64,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
 }
 
+// one lane of the (converged) warp; ptxas then knows the guarded region is single-threaded and issues
+// TMA / tcgen05 instructions from uniform registers without per-instruction ELECT loops
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// programmatic dependent launch: let the next kernel of the stream start its prologue now / wait until the
+// previous kernel of the stream has completed and its writes are visible
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
@@ -132,6 +152,15 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* s
         "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group"
         " [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
         "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group"
+        " [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+        "r"(smem_u32(src)), "r"(c0), "r"(c1)
         : "memory");
 }
 

@@ -34,8 +34,8 @@ static constexpr int NUM_THREADS = 64 + EPI_GROUPS * 128;     // TMA warp + MMA 
 
 static constexpr int MAX_STAGES = 8;
 static constexpr int SMEM_TOTAL = 232448;   // 227 KB: the whole SM, one persistent CTA per SM
-// control block at the end of the carve-up: barriers, tmem pointer, bias tiles of both groups
-static constexpr int CTRL_BYTES = 512 + EPI_GROUPS * 256 * 2;
+// control block at the end of the carve-up: barriers, tmem pointer
+static constexpr int CTRL_BYTES = 512;
 static constexpr int SMEM_USABLE = SMEM_TOTAL - 1024 /*alignment slack*/ - CTRL_BYTES;
 
 template <int BLOCK_N>
@@ -54,35 +54,48 @@ __device__ __forceinline__ float wsilu_f(float x)
     return 0.5f * x * (1.f + t);
 }
 
-__device__ __forceinline__ void add_half8(float (&o)[8], const uint4& r)
+// 16-byte residual load.  Keeps the default L1 allocation on purpose: a thread walks its own row 16 bytes at a
+// time, so 7 of 8 loads of a 128-byte line are L1 hits (L1::no_allocate turned them into 8 L2 requests: 40.7 us
+// instead of 25.8 us for the M=32640, N=K=384 shortcut GEMM)
+__device__ __forceinline__ uint4 ld_stream16(const __half* p)
 {
-    const __half2* rh = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(rh[j]);
-        o[2 * j] += f.x;
-        o[2 * j + 1] += f.y;
-    }
+    return *reinterpret_cast<const uint4*>(p);
+}
+
+// pull one 16-byte piece (hence its 128-byte line) into L1
+__device__ __forceinline__ void l1_touch(const __half* p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
+// d = a * b + c with fp16 a, b and fp32 c, d in one instruction (SASS FHFMA, .H0/.H1 operand selectors)
+__device__ __forceinline__ float fma_f32_f16(uint16_t a, uint16_t b, float c)
+{
+    asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(c) : "h"(a), "h"(b));
+    return c;
 }
 
 struct TileCoord {
     int n0, ox0, oy0, oc0, opx, opy;
 };
 
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) { return (__umulhi(x, f.mul) + x) >> f.shr; }
+
 template <int BLOCK_N>
 __device__ __forceinline__ TileCoord tile_coord(const PwGemmParams& p, int tile)
 {
     TileCoord t;
-    const int nt = tile % p.n_tiles;
-    const int mt = tile / p.n_tiles;
+    const int mt = static_cast<int>(fdiv(tile, p.fd_n_tiles));
+    const int nt = tile - mt * p.n_tiles;
+    const int ty = static_cast<int>(fdiv(mt, p.fd_tiles_x));
     t.n0 = nt * BLOCK_N;
-    t.ox0 = (mt % p.tiles_x) * p.bw;
-    t.oy0 = (mt / p.tiles_x) * p.bh;
+    t.ox0 = (mt - ty * p.tiles_x) * p.bw;
+    t.oy0 = ty * p.bh;
     t.oc0 = p.chunk_add ? t.n0 / 4 : t.n0;
     t.opx = 0;
     t.opy = 0;
     if (p.phase_c > 0) {  // tconv: this N tile is one 2x2 phase of the upsampled image
-        const int phase = t.n0 / p.phase_c;
+        const int phase = static_cast<int>(fdiv(t.n0, p.fd_phase_c));
         t.oc0 = t.n0 - phase * p.phase_c;
         t.opx = phase & 1;
         t.opy = phase >> 1;
@@ -92,7 +105,16 @@ __device__ __forceinline__ TileCoord tile_coord(const PwGemmParams& p, int tile)
 
 // Persistent kernel: grid = min(#tiles, #SMs), one CTA per SM, tiles assigned round-robin with the
 // N tile fastest so that concurrently running CTAs share the same activation tile in L2.
-template <int BLOCK_N>
+__device__ __forceinline__ void trace_mark(const PwGemmParams& p, int slot)
+{
+    if (p.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[blockIdx.x * 64 + slot] = t;
+    }
+}
+
+template <int BLOCK_N, bool CHUNK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
 {
@@ -116,20 +138,20 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;             // [2]
     uint64_t* slab_bar = tmem_empty_bar + 2;                  // [1]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ctrl + 256);
-    __half* bias_all = reinterpret_cast<__half*>(ctrl + 512);
+    uint32_t* stage_clk = reinterpret_cast<uint32_t*>(ctrl + 272);  // [48] SM-clock marks of the first 24 k-blocks (trace)
 
     // tile schedule: a cluster of CS CTAs owns CS consecutive N tiles of one pixel tile (the activation tile is
     // TMA-multicast to all of them); work items (pixel tile, N group) are dealt round-robin to the clusters.
     // With CS == 1 this degenerates to one CTA per (pixel tile, N tile), N fastest.
     const int CS = p.cluster;
     const int rank = (CS > 1) ? static_cast<int>(cluster_ctarank()) : 0;
-    const int cid = blockIdx.x / CS;
+    const int cid = (CS > 1) ? blockIdx.x / CS : blockIdx.x;
     const int items = p.m_tiles * p.n_groups;
     // weight-resident CTAs without a cluster are pinned to N tile (blockIdx % n_tiles) and stride over its pixel tiles
     const bool pinned = p.b_resident && CS == 1;
-    const int pin_nt = blockIdx.x % p.n_tiles;
-    const int pin_j = blockIdx.x / p.n_tiles;
-    const int pin_ctas = (static_cast<int>(gridDim.x) - pin_nt + p.n_tiles - 1) / p.n_tiles;
+    const int pin_j = static_cast<int>(fdiv(blockIdx.x, p.fd_n_tiles));
+    const int pin_nt = blockIdx.x - pin_j * p.n_tiles;
+    const int pin_ctas = static_cast<int>(fdiv(gridDim.x - pin_nt + p.n_tiles - 1, p.fd_n_tiles));
     auto tile_of = [&](int i) -> int {  // global tile id (mt * n_tiles + nt) of this CTA's i-th tile, or -1
         if (pinned) {
             const int mt = pin_j + i * pin_ctas;
@@ -137,7 +159,7 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
         }
         const int w = cid + i * p.num_clusters;
         if (w >= items) return -1;
-        const int mt = w / p.n_groups;
+        const int mt = static_cast<int>(fdiv(w, p.fd_n_groups));
         const int ng = w - mt * p.n_groups;
         return mt * p.n_tiles + ng * CS + rank;
     };
@@ -146,6 +168,7 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) trace_mark(p, 0);  // entry
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tm_a);
@@ -171,9 +194,15 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
     if (CS > 1) cluster_sync_all();  // barriers of every CTA are initialised before any remote arrive / multicast
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // programmatic dependent launch: everything above touched only this CTA's smem / TMEM and overlapped the tail
+    // of the previous kernel; from here on its output is read
+    griddep_launch_dependents();
+    griddep_wait();
+    if (threadIdx.x == 0) trace_mark(p, 1);  // setup done
+    if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 64 + 15] = static_cast<uint32_t>(clock64());  // SM clock at mark 1
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // ------------------------------------------------------------ TMA producer
             if (p.b_resident) {
                 // the weight slab of this CTA's N tile: loaded once, reused by every M tile
@@ -182,23 +211,32 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
                     tma_load_2d(smem + kb * Cfg::B_STAGE_BYTES, &p.tm_b, slab_bar, kb * BLOCK_K, my_nt * BLOCK_N);
                 }
             }
+            // stage / phase / tap counters are kept incrementally: this loop runs on ONE thread and its instruction
+            // latency chain bounds how fast k-blocks can be requested (measured 0.32 us per k-block with the
+            // straightforward it % STAGES, kb / kblk_per_tap formulation: three integer divisions per iteration)
             uint32_t it = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            int mc_turn = 0;  // it % CS
+            const uint32_t stage_tx = p.b_resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES;
+            const int num_kblocks = p.num_kblocks;
+            const int kblk_per_tap = p.kblk_per_tap;
+            const bool lin = p.linear != 0;
             for (int i = 0;; ++i) {
                 const int tile = tile_of(i);
                 if (tile < 0) break;
                 const TileCoord tc = tile_coord<BLOCK_N>(p, tile);
-                for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
+                int tap = 0, kc = 0;
+                for (int kb = 0; kb < num_kblocks; ++kb, ++it) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
-                    const int tap = kb / p.kblk_per_tap;
-                    const int kc = kb - tap * p.kblk_per_tap;
                     uint8_t* a_dst = a_base + s * a_stride;
-                    mbar_expect_tx(&full_bar[s], p.b_resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES);
-                    if (CS == 1) {
+                    mbar_expect_tx(&full_bar[s], stage_tx);
+                    if (lin) {
+                        tma_load_2d(a_dst, &p.tm_a, &full_bar[s], kc * BLOCK_K, tc.ox0);
+                    } else if (CS == 1) {
                         tma_load_5d(a_dst, &p.tm_a, &full_bar[s], kc * BLOCK_K, p.tap_px[tap],
                                     tc.ox0 + p.tap_dx[tap], p.tap_py[tap], tc.oy0 + p.tap_dy[tap]);
-                    } else if (static_cast<int>(it % CS) == rank) {
+                    } else if (mc_turn == rank) {
                         // this CTA fetches the k-block for the whole cluster (one L2 read instead of CS)
                         tma_load_5d_mc(a_dst, &p.tm_a, &full_bar[s], kc * BLOCK_K, p.tap_px[tap],
                                        tc.ox0 + p.tap_dx[tap], p.tap_py[tap], tc.oy0 + p.tap_dy[tap], mc_mask);
@@ -206,36 +244,49 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
                     if (!p.b_resident) {
                         tma_load_2d(a_dst + A_STAGE_BYTES, &p.tm_b, &full_bar[s], kb * BLOCK_K, tc.n0);
                     }
+                    if (it == 0) trace_mark(p, 2);  // first stage requested
+                    if (p.trace && it < 24) stage_clk[it] = static_cast<uint32_t>(clock64());
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                    if (++kc == kblk_per_tap) { kc = 0; ++tap; }
+                    if (++mc_turn == CS) mc_turn = 0;
                 }
             }
+            trace_mark(p, 3);  // last stage requested
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // ------------------------------------------------------------ MMA issuer
             constexpr uint32_t idesc = make_idesc_f16_f32(BLOCK_M, BLOCK_N);
             uint32_t it = 0;
-            if (p.b_resident) {
+            int s = 0;
+            uint32_t ph = 0;
+            const int num_kblocks = p.num_kblocks;
+            const bool resident = p.b_resident != 0;
+            const bool do_mma = !(p.dbg & 1);
+            if (resident) {
                 mbar_wait(slab_bar, 0);
                 tcgen05_fence_after();
             }
-            for (int i = 0; tile_of(i) >= 0; ++i) {
+            int my_tiles = 0;
+            while (tile_of(my_tiles) >= 0) ++my_tiles;
+            for (int i = 0; i < my_tiles; ++i) {
                 const int g = i & 1;
                 const uint32_t u = static_cast<uint32_t>(i >> 1);
                 mbar_wait(&tmem_empty_bar[g], (u & 1) ^ 1);  // epilogue drained this accumulator
                 tcgen05_fence_after();
                 const uint32_t acc = tmem_base + g * Cfg::ACC_COLS;
-                for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
+                for (int kb = 0; kb < num_kblocks; ++kb, ++it) {
                     mbar_wait(&full_bar[s], ph);
                     tcgen05_fence_after();
+                    if (it == 0) trace_mark(p, 4);  // first stage landed
+                    if (p.trace && it < 24) stage_clk[24 + it] = static_cast<uint32_t>(clock64());
                     const uint32_t a_addr = smem_u32(a_base + s * a_stride);
-                    const uint32_t b_addr = p.b_resident ? smem_u32(smem + kb * Cfg::B_STAGE_BYTES)
-                                                         : a_addr + A_STAGE_BYTES;
+                    const uint32_t b_addr = resident ? smem_u32(smem + kb * Cfg::B_STAGE_BYTES)
+                                                     : a_addr + A_STAGE_BYTES;
                     const uint64_t a_desc = make_kmajor_sw128_desc(a_addr);
                     const uint64_t b_desc = make_kmajor_sw128_desc(b_addr);
-                    if (!(p.dbg & 1)) {
+                    if (do_mma) {
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                             // advance 16 fp16 = 32 B inside the 128 B swizzle span: +2 in 16 B units
@@ -244,34 +295,54 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
                     }
                     if (CS == 1) umma_commit(&empty_bar[s]);
                     else umma_commit_mc(&empty_bar[s], mc_mask);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&tmem_full_bar[g]);
+                if (i == 0) trace_mark(p, 5);  // first tile issued
             }
+            trace_mark(p, 6);  // last tile issued
         }
         __syncwarp();
     } else {
         // ---------------------------------------------------------------- epilogue (2 groups x 4 warps)
+        // Latency-bound by construction (one warp per TMEM lane quarter), so everything it waits for is requested
+        // one 32-column chunk ahead: the next tcgen05.ld, and bias / quant-scale / residual vectors as 16-byte global
+        // loads into registers.  One named barrier per store box; no divergent branches, no integer divisions.
         const int g = (warp - 2) >> 2;       // group <-> accumulator buffer
         const int q = warp & 3;              // TMEM lane quarter this warp may touch
         const int row = q * 32 + lane;
-        const int tg = (warp - 2 - 4 * g) * 32 + lane;  // thread index inside the group
-        const bool issuer = (tg == 0);
+        const bool issuer = (warp == 2 + 4 * g) && lane == 0;
         const uint32_t bar_id = 1 + g;
-        // output sub-tile = one TMA store box: 64 columns (SWIZZLE_128B rows) or, for the 128-wide chunk-add
-        // tile, 32 columns (SWIZZLE_64B rows)
-        const bool out32 = p.chunk_add && BLOCK_N == 128;
-        const int sub_bytes = out32 ? SUB_TILE_BYTES / 2 : SUB_TILE_BYTES;
-        uint8_t* stage_g = staging + g * p.staging_bufs * sub_bytes;
-        __half* bias_s = bias_all + g * BLOCK_N;
-        const __half* qs = p.qscale;
-        constexpr int NC = BLOCK_N / 32;                     // accumulator chunks of 32 columns per tile
-        const int chunks_per_sub = p.chunk_add ? NC : 2;     // accumulator chunks feeding one store box
-        const int out_chunks = out32 ? 4 : 8;                // 16-byte output chunks per store-box row
-        uint32_t cnt = 0;  // store-buffer counter of this group
+        constexpr bool OUT32 = CHUNK && BLOCK_N == 128;  // 32-column store box (SWIZZLE_64B rows)
+        constexpr int SUB_BYTES = OUT32 ? SUB_TILE_BYTES / 2 : SUB_TILE_BYTES;
+        uint8_t* stage_g = staging + g * p.staging_bufs * SUB_BYTES;
+        constexpr int NC = BLOCK_N / 32;     // accumulator chunks of 32 columns per tile
+        const bool two_bufs = p.staging_bufs == 2;
+        const bool has_bias = p.bias != nullptr;
+        const bool has_q = p.qscale != nullptr;
+        const int n_res = p.n_res;
+        const bool act = p.act == ACT_WSILU;
+        uint32_t cnt = 0;  // store-box counter of this group
+        const uint16_t ONE = 0x3C00;  // fp16 1.0: fma_f32_f16(h, ONE, x) == x + float(h) in one FHFMA
 
         auto sw_off = [&](int chunk) -> uint32_t {
-            return out32 ? static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4))
+            return OUT32 ? static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4))
                          : sw128_offset(row, chunk);
+        };
+        // publish a finished store box: every earlier store of this group has left its staging buffer (so the buffer
+        // the NEXT box writes is free), all 128 rows are written, then one thread issues the TMA store
+        auto publish = [&](uint8_t* sbuf, const TileCoord& tc, int c0) {
+            fence_proxy_async_smem();
+            if (issuer) tma_store_wait_read<0>();
+            named_bar_sync(bar_id, 128);
+            if (issuer) {
+                if (p.linear) tma_store_2d(&p.tm_c, sbuf, c0, tc.ox0);
+                else tma_store_5d(&p.tm_c, sbuf, c0, tc.opx, tc.ox0, tc.opy, tc.oy0);
+                tma_store_commit();
+                if (!two_bufs) tma_store_wait_read<0>();
+            }
+            if (!two_bufs) named_bar_sync(bar_id, 128);
+            ++cnt;
         };
 
         for (int i = g;; i += 2) {
@@ -279,150 +350,221 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
             if (tile < 0) break;
             const TileCoord tc = tile_coord<BLOCK_N>(p, tile);
             const uint32_t u = static_cast<uint32_t>(i >> 1);
-            for (int c = tg; c < BLOCK_N; c += 128) {
-                bias_s[c] = p.bias ? p.bias[tc.n0 + c] : __float2half(0.f);
-            }
-            // residual rows of this thread (same pixel grid as the output)
+            // residual rows of this thread (same pixel grid as the output); rows past the edge are clamped to a valid
+            // one — their results are clipped by the TMA store
             const __half* r1_row = nullptr;
             const __half* r2_row = nullptr;
-            if (p.n_res > 0) {
-                const long long x = tc.ox0 + (row % p.bw);
-                const long long y = tc.oy0 + (row / p.bw);
-                if (x < p.res_w && y < p.res_h) {
-                    r1_row = p.r1 + (y * p.res_w + x) * p.r1_pitch + tc.oc0;
-                    if (p.n_res > 1) r2_row = p.r2 + (y * p.res_w + x) * p.r2_pitch + tc.oc0;
-                }
+            if (n_res > 0) {
+                const int ry = static_cast<int>(fdiv(row, p.fd_bw));
+                long long x = tc.ox0 + (row - ry * p.bw);
+                long long y = tc.oy0 + ry;
+                x = x < p.res_w ? x : p.res_w - 1;
+                y = y < p.res_h ? y : p.res_h - 1;
+                r1_row = p.r1 + (y * p.res_w + x) * p.r1_pitch + tc.oc0;
+                r2_row = (n_res > 1) ? p.r2 + (y * p.res_w + x) * p.r2_pitch + tc.oc0 : r1_row;
             }
-            mbar_wait(&tmem_full_bar[g], u & 1);
-            tcgen05_fence_after();
+            const uint4* bias_v = reinterpret_cast<const uint4*>(p.bias + tc.n0);
+            const uint4* q_v = reinterpret_cast<const uint4*>(p.qscale + tc.oc0);
             const uint32_t acc = tmem_base + g * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
-            if (p.dbg & 2) {  // micro-benchmark: drain nothing, just hand the accumulator back
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
-                continue;
-            }
+            const uint4 zero4 = make_uint4(0, 0, 0, 0);
+            // warm L1 with this tile's bias / scale vectors while the accumulator is still being produced: the
+            // per-chunk loads below are then warp-uniform L1 hits (their miss latency used to be exposed once per
+            // 128-byte line, i.e. every other chunk)
+            if (has_bias && lane * 8 < BLOCK_N) l1_touch(p.bias + tc.n0 + lane * 8);
+            if (has_q && lane * 8 < (CHUNK ? BLOCK_N / 4 : BLOCK_N)) l1_touch(p.qscale + tc.oc0 + lane * 8);
 
-            // software-pipelined TMEM reads: chunk a+1 is in flight while chunk a is processed
-            uint32_t vn[32];
-            tmem_ld_32x32b_x32(acc, vn);
-            uint8_t* sbuf = nullptr;
-            bool res_ready = false;
-            uint4 r2v[8];
-            // NOT unrolled: the body is ~0.5 K instructions; unrolling NC x made the kernel 50-150 KB of SASS and
-            // the persistent loop thrashed the instruction cache (every launch also started I$-cold)
-#pragma unroll 1
-            for (int a = 0; a < NC; ++a) {
-                const int sub = a / chunks_per_sub;
-                const int a_in = a - sub * chunks_per_sub;
-                if (a_in == 0) {
-                    // ---- enter a store box: its staging buffer must be free again
-                    sbuf = stage_g + ((p.staging_bufs == 2) ? (cnt & 1) : 0) * sub_bytes;
-                    if (r2_row) {
+            if constexpr (!CHUNK) {
+                // ------------------------------------------------ plain tile: 32 accumulator columns -> 32 outputs
+                uint4 n1[4];  // first residual of the NEXT chunk (L2 latency); bias / scale / second residual are
+                              // requested at the top of their own chunk (warp-uniform L1 hits, resp. rarely used)
+                auto prefetch = [&](int a) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (j < out_chunks) r2v[j] = *reinterpret_cast<const uint4*>(r2_row + sub * 64 + j * 8);
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        if (n_res > 0) n1[j] = ld_stream16(r1_row + a * 32 + j * 8);
                     }
-                    if (issuer) {
-                        if (p.staging_bufs == 2) tma_store_wait_read<1>();
-                        else tma_store_wait_read<0>();
-                    }
-                    named_bar_sync(bar_id, 128);
-                    // first residual: asynchronous copy of this thread's row segment into its own slots of the
-                    // staging tile (L2 latency overlaps the TMEM loads and the activation math)
-                    if (r1_row) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (j < out_chunks) cp_async_16(sbuf + sw_off(j), r1_row + sub * 64 + j * 8);
-                        }
-                    }
-                    cp_async_commit();
-                    res_ready = false;
-                }
-                uint32_t v[32];
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = vn[j];
-                if (a + 1 < NC) {
-                    tmem_ld_32x32b_x32(acc + (a + 1) * 32, vn);
-                } else {
-                    // every tcgen05.ld of this tile has completed: hand the accumulator back to the MMA warp
+                };
+                prefetch(0);
+                mbar_wait(&tmem_full_bar[g], u & 1);
+                tcgen05_fence_after();
+                if (lane == 0 && q == 0) trace_mark(p, i == 0 ? 7 : (i == 1 ? 9 : 11));
+                if (p.dbg & 2) {  // micro-benchmark: drain nothing, just hand the accumulator back
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
+                    continue;
                 }
-                if (p.chunk_add) {
-                    float o[8];
+                uint32_t vn[32];
+                tmem_ld_32x32b_x32(acc, vn);
+                uint8_t* sbuf = nullptr;
+#pragma unroll 1
+                for (int a = 0; a < NC; ++a) {
+                    uint4 cb[4], cq[4], c1[4], c2[4];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float s4 = 0.f;
+                    for (int j = 0; j < 4; ++j) {
+                        cb[j] = has_bias ? __ldg(bias_v + a * 4 + j) : zero4;
+                        if (has_q) cq[j] = __ldg(q_v + a * 4 + j);
+                        if (n_res > 1) c2[j] = ld_stream16(r2_row + a * 32 + j * 8);
+                        c1[j] = n1[j];
+                    }
+                    uint32_t v[32];
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float t = __uint_as_float(v[4 * j + e]) + __half2float(bias_s[a * 32 + 4 * j + e]);
-                            s4 += (p.act == ACT_WSILU) ? wsilu_f(t) : t;
+                    for (int j = 0; j < 32; ++j) v[j] = vn[j];
+                    if (a + 1 < NC) {
+                        tmem_ld_32x32b_x32(acc + (a + 1) * 32, vn);
+                        prefetch(a + 1);
+                    } else {
+                        // every tcgen05.ld of this tile has completed: hand the accumulator back to the MMA warp
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
+                    }
+                    if ((a & 1) == 0) sbuf = stage_g + (two_bufs ? (cnt & 1) : 0) * SUB_BYTES;
+                    // one pass per epilogue term over the 32 columns: each optional term is a warp-uniform branch
+                    // around a short unrolled loop (keeps the kernel small: no per-combination code clones)
+                    const uint32_t* bw = reinterpret_cast<const uint32_t*>(cb);
+                    const uint32_t* qw = reinterpret_cast<const uint32_t*>(cq);
+                    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(c1);
+                    const uint32_t* w2 = reinterpret_cast<const uint32_t*>(c2);
+                    float t[32];
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        t[e] = fma_f32_f16(static_cast<uint16_t>(bw[e >> 1] & 0xffffu), ONE, __uint_as_float(v[e]));
+                        t[e + 1] = fma_f32_f16(static_cast<uint16_t>(bw[e >> 1] >> 16), ONE, __uint_as_float(v[e + 1]));
+                    }
+                    if (act) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) t[e] = wsilu_f(t[e]);
+                    }
+                    if (n_res > 0) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 2) {
+                            t[e] = fma_f32_f16(static_cast<uint16_t>(w1[e >> 1] & 0xffffu), ONE, t[e]);
+                            t[e + 1] = fma_f32_f16(static_cast<uint16_t>(w1[e >> 1] >> 16), ONE, t[e + 1]);
                         }
-                        o[j] = s4;
                     }
-                    uint8_t* dst = sbuf + sw_off(a_in);
-                    if (r1_row) {
-                        if (!res_ready) { cp_async_wait_all(); res_ready = true; }
-                        add_half8(o, *reinterpret_cast<const uint4*>(dst));
-                    }
-                    if (r2_row) add_half8(o, r2v[a_in & 7]);
-                    if (qs) {
+                    if (n_res > 1) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] *= __half2float(qs[tc.oc0 + a * 8 + j]);
+                        for (int e = 0; e < 32; e += 2) {
+                            t[e] = fma_f32_f16(static_cast<uint16_t>(w2[e >> 1] & 0xffffu), ONE, t[e]);
+                            t[e + 1] = fma_f32_f16(static_cast<uint16_t>(w2[e >> 1] >> 16), ONE, t[e + 1]);
+                        }
                     }
-                    uint4 w;
-                    __half2* wh = reinterpret_cast<__half2*>(&w);
+                    if (has_q) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) wh[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
-                    *reinterpret_cast<uint4*>(dst) = w;
-                } else {
+                        for (int e = 0; e < 32; e += 2) {
+                            const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qw[e >> 1]));
+                            t[e] *= qf.x;
+                            t[e + 1] *= qf.y;
+                        }
+                    }
 #pragma unroll
                     for (int gq = 0; gq < 4; ++gq) {
-                        const int oc = a_in * 4 + gq;  // 16-byte chunk inside the store box
-                        float o[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float t = __uint_as_float(v[gq * 8 + j]) + __half2float(bias_s[a * 32 + gq * 8 + j]);
-                            o[j] = (p.act == ACT_WSILU) ? wsilu_f(t) : t;
-                        }
-                        uint8_t* dst = sbuf + sw128_offset(row, oc);
-                        if (r1_row) {
-                            if (!res_ready) { cp_async_wait_all(); res_ready = true; }
-                            add_half8(o, *reinterpret_cast<const uint4*>(dst));
-                        }
-                        if (r2_row) add_half8(o, r2v[oc & 7]);
-                        if (qs) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] *= __half2float(qs[tc.oc0 + a * 32 + gq * 8 + j]);
-                        }
                         uint4 w;
-                        __half2* wh = reinterpret_cast<__half2*>(&w);
+                        uint32_t* ww = reinterpret_cast<uint32_t*>(&w);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) wh[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
-                        *reinterpret_cast<uint4*>(dst) = w;
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const __half2 h = __floats2half2_rn(t[gq * 8 + jj * 2], t[gq * 8 + jj * 2 + 1]);
+                            ww[jj] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        *reinterpret_cast<uint4*>(sbuf + sw128_offset(row, (a & 1) * 4 + gq)) = w;
                     }
+                    if (a & 1) publish(sbuf, tc, tc.oc0 + (a >> 1) * 64);
                 }
-                if (a_in == chunks_per_sub - 1) {
-                    // ---- leave the store box: publish it
-                    fence_proxy_async_smem();
-                    named_bar_sync(bar_id, 128);
-                    if (issuer) {
-                        tma_store_5d(&p.tm_c, sbuf, tc.oc0 + sub * 64, tc.opx, tc.ox0, tc.opy, tc.oy0);
-                        tma_store_commit();
+            } else {
+                // ------------------------------------------------ 4 -> 1 fold: 32 accumulator columns -> 8 outputs
+                uint4 nb[4], nq, n1, n2;
+                auto prefetch = [&](int a) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) nb[j] = has_bias ? __ldg(bias_v + a * 4 + j) : zero4;
+                    if (has_q) nq = __ldg(q_v + a);
+                    if (n_res > 0) n1 = ld_stream16(r1_row + a * 8);
+                    if (n_res > 1) n2 = ld_stream16(r2_row + a * 8);
+                };
+                prefetch(0);
+                mbar_wait(&tmem_full_bar[g], u & 1);
+                tcgen05_fence_after();
+                if (lane == 0 && q == 0) trace_mark(p, i == 0 ? 7 : (i == 1 ? 9 : 11));
+                if (p.dbg & 2) {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
+                    continue;
+                }
+                uint32_t vn[32];
+                tmem_ld_32x32b_x32(acc, vn);
+                uint8_t* sbuf = stage_g + (two_bufs ? (cnt & 1) : 0) * SUB_BYTES;
+#pragma unroll 1
+                for (int a = 0; a < NC; ++a) {
+                    uint4 cb[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cb[j] = nb[j];
+                    const uint4 cq = nq, c1 = n1, c2 = n2;
+                    uint32_t v[32];
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = vn[j];
+                    if (a + 1 < NC) {
+                        tmem_ld_32x32b_x32(acc + (a + 1) * 32, vn);
+                        prefetch(a + 1);
+                    } else {
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
                     }
-                    ++cnt;
+                    const uint32_t* bw = reinterpret_cast<const uint32_t*>(cb);
+                    const uint32_t* qw = reinterpret_cast<const uint32_t*>(&cq);
+                    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(&c1);
+                    const uint32_t* w2 = reinterpret_cast<const uint32_t*>(&c2);
+                    uint4 w;
+                    uint32_t* ww = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        float o[2];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int j = jj * 2 + h;  // output column of this chunk; folds acc columns 4j .. 4j+3
+                            float s4 = 0.f;
+#pragma unroll
+                            for (int e = 0; e < 4; e += 2) {
+                                const uint32_t bword = bw[(4 * j + e) >> 1];
+                                float t0 = fma_f32_f16(static_cast<uint16_t>(bword & 0xffffu), ONE, __uint_as_float(v[4 * j + e]));
+                                float t1 = fma_f32_f16(static_cast<uint16_t>(bword >> 16), ONE, __uint_as_float(v[4 * j + e + 1]));
+                                if (act) { t0 = wsilu_f(t0); t1 = wsilu_f(t1); }
+                                s4 += t0;
+                                s4 += t1;
+                            }
+                            o[h] = s4;
+                        }
+                        if (n_res > 0) {
+                            o[0] = fma_f32_f16(static_cast<uint16_t>(w1[jj] & 0xffffu), ONE, o[0]);
+                            o[1] = fma_f32_f16(static_cast<uint16_t>(w1[jj] >> 16), ONE, o[1]);
+                        }
+                        if (n_res > 1) {
+                            o[0] = fma_f32_f16(static_cast<uint16_t>(w2[jj] & 0xffffu), ONE, o[0]);
+                            o[1] = fma_f32_f16(static_cast<uint16_t>(w2[jj] >> 16), ONE, o[1]);
+                        }
+                        if (has_q) {
+                            const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qw[jj]));
+                            o[0] *= qf.x;
+                            o[1] *= qf.y;
+                        }
+                        const __half2 h2 = __floats2half2_rn(o[0], o[1]);
+                        ww[jj] = *reinterpret_cast<const uint32_t*>(&h2);
+                    }
+                    *reinterpret_cast<uint4*>(sbuf + sw_off(a)) = w;
                 }
+                publish(sbuf, tc, tc.oc0);
             }
+            if (lane == 0 && q == 0) trace_mark(p, i == 0 ? 8 : (i == 1 ? 10 : 12));  // epilogue of tile i done
         }
         if (issuer) tma_store_wait_read<0>();
+        if (lane == 0 && q == 0) trace_mark(p, 13 + g);  // group drained
         __syncwarp();
     }
 
     __syncthreads();
+    if (p.trace && threadIdx.x < 48) p.trace[blockIdx.x * 64 + 16 + threadIdx.x] = stage_clk[threadIdx.x];
     if (CS > 1) cluster_sync_all();  // no CTA may exit while peers can still multicast into it / arrive on its barriers
     if (warp == 1) {
         tcgen05_fence_after();
@@ -490,17 +632,26 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
 }
 
 // 5-D map of an NHWC view.  split2: expose the 2x2 pixel phases as dims 1 and 3.
-static int encode_act_map(CUtensorMap* m, const ActView& v, bool split2, bool linear, int bw, int bh,
+static int encode_act_map(CUtensorMap* m, const ActView& v, bool split2, bool linear, bool lin2d, int bw, int bh,
                           int box_c = 64)
 {
     const uint64_t pb = static_cast<uint64_t>(v.pitch) * 2;
     uint64_t dims[5];
     uint64_t st[4];
     uint32_t box[5] = { static_cast<uint32_t>(box_c), 1, static_cast<uint32_t>(bw), 1, static_cast<uint32_t>(bh) };
-    if (linear) {
+    if (linear && !lin2d) {
         const uint64_t M = static_cast<uint64_t>(v.W) * v.H;
         dims[0] = v.C; dims[1] = 1; dims[2] = M; dims[3] = 1; dims[4] = 1;
         st[0] = pb; st[1] = pb; st[2] = M * pb; st[3] = M * pb;
+    } else if (linear) {
+        // 1x1: a genuine 2-D [pixels][channels] map
+        const uint64_t M = static_cast<uint64_t>(v.W) * v.H;
+        uint64_t d2[2] = { static_cast<uint64_t>(v.C), M };
+        uint64_t s2[1] = { pb };
+        uint32_t b2[2] = { static_cast<uint32_t>(box_c), static_cast<uint32_t>(bw * bh) };
+        if (b2[0] > d2[0]) b2[0] = static_cast<uint32_t>(d2[0]);
+        return encode_map(m, v.ptr, 2, d2, s2, b2,
+                          box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     } else if (split2) {
         dims[0] = v.C; dims[1] = 2; dims[2] = v.W / 2; dims[3] = 2; dims[4] = v.H / 2;
         st[0] = pb; st[1] = 2 * pb; st[2] = static_cast<uint64_t>(v.W) * pb;
@@ -522,6 +673,16 @@ struct TilePlan {
     int staging_bufs = 2;
     int cluster = 1;
 };
+
+static FastDiv make_fastdiv(uint32_t d)
+{
+    FastDiv f;
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;  // ceil(log2 d)
+    f.shr = s;
+    f.mul = static_cast<uint32_t>(((1ull << 32) * ((1ull << s) - d)) / d + 1);
+    return f;
+}
 
 // Chooses the N tile, the cluster size and the smem carve-up.
 // Measured on B200 (tools/gemm_micro.py, DCVC_B200_GEMM_DBG=3): the activation stream out of L2/HBM tops out at
@@ -620,7 +781,7 @@ static int max_clusters_for(int cluster)
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, pw_gemm_kernel<BN>, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&n, pw_gemm_kernel<BN, false>, &cfg) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -747,7 +908,8 @@ int gemm_plan(GemmOp& op)
     if (op.res2.ptr && !op.res1.ptr) { g_err = "gemm_plan: res2 without res1"; return 1; }
 
     const bool in_split = (op.kind == GEMM_CONV3X3_S2 || op.kind == GEMM_CONV2X2_S2);
-    if (encode_act_map(&p.tm_a, op.in, in_split, linear, p.bw, p.bh)) return 1;
+    const bool lin2d = linear && tp.cluster == 1;  // the cluster path multicasts 5-D boxes
+    if (encode_act_map(&p.tm_a, op.in, in_split, linear, lin2d, p.bw, p.bh)) return 1;
     {
         const uint64_t Ktot = static_cast<uint64_t>(taps) * C;
         uint64_t dims[2] = { Ktot, static_cast<uint64_t>(op.N) };
@@ -757,7 +919,7 @@ int gemm_plan(GemmOp& op)
     }
     const bool out_split = (op.kind == GEMM_TCONV2X2);
     const int out_box_c = (op.chunk_add && bn == 128) ? 32 : 64;
-    if (encode_act_map(&p.tm_c, op.out, out_split, linear, p.bw, p.bh, out_box_c)) return 1;
+    if (encode_act_map(&p.tm_c, op.out, out_split, linear, lin2d, p.bw, p.bh, out_box_c)) return 1;
     if (op.res1.ptr) {
         if (op.kind == GEMM_TCONV2X2) { g_err = "gemm_plan: tconv takes no residual"; return 1; }
         const ActView* rs[2] = { &op.res1, &op.res2 };
@@ -795,12 +957,19 @@ int gemm_plan(GemmOp& op)
         if (tp.resident && p.cluster == 1) p.num_clusters -= p.num_clusters % p.n_tiles;
     }
     p.m_tiles = static_cast<int>(m_tiles);
+    p.linear = lin2d ? 1 : 0;
+    p.fd_n_tiles = make_fastdiv(p.n_tiles);
+    p.fd_n_groups = make_fastdiv(p.n_groups);
+    p.fd_tiles_x = make_fastdiv(p.tiles_x);
+    p.fd_phase_c = make_fastdiv(p.phase_c > 0 ? p.phase_c : 1);
+    p.fd_bw = make_fastdiv(p.bw);
     op.grid = dim3(p.num_clusters * p.cluster, 1, 1);
     op.smem = SMEM_TOTAL;
     p.b_resident = tp.resident ? 1 : 0;
     p.num_stages = tp.stages;
     p.staging_bufs = tp.staging_bufs;
     if (const char* d = getenv("DCVC_B200_GEMM_DBG")) p.dbg = atoi(d);
+    if (const char* d = getenv("DCVC_B200_GEMM_TRACE")) p.trace = reinterpret_cast<unsigned long long*>(strtoull(d, nullptr, 0));
     op.stages = p.num_stages;
     if (p.num_stages < 2) { g_err = "gemm_plan: pipeline does not fit"; return 1; }
     if (!op.chunk_add && bn % 64 != 0) { g_err = "gemm_plan: BLOCK_N must be a multiple of 64"; return 1; }
@@ -809,20 +978,22 @@ int gemm_plan(GemmOp& op)
     return 0;
 }
 
-template <int BN>
+template <int BN, bool CHUNK>
 static cudaError_t set_attr()
 {
-    return cudaFuncSetAttribute(pw_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    return cudaFuncSetAttribute(pw_gemm_kernel<BN, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
 }
 
 int gemm_init()
 {
     static bool done = false;
     if (done) return 0;
-    cudaError_t e = set_attr<64>();
-    if (e == cudaSuccess) e = set_attr<128>();
-    if (e == cudaSuccess) e = set_attr<192>();
-    if (e == cudaSuccess) e = set_attr<256>();
+    cudaError_t e = set_attr<64, false>();
+    if (e == cudaSuccess) e = set_attr<128, false>();
+    if (e == cudaSuccess) e = set_attr<192, false>();
+    if (e == cudaSuccess) e = set_attr<256, false>();
+    if (e == cudaSuccess) e = set_attr<128, true>();
+    if (e == cudaSuccess) e = set_attr<256, true>();
     if (e != cudaSuccess) {
         g_err = std::string("cudaFuncSetAttribute(pw_gemm): ") + cudaGetErrorString(e);
         return 1;
@@ -831,7 +1002,10 @@ int gemm_init()
     return 0;
 }
 
-template <int BN>
+// DCVC_B200_PDL=0 turns programmatic dependent launch off (debugging)
+static const bool g_pdl = []() { const char* e = getenv("DCVC_B200_PDL"); return !(e && e[0] == '0'); }();
+
+template <int BN, bool CHUNK>
 static cudaError_t launch_bn(const GemmOp& op, cudaStream_t stream)
 {
     cudaLaunchConfig_t cfg;
@@ -840,14 +1014,16 @@ static cudaError_t launch_bn(const GemmOp& op, cudaStream_t stream)
     cfg.blockDim = dim3(NUM_THREADS, 1, 1);
     cfg.dynamicSmemBytes = op.smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = op.p.cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, pw_gemm_kernel<BN>, op.p);
+    cfg.numAttrs = g_pdl ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, pw_gemm_kernel<BN, CHUNK>, op.p);
 }
 
 int gemm_launch(const GemmOp& op, cudaStream_t stream)
@@ -855,11 +1031,13 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream)
     if (!op.planned) { g_err = "gemm_launch: op not planned"; return 1; }
     if (gemm_init()) return 1;
     cudaError_t e;
-    switch (op.block_n) {
-    case 64: e = launch_bn<64>(op, stream); break;
-    case 128: e = launch_bn<128>(op, stream); break;
-    case 192: e = launch_bn<192>(op, stream); break;
-    case 256: e = launch_bn<256>(op, stream); break;
+    switch (op.block_n + (op.chunk_add ? 1 : 0)) {
+    case 64: e = launch_bn<64, false>(op, stream); break;
+    case 128: e = launch_bn<128, false>(op, stream); break;
+    case 192: e = launch_bn<192, false>(op, stream); break;
+    case 256: e = launch_bn<256, false>(op, stream); break;
+    case 129: e = launch_bn<128, true>(op, stream); break;
+    case 257: e = launch_bn<256, true>(op, stream); break;
     default: g_err = "gemm_launch: bad block_n"; return 1;
     }
     if (e != cudaSuccess) {

@@ -33,6 +33,12 @@ enum GemmKind : int {
 
 enum GemmAct : int { ACT_NONE = 0, ACT_WSILU = 1 };
 
+// x / d for x < 2^31 as mulhi + add + shift (the kernel's scheduling loops run on single threads: a hardware
+// integer division is ~40 dependent instructions there)
+struct FastDiv {
+    uint32_t mul, shr;
+};
+
 struct alignas(64) PwGemmParams {
     CUtensorMap tm_a;
     CUtensorMap tm_b;
@@ -53,7 +59,10 @@ struct alignas(64) PwGemmParams {
     int cluster;           // CTAs per cluster = N tiles that share one multicast activation tile (1: no cluster)
     int n_groups;          // n_tiles / cluster
     int num_clusters;      // gridDim.x / cluster
+    int linear;            // 1x1: tm_a / tm_c are plain 2-D [pixels][channels] maps (a 5-D box costs the TMA unit ~4
+                           // cycles per row to walk, measured 0.25 us per 128-row k-block; 2-D rows stream)
     int dbg;               // micro-benchmark switches (env DCVC_B200_GEMM_DBG): 1 = no MMA, 2 = no epilogue body
+    unsigned long long* trace;  // env DCVC_B200_GEMM_TRACE=<device address>: 16 globaltimer slots per CTA (tools/gemm_trace.py)
     int num_kblocks;       // taps * C / 64
     int kblk_per_tap;      // C / 64
     int bw, bh;            // pixel tile, bw*bh == 128
@@ -61,6 +70,7 @@ struct alignas(64) PwGemmParams {
     int chunk_add;         // 1: out[:, j] = sum_{i<4} act(acc[:, 4j+i])
     int n_res;             // 0,1,2 residual operands (same geometry as the output)
     int phase_c;           // tconv: output channels per 2x2 phase (0: not a tconv)
+    FastDiv fd_n_tiles, fd_n_groups, fd_tiles_x, fd_phase_c, fd_bw;
     int8_t tap_px[9];
     int8_t tap_py[9];
     int8_t tap_dx[9];
