@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libdcvc_b200.so")
 
 SOURCES = [
     "pw_gemm.cu",
+    "pw_gemm_ares.cu",
     "elementwise.cu",
     "rans_host.cpp",
     "c_api_ops.cu",

@@ -21,65 +21,10 @@
 #include <string>
 
 #include "ptx.cuh"
+#include "pw_gemm_epilogue.cuh"
+#include "pw_gemm_internal.cuh"
 
 namespace dcvc {
-
-static constexpr int BLOCK_M = 128;
-static constexpr int BLOCK_K = 64;
-static constexpr int UMMA_K = 16;
-static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-static constexpr int SUB_TILE_BYTES = BLOCK_M * 64 * 2;      // one [128][64] fp16 store box
-static constexpr int EPI_GROUPS = 2;                          // one per TMEM accumulator buffer
-static constexpr int NUM_THREADS = 64 + EPI_GROUPS * 128;     // TMA warp + MMA warp + 2 x 4 epilogue warps
-
-static constexpr int MAX_STAGES = 8;
-static constexpr int SMEM_TOTAL = 232448;   // 227 KB: the whole SM, one persistent CTA per SM
-// control block at the end of the carve-up: barriers, tmem pointer
-static constexpr int CTRL_BYTES = 512;
-static constexpr int SMEM_USABLE = SMEM_TOTAL - 1024 /*alignment slack*/ - CTRL_BYTES;
-
-template <int BLOCK_N>
-struct TileCfg {
-    static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int ACC_COLS = (BLOCK_N <= 64) ? 64 : (BLOCK_N <= 128 ? 128 : 256);
-    static constexpr int TMEM_COLS = 2 * ACC_COLS;  // double-buffered accumulator
-};
-
-__device__ __forceinline__ float wsilu_f(float x)
-{
-    // x * sigmoid(4x) = 0.5 x (1 + tanh(2x))   (reference: src/layers/layers.py:106-111); one MUFU op
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(2.f * x));
-    return 0.5f * x * (1.f + t);
-}
-
-// 16-byte residual load.  Keeps the default L1 allocation on purpose: a thread walks its own row 16 bytes at a
-// time, so 7 of 8 loads of a 128-byte line are L1 hits (L1::no_allocate turned them into 8 L2 requests: 40.7 us
-// instead of 25.8 us for the M=32640, N=K=384 shortcut GEMM)
-__device__ __forceinline__ uint4 ld_stream16(const __half* p)
-{
-    return *reinterpret_cast<const uint4*>(p);
-}
-
-// pull one 16-byte piece (hence its 128-byte line) into L1
-__device__ __forceinline__ void l1_touch(const __half* p)
-{
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
-
-// d = a * b + c with fp16 a, b and fp32 c, d in one instruction (SASS FHFMA, .H0/.H1 operand selectors)
-__device__ __forceinline__ float fma_f32_f16(uint16_t a, uint16_t b, float c)
-{
-    asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(c) : "h"(a), "h"(b));
-    return c;
-}
-
-struct TileCoord {
-    int n0, ox0, oy0, oc0, opx, opy;
-};
-
-__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) { return (__umulhi(x, f.mul) + x) >> f.shr; }
 
 template <int BLOCK_N>
 __device__ __forceinline__ TileCoord tile_coord(const PwGemmParams& p, int tile)
@@ -105,15 +50,6 @@ __device__ __forceinline__ TileCoord tile_coord(const PwGemmParams& p, int tile)
 
 // Persistent kernel: grid = min(#tiles, #SMs), one CTA per SM, tiles assigned round-robin with the
 // N tile fastest so that concurrently running CTAs share the same activation tile in L2.
-__device__ __forceinline__ void trace_mark(const PwGemmParams& p, int slot)
-{
-    if (p.trace) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        p.trace[blockIdx.x * 64 + slot] = t;
-    }
-}
-
 template <int BLOCK_N, bool CHUNK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
@@ -305,261 +241,31 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
         __syncwarp();
     } else {
         // ---------------------------------------------------------------- epilogue (2 groups x 4 warps)
-        // Latency-bound by construction (one warp per TMEM lane quarter), so everything it waits for is requested
-        // one 32-column chunk ahead: the next tcgen05.ld, and bias / quant-scale / residual vectors as 16-byte global
-        // loads into registers.  One named barrier per store box; no divergent branches, no integer divisions.
-        const int g = (warp - 2) >> 2;       // group <-> accumulator buffer
-        const int q = warp & 3;              // TMEM lane quarter this warp may touch
-        const int row = q * 32 + lane;
-        const bool issuer = (warp == 2 + 4 * g) && lane == 0;
-        const uint32_t bar_id = 1 + g;
-        constexpr bool OUT32 = CHUNK && BLOCK_N == 128;  // 32-column store box (SWIZZLE_64B rows)
+        constexpr bool OUT32 = CHUNK && BLOCK_N == 128;
         constexpr int SUB_BYTES = OUT32 ? SUB_TILE_BYTES / 2 : SUB_TILE_BYTES;
-        uint8_t* stage_g = staging + g * p.staging_bufs * SUB_BYTES;
-        constexpr int NC = BLOCK_N / 32;     // accumulator chunks of 32 columns per tile
-        const bool two_bufs = p.staging_bufs == 2;
-        const bool has_bias = p.bias != nullptr;
-        const bool has_q = p.qscale != nullptr;
-        const int n_res = p.n_res;
-        const bool act = p.act == ACT_WSILU;
-        uint32_t cnt = 0;  // store-box counter of this group
-        const uint16_t ONE = 0x3C00;  // fp16 1.0: fma_f32_f16(h, ONE, x) == x + float(h) in one FHFMA
-
-        auto sw_off = [&](int chunk) -> uint32_t {
-            return OUT32 ? static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4))
-                         : sw128_offset(row, chunk);
-        };
-        // publish a finished store box: every earlier store of this group has left its staging buffer (so the buffer
-        // the NEXT box writes is free), all 128 rows are written, then one thread issues the TMA store
-        auto publish = [&](uint8_t* sbuf, const TileCoord& tc, int c0) {
-            fence_proxy_async_smem();
-            if (issuer) tma_store_wait_read<0>();
-            named_bar_sync(bar_id, 128);
-            if (issuer) {
-                if (p.linear) tma_store_2d(&p.tm_c, sbuf, c0, tc.ox0);
-                else tma_store_5d(&p.tm_c, sbuf, c0, tc.opx, tc.ox0, tc.opy, tc.oy0);
-                tma_store_commit();
-                if (!two_bufs) tma_store_wait_read<0>();
-            }
-            if (!two_bufs) named_bar_sync(bar_id, 128);
-            ++cnt;
-        };
-
+        EpiWarp ew;
+        ew.g = (warp - 2) >> 2;
+        ew.q = warp & 3;
+        ew.lane = lane;
+        ew.row = ew.q * 32 + lane;
+        ew.issuer = (warp == 2 + 4 * ew.g) && lane == 0;
+        ew.two_bufs = p.staging_bufs == 2;
+        ew.bar_id = 1 + ew.g;
+        ew.stage_g = staging + ew.g * p.staging_bufs * SUB_BYTES;
+        ew.cnt = 0;
+        const int g = ew.g;
         for (int i = g;; i += 2) {
             const int tile = tile_of(i);
             if (tile < 0) break;
             const TileCoord tc = tile_coord<BLOCK_N>(p, tile);
             const uint32_t u = static_cast<uint32_t>(i >> 1);
-            // residual rows of this thread (same pixel grid as the output); rows past the edge are clamped to a valid
-            // one — their results are clipped by the TMA store
-            const __half* r1_row = nullptr;
-            const __half* r2_row = nullptr;
-            if (n_res > 0) {
-                const int ry = static_cast<int>(fdiv(row, p.fd_bw));
-                long long x = tc.ox0 + (row - ry * p.bw);
-                long long y = tc.oy0 + ry;
-                x = x < p.res_w ? x : p.res_w - 1;
-                y = y < p.res_h ? y : p.res_h - 1;
-                r1_row = p.r1 + (y * p.res_w + x) * p.r1_pitch + tc.oc0;
-                r2_row = (n_res > 1) ? p.r2 + (y * p.res_w + x) * p.r2_pitch + tc.oc0 : r1_row;
-            }
-            const uint4* bias_v = reinterpret_cast<const uint4*>(p.bias + tc.n0);
-            const uint4* q_v = reinterpret_cast<const uint4*>(p.qscale + tc.oc0);
-            const uint32_t acc = tmem_base + g * Cfg::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
-            const uint4 zero4 = make_uint4(0, 0, 0, 0);
-            // warm L1 with this tile's bias / scale vectors while the accumulator is still being produced: the
-            // per-chunk loads below are then warp-uniform L1 hits (their miss latency used to be exposed once per
-            // 128-byte line, i.e. every other chunk)
-            if (has_bias && lane * 8 < BLOCK_N) l1_touch(p.bias + tc.n0 + lane * 8);
-            if (has_q && lane * 8 < (CHUNK ? BLOCK_N / 4 : BLOCK_N)) l1_touch(p.qscale + tc.oc0 + lane * 8);
-
-            if constexpr (!CHUNK) {
-                // ------------------------------------------------ plain tile: 32 accumulator columns -> 32 outputs
-                uint4 n1[4];  // first residual of the NEXT chunk (L2 latency); bias / scale / second residual are
-                              // requested at the top of their own chunk (warp-uniform L1 hits, resp. rarely used)
-                auto prefetch = [&](int a) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (n_res > 0) n1[j] = ld_stream16(r1_row + a * 32 + j * 8);
-                    }
-                };
-                prefetch(0);
-                mbar_wait(&tmem_full_bar[g], u & 1);
-                tcgen05_fence_after();
-                if (lane == 0 && q == 0) trace_mark(p, i == 0 ? 7 : (i == 1 ? 9 : 11));
-                if (p.dbg & 2) {  // micro-benchmark: drain nothing, just hand the accumulator back
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
-                    continue;
-                }
-                uint32_t vn[32];
-                tmem_ld_32x32b_x32(acc, vn);
-                uint8_t* sbuf = nullptr;
-#pragma unroll 1
-                for (int a = 0; a < NC; ++a) {
-                    uint4 cb[4], cq[4], c1[4], c2[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        cb[j] = has_bias ? __ldg(bias_v + a * 4 + j) : zero4;
-                        if (has_q) cq[j] = __ldg(q_v + a * 4 + j);
-                        if (n_res > 1) c2[j] = ld_stream16(r2_row + a * 32 + j * 8);
-                        c1[j] = n1[j];
-                    }
-                    uint32_t v[32];
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = vn[j];
-                    if (a + 1 < NC) {
-                        tmem_ld_32x32b_x32(acc + (a + 1) * 32, vn);
-                        prefetch(a + 1);
-                    } else {
-                        // every tcgen05.ld of this tile has completed: hand the accumulator back to the MMA warp
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
-                    }
-                    if ((a & 1) == 0) sbuf = stage_g + (two_bufs ? (cnt & 1) : 0) * SUB_BYTES;
-                    // one pass per epilogue term over the 32 columns: each optional term is a warp-uniform branch
-                    // around a short unrolled loop (keeps the kernel small: no per-combination code clones)
-                    const uint32_t* bw = reinterpret_cast<const uint32_t*>(cb);
-                    const uint32_t* qw = reinterpret_cast<const uint32_t*>(cq);
-                    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(c1);
-                    const uint32_t* w2 = reinterpret_cast<const uint32_t*>(c2);
-                    float t[32];
-#pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        t[e] = fma_f32_f16(static_cast<uint16_t>(bw[e >> 1] & 0xffffu), ONE, __uint_as_float(v[e]));
-                        t[e + 1] = fma_f32_f16(static_cast<uint16_t>(bw[e >> 1] >> 16), ONE, __uint_as_float(v[e + 1]));
-                    }
-                    if (act) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) t[e] = wsilu_f(t[e]);
-                    }
-                    if (n_res > 0) {
-#pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
-                            t[e] = fma_f32_f16(static_cast<uint16_t>(w1[e >> 1] & 0xffffu), ONE, t[e]);
-                            t[e + 1] = fma_f32_f16(static_cast<uint16_t>(w1[e >> 1] >> 16), ONE, t[e + 1]);
-                        }
-                    }
-                    if (n_res > 1) {
-#pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
-                            t[e] = fma_f32_f16(static_cast<uint16_t>(w2[e >> 1] & 0xffffu), ONE, t[e]);
-                            t[e + 1] = fma_f32_f16(static_cast<uint16_t>(w2[e >> 1] >> 16), ONE, t[e + 1]);
-                        }
-                    }
-                    if (has_q) {
-#pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
-                            const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qw[e >> 1]));
-                            t[e] *= qf.x;
-                            t[e + 1] *= qf.y;
-                        }
-                    }
-#pragma unroll
-                    for (int gq = 0; gq < 4; ++gq) {
-                        uint4 w;
-                        uint32_t* ww = reinterpret_cast<uint32_t*>(&w);
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const __half2 h = __floats2half2_rn(t[gq * 8 + jj * 2], t[gq * 8 + jj * 2 + 1]);
-                            ww[jj] = *reinterpret_cast<const uint32_t*>(&h);
-                        }
-                        *reinterpret_cast<uint4*>(sbuf + sw128_offset(row, (a & 1) * 4 + gq)) = w;
-                    }
-                    if (a & 1) publish(sbuf, tc, tc.oc0 + (a >> 1) * 64);
-                }
-            } else {
-                // ------------------------------------------------ 4 -> 1 fold: 32 accumulator columns -> 8 outputs
-                uint4 nb[4], nq, n1, n2;
-                auto prefetch = [&](int a) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) nb[j] = has_bias ? __ldg(bias_v + a * 4 + j) : zero4;
-                    if (has_q) nq = __ldg(q_v + a);
-                    if (n_res > 0) n1 = ld_stream16(r1_row + a * 8);
-                    if (n_res > 1) n2 = ld_stream16(r2_row + a * 8);
-                };
-                prefetch(0);
-                mbar_wait(&tmem_full_bar[g], u & 1);
-                tcgen05_fence_after();
-                if (lane == 0 && q == 0) trace_mark(p, i == 0 ? 7 : (i == 1 ? 9 : 11));
-                if (p.dbg & 2) {
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
-                    continue;
-                }
-                uint32_t vn[32];
-                tmem_ld_32x32b_x32(acc, vn);
-                uint8_t* sbuf = stage_g + (two_bufs ? (cnt & 1) : 0) * SUB_BYTES;
-#pragma unroll 1
-                for (int a = 0; a < NC; ++a) {
-                    uint4 cb[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) cb[j] = nb[j];
-                    const uint4 cq = nq, c1 = n1, c2 = n2;
-                    uint32_t v[32];
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = vn[j];
-                    if (a + 1 < NC) {
-                        tmem_ld_32x32b_x32(acc + (a + 1) * 32, vn);
-                        prefetch(a + 1);
-                    } else {
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
-                    }
-                    const uint32_t* bw = reinterpret_cast<const uint32_t*>(cb);
-                    const uint32_t* qw = reinterpret_cast<const uint32_t*>(&cq);
-                    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(&c1);
-                    const uint32_t* w2 = reinterpret_cast<const uint32_t*>(&c2);
-                    uint4 w;
-                    uint32_t* ww = reinterpret_cast<uint32_t*>(&w);
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        float o[2];
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int j = jj * 2 + h;  // output column of this chunk; folds acc columns 4j .. 4j+3
-                            float s4 = 0.f;
-#pragma unroll
-                            for (int e = 0; e < 4; e += 2) {
-                                const uint32_t bword = bw[(4 * j + e) >> 1];
-                                float t0 = fma_f32_f16(static_cast<uint16_t>(bword & 0xffffu), ONE, __uint_as_float(v[4 * j + e]));
-                                float t1 = fma_f32_f16(static_cast<uint16_t>(bword >> 16), ONE, __uint_as_float(v[4 * j + e + 1]));
-                                if (act) { t0 = wsilu_f(t0); t1 = wsilu_f(t1); }
-                                s4 += t0;
-                                s4 += t1;
-                            }
-                            o[h] = s4;
-                        }
-                        if (n_res > 0) {
-                            o[0] = fma_f32_f16(static_cast<uint16_t>(w1[jj] & 0xffffu), ONE, o[0]);
-                            o[1] = fma_f32_f16(static_cast<uint16_t>(w1[jj] >> 16), ONE, o[1]);
-                        }
-                        if (n_res > 1) {
-                            o[0] = fma_f32_f16(static_cast<uint16_t>(w2[jj] & 0xffffu), ONE, o[0]);
-                            o[1] = fma_f32_f16(static_cast<uint16_t>(w2[jj] >> 16), ONE, o[1]);
-                        }
-                        if (has_q) {
-                            const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qw[jj]));
-                            o[0] *= qf.x;
-                            o[1] *= qf.y;
-                        }
-                        const __half2 h2 = __floats2half2_rn(o[0], o[1]);
-                        ww[jj] = *reinterpret_cast<const uint32_t*>(&h2);
-                    }
-                    *reinterpret_cast<uint4*>(sbuf + sw_off(a)) = w;
-                }
-                publish(sbuf, tc, tc.oc0);
-            }
-            if (lane == 0 && q == 0) trace_mark(p, i == 0 ? 8 : (i == 1 ? 10 : 12));  // epilogue of tile i done
+            const uint32_t acc = tmem_base + g * Cfg::ACC_COLS + (static_cast<uint32_t>(ew.q * 32) << 16);
+            epilogue_tile<BLOCK_N, CHUNK>(p, tc, acc, &tmem_full_bar[g], u & 1, &tmem_empty_bar[g], 0u, ew,
+                                          i == 0 ? 7 : (i == 1 ? 9 : 11));
+            if (lane == 0 && ew.q == 0) trace_mark(p, i == 0 ? 8 : (i == 1 ? 10 : 12));  // epilogue of tile i done
         }
-        if (issuer) tma_store_wait_read<0>();
-        if (lane == 0 && q == 0) trace_mark(p, 13 + g);  // group drained
+        if (ew.issuer) tma_store_wait_read<0>();
+        if (lane == 0 && ew.q == 0) trace_mark(p, 13 + g);  // group drained
         __syncwarp();
     }
 
@@ -576,6 +282,7 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
 
 static thread_local std::string g_err;
 const char* gemm_last_error() { return g_err.c_str(); }
+void gemm_set_error(const std::string& e) { g_err = e; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -595,9 +302,8 @@ static EncodeTiledFn get_encode_fn()
     return fn;
 }
 
-static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box,
-                      CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B)
+int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims,
+               const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
@@ -632,8 +338,7 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
 }
 
 // 5-D map of an NHWC view.  split2: expose the 2x2 pixel phases as dims 1 and 3.
-static int encode_act_map(CUtensorMap* m, const ActView& v, bool split2, bool linear, bool lin2d, int bw, int bh,
-                          int box_c = 64)
+int encode_act_map(CUtensorMap* m, const ActView& v, bool split2, bool linear, bool lin2d, int bw, int bh, int box_c)
 {
     const uint64_t pb = static_cast<uint64_t>(v.pitch) * 2;
     uint64_t dims[5];
@@ -674,7 +379,7 @@ struct TilePlan {
     int cluster = 1;
 };
 
-static FastDiv make_fastdiv(uint32_t d)
+FastDiv make_fastdiv(uint32_t d)
 {
     FastDiv f;
     uint32_t s = 0;
@@ -890,6 +595,32 @@ int gemm_plan(GemmOp& op)
             if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) num_sms = v;
         }
     }
+    {
+        // geometry checks shared by both kernels
+        const int out_c = op.chunk_add ? op.N / 4 : (op.kind == GEMM_TCONV2X2 ? op.N / 4 : op.N);
+        if (op.out.C != out_c) { g_err = "gemm_plan: out.C does not match N"; return 1; }
+        if (op.res2.ptr && !op.res1.ptr) { g_err = "gemm_plan: res2 without res1"; return 1; }
+        if (op.res1.ptr) {
+            if (op.kind == GEMM_TCONV2X2) { g_err = "gemm_plan: tconv takes no residual"; return 1; }
+            const ActView* rs[2] = { &op.res1, &op.res2 };
+            for (int i = 0; i < (op.res2.ptr ? 2 : 1); ++i) {
+                if (rs[i]->W != op.out.W || rs[i]->H != op.out.H || rs[i]->C != op.out.C || (rs[i]->pitch % 8) ||
+                    (reinterpret_cast<uintptr_t>(rs[i]->ptr) & 15)) {
+                    g_err = "gemm_plan: residual geometry mismatch";
+                    return 1;
+                }
+            }
+        }
+    }
+    if (op.kind == GEMM_PW) {
+        // 1x1 ops with K <= 512: the A-resident / CTA-pair kernel (pw_gemm_ares.cu)
+        const int r = ares_plan(op, num_sms);
+        if (r == 0) return 0;
+        if (r == 2) return 1;
+        memset(&p, 0, sizeof(p));
+        p.tap_px[0] = p.tap_py[0] = p.tap_dx[0] = p.tap_dy[0] = 0;
+        p.bw = 128; p.bh = 1;
+    }
     const TilePlan tp = pick_tile_plan(n_unit, op.N, op.chunk_add != 0, m_tiles, taps * C / 64, num_sms);
     const int bn = tp.bn;
     if (bn == 0 || op.N % bn != 0) { g_err = "gemm_plan: unsupported N"; return 1; }
@@ -998,12 +729,14 @@ int gemm_init()
         g_err = std::string("cudaFuncSetAttribute(pw_gemm): ") + cudaGetErrorString(e);
         return 1;
     }
+    if (ares_init()) return 1;
     done = true;
     return 0;
 }
 
 // DCVC_B200_PDL=0 turns programmatic dependent launch off (debugging)
 static const bool g_pdl = []() { const char* e = getenv("DCVC_B200_PDL"); return !(e && e[0] == '0'); }();
+bool gemm_pdl_enabled() { return g_pdl; }
 
 template <int BN, bool CHUNK>
 static cudaError_t launch_bn(const GemmOp& op, cudaStream_t stream)
@@ -1031,6 +764,14 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream)
     if (!op.planned) { g_err = "gemm_launch: op not planned"; return 1; }
     if (gemm_init()) return 1;
     cudaError_t e;
+    if (op.ares) {
+        e = ares_launch(op, stream);
+        if (e != cudaSuccess) {
+            g_err = std::string("pw_gemm_ares launch failed: ") + cudaGetErrorString(e);
+            return 1;
+        }
+        return 0;
+    }
     switch (op.block_n + (op.chunk_add ? 1 : 0)) {
     case 64: e = launch_bn<64, false>(op, stream); break;
     case 128: e = launch_bn<128, false>(op, stream); break;

@@ -63,6 +63,8 @@ struct alignas(64) PwGemmParams {
                            // cycles per row to walk, measured 0.25 us per 128-row k-block; 2-D rows stream)
     int dbg;               // micro-benchmark switches (env DCVC_B200_GEMM_DBG): 1 = no MMA, 2 = no epilogue body
     unsigned long long* trace;  // env DCVC_B200_GEMM_TRACE=<device address>: 16 globaltimer slots per CTA (tools/gemm_trace.py)
+    int ares_ctas;         // 0: streaming kernel; 1 / 2: A-resident kernel on single CTAs / CTA pairs (pw_gemm_ares.cu)
+    int tiles_per_group;   // A-resident kernel: N tiles one work item runs through with its activation tile resident
     int num_kblocks;       // taps * C / 64
     int kblk_per_tap;      // C / 64
     int bw, bh;            // pixel tile, bw*bh == 128
@@ -90,6 +92,7 @@ struct GemmOp {
     PwGemmParams p;
     dim3 grid;
     int block_n = 0;
+    int ares = 0;       // 0: streaming kernel, 1 / 2: A-resident kernel with 1 / 2 CTAs per work item
     int stages = 0;
     size_t smem = 0;
     bool planned = false;
