@@ -117,7 +117,7 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
         mbar_init(slab_bar, 1);
         for (int g = 0; g < 2; ++g) {
             mbar_init(&tmem_full_bar[g], 1);
-            mbar_init(&tmem_empty_bar[g], 4);  // one arrival per epilogue warp of the group
+            mbar_init(&tmem_empty_bar[g], 8);  // one arrival per epilogue warp serving the buffer
         }
         mbar_fence_init();
     }
@@ -241,19 +241,15 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
         __syncwarp();
     } else {
         // ---------------------------------------------------------------- epilogue (2 groups x 4 warps)
-        constexpr bool OUT32 = CHUNK && BLOCK_N == 128;
-        constexpr int SUB_BYTES = OUT32 ? SUB_TILE_BYTES / 2 : SUB_TILE_BYTES;
         EpiWarp ew;
-        ew.g = (warp - 2) >> 2;
         ew.q = warp & 3;
         ew.lane = lane;
-        ew.row = ew.q * 32 + lane;
-        ew.issuer = (warp == 2 + 4 * ew.g) && lane == 0;
-        ew.two_bufs = p.staging_bufs == 2;
-        ew.bar_id = 1 + ew.g;
-        ew.stage_g = staging + ew.g * p.staging_bufs * SUB_BYTES;
+        ew.b = ((warp - 2) >> 2) & 1;
+        ew.h = (warp - 2) >> 3;
+        ew.slabs = p.staging_bufs;
+        ew.slab = staging + (warp - 2) * p.staging_bufs * EPI_SLAB_BYTES;
         ew.cnt = 0;
-        const int g = ew.g;
+        const int g = ew.b;
         for (int i = g;; i += 2) {
             const int tile = tile_of(i);
             if (tile < 0) break;
@@ -262,10 +258,10 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
             const uint32_t acc = tmem_base + g * Cfg::ACC_COLS + (static_cast<uint32_t>(ew.q * 32) << 16);
             epilogue_tile<BLOCK_N, CHUNK>(p, tc, acc, &tmem_full_bar[g], u & 1, &tmem_empty_bar[g], 0u, ew,
                                           i == 0 ? 7 : (i == 1 ? 9 : 11));
-            if (lane == 0 && ew.q == 0) trace_mark(p, i == 0 ? 8 : (i == 1 ? 10 : 12));  // epilogue of tile i done
+            if (lane == 0 && ew.q == 0 && ew.h == 0) trace_mark(p, i == 0 ? 8 : (i == 1 ? 10 : 12));  // epilogue of tile i done
         }
-        if (ew.issuer) tma_store_wait_read<0>();
-        if (lane == 0 && ew.q == 0) trace_mark(p, 13 + g);  // group drained
+        if (lane == 0) tma_store_wait_read<0>();
+        if (lane == 0 && ew.q == 0 && ew.h == 0) trace_mark(p, 13 + g);  // group drained
         __syncwarp();
     }
 
@@ -408,11 +404,10 @@ static TilePlan pick_tile_plan(int n_unit, int n_total, bool chunk_add, long lon
     for (int ci = 0; ci < 4; ++ci) {
         const int bn = cand_all[ci];
         if (n_unit % bn) continue;
-        if (chunk_add && bn != 128 && bn != 256) continue;  // 4->1 fold: the store box is 32 or 64 output columns
+        if (chunk_add && bn != 256) continue;  // 4->1 fold: 128 accumulator columns per epilogue warp -> one 32-column store box
         if (force_bn && bn != force_bn) continue;
         const int n_tiles = n_total / bn;
-        const int out_cols = chunk_add ? bn / 4 : bn;
-        const int sub_bytes = (out_cols == 32) ? SUB_TILE_BYTES / 2 : SUB_TILE_BYTES;
+        const int sub_bytes = SUB_TILE_BYTES;
         const int b_stage = bn * BLOCK_K * 2;
         const int slab = num_kblocks * b_stage;
         // cluster size.  Measured (tools/micro.sh, r1): with clusters of 3-6 CTAs the per-k-block cluster-wide
@@ -649,8 +644,9 @@ int gemm_plan(GemmOp& op)
         if (encode_map(&p.tm_b, op.weight, 2, dims, st, box)) return 1;
     }
     const bool out_split = (op.kind == GEMM_TCONV2X2);
-    const int out_box_c = (op.chunk_add && bn == 128) ? 32 : 64;
-    if (encode_act_map(&p.tm_c, op.out, out_split, linear, lin2d, p.bw, p.bh, out_box_c)) return 1;
+    // store box of one epilogue warp: 32 pixels (rows 32q .. 32q+31 of the tile) x 32 channels, SWIZZLE_64B
+    p.epi_rows_y = linear ? 1 : 32 / p.bw;
+    if (encode_act_map(&p.tm_c, op.out, out_split, linear, lin2d, linear ? 32 : p.bw, linear ? 1 : 32 / p.bw, 32)) return 1;
     if (op.res1.ptr) {
         if (op.kind == GEMM_TCONV2X2) { g_err = "gemm_plan: tconv takes no residual"; return 1; }
         const ActView* rs[2] = { &op.res1, &op.res2 };
@@ -704,7 +700,7 @@ int gemm_plan(GemmOp& op)
     op.stages = p.num_stages;
     if (p.num_stages < 2) { g_err = "gemm_plan: pipeline does not fit"; return 1; }
     if (!op.chunk_add && bn % 64 != 0) { g_err = "gemm_plan: BLOCK_N must be a multiple of 64"; return 1; }
-    if (op.chunk_add && bn != 128 && bn != 256) { g_err = "gemm_plan: chunk-add needs BLOCK_N 128 or 256"; return 1; }
+    if (op.chunk_add && bn != 256) { g_err = "gemm_plan: chunk-add needs BLOCK_N 256"; return 1; }
     op.planned = true;
     return 0;
 }
@@ -723,7 +719,6 @@ int gemm_init()
     if (e == cudaSuccess) e = set_attr<128, false>();
     if (e == cudaSuccess) e = set_attr<192, false>();
     if (e == cudaSuccess) e = set_attr<256, false>();
-    if (e == cudaSuccess) e = set_attr<128, true>();
     if (e == cudaSuccess) e = set_attr<256, true>();
     if (e != cudaSuccess) {
         g_err = std::string("cudaFuncSetAttribute(pw_gemm): ") + cudaGetErrorString(e);
@@ -777,7 +772,6 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream)
     case 128: e = launch_bn<128, false>(op, stream); break;
     case 192: e = launch_bn<192, false>(op, stream); break;
     case 256: e = launch_bn<256, false>(op, stream); break;
-    case 129: e = launch_bn<128, true>(op, stream); break;
     case 257: e = launch_bn<256, true>(op, stream); break;
     default: g_err = "gemm_launch: bad block_n"; return 1;
     }

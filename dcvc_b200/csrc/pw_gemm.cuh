@@ -55,7 +55,7 @@ struct alignas(64) PwGemmParams {
     int m_tiles;           // tiles_x * tiles_y
     int b_resident;        // 1: the CTA keeps the whole [BLOCK_N][K] weight slab of its N tile in smem
     int num_stages;        // pipeline depth (A+B stages when streaming, A-only stages when b_resident)
-    int staging_bufs;      // store staging buffers per epilogue group (1 or 2)
+    int staging_bufs;      // staging slabs per epilogue warp (1 or 2)
     int cluster;           // CTAs per cluster = N tiles that share one multicast activation tile (1: no cluster)
     int n_groups;          // n_tiles / cluster
     int num_clusters;      // gridDim.x / cluster
@@ -68,6 +68,7 @@ struct alignas(64) PwGemmParams {
     int num_kblocks;       // taps * C / 64
     int kblk_per_tap;      // C / 64
     int bw, bh;            // pixel tile, bw*bh == 128
+    int epi_rows_y;        // 32 / bw: image rows covered by one epilogue warp's 32 pixels (5-D tiles)
     int act;               // GemmAct
     int chunk_add;         // 1: out[:, j] = sum_{i<4} act(acc[:, 4j+i])
     int n_res;             // 0,1,2 residual operands (same geometry as the output)

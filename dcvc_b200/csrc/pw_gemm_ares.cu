@@ -79,7 +79,7 @@ pw_gemm_ares_kernel(const __grid_constant__ PwGemmParams p)
         }
         for (int g = 0; g < 2; ++g) {
             mbar_init(&tmem_full_bar[g], 1);
-            mbar_init(&tmem_empty_bar[g], 4 * CTAS);  // one arrival per epilogue warp of the group, both CTAs
+            mbar_init(&tmem_empty_bar[g], 8 * CTAS);  // one arrival per epilogue warp serving the buffer, both CTAs
         }
         mbar_fence_init();
     }
@@ -194,19 +194,15 @@ pw_gemm_ares_kernel(const __grid_constant__ PwGemmParams p)
         __syncwarp();
     } else {
         // ---------------------------------------------------------------- epilogue (2 groups x 4 warps, both CTAs)
-        constexpr bool OUT32 = CHUNK && BLOCK_N == 128;
-        constexpr int SUB_BYTES = OUT32 ? SUB_TILE_BYTES / 2 : SUB_TILE_BYTES;
         EpiWarp ew;
-        ew.g = (warp - 2) >> 2;
         ew.q = warp & 3;
         ew.lane = lane;
-        ew.row = ew.q * 32 + lane;
-        ew.issuer = (warp == 2 + 4 * ew.g) && lane == 0;
-        ew.two_bufs = p.staging_bufs == 2;
-        ew.bar_id = 1 + ew.g;
-        ew.stage_g = staging + ew.g * p.staging_bufs * SUB_BYTES;
+        ew.b = ((warp - 2) >> 2) & 1;
+        ew.h = (warp - 2) >> 3;
+        ew.slabs = p.staging_bufs;
+        ew.slab = staging + (warp - 2) * p.staging_bufs * EPI_SLAB_BYTES;
         ew.cnt = 0;
-        const int g = ew.g;
+        const int g = ew.b;
         const uint32_t empty_remote = PAIR ? mapa_u32(smem_u32(&tmem_empty_bar[g]), 0) : 0u;
         const uint32_t acc = tmem_base + g * Cfg::ACC_COLS + (static_cast<uint32_t>(ew.q * 32) << 16);
         uint32_t t = 0;
@@ -224,11 +220,11 @@ pw_gemm_ares_kernel(const __grid_constant__ PwGemmParams p)
                 tc.oc0 = CHUNK ? tc.n0 / 4 : tc.n0;
                 epilogue_tile<BLOCK_N, CHUNK>(p, tc, acc, &tmem_full_bar[g], (t >> 1) & 1, &tmem_empty_bar[g], empty_remote,
                                               ew, t == 0 ? 7 : (t == 1 ? 9 : 11));
-                if (lane == 0 && ew.q == 0) trace_mark(p, t == 0 ? 8 : (t == 1 ? 10 : 12));
+                if (lane == 0 && ew.q == 0 && ew.h == 0) trace_mark(p, t == 0 ? 8 : (t == 1 ? 10 : 12));
             }
         }
-        if (ew.issuer) tma_store_wait_read<0>();
-        if (lane == 0 && ew.q == 0) trace_mark(p, 13 + g);  // group drained
+        if (lane == 0) tma_store_wait_read<0>();
+        if (lane == 0 && ew.q == 0 && ew.h == 0) trace_mark(p, 13 + g);  // group drained
         __syncwarp();
     }
 
@@ -256,7 +252,6 @@ static cudaError_t ares_set_attr_all()
     if (e == cudaSuccess) e = ares_set_attr<128, false, CTAS>();
     if (e == cudaSuccess) e = ares_set_attr<192, false, CTAS>();
     if (e == cudaSuccess) e = ares_set_attr<256, false, CTAS>();
-    if (e == cudaSuccess) e = ares_set_attr<128, true, CTAS>();
     if (e == cudaSuccess) e = ares_set_attr<256, true, CTAS>();
     return e;
 }
@@ -321,7 +316,7 @@ int ares_plan(GemmOp& op, int num_sms)
     if (const char* f = getenv("DCVC_B200_GEMM_BN")) force_bn = atoi(f);
     for (int i = 0; i < 4 && !bn; ++i) {
         if (op.N % cand[i]) continue;
-        if (op.chunk_add && cand[i] != 128 && cand[i] != 256) continue;
+        if (op.chunk_add && cand[i] != 256) continue;
         if (force_bn && cand[i] != force_bn) continue;
         bn = cand[i];
     }
@@ -333,8 +328,7 @@ int ares_plan(GemmOp& op, int num_sms)
     const int max_grps = ctas == 2 ? max_active_pairs(num_sms) : num_sms;
 
     // smem carve-up
-    const int out_cols = op.chunk_add ? bn / 4 : bn;
-    const int sub_bytes = (out_cols == 32) ? SUB_TILE_BYTES / 2 : SUB_TILE_BYTES;
+    const int sub_bytes = SUB_TILE_BYTES;
     const int b_stage = bn / ctas * BLOCK_K * 2;
     int staging_bufs = 2;
     int stages = (SMEM_USABLE - nkb * A_STAGE_BYTES - EPI_GROUPS * staging_bufs * sub_bytes) / b_stage;
@@ -391,8 +385,8 @@ int ares_plan(GemmOp& op, int num_sms)
         uint32_t box[2] = { 64, static_cast<uint32_t>(bn / ctas) };
         if (encode_map(&p.tm_b, op.weight, 2, dims, st, box)) return 2;
     }
-    const int out_box_c = (op.chunk_add && bn == 128) ? 32 : 64;
-    if (encode_act_map(&p.tm_c, op.out, false, true, true, BLOCK_M, 1, out_box_c)) return 2;
+    p.epi_rows_y = 1;
+    if (encode_act_map(&p.tm_c, op.out, false, true, true, 32, 1, 32)) return 2;
     if (op.res1.ptr) {
         p.r1 = static_cast<const __half*>(op.res1.ptr);
         p.r1_pitch = op.res1.pitch;
@@ -463,7 +457,6 @@ static cudaError_t ares_launch_ctas(const GemmOp& op, cudaStream_t stream)
     case 128: return ares_launch_bn<128, false, CTAS>(op, stream);
     case 192: return ares_launch_bn<192, false, CTAS>(op, stream);
     case 256: return ares_launch_bn<256, false, CTAS>(op, stream);
-    case 129: return ares_launch_bn<128, true, CTAS>(op, stream);
     case 257: return ares_launch_bn<256, true, CTAS>(op, stream);
     default: return cudaErrorInvalidValue;
     }

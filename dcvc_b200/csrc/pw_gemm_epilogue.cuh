@@ -3,23 +3,24 @@
 // residuals, per-channel quant scale.  One call drains one [128 pixels][BLOCK_N] accumulator tile with the four
 // warps of an epilogue group (one warp per TMEM lane quarter).
 //
-// Latency-bound by construction, so everything it waits for is requested one 32-column chunk ahead: the next
-// tcgen05.ld, and bias / quant-scale / residual vectors as 16-byte global loads into registers.  One named barrier
-// per store box; no divergent branches, no integer divisions.
+// Sixteen epilogue warps per CTA (four per SM sub-partition hide each other's TMEM / L1 / store latencies; measured
+// with ncu on the previous 8-warp version: 27 % issue utilisation, 3.5 us to drain one 128x192 tile).  A warp owns
+// 32 accumulator rows x half the columns of a tile, stages 32 output columns at a time in its own 2 KB slab and
+// stores it with its own TMA store: no cross-warp barriers, no divergent branches, no integer divisions.
 #pragma once
 #include "ptx.cuh"
 #include "pw_gemm.cuh"
 
 namespace dcvc {
 
-static constexpr int EPI_SUB_TILE_BYTES = 128 * 64 * 2;  // one [128][64] fp16 store box
 
 __device__ __forceinline__ float wsilu_f(float x)
 {
     // x * sigmoid(4x) = 0.5 x (1 + tanh(2x))   (reference: src/layers/layers.py:106-111); one MUFU op
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(2.f * x));
-    return 0.5f * x * (1.f + t);
+    const float h = 0.5f * x;
+    return fmaf(h, t, h);
 }
 
 // 16-byte residual load.  Keeps the default L1 allocation on purpose: a thread walks its own row 16 bytes at a
@@ -43,6 +44,24 @@ __device__ __forceinline__ float fma_f32_f16(uint16_t a, uint16_t b, float c)
     return c;
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+// 16-byte global -> shared copy that bypasses registers and L1 (LDGSTS)
+__device__ __forceinline__ void ldgsts16(uint32_t smem_addr, const void* gptr)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+
 struct TileCoord {
     int n0, ox0, oy0, oc0, opx, opy;
 };
@@ -58,36 +77,39 @@ __device__ __forceinline__ void trace_mark(const PwGemmParams& p, int slot)
     }
 }
 
-// per-thread state of an epilogue warp
+// per-thread state of an epilogue warp.  16 epilogue warps per CTA: warp (b, h, q) drains TMEM lane quarter q
+// (accumulator rows 32q .. 32q+31) of column half h of every tile that lands in accumulator buffer b.
 struct EpiWarp {
-    int g;              // epilogue group <-> accumulator buffer
-    int q;              // TMEM lane quarter this warp may touch
+    int q;           // TMEM lane quarter this warp may touch (warp index & 3)
     int lane;
-    int row;            // q * 32 + lane: the accumulator row (pixel of the tile) this thread owns
-    bool issuer;        // the thread of the group that issues TMA stores
-    bool two_bufs;      // two staging buffers per group
-    uint32_t bar_id;    // named barrier of the group
-    uint8_t* stage_g;   // staging buffers of the group
-    uint32_t cnt;       // store-box counter of the group
+    int b;           // accumulator buffer served
+    int h;           // column half served
+    uint8_t* slab;   // this warp's staging slabs ([32 rows][64 B], SWIZZLE_64B), `slabs` of them (generic pointer: TMA source)
+    int slabs;       // 1 or 2
+    uint32_t cnt;    // store counter (slab ring)
 };
 
-// acc: TMEM address of the accumulator buffer including this warp's lane offset.
+static constexpr int EPI_SLAB_BYTES = 32 * 64;  // one [32 rows][32 fp16] store box
+
+// Drains this warp's share of one accumulator tile: rows 32q..32q+31, accumulator columns [h*BLOCK_N/2, (h+1)*BLOCK_N/2).
+// acc: TMEM address of the accumulator buffer including this warp's lane offset (column 0 of the tile).
 // full_bar / full_parity: "accumulator complete" barrier (local).  The accumulator is handed back by one arrival
 // per warp on the "accumulator drained" barrier: `empty_remote` != 0 is its shared::cluster address (CTA-pair
 // kernel: the barrier lives in the leader CTA), otherwise `empty_local` is used.
+// Every 32 output columns leave through the warp's own staging slab and its own TMA store (box = 32 rows x 32
+// columns): no cross-warp barrier anywhere in the epilogue.
 template <int BLOCK_N, bool CHUNK>
 __device__ __forceinline__ void epilogue_tile(const PwGemmParams& p, const TileCoord& tc, uint32_t acc, uint64_t* full_bar,
                                               uint32_t full_parity, uint64_t* empty_local, uint32_t empty_remote,
                                               EpiWarp& w, int trace_slot)
 {
-    constexpr bool OUT32 = CHUNK && BLOCK_N == 128;  // 32-column store box (SWIZZLE_64B rows)
-    constexpr int SUB_BYTES = OUT32 ? EPI_SUB_TILE_BYTES / 2 : EPI_SUB_TILE_BYTES;
-    constexpr int NC = BLOCK_N / 32;  // accumulator chunks of 32 columns per tile
-    const int row = w.row, lane = w.lane, q = w.q;
-    const bool two_bufs = w.two_bufs;
-    const bool issuer = w.issuer;
-    const uint32_t bar_id = w.bar_id;
-    uint8_t* stage_g = w.stage_g;
+    static_assert(!CHUNK || BLOCK_N == 256, "the 4:1 fold is built for 256-column tiles");
+    constexpr int HALF = BLOCK_N / 2;  // accumulator columns per warp
+    constexpr int NC = HALF / 32;      // 32-column chunks per warp
+    const int lane = w.lane, q = w.q;
+    const int row = q * 32 + lane;
+    const int col0 = w.h * HALF;                      // first accumulator column of this warp
+    const int ocol0 = CHUNK ? col0 / 4 : col0;        // first output column (relative to tc.oc0)
     const bool has_bias = p.bias != nullptr;
     const bool has_q = p.qscale != nullptr;
     const int n_res = p.n_res;
@@ -95,7 +117,7 @@ __device__ __forceinline__ void epilogue_tile(const PwGemmParams& p, const TileC
     const uint16_t ONE = 0x3C00;  // fp16 1.0: fma_f32_f16(h, ONE, x) == x + float(h) in one FHFMA
 
     auto hand_back = [&]() {
-        // every tcgen05.ld of this tile has completed: hand the accumulator back to the MMA warp
+        // every tcgen05.ld of this warp for this tile has completed: hand the accumulator back to the MMA warp
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -103,24 +125,28 @@ __device__ __forceinline__ void epilogue_tile(const PwGemmParams& p, const TileC
             else mbar_arrive(empty_local);
         }
     };
-    auto sw_off = [&](int chunk) -> uint32_t {
-        return OUT32 ? static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4))
-                     : sw128_offset(row, chunk);
+    // staging slab for the next store box: the store that last used it has finished reading it
+    auto acquire_slab = [&]() -> uint8_t* {
+        if (lane == 0) {
+            if (w.slabs == 2) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+        }
+        __syncwarp();
+        return w.slab + (w.slabs == 2 ? (w.cnt & 1) : 0) * EPI_SLAB_BYTES;
     };
-    // publish a finished store box: every earlier store of this group has left its staging buffer (so the buffer
-    // the NEXT box writes is free), all 128 rows are written, then one thread issues the TMA store
+    // all 32 rows of the box are written: one lane issues the TMA store of [32 rows][32 columns] at output column c0
     auto publish = [&](uint8_t* sbuf, int c0) {
         fence_proxy_async_smem();
-        if (issuer) tma_store_wait_read<0>();
-        named_bar_sync(bar_id, 128);
-        if (issuer) {
-            if (p.linear) tma_store_2d(&p.tm_c, sbuf, c0, tc.ox0);
-            else tma_store_5d(&p.tm_c, sbuf, c0, tc.opx, tc.ox0, tc.opy, tc.oy0);
+        __syncwarp();
+        if (lane == 0) {
+            if (p.linear) tma_store_2d(&p.tm_c, sbuf, c0, tc.ox0 + q * 32);
+            else tma_store_5d(&p.tm_c, sbuf, c0, tc.opx, tc.ox0, tc.opy, tc.oy0 + q * p.epi_rows_y);
             tma_store_commit();
-            if (!two_bufs) tma_store_wait_read<0>();
         }
-        if (!two_bufs) named_bar_sync(bar_id, 128);
         ++w.cnt;
+    };
+    auto sw64 = [&](int chunk16) -> uint32_t {
+        return static_cast<uint32_t>(lane * 64 + ((chunk16 ^ ((lane >> 1) & 3)) << 4));
     };
 
     // residual rows of this thread (same pixel grid as the output); rows past the edge are clamped to a valid
@@ -133,66 +159,78 @@ __device__ __forceinline__ void epilogue_tile(const PwGemmParams& p, const TileC
         long long y = tc.oy0 + ry;
         x = x < p.res_w ? x : p.res_w - 1;
         y = y < p.res_h ? y : p.res_h - 1;
-        r1_row = p.r1 + (y * p.res_w + x) * p.r1_pitch + tc.oc0;
-        r2_row = (n_res > 1) ? p.r2 + (y * p.res_w + x) * p.r2_pitch + tc.oc0 : r1_row;
+        r1_row = p.r1 + (y * p.res_w + x) * p.r1_pitch + tc.oc0 + ocol0;
+        r2_row = (n_res > 1) ? p.r2 + (y * p.res_w + x) * p.r2_pitch + tc.oc0 + ocol0 : r1_row;
     }
-    const uint4* bias_v = reinterpret_cast<const uint4*>(p.bias + tc.n0);
-    const uint4* q_v = reinterpret_cast<const uint4*>(p.qscale + tc.oc0);
+    const uint4* bias_v = reinterpret_cast<const uint4*>(p.bias + tc.n0 + col0);
+    const uint4* q_v = reinterpret_cast<const uint4*>(p.qscale + tc.oc0 + ocol0);
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
-    // warm L1 with this tile's bias / scale vectors while the accumulator is still being produced: the
-    // per-chunk loads below are then warp-uniform L1 hits (their miss latency used to be exposed once per
-    // 128-byte line, i.e. every other chunk)
-    if (has_bias && lane * 8 < BLOCK_N) l1_touch(p.bias + tc.n0 + lane * 8);
-    if (has_q && lane * 8 < (CHUNK ? BLOCK_N / 4 : BLOCK_N)) l1_touch(p.qscale + tc.oc0 + lane * 8);
+    // warm L1 with this warp's bias / scale vectors while the accumulator is still being produced
+    if (has_bias && lane * 8 < HALF) l1_touch(p.bias + tc.n0 + col0 + lane * 8);
+    if (has_q && lane * 8 < (CHUNK ? HALF / 4 : HALF)) l1_touch(p.qscale + tc.oc0 + ocol0 + lane * 8);
 
     if constexpr (!CHUNK) {
-        // ------------------------------------------------ plain tile: 32 accumulator columns -> 32 outputs
-        uint4 n1[4];  // first residual of the NEXT chunk (L2 latency); bias / scale / second residual are
-                      // requested at the top of their own chunk (warp-uniform L1 hits, resp. rarely used)
-        auto prefetch = [&](int a) {
+        // ------------------------------------------------ plain tile: 32 accumulator columns -> 32 outputs -> one store
+        // First residual: fetched warp-coalesced (one LDGSTS moves 8 rows x 64 B: lane l copies piece l & 3 of rows
+        // (l >> 2) + 8 j) straight into the staging slab the chunk is stored from; each thread then picks up its own
+        // row from there.  (One thread walking its own row with 16-byte loads — the previous scheme — makes every
+        // load instruction touch 32 different lines: the LSU was the bottleneck of the shortcut GEMMs.)
+        const __half* rr[4];
+        if (n_res > 0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (n_res > 0) n1[j] = ld_stream16(r1_row + a * 32 + j * 8);
+                const int r = q * 32 + (lane >> 2) + 8 * j;
+                const int ry = static_cast<int>(fdiv(r, p.fd_bw));
+                long long x = tc.ox0 + (r - ry * p.bw);
+                long long y = tc.oy0 + ry;
+                x = x < p.res_w ? x : p.res_w - 1;
+                y = y < p.res_h ? y : p.res_h - 1;
+                rr[j] = p.r1 + (y * p.res_w + x) * p.r1_pitch + tc.oc0 + ocol0 + (lane & 3) * 8;
             }
-        };
-        prefetch(0);
+        }
+        const uint32_t slab0 = smem_u32(w.slab);
+        const uint32_t my_sw = static_cast<uint32_t>(lane * 64);
+        const uint32_t my_x = static_cast<uint32_t>((lane >> 1) & 3);
         mbar_wait(full_bar, full_parity);
         tcgen05_fence_after();
-        if (lane == 0 && q == 0 && trace_slot >= 0) trace_mark(p, trace_slot);
+        if (lane == 0 && q == 0 && w.h == 0 && trace_slot >= 0) trace_mark(p, trace_slot);
         if (p.dbg & 2) {  // micro-benchmark: drain nothing, just hand the accumulator back
             hand_back();
             return;
         }
-        uint32_t vn[32];
-        tmem_ld_32x32b_x32(acc, vn);
-        uint8_t* sbuf = nullptr;
+        // per-phase SM-clock marks of the first tile's chunks (tools/gemm_trace.py): slots 16 + 8a + k
+        const bool tr = p.trace && trace_slot == 7 && q == 0 && w.h == 0 && lane == 0;
+        auto clk = [&](int a, int k) {
+            if (tr && a < 4) p.trace[blockIdx.x * 64 + 16 + a * 8 + k] = static_cast<unsigned long long>(clock64());
+        };
 #pragma unroll 1
         for (int a = 0; a < NC; ++a) {
-            uint4 cb[4], cq[4], c1[4], c2[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                cb[j] = has_bias ? __ldg(bias_v + a * 4 + j) : zero4;
-                if (has_q) cq[j] = __ldg(q_v + a * 4 + j);
-                if (n_res > 1) c2[j] = ld_stream16(r2_row + a * 32 + j * 8);
-                c1[j] = n1[j];
-            }
+            clk(a, 0);
             uint32_t v[32];
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = vn[j];
-            if (a + 1 < NC) {
-                tmem_ld_32x32b_x32(acc + (a + 1) * 32, vn);
-                prefetch(a + 1);
-            } else {
-                hand_back();
+            tmem_ld_32x32b_x32(acc + col0 + a * 32, v);
+            // staging slab of this chunk: the store that last used it has finished reading it
+            if (lane == 0) {
+                if (w.slabs == 2) tma_store_wait_read<1>();
+                else tma_store_wait_read<0>();
             }
-            if ((a & 1) == 0) sbuf = stage_g + (two_bufs ? (w.cnt & 1) : 0) * SUB_BYTES;
-            // one pass per epilogue term over the 32 columns: each optional term is a warp-uniform branch
-            // around a short unrolled loop (keeps the kernel small: no per-combination code clones)
+            __syncwarp();
+            const uint32_t sb = (w.slabs == 2 ? (w.cnt & 1) : 0) * EPI_SLAB_BYTES;
+            const uint32_t sbuf = slab0 + sb;
+            if (n_res > 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t rj = static_cast<uint32_t>((lane >> 2) + 8 * j);
+                    ldgsts16(sbuf + rj * 64 + ((static_cast<uint32_t>(lane & 3) ^ ((rj >> 1) & 3)) << 4), rr[j] + a * 32);
+                }
+                cp_async_commit();
+            }
+            uint4 cb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cb[j] = has_bias ? __ldg(bias_v + a * 4 + j) : zero4;
+            tmem_ld_wait();
+            clk(a, 1);
+            if (a + 1 == NC) hand_back();
             const uint32_t* bw = reinterpret_cast<const uint32_t*>(cb);
-            const uint32_t* qw = reinterpret_cast<const uint32_t*>(cq);
-            const uint32_t* w1 = reinterpret_cast<const uint32_t*>(c1);
-            const uint32_t* w2 = reinterpret_cast<const uint32_t*>(c2);
             float t[32];
 #pragma unroll
             for (int e = 0; e < 32; e += 2) {
@@ -203,14 +241,26 @@ __device__ __forceinline__ void epilogue_tile(const PwGemmParams& p, const TileC
 #pragma unroll
                 for (int e = 0; e < 32; ++e) t[e] = wsilu_f(t[e]);
             }
+            clk(a, 2);
             if (n_res > 0) {
+                cp_async_wait_all();
+                __syncwarp();
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    t[e] = fma_f32_f16(static_cast<uint16_t>(w1[e >> 1] & 0xffffu), ONE, t[e]);
-                    t[e + 1] = fma_f32_f16(static_cast<uint16_t>(w1[e >> 1] >> 16), ONE, t[e + 1]);
+                for (int gq = 0; gq < 4; ++gq) {
+                    const uint4 r = lds128(sbuf + my_sw + ((static_cast<uint32_t>(gq) ^ my_x) << 4));
+                    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(&r);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        t[gq * 8 + 2 * e] = fma_f32_f16(static_cast<uint16_t>(w1[e] & 0xffffu), ONE, t[gq * 8 + 2 * e]);
+                        t[gq * 8 + 2 * e + 1] = fma_f32_f16(static_cast<uint16_t>(w1[e] >> 16), ONE, t[gq * 8 + 2 * e + 1]);
+                    }
                 }
             }
             if (n_res > 1) {
+                uint4 c2[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c2[j] = ld_stream16(r2_row + a * 32 + j * 8);
+                const uint32_t* w2 = reinterpret_cast<const uint32_t*>(c2);
 #pragma unroll
                 for (int e = 0; e < 32; e += 2) {
                     t[e] = fma_f32_f16(static_cast<uint16_t>(w2[e >> 1] & 0xffffu), ONE, t[e]);
@@ -218,6 +268,10 @@ __device__ __forceinline__ void epilogue_tile(const PwGemmParams& p, const TileC
                 }
             }
             if (has_q) {
+                uint4 cq[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cq[j] = __ldg(q_v + a * 4 + j);
+                const uint32_t* qw = reinterpret_cast<const uint32_t*>(cq);
 #pragma unroll
                 for (int e = 0; e < 32; e += 2) {
                     const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qw[e >> 1]));
@@ -225,56 +279,44 @@ __device__ __forceinline__ void epilogue_tile(const PwGemmParams& p, const TileC
                     t[e + 1] *= qf.y;
                 }
             }
+            clk(a, 3);
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq) {
                 uint4 o;
                 uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                    const __half2 h = __floats2half2_rn(t[gq * 8 + jj * 2], t[gq * 8 + jj * 2 + 1]);
-                    ow[jj] = *reinterpret_cast<const uint32_t*>(&h);
+                    const __half2 h2 = __floats2half2_rn(t[gq * 8 + jj * 2], t[gq * 8 + jj * 2 + 1]);
+                    ow[jj] = *reinterpret_cast<const uint32_t*>(&h2);
                 }
-                *reinterpret_cast<uint4*>(sbuf + sw128_offset(row, (a & 1) * 4 + gq)) = o;
+                sts128(sbuf + my_sw + ((static_cast<uint32_t>(gq) ^ my_x) << 4), o);
             }
-            if (a & 1) publish(sbuf, tc.oc0 + (a >> 1) * 64);
+            clk(a, 4);
+            publish(w.slab + sb, tc.oc0 + ocol0 + a * 32);
+            clk(a, 5);
         }
     } else {
-        // ------------------------------------------------ 4 -> 1 fold: 32 accumulator columns -> 8 outputs
-        uint4 nb[4], nq, n1, n2;
-        auto prefetch = [&](int a) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) nb[j] = has_bias ? __ldg(bias_v + a * 4 + j) : zero4;
-            if (has_q) nq = __ldg(q_v + a);
-            if (n_res > 0) n1 = ld_stream16(r1_row + a * 8);
-            if (n_res > 1) n2 = ld_stream16(r2_row + a * 8);
-        };
-        prefetch(0);
+        // ------------------------------------------------ 4 -> 1 fold: 4 x 32 accumulator columns -> 32 outputs -> one store
         mbar_wait(full_bar, full_parity);
         tcgen05_fence_after();
-        if (lane == 0 && q == 0 && trace_slot >= 0) trace_mark(p, trace_slot);
+        if (lane == 0 && q == 0 && w.h == 0 && trace_slot >= 0) trace_mark(p, trace_slot);
         if (p.dbg & 2) {
             hand_back();
             return;
         }
-        uint32_t vn[32];
-        tmem_ld_32x32b_x32(acc, vn);
-        uint8_t* sbuf = stage_g + (two_bufs ? (w.cnt & 1) : 0) * SUB_BYTES;
+        uint8_t* sbuf = acquire_slab();
 #pragma unroll 1
         for (int a = 0; a < NC; ++a) {
-            uint4 cb[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) cb[j] = nb[j];
-            const uint4 cq = nq, c1 = n1, c2 = n2;
             uint32_t v[32];
-            tmem_ld_wait();
+            tmem_ld_32x32b_x32(acc + col0 + a * 32, v);
+            uint4 cb[4], cq = zero4, c1 = zero4, c2 = zero4;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = vn[j];
-            if (a + 1 < NC) {
-                tmem_ld_32x32b_x32(acc + (a + 1) * 32, vn);
-                prefetch(a + 1);
-            } else {
-                hand_back();
-            }
+            for (int j = 0; j < 4; ++j) cb[j] = has_bias ? __ldg(bias_v + a * 4 + j) : zero4;
+            if (has_q) cq = __ldg(q_v + a);
+            if (n_res > 0) c1 = ld_stream16(r1_row + a * 8);
+            if (n_res > 1) c2 = ld_stream16(r2_row + a * 8);
+            tmem_ld_wait();
+            if (a + 1 == NC) hand_back();
             const uint32_t* bw = reinterpret_cast<const uint32_t*>(cb);
             const uint32_t* qw = reinterpret_cast<const uint32_t*>(&cq);
             const uint32_t* w1 = reinterpret_cast<const uint32_t*>(&c1);
@@ -285,8 +327,8 @@ __device__ __forceinline__ void epilogue_tile(const PwGemmParams& p, const TileC
             for (int jj = 0; jj < 4; ++jj) {
                 float o[2];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = jj * 2 + h;  // output column of this chunk; folds acc columns 4j .. 4j+3
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int j = jj * 2 + hh;  // output column of this chunk; folds acc columns 4j .. 4j+3
                     float s4 = 0.f;
 #pragma unroll
                     for (int e = 0; e < 4; e += 2) {
@@ -297,7 +339,7 @@ __device__ __forceinline__ void epilogue_tile(const PwGemmParams& p, const TileC
                         s4 += t0;
                         s4 += t1;
                     }
-                    o[h] = s4;
+                    o[hh] = s4;
                 }
                 if (n_res > 0) {
                     o[0] = fma_f32_f16(static_cast<uint16_t>(w1[jj] & 0xffffu), ONE, o[0]);
@@ -315,9 +357,9 @@ __device__ __forceinline__ void epilogue_tile(const PwGemmParams& p, const TileC
                 const __half2 h2 = __floats2half2_rn(o[0], o[1]);
                 ow[jj] = *reinterpret_cast<const uint32_t*>(&h2);
             }
-            *reinterpret_cast<uint4*>(sbuf + sw_off(a)) = o4;
+            *reinterpret_cast<uint4*>(sbuf + sw64(a)) = o4;
         }
-        publish(sbuf, tc.oc0);
+        publish(sbuf, tc.oc0 + ocol0);
     }
 }
 

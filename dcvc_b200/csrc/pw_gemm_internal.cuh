@@ -12,9 +12,10 @@ static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;
 static constexpr int UMMA_K = 16;
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-static constexpr int SUB_TILE_BYTES = EPI_SUB_TILE_BYTES;    // one [128][64] fp16 store box
+static constexpr int EPI_WARPS = 16;                          // 2 accumulator buffers x 2 column halves x 4 lane quarters
+static constexpr int SUB_TILE_BYTES = EPI_WARPS / 2 * EPI_SLAB_BYTES;  // staging per slab index and accumulator buffer (16 KB)
 static constexpr int EPI_GROUPS = 2;                          // one per TMEM accumulator buffer
-static constexpr int NUM_THREADS = 64 + EPI_GROUPS * 128;     // TMA warp + MMA warp + 2 x 4 epilogue warps
+static constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;       // TMA warp + MMA warp + 16 epilogue warps
 
 static constexpr int MAX_STAGES = 8;
 static constexpr int SMEM_TOTAL = 232448;   // 227 KB: the whole SM, one persistent CTA per SM

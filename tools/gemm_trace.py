@@ -49,6 +49,19 @@ for c in (0, 1, 73, 147):
     if c < rel.shape[0]:
         print(f"cta{c:<6} " + " ".join(f"{rel[c, i]:8.2f}" for i in range(len(names))))
 
+if os.environ.get("DCVC_B200_GEMM_ARES", "0") == "1":
+    # A-resident kernel: per-phase SM-clock marks of the first tile's chunks, epilogue warp (q=0, h=0)
+    raw = trace.cpu().numpy().reshape(148, 64).astype(np.int64)[used]
+    ph = ["ldtm_issue", "ldtm_done", "math_done", "res_q_done", "sts_done", "store_issued"]
+    for a in range(4):
+        c = raw[:, 16 + a * 8:16 + a * 8 + 6]
+        ok = (c > 0).all(axis=1)
+        if not ok.any():
+            continue
+        d = np.diff(c[ok], axis=1)
+        print(f"chunk {a}: " + "  ".join(f"{ph[k]}->{ph[k+1]} {np.median(d[:, k]):.0f}" for k in range(5)) +
+              (f"  | chunk period {np.median(raw[ok, 16 + (a + 1) * 8] - raw[ok, 16 + a * 8]):.0f} clk" if a < 3 and (raw[ok, 16 + (a + 1) * 8] > 0).all() else ""))
+    sys.exit(0)
 # per-stage TMA timeline of the first 24 k-block loads in SM clocks (cheap clock64 marks kept in smem): request
 # (producer thread) and landing as seen by the MMA thread, relative to the "setup done" mark
 raw = trace.cpu().numpy().reshape(148, 64).astype(np.int64)[used]
