@@ -1,13 +1,7 @@
 // rans_host.cpp — see rans_host.h.  Own implementation of the reference bitstream format.
 #include "rans_host.h"
 
-#include <limits.h>
-#include <stdlib.h>
 #include <string.h>
-
-#if defined(__x86_64__)
-#include <immintrin.h>
-#endif
 
 #include <algorithm>
 #include <numeric>
@@ -142,124 +136,6 @@ inline int8_t dec_symbol(uint32_t& x, ByteReader& r, const int32_t* cdf_row, int
     return static_cast<int8_t>((value & 1) ? (value + 1) / 2 : -((value + 1) / 2));
 }
 
-// ---- fast decode path -----------------------------------------------------------------------
-// Rows of the decode table are the CDF rows padded to kDecRow entries with INT32_MAX, so the symbol is
-// a branch-free count  s = #{i >= 1 : cdf[i] <= cum}  (the reference walks the row linearly,
-// rans.cpp:108-142: one unpredictable branch per step).  AVX2 does the 24 compares in three
-// instructions; the scalar fallback counts the same way.
-constexpr int kDecRow = 24;
-
-inline int count_le_scalar(const int32_t* row, int32_t cum)
-{
-    int s = 0;
-    for (int i = 0; i < kDecRow; ++i) s += (row[i] <= cum) ? 1 : 0;
-    return s;
-}
-
-#if defined(__x86_64__)
-__attribute__((target("avx2,popcnt"))) inline int count_le_avx2(const int32_t* row, int32_t cum)
-{
-    const __m256i c = _mm256_set1_epi32(cum);
-    const __m256i g0 = _mm256_cmpgt_epi32(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(row)), c);
-    const __m256i g1 = _mm256_cmpgt_epi32(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(row + 8)), c);
-    const __m256i g2 = _mm256_cmpgt_epi32(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(row + 16)), c);
-    const unsigned m = static_cast<unsigned>(_mm256_movemask_ps(_mm256_castsi256_ps(g0))) |
-                       (static_cast<unsigned>(_mm256_movemask_ps(_mm256_castsi256_ps(g1))) << 8) |
-                       (static_cast<unsigned>(_mm256_movemask_ps(_mm256_castsi256_ps(g2))) << 16);
-    return kDecRow - _mm_popcnt_u32(m);
-}
-#endif
-
-template <bool AVX2>
-#if defined(__x86_64__)
-__attribute__((target("avx2,popcnt")))
-#endif
-inline int8_t dec_symbol_fast(uint32_t& x, ByteReader& r, const int32_t* row, int maxv)
-{
-    const int32_t cum = static_cast<int32_t>(x & kProbMask);
-    int s;
-#if defined(__x86_64__)
-    if (AVX2) s = count_le_avx2(row, cum) - 1;
-    else
-#endif
-        s = count_le_scalar(row, cum) - 1;
-    uint64_t sf;
-    memcpy(&sf, row + s, 8);  // row[s], row[s + 1] in one load
-    const uint32_t start = static_cast<uint32_t>(sf);
-    const uint32_t freq = static_cast<uint32_t>(sf >> 32) - start;
-    x = freq * (x >> kScaleBits) + static_cast<uint32_t>(cum) - start;
-    {
-        // renormalisation without data-dependent branches: x >= 2^7 here, so 0, 1 or 2 bytes are due
-        // (the stream buffer carries 8 zero bytes of padding; reads past it return zeros as ByteReader::next does)
-        const size_t lp = r.pos < r.size ? r.pos : r.size;
-        const uint32_t b0 = r.p[lp], b1 = r.p[lp + 1];
-        const uint32_t n = (x < kStateLow ? 1u : 0u) + (x < (kStateLow >> 8) ? 1u : 0u);
-        const uint32_t x1 = (x << 8) | b0;
-        const uint32_t x2 = (x1 << 8) | b1;
-        x = n == 0 ? x : (n == 1 ? x1 : x2);
-        r.pos += n;
-    }
-    int32_t value = s;
-    if (__builtin_expect(value == maxv, 0)) {
-        int32_t v = static_cast<int32_t>(dec_bits(x, r));
-        int32_t n_digits = v;
-        while (v == kBypassMax) {
-            v = static_cast<int32_t>(dec_bits(x, r));
-            n_digits += v;
-        }
-        int32_t raw = 0;
-        for (int j = 0; j < n_digits; ++j) {
-            v = static_cast<int32_t>(dec_bits(x, r));
-            raw |= v << (j * kBypassBits);
-        }
-        value = raw + maxv;
-    }
-    const int32_t mag = (value + 1) >> 1;
-    return static_cast<int8_t>((value & 1) ? mag : -mag);
-}
-
-template <bool AVX2>
-#if defined(__x86_64__)
-__attribute__((target("avx2,popcnt")))
-#endif
-void decode_y_range(int8_t* out, const uint8_t* cdf_rows, int off, int len, uint32_t& state, ByteReader& r,
-                    const int32_t* table, const int8_t* max_value)
-{
-    uint32_t x = state;
-    for (int k = off; k < off + len; ++k) {
-        const int row = cdf_rows[k];
-        out[k] = dec_symbol_fast<AVX2>(x, r, table + static_cast<size_t>(row) * kDecRow, max_value[row]);
-    }
-    state = x;
-}
-
-template <bool AVX2>
-#if defined(__x86_64__)
-__attribute__((target("avx2,popcnt")))
-#endif
-void decode_z_range(int8_t* out, int off, int len, int cdf_offset, int ch, uint32_t& state, ByteReader& r,
-                    const int32_t* table, const int8_t* max_value)
-{
-    uint32_t x = state;
-    int c = off % ch;
-    for (int k = off; k < off + len; ++k) {
-        const int row = c + cdf_offset;
-        out[k] = dec_symbol_fast<AVX2>(x, r, table + static_cast<size_t>(row) * kDecRow, max_value[row]);
-        if (++c == ch) c = 0;
-    }
-    state = x;
-}
-
-bool cpu_has_avx2()
-{
-#if defined(__x86_64__)
-    static const bool ok = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt");
-    return ok;
-#else
-    return false;
-#endif
-}
-
 // Trailing bytes two streams may share when the second is stored reversed behind the first
 // (py_rans.cpp:14-34).
 int shared_tail_bytes(const uint8_t* a, int na, const uint8_t* b, int nb)
@@ -358,13 +234,6 @@ void RansCodec::set_cdf(const int32_t* cdf, const int32_t* cdf_sizes, int rows, 
     s.cdf.assign(cdf, cdf + static_cast<size_t>(rows) * width);
     s.max_value.resize(rows);
     for (int i = 0; i < rows; ++i) s.max_value[i] = static_cast<int8_t>(cdf_sizes[i] - 2);
-    // decode table: rows padded with INT32_MAX behind their cdf_length entries (see dec_symbol_fast)
-    s.dec_ok = width <= kDecRow;
-    s.dec_table.assign(static_cast<size_t>(rows) * kDecRow, INT_MAX);
-    for (int i = 0; i < rows && s.dec_ok; ++i) {
-        const int len = std::max(0, std::min(width, cdf_sizes[i]));
-        for (int k = 0; k < len; ++k) s.dec_table[static_cast<size_t>(i) * kDecRow + k] = cdf[static_cast<size_t>(i) * width + k];
-    }
 }
 
 void RansCodec::encode(const std::vector<EncodeJob>& jobs, int n_parallel, std::vector<uint8_t>& out)
@@ -456,9 +325,6 @@ void RansCodec::set_stream(const uint8_t* data, int size, int n_parallel)
 {
     const int n = std::max(1, std::min(kMaxEcParallel, n_parallel));
     dec_n_ = n;
-    // DCVC_B200_RANS_SCALAR=1 forces the portable symbol search (tests run both)
-    const char* force_scalar = getenv("DCVC_B200_RANS_SCALAR");
-    dec_avx2_ = cpu_has_avx2() && !(force_scalar && force_scalar[0] == '1');
     auto load = [&](int i, const uint8_t* p, int len, bool reversed) {
         DecStream& d = dec_[i];
         d.bytes.resize(static_cast<size_t>(std::max(len, 0)) + 8);
@@ -517,14 +383,9 @@ void RansCodec::decode_z(int8_t* out, int total, int cdf_offset, int ch)
         DecStream& d = dec_[i];
         ByteReader r{ d.bytes.data(), d.pos, d.bytes.size() };
         uint32_t x = d.state;
-        if (cs.dec_ok) {
-            if (dec_avx2_) decode_z_range<true>(out, off, len, cdf_offset, ch, x, r, cs.dec_table.data(), cs.max_value.data());
-            else decode_z_range<false>(out, off, len, cdf_offset, ch, x, r, cs.dec_table.data(), cs.max_value.data());
-        } else {
-            for (int k = off; k < off + len; ++k) {
-                const int row = (k % ch) + cdf_offset;
-                out[k] = dec_symbol(x, r, cs.cdf.data() + static_cast<size_t>(row) * cs.width, cs.max_value[row]);
-            }
+        for (int k = off; k < off + len; ++k) {
+            const int row = (k % ch) + cdf_offset;
+            out[k] = dec_symbol(x, r, cs.cdf.data() + static_cast<size_t>(row) * cs.width, cs.max_value[row]);
         }
         d.state = x;
         d.pos = r.pos;
@@ -542,14 +403,9 @@ void RansCodec::decode_y(int8_t* out, const uint8_t* cdf_rows, int total)
         DecStream& d = dec_[i];
         ByteReader r{ d.bytes.data(), d.pos, d.bytes.size() };
         uint32_t x = d.state;
-        if (cs.dec_ok) {
-            if (dec_avx2_) decode_y_range<true>(out, cdf_rows, off, len, x, r, cs.dec_table.data(), cs.max_value.data());
-            else decode_y_range<false>(out, cdf_rows, off, len, x, r, cs.dec_table.data(), cs.max_value.data());
-        } else {
-            for (int k = off; k < off + len; ++k) {
-                const int row = cdf_rows[k];
-                out[k] = dec_symbol(x, r, cs.cdf.data() + static_cast<size_t>(row) * cs.width, cs.max_value[row]);
-            }
+        for (int k = off; k < off + len; ++k) {
+            const int row = cdf_rows[k];
+            out[k] = dec_symbol(x, r, cs.cdf.data() + static_cast<size_t>(row) * cs.width, cs.max_value[row]);
         }
         d.state = x;
         d.pos = r.pos;

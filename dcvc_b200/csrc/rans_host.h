@@ -43,8 +43,6 @@ struct CdfSet {
     int width = 0;                 // entries per row (max_length + 2)
     std::vector<int32_t> cdf;      // [rows][width]
     std::vector<int8_t> max_value; // cdf_length - 2: the escape symbol of each row
-    std::vector<int32_t> dec_table; // [rows][24]: rows padded with INT32_MAX for the branch-free symbol search
-    bool dec_ok = false;
 };
 
 struct EncodeJob {
@@ -76,7 +74,6 @@ private:
     CdfSet sets_[2];
     ForkJoin pool_;
     int dec_n_ = 1;
-    bool dec_avx2_ = false;
     struct DecStream {
         std::vector<uint8_t> bytes;
         uint32_t state = 0;

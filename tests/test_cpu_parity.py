@@ -122,12 +122,8 @@ def tables(lib):
     return zc, zl, yc, yl
 
 
-@pytest.mark.parametrize("scalar_search", [False, True])
-def test_rans_streams_bit_identical_to_reference(lib, tables, scalar_search, monkeypatch):
-    """product coder vs byte streams produced by the reference's own coder (golden); the decoder's AVX2 and
-    portable symbol searches (csrc/rans_host.cpp: dec_symbol_fast) must both reproduce the symbols"""
-    if scalar_search:
-        monkeypatch.setenv("DCVC_B200_RANS_SCALAR", "1")
+def test_rans_streams_bit_identical_to_reference(lib, tables):
+    """product coder vs byte streams produced by the reference's own coder (golden)"""
     g = np.load(os.path.join(GOLD, "rans_streams.npz"))
     r = _Rans(lib, *tables)
     keys = sorted({k.rsplit("_", 1)[0] for k in g.files})
