@@ -120,7 +120,13 @@ def run_ours(args):
     totals = model.proxy.debug_fetch("totals", np.int32)
     n_sym = int(totals.sum())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    host_out = torch.empty(dec["x_hat"].shape, dtype=torch.float16).pin_memory()
+    # e2e result = the decoded picture as the reference's driver writes it: 8-bit YUV 4:2:0 planes
+    # (test_video.py:352-361), converted on the device (dcvc_b200/frame_io.py) and copied to pinned host memory
+    from dcvc_b200 import frame_io
+    dev_planes = (torch.empty((H, W), dtype=torch.uint8, device=device),
+                  torch.empty((H // 2, W // 2), dtype=torch.uint8, device=device),
+                  torch.empty((H // 2, W // 2), dtype=torch.uint8, device=device))
+    host_planes = tuple(torch.empty(t.shape, dtype=torch.uint8).pin_memory() for t in dev_planes)
 
     def barrier():
         if world > 1:
@@ -143,8 +149,10 @@ def run_ours(args):
 
     def step_dec_e2e():
         out = model.decompress(bs, sps, QP, enc["ec_parallel"])["x_hat"]
-        host_out.copy_(out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller owns the host copy when the step ends
+        frame_io.frame_to_yuv420(out, H, W, out=dev_planes)
+        for hp, dp in zip(host_planes, dev_planes):
+            hp.copy_(dp, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller owns the host planes when the step ends
 
     def step_enc():
         model.compress(x, QP, pad_b, pad_r)
@@ -222,7 +230,8 @@ def run_ours(args):
                        "l2": "flushed between timed steps (256 MiB memset outside the timed interval)",
                        "weights": "seeded synthetic checkpoint (no checkpoints offline)"},
             "e2e": {"value": round(world * args.steps / (tot_e2e * 1e-3), 2), "unit": "frames/s",
-                    "h2d_bytes_per_step": int(65280 + n_sym), "d2h_bytes_per_step": int(n_sym + 16 + host_out.numel() * 2),
+                    "h2d_bytes_per_step": int(65280 + n_sym), "d2h_bytes_per_step": int(n_sym + 16 + sum(t.numel() for t in host_planes)),
+                    "result": "8-bit YUV 4:2:0 planes in pinned host memory (frame_to_yuv420 on the device)",
                     "bitstream_bytes": len(bs)},
             "encode_fps": round(world * args.steps / (tot_enc * 1e-3), 2),
             "gpu_only_ms_per_decode": round(gpu_only_ms, 4),

@@ -37,7 +37,7 @@ class EntropyStep(C.Structure):
 
 
 GEMM_PW, GEMM_CONV3X3_S2, GEMM_CONV2X2_S2, GEMM_TCONV2X2 = 0, 1, 2, 3
-ACT_NONE, ACT_WSILU = 0, 1
+ACT_NONE, ACT_WSILU, ACT_GDN, ACT_IGDN = 0, 1, 2, 3
 KIND_INTRA, KIND_HTS, KIND_HTL, KIND_LD = 0, 1, 2, 3
 DTYPE_F16, DTYPE_I32, DTYPE_F32 = 0, 1, 2
 
@@ -57,6 +57,11 @@ SIGNATURES = {
     "dcvc_op_pad_crop": (C.c_int, [C.POINTER(View), C.POINTER(View), _P]),
     "dcvc_op_scale_channels": (C.c_int, [C.POINTER(View), _P, C.POINTER(View), _P]),
     "dcvc_op_round_z": (C.c_int, [_P, _P, _P, _L, _P]),
+    "dcvc_op_yuv420_to_frame": (C.c_int, [_P, _P, _P, _I, _I, _P, _L, _L, _L, _P]),
+    "dcvc_op_frame_to_yuv420": (C.c_int, [_P, _L, _L, _L, _I, _I, _P, _P, _P, _P]),
+    "dcvc_op_sse_u8": (C.c_int, [_P, _P, _L, _P, _P]),
+    "dcvc_op_square": (C.c_int, [C.POINTER(View), C.POINTER(View), _P]),
+    "dcvc_op_warp_bilinear": (C.c_int, [C.POINTER(View), _P, _L, _L, _L, C.POINTER(View), _P]),
     "dcvc_op_int8_to_half": (C.c_int, [_P, _P, _L, _P]),
     "dcvc_op_entropy_enc_step": (C.c_int, [C.POINTER(EntropyStep), _P]),
     "dcvc_op_entropy_dec_index": (C.c_int, [C.POINTER(EntropyStep), _P]),

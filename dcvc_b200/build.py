@@ -22,6 +22,8 @@ SOURCES = [
     "pw_gemm.cu",
     "pw_gemm_ares.cu",
     "elementwise.cu",
+    "frame_io.cu",
+    "family_ops.cu",
     "rans_host.cpp",
     "c_api_ops.cu",
     "codec.cu",

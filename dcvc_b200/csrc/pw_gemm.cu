@@ -595,6 +595,10 @@ int gemm_plan(GemmOp& op)
         const int out_c = op.chunk_add ? op.N / 4 : (op.kind == GEMM_TCONV2X2 ? op.N / 4 : op.N);
         if (op.out.C != out_c) { g_err = "gemm_plan: out.C does not match N"; return 1; }
         if (op.res2.ptr && !op.res1.ptr) { g_err = "gemm_plan: res2 without res1"; return 1; }
+        if (op.act >= ACT_GDN && (!op.res1.ptr || op.res2.ptr || op.chunk_add || op.kind != GEMM_PW)) {
+            g_err = "gemm_plan: GDN / IGDN is a 1x1 op with exactly one residual operand (x) and no chunk-add";
+            return 1;
+        }
         if (op.res1.ptr) {
             if (op.kind == GEMM_TCONV2X2) { g_err = "gemm_plan: tconv takes no residual"; return 1; }
             const ActView* rs[2] = { &op.res1, &op.res2 };

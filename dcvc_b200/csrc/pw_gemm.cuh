@@ -31,7 +31,9 @@ enum GemmKind : int {
     GEMM_TCONV2X2 = 3,   // 1x1 + pixel_shuffle(2)   (reference transposed_conv, layers_proxy.cpp:314-323)
 };
 
-enum GemmAct : int { ACT_NONE = 0, ACT_WSILU = 1 };
+// ACT_GDN / ACT_IGDN: out = res1 * rsqrt(acc + bias) resp. res1 * sqrt(acc + bias) — generalised divisive normalisation
+// (DCVC-family/DCVC/src/layers/gdn.py:52-67) as an epilogue of the 1x1 GEMM over x^2; res1 carries x
+enum GemmAct : int { ACT_NONE = 0, ACT_WSILU = 1, ACT_GDN = 2, ACT_IGDN = 3 };
 
 // x / d for x < 2^31 as mulhi + add + shift (the kernel's scheduling loops run on single threads: a hardware
 // integer division is ~40 dependent instructions there)

@@ -114,6 +114,7 @@ __device__ __forceinline__ void epilogue_tile(const PwGemmParams& p, const TileC
     const bool has_q = p.qscale != nullptr;
     const int n_res = p.n_res;
     const bool act = p.act == ACT_WSILU;
+    const bool gdn = p.act >= ACT_GDN;
     const uint16_t ONE = 0x3C00;  // fp16 1.0: fma_f32_f16(h, ONE, x) == x + float(h) in one FHFMA
 
     auto hand_back = [&]() {
@@ -249,10 +250,20 @@ __device__ __forceinline__ void epilogue_tile(const PwGemmParams& p, const TileC
                 for (int gq = 0; gq < 4; ++gq) {
                     const uint4 r = lds128(sbuf + my_sw + ((static_cast<uint32_t>(gq) ^ my_x) << 4));
                     const uint32_t* w1 = reinterpret_cast<const uint32_t*>(&r);
+                    if (gdn) {
+                        // divisive normalisation: the "residual" operand is x, the accumulator beta + gamma . x^2
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        t[gq * 8 + 2 * e] = fma_f32_f16(static_cast<uint16_t>(w1[e] & 0xffffu), ONE, t[gq * 8 + 2 * e]);
-                        t[gq * 8 + 2 * e + 1] = fma_f32_f16(static_cast<uint16_t>(w1[e] >> 16), ONE, t[gq * 8 + 2 * e + 1]);
+                        for (int e = 0; e < 8; ++e) {
+                            const float xv = fma_f32_f16(static_cast<uint16_t>(e & 1 ? w1[e >> 1] >> 16 : w1[e >> 1] & 0xffffu), ONE, 0.f);
+                            const float nv = t[gq * 8 + e];
+                            t[gq * 8 + e] = xv * (p.act == ACT_GDN ? rsqrtf(nv) : sqrtf(nv));
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            t[gq * 8 + 2 * e] = fma_f32_f16(static_cast<uint16_t>(w1[e] & 0xffffu), ONE, t[gq * 8 + 2 * e]);
+                            t[gq * 8 + 2 * e + 1] = fma_f32_f16(static_cast<uint16_t>(w1[e] >> 16), ONE, t[gq * 8 + 2 * e + 1]);
+                        }
                     }
                 }
             }

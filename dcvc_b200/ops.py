@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (ACT_NONE, ACT_WSILU, GEMM_CONV2X2_S2, GEMM_CONV3X3_S2, GEMM_PW, GEMM_TCONV2X2,
+from ._lib import (ACT_GDN, ACT_IGDN, ACT_NONE, ACT_WSILU, GEMM_CONV2X2_S2, GEMM_CONV3X3_S2, GEMM_PW, GEMM_TCONV2X2,
                    EntropyStep, GemmDesc, View)
 
 
@@ -178,3 +178,33 @@ def entropy_dec_restore(b, step, scales, means, acc, skip_thres, decoded_i8):
     a = _estep(b, step, scales, means, acc, skip_thres, decoded=decoded_i8)
     _lib.check(lib.dcvc_op_entropy_dec_restore(C.byref(a), _stream()), "op_entropy_dec_restore")
     return acc
+
+
+# ------------------------------------------------------------------ DCVC-family ops named by north_star (§8 f4)
+def square(x, out):
+    lib = _lib.load()
+    vi, vo = view_of(x), view_of(out)
+    _lib.check(lib.dcvc_op_square(C.byref(vi), C.byref(vo), _stream()), "op_square")
+    return out
+
+
+def gdn(x, gamma, beta, out, inverse=False, scratch=None):
+    """Generalised divisive normalisation (DCVC-family/DCVC/src/layers/gdn.py:52-67) on an NHWC fp16 tensor:
+    out = x * rsqrt(beta + gamma . x^2) (inverse: * sqrt): the elementwise square, then ONE pw_gemm whose epilogue
+    multiplies the block input (residual operand) by rsqrt / sqrt of the accumulator.
+    gamma: effective [C, C] (after the non-negative reparametrisation), beta: effective [C]."""
+    Cc = x.shape[2]
+    sq = scratch if scratch is not None else torch.empty_like(x)
+    square(x, sq)
+    wp = pack_weight(GEMM_PW, gamma.reshape(Cc, Cc, 1, 1))
+    return gemm(GEMM_PW, sq, wp, Cc, out, bias=beta.half().to(x.device), act=ACT_IGDN if inverse else ACT_GDN, res1=x)
+
+
+def warp_bilinear(im, flow, out):
+    """bilinear backward warp with border clamp (block_mc_kernel.cu:25-73): im/out fp16 [H,W,C], flow fp16 [2,H,W]"""
+    assert flow.dtype == torch.float16 and flow.is_cuda and flow.dim() == 3 and flow.shape[0] == 2
+    lib = _lib.load()
+    vi, vo = view_of(im), view_of(out)
+    _lib.check(lib.dcvc_op_warp_bilinear(C.byref(vi), flow.data_ptr(), flow.stride(0), flow.stride(1), flow.stride(2),
+                                         C.byref(vo), _stream()), "op_warp_bilinear")
+    return out

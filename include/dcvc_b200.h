@@ -38,7 +38,8 @@ typedef struct dcvc_view {
 } dcvc_view;
 
 enum { DCVC_GEMM_PW = 0, DCVC_GEMM_CONV3X3_S2 = 1, DCVC_GEMM_CONV2X2_S2 = 2, DCVC_GEMM_TCONV2X2 = 3 };
-enum { DCVC_ACT_NONE = 0, DCVC_ACT_WSILU = 1 };
+/* GDN / IGDN: out = res1 * rsqrt(acc + bias) / res1 * sqrt(acc + bias) (DCVC-family/DCVC/src/layers/gdn.py:52-67) */
+enum { DCVC_ACT_NONE = 0, DCVC_ACT_WSILU = 1, DCVC_ACT_GDN = 2, DCVC_ACT_IGDN = 3 };
 
 /*
  * Dense contraction with fused epilogue: out = [chunk_add4]( act( in (*) W + bias ) ) [+ res1] [+ res2] [* qscale]
@@ -81,6 +82,31 @@ int dcvc_op_scale_channels(const dcvc_view* in, const void* q, const dcvc_view* 
 /* round_z_cuda / int8_to_dtype_cuda (elementwise/stream.cu:862-894, 454-482) */
 int dcvc_op_round_z(const void* z, void* z_hat, void* z_i8, int64_t n, void* stream);
 int dcvc_op_int8_to_half(const void* x, void* out, int64_t n, void* stream);
+
+/* ---- frame IO on the device: the callers' pre/post-processing either side of the codec ----
+ * 8-bit YUV 4:2:0 planes (y [H][W], u, v [H/2][W/2], device) -> fp16 model input channels 0..2 of x
+ * ([1,3,H,W] with element strides sc,sh,sw): nearest-neighbour chroma upsampling (ycbcr420_to_444_np,
+ * src/utils/transforms.py:69-80) and x.half() / 255 - 0.5 (test_video.py:115-122).  H, W even. */
+int dcvc_op_yuv420_to_frame(const void* y, const void* u, const void* v, int32_t H, int32_t W, void* x,
+                            int64_t sc, int64_t sh, int64_t sw, void* stream);
+/* fp16 reconstruction x_hat[:, :, :H, :W] -> 8-bit YUV 4:2:0 planes exactly as the reference saves frames
+ * (test_video.py:355-361: x_hat + 0.5, yuv_444_to_420 = 2x2 chroma average (transforms.py:83-90), * 255, clamp,
+ * Y rounded half-to-even, UV truncated). */
+int dcvc_op_frame_to_yuv420(const void* x_hat, int64_t sc, int64_t sh, int64_t sw, int32_t H, int32_t W,
+                            void* y, void* u, void* v, void* stream);
+/* *sse_u64 += sum (a[i] - b[i])^2 over two 8-bit device arrays: the integer numerator of calc_psnr
+ * (src/utils/metrics.py:10-24), so PSNR needs no frame on the host */
+int dcvc_op_sse_u8(const void* a, const void* b, int64_t n, void* sse_u64, void* stream);
+
+/* ---- ops of the older DCVC-family codecs that north_star names ----
+ * out = in * in, elementwise: the A operand of the GDN GEMM (gdn.py:58: F.conv2d(x ** 2, gamma, beta)) */
+int dcvc_op_square(const dcvc_view* in, const dcvc_view* out, void* stream);
+/* bilinear backward warp with border clamp (DCVC-family/DCVC-FM/src/models/extensions/block_mc_kernel.cu:25-73,
+ * == grid_sample(bilinear, border, align_corners=True), block_mc.py:47-58): out(y, x, :) = sum of the 4 neighbours
+ * of im at (x + flow_x(y, x), y + flow_y(y, x)); im / out NHWC fp16, flow fp16 [2][H][W] with element strides
+ * (fc, fh, fw); half arithmetic as the reference's __half kernel (fp32 positions, half weights, hfma chain). */
+int dcvc_op_warp_bilinear(const dcvc_view* im, const void* flow, int64_t fc, int64_t fh, int64_t fw,
+                          const dcvc_view* out, void* stream);
 
 /* Entropy-parameter path, one 4x-mask step (elementwise/stream.cu:77-173, 175-420, 548-630,
  * 756-818, 896-949).  Buffers: see dcvc_entropy_step. */

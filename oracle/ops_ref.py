@@ -168,3 +168,85 @@ def entropy_dec_restore_np(step, scales, means, skip_thres, decoded):
     out = np.zeros((H, W, Cc), dtype=np.float16)
     np.put_along_axis(out, ch, yh_w, axis=2)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- frame IO (§8 f2)
+def yuv420_to_frame(y: np.ndarray, u: np.ndarray, v: np.ndarray) -> torch.Tensor:
+    """get_src_frame for yuv420 sources (/root/reference/test_video.py:66-122): ycbcr420_to_444_np nearest-neighbour
+    chroma (src/utils/transforms.py:69-80: scipy.ndimage.zoom(uv, (1, 2, 2), order=0) == 2x2 replication), then on the
+    device x.half(); x / 255.0; x - 0.5 (fp32 op-math, one rounding to half per op).  Returns fp16 [1,3,H,W]."""
+    uv = np.stack([u, v]).astype(np.float32)
+    uv = uv.repeat(2, axis=1).repeat(2, axis=2)
+    yuv = np.concatenate([y[None].astype(np.float32), uv], axis=0)
+    x = torch.from_numpy(yuv).unsqueeze(0).half()
+    x = (x.float() / 255.0).half()
+    x = (x.float() - 0.5).half()
+    return x
+
+
+def frame_to_yuv420(x_hat: torch.Tensor, height: int, width: int):
+    """the reference's save path (/root/reference/test_video.py:352-361) on x_hat[:, :, :height, :width]:
+    yuv_444_to_420(x_hat + 0.5) (src/utils/transforms.py:83-90: avg_pool2d 2x2, fp32 accumulate), * 255, clamp,
+    Y .round() (half to even) .byte(), UV .byte() (truncation).  Every op rounds to half once."""
+    x = x_hat[:, :, :height, :width].half()
+    x = (x.float() + 0.5).half()
+    y = x[:, :1]
+    uv = x[:, 1:]
+    uv = F.avg_pool2d(uv.float(), kernel_size=2, stride=2).half()
+    y = torch.clamp((y.float() * 255).half().float(), 0, 255).round().to(torch.uint8)
+    uv = torch.clamp((uv.float() * 255).half().float(), 0, 255).to(torch.uint8)
+    return y[0, 0].numpy(), uv[0, 0].numpy(), uv[0, 1].numpy()
+
+
+# ------------------------------------------------------------------------- DCVC-family ops named by north_star (§8 f4)
+def gdn(x, gamma, beta, inverse=False):
+    """GDN.forward (/root/reference/DCVC-family/DCVC/src/layers/gdn.py:52-67) with the effective (reparametrised)
+    gamma [C,C] and beta [C]: norm = conv2d(x^2, gamma, beta); out = x * rsqrt(norm) (inverse: x * sqrt(norm))."""
+    Cc = x.shape[1]
+    norm = F.conv2d(x ** 2, gamma.reshape(Cc, Cc, 1, 1), beta)
+    norm = torch.sqrt(norm) if inverse else torch.rsqrt(norm)
+    return x * norm
+
+
+def torch_warp(feature, flow):
+    """the reference's PyTorch fallback (/root/reference/DCVC-family/DCVC-FM/src/models/block_mc.py:34-58):
+    grid_sample(bilinear, padding_mode='border', align_corners=True) on fp32"""
+    B, _, H, W = flow.shape
+    hor = torch.linspace(-1.0, 1.0, W).view(1, 1, 1, W).expand(B, -1, H, -1)
+    ver = torch.linspace(-1.0, 1.0, H).view(1, 1, H, 1).expand(B, -1, -1, W)
+    grid = torch.cat([hor, ver], 1) + torch.cat([flow[:, 0:1] / ((W - 1.0) / 2.0), flow[:, 1:2] / ((H - 1.0) / 2.0)], 1)
+    return F.grid_sample(feature, grid.permute(0, 2, 3, 1), mode="bilinear", padding_mode="border", align_corners=True)
+
+
+def warp_bilinear_half(im: np.ndarray, flow: np.ndarray) -> np.ndarray:
+    """block_mc_forward_kernel<__half> (/root/reference/DCVC-family/DCVC-FM/src/models/extensions/block_mc_kernel.cu:
+    25-73) restated in numpy: im fp16 [C,H,W], flow fp16 [2,H,W]; fp32 positions / weights, weights rounded to half,
+    four chained half FMAs (one rounding each; evaluated exactly in float64 before the rounding)."""
+    Cc, H, W = im.shape
+    f32 = np.float32
+    xs = np.arange(W, dtype=f32)[None, :]
+    ys = np.arange(H, dtype=f32)[:, None]
+    x_pos = np.clip(flow[0].astype(f32) + xs, f32(0), f32(W - 1)).astype(f32)
+    y_pos = np.clip(flow[1].astype(f32) + ys, f32(0), f32(H - 1)).astype(f32)
+    x0 = np.floor(x_pos).astype(np.int64)
+    y0 = np.floor(y_pos).astype(np.int64)
+    x1 = np.minimum(x0 + 1, W - 1)
+    y1 = np.minimum(y0 + 1, H - 1)
+    w_r = (x_pos - x0.astype(f32)).astype(f32)
+    w_l = (f32(1) - w_r).astype(f32)
+    w_b = (y_pos - y0.astype(f32)).astype(f32)
+    w_t = (f32(1) - w_b).astype(f32)
+    wa = (w_l * w_t).astype(f32).astype(np.float16)
+    wb = (w_l * w_b).astype(f32).astype(np.float16)
+    wc = (w_r * w_t).astype(f32).astype(np.float16)
+    wd = (w_r * w_b).astype(f32).astype(np.float16)
+
+    def fma(a, b, c):
+        return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float16)
+
+    r = np.zeros((Cc, H, W), dtype=np.float16)
+    r = fma(im[:, y0, x0], wa[None], r)
+    r = fma(im[:, y1, x0], wb[None], r)
+    r = fma(im[:, y0, x1], wc[None], r)
+    r = fma(im[:, y1, x1], wd[None], r)
+    return r

@@ -270,3 +270,29 @@ def test_hts_oracle_compress_decompress_consistency():
         assert np.array_equal(e["y_hat"].view(np.uint16), d["y_hat"].view(np.uint16)), f"chunk {c}"
         assert torch.equal(enc.feature_p, dec.feature_p), f"decoder state drifted at chunk {c}"
         assert len(d["x_hat"]) == 8 and d["x_hat"][0].shape == (1, 3, 64, 64)
+
+
+def test_frame_io_oracle_matches_reference_expressions():
+    """oracle/ops_ref.py frame IO restatements vs the reference driver's own expressions
+    (test_video.py:74-76,115-122,352-361; transforms.py:69-90) evaluated with torch CPU half arithmetic"""
+    import scipy.ndimage
+    import torch.nn.functional as F
+    from oracle import ops_ref
+    rng = np.random.default_rng(5)
+    y = rng.integers(0, 256, (34, 50), dtype=np.uint8)
+    u = rng.integers(0, 256, (17, 25), dtype=np.uint8)
+    v = rng.integers(0, 256, (17, 25), dtype=np.uint8)
+    uv = scipy.ndimage.zoom(np.stack([u, v]).astype(np.float32), (1, 2, 2), order=0)       # ycbcr420_to_444_np
+    x = torch.from_numpy(np.concatenate([y[None].astype(np.float32), uv], axis=0)).unsqueeze(0)
+    x = x.half()
+    x = x / 255.0
+    x = x - 0.5
+    assert torch.equal(ops_ref.yuv420_to_frame(y, u, v), x)
+    g = torch.Generator().manual_seed(2)
+    x_hat = (torch.rand(1, 3, 48, 64, generator=g) * 1.1 - 0.55).half()
+    xs = x_hat[:, :, :34, :50] + 0.5
+    y_rec, uv_rec = xs[:, :1], F.avg_pool2d(xs[:, 1:], kernel_size=2, stride=2)           # yuv_444_to_420
+    y_rec = torch.clamp(y_rec * 255, 0, 255).round().byte().squeeze(0).numpy()
+    uv_rec = torch.clamp(uv_rec * 255, 0, 255).byte().squeeze(0).numpy()
+    ry, ru, rv = ops_ref.frame_to_yuv420(x_hat, 34, 50)
+    assert np.array_equal(ry, y_rec[0]) and np.array_equal(ru, uv_rec[0]) and np.array_equal(rv, uv_rec[1])

@@ -250,3 +250,86 @@ def test_entropy_steps_bit_exact(H, W, skip):
     torch.cuda.synchronize()
     assert np.array_equal(acc_d.cpu().numpy().view(np.uint16), acc_ref.view(np.uint16))
     assert torch.equal(cat[..., C_:], torch.full_like(cat[..., C_:], 7.0))
+
+
+# ------------------------------------------------------------------------------------------ frame IO (§8 f2)
+@pytest.mark.parametrize("H,W", [(16, 16), (34, 50), (256, 256), (1080, 1920)])
+def test_yuv420_to_frame_bit_exact(H, W):
+    from dcvc_b200 import frame_io
+    from oracle import ops_ref
+    rng = np.random.default_rng(H + W)
+    y = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    u = rng.integers(0, 256, (H // 2, W // 2), dtype=np.uint8)
+    v = rng.integers(0, 256, (H // 2, W // 2), dtype=np.uint8)
+    ref = ops_ref.yuv420_to_frame(y, u, v)
+    got = frame_io.yuv420_to_frame(torch.from_numpy(y).cuda(), torch.from_numpy(u).cuda(), torch.from_numpy(v).cuda())
+    torch.cuda.synchronize()
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got.cpu(), ref)
+    # into channels 3..5 of a stacked chunk input, NCHW-contiguous (generic-stride path)
+    chunk = torch.zeros((1, 24, H, W), dtype=torch.float16, device="cuda")
+    frame_io.yuv420_to_frame(torch.from_numpy(y).cuda(), torch.from_numpy(u).cuda(), torch.from_numpy(v).cuda(), out=chunk, channel=3)
+    torch.cuda.synchronize()
+    assert torch.equal(chunk[:, 3:6].cpu(), ref) and chunk[:, :3].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("H,W,Hp,Wp,cl", [(16, 16, 16, 16, True), (34, 50, 48, 64, True), (34, 50, 48, 64, False),
+                                          (1080, 1920, 1088, 1920, True)])
+def test_frame_to_yuv420_bit_exact(H, W, Hp, Wp, cl):
+    from dcvc_b200 import frame_io
+    from oracle import ops_ref
+    gen = torch.Generator().manual_seed(H * 7 + W)
+    # reconstruction-like values in and slightly beyond [-0.5, 0.5], including exact .5/255 ties
+    x = (torch.rand(1, 3, Hp, Wp, generator=gen) * 1.1 - 0.55).half()
+    x[0, :, 0, :8] = torch.tensor([-0.5, 0.5, 0.0, 1.5 / 255 - 0.5, 2.5 / 255 - 0.5, -0.6, 0.6, 0.25]).half()
+    ry, ru, rv = ops_ref.frame_to_yuv420(x, H, W)
+    xd = x.cuda()
+    if cl:
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    y, u, v = frame_io.frame_to_yuv420(xd, H, W)
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), ry) and np.array_equal(u.cpu().numpy(), ru) and np.array_equal(v.cpu().numpy(), rv)
+    # PSNR numerator on the device == numpy
+    src = torch.randint(0, 256, (H, W), dtype=torch.uint8, generator=gen)
+    sse = frame_io.sse_u8(y, src.cuda())
+    torch.cuda.synchronize()
+    want = int(((ry.astype(np.int64) - src.numpy().astype(np.int64)) ** 2).sum())
+    assert int(sse.item()) == want
+
+
+# ---------------------------------------------------------------- DCVC-family ops named by north_star (§8 f4)
+@pytest.mark.parametrize("H,W,C", [(16, 24, 64), (68, 120, 128), (135, 240, 64)])
+def test_warp_bilinear(H, W, C):
+    """bit-exact vs the numpy restatement of the reference's __half kernel; within fp16 rounding of the reference's
+    PyTorch fallback (grid_sample, fp32)"""
+    from dcvc_b200 import ops
+    from oracle import ops_ref
+    gen = torch.Generator().manual_seed(H + W + C)
+    im = _rand(gen, 1, C, H, W)
+    flow = (torch.randn(1, 2, H, W, generator=gen) * 6).half()
+    flow[0, :, 0, :4] = torch.tensor([[0.0, -100.0, 100.0, 0.5], [0.0, 100.0, -100.0, 0.25]]).half()  # exact / far OOB
+    out = torch.zeros(H, W, C, dtype=torch.float16, device="cuda")
+    ops.warp_bilinear(_nhwc(im), flow[0].cuda().contiguous(), out)
+    torch.cuda.synchronize()
+    got = out.permute(2, 0, 1).cpu().numpy()
+    ref_h = ops_ref.warp_bilinear_half(im[0].half().numpy(), flow[0].numpy())
+    assert np.array_equal(got.view(np.uint16), ref_h.view(np.uint16))
+    ref_t = ops_ref.torch_warp(im, flow.float())
+    _close(torch.from_numpy(got.astype(np.float32)).unsqueeze(0), ref_t, rel=4e-3, abs_=4e-3)
+
+
+@pytest.mark.parametrize("H,W,C,inverse", [(16, 16, 64, False), (34, 60, 128, False), (34, 60, 192, True)])
+def test_gdn(H, W, C, inverse):
+    """GDN / IGDN = square + one pw_gemm with the rsqrt / sqrt epilogue, vs GDN.forward in fp32
+    (tolerance: fp16 storage of x^2 and of the output, rsqrt.approx)"""
+    from dcvc_b200 import ops
+    from oracle import ops_ref
+    gen = torch.Generator().manual_seed(C + H)
+    x = _rand(gen, 1, C, H, W)
+    gamma = (0.1 * torch.eye(C) + 0.01 * torch.rand(C, C, generator=gen)).half().float()
+    beta = (1.0 + 0.1 * torch.rand(C, generator=gen)).half().float()
+    ref = ops_ref.gdn(x, gamma, beta, inverse)
+    out = torch.zeros(H, W, C, dtype=torch.float16, device="cuda")
+    ops.gdn(_nhwc(x), gamma, beta, out, inverse=inverse)
+    torch.cuda.synchronize()
+    _close(_nchw(out), ref, rel=6e-3, abs_=2e-3)
