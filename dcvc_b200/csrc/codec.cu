@@ -121,6 +121,7 @@ void IntraCodec::clear_plan()
 {
     Segment* segs[] = { &enc0_, &enc1_seg_, &dec0_, &dec_step_[0], &dec_step_[1], &dec_step_[2], &dec_step_[3], &dec4_ };
     for (Segment* s : segs) s->reset();
+    flags_reset();
     if (h_totals_) { cudaFreeHost(h_totals_); h_totals_ = nullptr; }
     for (int k = 0; k < 4; ++k) if (h_sym_[k]) { cudaFreeHost(h_sym_[k]); h_sym_[k] = nullptr; }
     if (h_idx_) { cudaFreeHost(h_idx_); h_idx_ = nullptr; }

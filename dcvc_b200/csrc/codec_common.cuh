@@ -132,6 +132,15 @@ struct Segment {
     std::vector<std::string> notes;
     cudaGraphExec_t exec = nullptr;
     int launches = 0;
+    // tile-level chaining of consecutive 1x1 GEMMs (pw_gemm.cuh: done_flags / wait_a): the flag words of this
+    // segment's ops (zeroed at the start of every run) and the most recent chain-capable producer
+    int* flag_begin = nullptr;
+    size_t flag_words = 0;
+    const int* last_flags = nullptr;
+    int last_need = 0;
+    const void* last_out = nullptr;
+    int last_W = 0, last_H = 0, last_C = 0, last_pitch = 0;
+    void break_chain() { last_flags = nullptr; }
     void annotate(int kind, double bytes, double fl)
     {
         while (kinds.size() < ops.size()) {
@@ -142,6 +151,7 @@ struct Segment {
     }
     void elem(OpFn f)
     {
+        break_chain();
         annotate(OP_ELEM, 0, 0);
         ops.push_back(std::move(f));
         annotate(OP_ELEM, 0, 0);
@@ -157,6 +167,9 @@ struct Segment {
         exec = nullptr;
         ops.clear(); kinds.clear(); alg_bytes.clear(); flops.clear();
         launches = 0;
+        flag_begin = nullptr;
+        flag_words = 0;
+        break_chain();
     }
 };
 
@@ -177,6 +190,7 @@ public:
     explicit CodecBase(int device) : device_(device) {}
     virtual ~CodecBase()
     {
+        if (flags_base_) cudaFree(flags_base_);
         if (copy_stream_) cudaStreamDestroy(copy_stream_);
         if (own_stream_) cudaStreamDestroy(own_stream_);
         if (ev_hop_) cudaEventDestroy(ev_hop_);
@@ -352,12 +366,22 @@ protected:
         if (gemm_init()) throw std::runtime_error(gemm_last_error());
         const char* g = getenv("DCVC_B200_GRAPHS");
         use_graphs_ = !(g && g[0] == '0');
+        // tile-level chaining of the DepthConvBlock GEMMs is an opt-in experiment (DCVC_B200_GEMM_CHAIN=1): parity-green,
+        // but measured 4 % SLOWER end to end on B200 (Intra 1080p decode 2.80 vs 2.70 ms of GPU time, HT-S 5.93 vs
+        // 5.71 ms) — see DESIGN.md "experiments"
+        const char* ch = getenv("DCVC_B200_GEMM_CHAIN");
+        chain_enabled_ = ch && ch[0] == '1';
+        if (!flags_base_) {
+            flags_cap_ = (8u << 20) / sizeof(int);
+            CK(cudaMalloc(&flags_base_, flags_cap_ * sizeof(int)));
+        }
+        flags_used_ = 0;
         finalized_ = true;
     }
 
     // ------------------------------------------------------------------ op builders
     void add_gemm(Segment& s, int kind, const ActView& in, const ActView& out, const __half* w, const __half* bias,
-                  int N, int act, int chunk, const ActView* r1, const ActView* r2, const __half* q)
+                  int N, int act, int chunk, const ActView* r1, const ActView* r2, const __half* q, bool in_dcb = false)
     {
         auto op = std::make_shared<GemmOp>();
         op->kind = kind;
@@ -371,7 +395,40 @@ protected:
         op->N = N;
         op->act = act;
         op->chunk_add = chunk;
+        if (chain_enabled_ && in_dcb && kind == GEMM_PW && flags_base_) {
+            // Tile-level chaining, only between the 1x1 GEMMs of DepthConvBlocks: the op reports completed 128-pixel
+            // tiles; if the previous op of the segment was such a GEMM and wrote exactly this op's input view, the op
+            // waits per tile instead of for the whole previous grid.  Every other access of the block is then ordered
+            // too: residuals are produced by an op of the same chain at the same tile index (ffn.2's `o`) or are older
+            // than the last full-grid synchronisation (the depthwise conv between dc.0 and dc.3), and every buffer a
+            // chained op overwrites was last read by an op of its chain at the same tile index or before that
+            // synchronisation (the block ping-pongs X -> T1 -> T2 -> O -> T1 -> X).
+            const int m_tiles = static_cast<int>((static_cast<long long>(out.W) * out.H + 127) / 128);
+            if (flags_used_ + m_tiles <= flags_cap_) {
+                op->done_flags = flags_base_ + flags_used_;
+                if (!s.flag_begin) s.flag_begin = op->done_flags;
+                flags_used_ += m_tiles;
+                s.flag_words = static_cast<size_t>(flags_base_ + flags_used_ - s.flag_begin);
+                if (s.last_flags && s.last_out == in.ptr && s.last_W == in.W && s.last_H == in.H && s.last_C == in.C &&
+                    s.last_pitch == in.pitch) {
+                    op->wait_a = s.last_flags;
+                    op->wait_a_need = s.last_need;
+                    op->no_grid_wait = true;
+                }
+            }
+        }
         if (gemm_plan(*op)) throw std::runtime_error(std::string("gemm_plan: ") + gemm_last_error());
+        if (op->done_flags && op->ares == 0) {
+            s.last_flags = op->done_flags;
+            s.last_need = op->p.n_tiles * 8;
+            s.last_out = out.ptr;
+            s.last_W = out.W;
+            s.last_H = out.H;
+            s.last_C = out.C;
+            s.last_pitch = out.pitch;
+        } else {
+            s.break_chain();
+        }
         s.annotate(OP_ELEM, 0, 0);
         s.ops.push_back([op](cudaStream_t st) { return gemm_launch(*op, st); });
         s.out_views.resize(s.ops.size());
@@ -411,7 +468,7 @@ protected:
         if (w.adaptor) {
             bufX = (in.ptr == L.A) ? L.B : L.A;
             x = make_view(bufX, w.c, w.c, W, H);
-            add_gemm(s, GEMM_PW, in, x, w.wa, w.ba, w.c, ACT_NONE, 0, nullptr, nullptr, nullptr);
+            add_gemm(s, GEMM_PW, in, x, w.wa, w.ba, w.c, ACT_NONE, 0, nullptr, nullptr, nullptr, true);
         } else {
             x = in;
             bufX = static_cast<__half*>(const_cast<void*>(in.ptr));
@@ -423,19 +480,20 @@ protected:
         const ActView t1 = make_view(L.T1, w.inner, w.inner, W, H);
         const ActView t2 = make_view(L.T2, w.inner, w.inner, W, H);
         const ActView o = make_view(bufO, w.c, w.c, W, H);
-        add_gemm(s, GEMM_PW, x, t1, w.w0, w.b0, w.inner, ACT_WSILU, 0, nullptr, nullptr, nullptr);
+        add_gemm(s, GEMM_PW, x, t1, w.w0, w.b0, w.inner, ACT_WSILU, 0, nullptr, nullptr, nullptr, true);
         {
             const __half* wdw = w.wdw;
+            s.break_chain();  // 3x3 neighbourhoods: full-grid dependency on both sides
             s.annotate(OP_ELEM, 0, 0);
             s.ops.push_back([t1, t2, wdw](cudaStream_t st) { return launch_dw3x3(t1, t2, wdw, st); });
             s.out_views.resize(s.ops.size());
             s.out_views.back() = t2;
             s.annotate(OP_DW, 2.0 * 2 * W * H * w.inner, 2.0 * 9 * W * H * w.inner);
         }
-        add_gemm(s, GEMM_PW, t2, o, w.w3, w.b3, w.c, ACT_NONE, 0, &x, nullptr, nullptr);
-        add_gemm(s, GEMM_PW, o, t1, w.wf0, w.bf0, 4 * w.inner, ACT_WSILU, 1, nullptr, nullptr, nullptr);
+        add_gemm(s, GEMM_PW, t2, o, w.w3, w.b3, w.c, ACT_NONE, 0, &x, nullptr, nullptr, true);
+        add_gemm(s, GEMM_PW, o, t1, w.wf0, w.bf0, 4 * w.inner, ACT_WSILU, 1, nullptr, nullptr, nullptr, true);
         const ActView dst = out ? *out : x;
-        add_gemm(s, GEMM_PW, t1, dst, w.wf2, w.bf2, w.c, ACT_NONE, 0, &o, shortcut ? &x : nullptr, qscale);
+        add_gemm(s, GEMM_PW, t1, dst, w.wf2, w.bf2, w.c, ACT_NONE, 0, &o, shortcut ? &x : nullptr, qscale, true);
         return dst;
     }
 
@@ -443,6 +501,8 @@ protected:
     void run(Segment& s, cudaStream_t stream)
     {
         if (s.ops.empty()) return;
+        if (s.flag_words && !(use_graphs_ && s.exec && !profile_ && !getenv("DCVC_B200_OPSUM")))
+            CK(cudaMemsetAsync(s.flag_begin, 0, s.flag_words * sizeof(int), stream));  // (a graph carries its own memset node)
         if (profile_) {
             // per-op CUDA-event timing (graphs off).  All ops of the segment are enqueued back to back with an
             // event before and after each, and read only after the last one: the CPU runs ahead of the GPU, so an
@@ -498,6 +558,7 @@ protected:
             if (!s.exec) {
                 cudaGraph_t graph = nullptr;
                 CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                if (s.flag_words) cudaMemsetAsync(s.flag_begin, 0, s.flag_words * sizeof(int), stream);
                 int rc = 0;
                 for (auto& op : s.ops) {
                     rc = op(stream);
@@ -559,9 +620,14 @@ protected:
         }
     };
 
+    void flags_reset() { flags_used_ = 0; }  // with every re-plan (the segments are rebuilt)
+
     int device_;
     bool finalized_ = false;
     bool use_graphs_ = true;
+    bool chain_enabled_ = true;
+    int* flags_base_ = nullptr;
+    size_t flags_cap_ = 0, flags_used_ = 0;
     void* dbg_base_ = nullptr;      // activation arena (DCVC_B200_OPSUM)
     size_t dbg_bytes_ = 0;
     unsigned long long* opsum_dev_ = nullptr;

@@ -116,6 +116,7 @@ void HtsCodec::clear_plan()
 {
     Segment* segs[] = { &s_enc0_, &s_decoder_, &s_reset_head_, &s_fa_i_, &s_fa_m_, &s_fe_, &s_temporal_, &s_dec1_, &s_dec3_, &s_recon_ };
     for (Segment* s : segs) s->reset();
+    flags_reset();
     if (h_total_) { cudaFreeHost(h_total_); h_total_ = nullptr; }
     if (h_sym_) { cudaFreeHost(h_sym_); h_sym_ = nullptr; }
     if (h_idx_) { cudaFreeHost(h_idx_); h_idx_ = nullptr; }

@@ -175,6 +175,31 @@ __device__ __forceinline__ void tma_store_wait_read()
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
+// full completion (writes performed), not just "source read", of all but the N most recent bulk groups of this thread
+template <int N>
+__device__ __forceinline__ void tma_store_wait_done()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// orders generic-proxy accesses (flag loads / stores) against async-proxy accesses (TMA) of this thread, all state spaces
+__device__ __forceinline__ void fence_proxy_async_all()
+{
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v)
+{
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ void tma_store_wait0()
 {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
