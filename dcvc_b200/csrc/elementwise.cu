@@ -27,7 +27,7 @@ static inline int blocks_for(long long n, int threads) { return static_cast<int>
 // loaded once per thread (3 x 16 B, the x-1 / x+1 neighbours hit L1 because adjacent threads of the
 // CTA load them as their centre) and scattered into the <= 3 output rows it contributes to.  HBM/L2
 // traffic per output drops from ~3 input rows to (DW_TY + 2) / DW_TY.
-static constexpr int DW_TY = 4;
+static constexpr int DW_TY_DEFAULT = 4;
 
 // d = a * b + c with fp16 a, b and fp32 c, d in one instruction (FHFMA)
 __device__ __forceinline__ float fma_f32_f16(uint16_t a, uint16_t b, float c)
@@ -47,6 +47,7 @@ __device__ __forceinline__ void dw_load_row(const __half* in, int in_pitch, int 
     if (x + 1 < W) q[2] = *reinterpret_cast<const uint4*>(rowp + in_pitch);
 }
 
+template <int DW_TY>
 __global__ void __launch_bounds__(128)
 dw3x3_kernel(const __half* __restrict__ in, int in_pitch, __half* __restrict__ out, int out_pitch,
              const __half* __restrict__ w, int C, int W, int H)
@@ -107,7 +108,8 @@ dw3x3_kernel(const __half* __restrict__ in, int in_pitch, __half* __restrict__ o
     }
 }
 
-int launch_dw3x3(const ActView& in, const ActView& out, const __half* w, cudaStream_t s)
+template <int DW_TY>
+static int launch_dw3x3_ty(const ActView& in, const ActView& out, const __half* w, cudaStream_t s)
 {
     const long long total = static_cast<long long>(in.W) * (in.C / 8) * ((in.H + DW_TY - 1) / DW_TY);
     cudaLaunchConfig_t cfg;
@@ -121,10 +123,19 @@ int launch_dw3x3(const ActView& in, const ActView& out, const __half* w, cudaStr
     cfg.attrs = attr;
     const char* e = getenv("DCVC_B200_PDL");
     cfg.numAttrs = (e && e[0] == '0') ? 0 : 1;
-    cudaLaunchKernelEx(&cfg, dw3x3_kernel, static_cast<const __half*>(in.ptr), in.pitch,
+    cudaLaunchKernelEx(&cfg, dw3x3_kernel<DW_TY>, static_cast<const __half*>(in.ptr), in.pitch,
                        static_cast<__half*>(const_cast<void*>(out.ptr)), out.pitch, w, in.C, in.W, in.H);
     DCVC_LAUNCH_CHECK();
     return 0;
+}
+
+int launch_dw3x3(const ActView& in, const ActView& out, const __half* w, cudaStream_t s)
+{
+    // rows per thread: DCVC_B200_DW_TY = 2 | 4 | 8 (measurement switch; default 4)
+    static const int ty = []() { const char* e = getenv("DCVC_B200_DW_TY"); return e ? atoi(e) : DW_TY_DEFAULT; }();
+    if (ty == 2) return launch_dw3x3_ty<2>(in, out, w, s);
+    if (ty == 8) return launch_dw3x3_ty<8>(in, out, w, s);
+    return launch_dw3x3_ty<4>(in, out, w, s);
 }
 
 // ------------------------------------------------------------------------------- unshuffle8
