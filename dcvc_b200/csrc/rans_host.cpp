@@ -1,9 +1,11 @@
 // rans_host.cpp — see rans_host.h.  Own implementation of the reference bitstream format.
 #include "rans_host.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 #include <stdexcept>
 
@@ -160,8 +162,26 @@ inline void split_range(int total, int n, int i, int& off, int& len)
 }  // namespace
 
 // ------------------------------------------------------------------------------ ForkJoin
+namespace {
+inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+}
+inline int64_t now_us()
+{
+    return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
 ForkJoin::ForkJoin(int workers)
 {
+    // busy-waiting only pays when every worker has a hardware thread to itself
+    if (std::thread::hardware_concurrency() < 4u * static_cast<unsigned>(workers + 1)) spin_us_ = 0;
+    if (const char* e = getenv("DCVC_B200_RANS_SPIN_US")) spin_us_ = std::max(0, atoi(e));
     for (int i = 0; i < workers; ++i) threads_.emplace_back(&ForkJoin::worker_loop, this, i + 1);
 }
 
@@ -169,7 +189,7 @@ ForkJoin::~ForkJoin()
 {
     {
         std::lock_guard<std::mutex> lk(mu_);
-        stop_ = true;
+        stop_.store(true, std::memory_order_release);
     }
     cv_start_.notify_all();
     for (auto& t : threads_) t.join();
@@ -179,21 +199,30 @@ void ForkJoin::worker_loop(int id)
 {
     uint64_t seen = 0;
     for (;;) {
-        const std::function<void(int)>* fn = nullptr;
-        {
-            std::unique_lock<std::mutex> lk(mu_);
-            cv_start_.wait(lk, [&] { return stop_ || epoch_ != seen; });
-            if (stop_) return;
-            seen = epoch_;
-            if (id >= n_) continue;
-            fn = fn_;
+        // wait for the next epoch: spin first, then block
+        const int64_t deadline = now_us() + spin_us_;
+        int polls = 0;
+        while (epoch_.load(std::memory_order_acquire) == seen && !stop_.load(std::memory_order_acquire)) {
+            if ((++polls & 63) == 0) std::this_thread::yield();  // oversubscribed host: let a working thread have the core
+            if (spin_us_ == 0 || ((polls & 63) == 0 && now_us() > deadline)) {
+                std::unique_lock<std::mutex> lk(mu_);
+                sleepers_.fetch_add(1, std::memory_order_relaxed);
+                cv_start_.wait(lk, [&] { return stop_.load(std::memory_order_acquire) || epoch_.load(std::memory_order_acquire) != seen; });
+                sleepers_.fetch_sub(1, std::memory_order_relaxed);
+                break;
+            }
+            cpu_relax();
         }
-        (*fn)(id);
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            --pending_;
+        if (stop_.load(std::memory_order_acquire)) return;
+        seen = epoch_.load(std::memory_order_acquire);
+        // the job's task count travels in the low byte of the epoch word: a worker that is not part of job e may get
+        // here after the caller has already started preparing job e + 1
+        if (id >= static_cast<int>(seen & 0xff)) continue;
+        (*fn_)(id);  // published before the epoch moved; stable until every participant of this job has finished
+        if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+            std::lock_guard<std::mutex> lk(mu_);  // the caller may be between its predicate check and its wait
+            cv_done_.notify_one();
         }
-        cv_done_.notify_one();
     }
 }
 
@@ -204,17 +233,27 @@ void ForkJoin::run(int n, const std::function<void(int)>& fn)
         return;
     }
     if (n - 1 > static_cast<int>(threads_.size())) throw std::runtime_error("ForkJoin: too many tasks");
+    fn_ = &fn;
+    pending_.store(n - 1, std::memory_order_relaxed);
     {
         std::lock_guard<std::mutex> lk(mu_);
-        fn_ = &fn;
-        n_ = n;
-        pending_ = n - 1;
-        ++epoch_;
+        const uint64_t e = epoch_.load(std::memory_order_relaxed);
+        epoch_.store((((e >> 8) + 1) << 8) | static_cast<uint64_t>(n), std::memory_order_release);
     }
-    cv_start_.notify_all();
+    if (sleepers_.load(std::memory_order_acquire) > 0) cv_start_.notify_all();
     fn(0);
-    std::unique_lock<std::mutex> lk(mu_);
-    cv_done_.wait(lk, [&] { return pending_ == 0; });
+    // the other streams take about as long as ours: spin briefly, then block
+    const int64_t deadline = now_us() + 200;
+    int polls = 0;
+    while (pending_.load(std::memory_order_acquire) != 0) {
+        if ((++polls & 63) == 0) std::this_thread::yield();
+        if ((polls & 63) == 0 && now_us() > deadline) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_done_.wait(lk, [&] { return pending_.load(std::memory_order_acquire) == 0; });
+            break;
+        }
+        cpu_relax();
+    }
 }
 
 // ------------------------------------------------------------------------------ RansCodec

@@ -8,6 +8,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -19,6 +20,10 @@ namespace dcvc {
 constexpr int kMaxEcParallel = 8;  // py_rans.h:15
 
 // Fork-join helper: run fn(0..n-1), fn(0) on the caller, the rest on persistent workers.
+// The workers busy-wait for the next job for `spin_us` microseconds after finishing one before they block on a
+// condition variable (DCVC_B200_RANS_SPIN_US, default 2000; 0 = always block): a picture is decoded in five short
+// bursts of entropy decoding with GPU work in between, and a worker that went to sleep costs a futex wake-up per
+// burst and runs the burst on a core that has dropped out of its turbo state.
 class ForkJoin {
 public:
     explicit ForkJoin(int workers);
@@ -31,10 +36,11 @@ private:
     std::mutex mu_;
     std::condition_variable cv_start_, cv_done_;
     const std::function<void(int)>* fn_ = nullptr;
-    int n_ = 0;
-    uint64_t epoch_ = 0;
-    int pending_ = 0;
-    bool stop_ = false;
+    std::atomic<uint64_t> epoch_{0};   // (job counter << 8) | task count, stored (under mu_) once per run()
+    std::atomic<int> pending_{0};      // workers that have not finished the current job
+    std::atomic<int> sleepers_{0};     // workers blocked on cv_start_ (modified under mu_)
+    std::atomic<bool> stop_{false};
+    int spin_us_ = 2000;
 };
 
 // One set of quantised CDF rows (index 0: factorised z model, index 1: Gaussian y model).
