@@ -159,6 +159,65 @@ def hts_spec() -> "OrderedDict[str, tuple]":
     return s
 
 
+# DCVC-UF low-delay model constants (src/models/video_model_ld.py:16-21)
+LD_CH_SRC_D = 3 * 8 * 8
+LD_CH_Y = 128
+LD_CH_Z = 128
+LD_CH_D = 256
+LD_CH_M = 256
+
+
+def ld_spec() -> "OrderedDict[str, tuple]":
+    """state_dict layout of the low-delay DMC (src/models/video_model_ld.py:24-211).  Used by the oracle
+    (oracle/ld_oracle.py) and its goldens; the CUDA proxy for this model is not built yet."""
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    s["bit_estimator_z.h"] = (QP_NUM, LD_CH_Z, 4)
+    s["bit_estimator_z.b"] = (QP_NUM, LD_CH_Z, 4)
+    s["bit_estimator_z.a"] = (QP_NUM, LD_CH_Z, 3)
+    s["q_encoder"] = (QP_NUM, LD_CH_D)
+    s["q_decoder"] = (QP_NUM, LD_CH_D)
+    s["q_feature"] = (QP_NUM, LD_CH_Y * 2)
+    # FeatureAdaptorI / M, FeatureExtractor (:61-107)
+    depth_conv_block(s, "feature_adaptor_i.conv.0.", LD_CH_SRC_D, LD_CH_M, dcb2=True)
+    for i in range(1, 4):
+        depth_conv_block(s, f"feature_adaptor_i.conv.{i}.", LD_CH_M, LD_CH_M, dcb2=True)
+    depth_conv_block(s, "feature_adaptor_m.conv.0.", LD_CH_M + LD_CH_D, LD_CH_M, dcb2=True)
+    for i in range(1, 4):
+        depth_conv_block(s, f"feature_adaptor_m.conv.{i}.", LD_CH_M, LD_CH_M, dcb2=True)
+    for i in range(5):
+        depth_conv_block(s, f"feature_extractor.conv.{i}.", LD_CH_M, LD_CH_M, dcb2=True)
+    # Encoder (:43-58)
+    depth_conv_block(s, "encoder.conv1.0.", LD_CH_SRC_D + LD_CH_M, LD_CH_D, dcb2=True)
+    depth_conv_block(s, "encoder.conv1.1.", LD_CH_D, LD_CH_D, dcb2=True)
+    depth_conv_block(s, "encoder.conv2.", LD_CH_D, LD_CH_D, dcb2=True)
+    _conv(s, "encoder.down.", LD_CH_Y, LD_CH_D, k=3)
+    # HyperEncoder / HyperDecoder (:110-135)
+    depth_conv_block(s, "hyper_encoder.conv.0.", LD_CH_Y, LD_CH_Z, dcb2=True)
+    residual_block_stride2(s, "hyper_encoder.conv.1.", LD_CH_Z, LD_CH_Z, dcb2=True)
+    residual_block_stride2(s, "hyper_encoder.conv.2.", LD_CH_Z, LD_CH_Z, dcb2=True)
+    residual_block_upsample(s, "hyper_decoder.conv.0.", LD_CH_Z, LD_CH_Z, dcb2=True)
+    residual_block_upsample(s, "hyper_decoder.conv.1.", LD_CH_Z, LD_CH_Z, dcb2=True)
+    depth_conv_block(s, "hyper_decoder.conv.2.", LD_CH_Z, LD_CH_Y, dcb2=True)
+    # TemporalPriorEncoder (:182-188), PriorFusion (:138-149), SpatialPrior (:169-179)
+    residual_block_stride2(s, "temporal_prior_encoder.conv.", LD_CH_M, LD_CH_Y * 2, dcb2=True)
+    for i in range(3):
+        depth_conv_block(s, f"y_prior_fusion.conv.{i}.", LD_CH_Y * 3, LD_CH_Y * 3, dcb2=True)
+    _conv(s, "y_prior_fusion.conv.3.", LD_CH_Y * 3, LD_CH_Y * 3)
+    depth_conv_block(s, "y_spatial_prior.conv.0.", LD_CH_Y * 4, LD_CH_Y * 2, dcb2=True)
+    depth_conv_block(s, "y_spatial_prior.conv.1.", LD_CH_Y * 2, LD_CH_Y * 2, dcb2=True)
+    _conv(s, "y_spatial_prior.conv.2.", LD_CH_Y, LD_CH_Y * 2)
+    # Decoder (:24-40), ReconHead (:152-166)
+    _conv(s, "decoder.up.conv.0.", LD_CH_D * 4, LD_CH_Y, bias=False)
+    depth_conv_block(s, "decoder.conv1.0.", LD_CH_D + LD_CH_M, LD_CH_D, dcb2=True)
+    depth_conv_block(s, "decoder.conv1.1.", LD_CH_D, LD_CH_D, dcb2=True)
+    depth_conv_block(s, "decoder.conv1.2.", LD_CH_D, LD_CH_D, dcb2=True)
+    _conv(s, "decoder.conv2.", LD_CH_D, LD_CH_D)
+    for i in range(3):
+        depth_conv_block(s, f"recon_head.conv.{i}.", LD_CH_D, LD_CH_D, dcb2=True)
+    _conv(s, "recon_head.head.", LD_CH_SRC_D, LD_CH_D)
+    return s
+
+
 # hand-calibrated gains (checked with the reference modules on random inputs): keep z within a few
 # levels, the predicted (scale, mean) noise around the hand-set biases small, x_hat inside [-0.5, 0.5]
 _WEIGHT_GAIN = {
@@ -172,6 +231,9 @@ _WEIGHT_GAIN = {
     "decoder.conv1.0.adaptor.weight": 0.35,          # keep the memory/context recurrence contractive
     "feature_adaptor_m.conv.0.adaptor.weight": 0.35,
     "feature_adaptor_i.conv.0.adaptor.weight": 0.5,
+    # LD
+    "y_spatial_prior.conv.2.weight": 0.06,
+    "recon_head.head.weight": 0.5,
 }
 for _i in range(G_FRAME_DELAY):
     _WEIGHT_GAIN[f"recon_head.conv2.{_i}.3.weight"] = 0.5
@@ -213,13 +275,15 @@ def synth_state_dict(spec, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
             t = t * _WEIGHT_GAIN.get(name, 1.0)
         elif name.endswith(".bias"):
             t = torch.randn(shape, generator=g) * 0.02
-            if name == "y_prior_fusion.conv.3.bias" and shape[0] == 3 * G_CH_Y:   # HT: (q_dec, scales, means)
-                third = G_CH_Y
+            if name == "y_prior_fusion.conv.3.bias" and shape[0] in (3 * G_CH_Y, 3 * LD_CH_Y):   # HT / LD: (q_dec, scales, means)
+                third = shape[0] // 3
                 perm = torch.randperm(third, generator=g)
                 t[:third] = torch.rand(third, generator=g) * 1.0 + 0.6
                 t[third:2 * third] = torch.exp(torch.linspace(math.log(0.02), math.log(1.5), third))[perm]
                 t[2 * third:] = torch.randn(third, generator=g) * 0.3
             elif name == "y_spatial_prior.conv.3.bias" and shape[0] == G_CH_Y:    # HT-S: means only
+                t = torch.randn(shape, generator=g) * 0.3
+            elif name == "y_spatial_prior.conv.2.bias" and shape[0] == LD_CH_Y:   # LD: means only
                 t = torch.randn(shape, generator=g) * 0.3
             elif name in ("y_prior_fusion.conv.3.bias", "y_spatial_prior.conv.3.bias"):
                 half = shape[0] // 2

@@ -41,9 +41,38 @@ def synth_frame(h, w, seed, channels=3):
     return t.clamp(-0.5, 0.5).half().float()
 
 
+def make_ld():
+    """6. low-delay model: layout + a 4-frame forward sequence (state carried, reset on frame 1), seed 2"""
+    from src.models.video_model_ld import DMC as DMC_LD
+    from dcvc_b200.spec import ld_spec
+    p = DMC_LD()
+    with open(os.path.join(HERE, "ld_state_dict_layout.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in p.state_dict().items()}, f, indent=0, sort_keys=True)
+    p.load_state_dict(synth_state_dict(ld_spec(), 2), strict=True)
+    p.eval()
+    ref0 = synth_frame(64, 64, 700)
+    out = {"ref_frame": ref0.numpy()}
+    with torch.inference_mode():
+        p.clear_dpb()
+        p.ref_feature = torch.nn.functional.pixel_unshuffle(ref0, 8)
+        for c, reset in enumerate([False, True, False, False]):
+            x = synth_frame(64, 64, 800 + c)
+            qp = 10 + 15 * c
+            r = p.forward_one_frame(x, torch.tensor([qp]), reset_feature_memory=reset)
+            out[f"x{c}"] = x.numpy()
+            out[f"qp{c}"] = np.int32(qp)
+            out[f"x_hat{c}"] = r["x_hat"].numpy()
+            out[f"ref_feature{c}"] = p.ref_feature.numpy()
+    np.savez_compressed(os.path.join(HERE, "ld_forward_64x64.npz"), **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if "--only-ld" in sys.argv:   # adds the LD fixtures without regenerating the others
+        make_ld()
+        print("LD golden fixtures written to", HERE)
+        return
     # 1. state_dict layout of the reference model
     m = DMCI()
     layout = {k: list(v.shape) for k, v in m.state_dict().items()}
@@ -139,6 +168,7 @@ def main():
             out[f"x_hat{c}"] = torch.cat(r["x_hat"], 1).numpy()
             out[f"ref_feature{c}"] = p.ref_feature.numpy()
     np.savez_compressed(os.path.join(HERE, "hts_forward_64x64.npz"), **out)
+    make_ld()
     print("golden fixtures written to", HERE)
 
 

@@ -296,3 +296,27 @@ def test_frame_io_oracle_matches_reference_expressions():
     uv_rec = torch.clamp(uv_rec * 255, 0, 255).byte().squeeze(0).numpy()
     ry, ru, rv = ops_ref.frame_to_yuv420(x_hat, 34, 50)
     assert np.array_equal(ry, y_rec[0]) and np.array_equal(ru, uv_rec[0]) and np.array_equal(rv, uv_rec[1])
+
+
+def test_ld_spec_matches_reference_layout():
+    """dcvc_b200.spec.ld_spec vs the state_dict of the reference's low-delay DMC (fixture minted by importing it)"""
+    import json
+    from dcvc_b200.spec import ld_spec
+    ref = json.load(open(os.path.join(GOLD, "ld_state_dict_layout.json")))
+    mine = {k: list(v) for k, v in ld_spec().items()}
+    assert mine == ref
+
+
+def test_ld_oracle_forward_pinned_to_reference():
+    """oracle/ld_oracle.py (forward_one_frame + forward_prior_2x + state handling) vs the reference's own modules on
+    a 4-frame sequence with a feature-memory reset (tests/golden/make_golden.py, seed-2 synthetic checkpoint)"""
+    from dcvc_b200.spec import ld_spec, synth_state_dict
+    from oracle.ld_oracle import LdOracle
+    g = np.load(os.path.join(GOLD, "ld_forward_64x64.npz"))
+    o = LdOracle(synth_state_dict(ld_spec(), 2), emulate_fp16=False)
+    o.clear_dpb()
+    o.feature_p = torch.nn.functional.pixel_unshuffle(torch.from_numpy(g["ref_frame"]), 8)
+    for c, reset in enumerate([False, True, False, False]):
+        r = o.forward_one_frame(torch.from_numpy(g[f"x{c}"]), int(g[f"qp{c}"]), reset_feature_memory=reset)
+        assert (r["x_hat"] - torch.from_numpy(g[f"x_hat{c}"])).abs().max().item() < 2e-5
+        assert (o.feature_p - torch.from_numpy(g[f"ref_feature{c}"])).abs().max().item() < 2e-5
