@@ -1,6 +1,16 @@
 """CPU oracle for the DCVC-UF low-delay model (DMC of src/models/video_model_ld.py).  TEST INFRASTRUCTURE ONLY.
 
-Round-1 scope: the reference's pure-PyTorch training forward (`forward_one_frame`,
+Two restatements, both functional over a plain state_dict:
+
+* `compress` / `decompress` / `add_ref_feature_from_frame` — the control flow of the reference's CUDA proxy,
+  /root/reference/src/layers/extensions/inference/dmc_ld_proxy.cpp:407-418 (add_ref_feature_from_frame), :420-486
+  (compress), :488-593 (decompress), :639-658 (memory / context updates), with the half arithmetic of
+  elementwise/stream.cu (means-only refinement with fixed scales over the two checkerboard masks, one symbol stream
+  over the whole latent) and the reference's own rANS coder.  PARITY UNPINNED at the NN-output level (the CUDA proxy
+  cannot run in the authoring container); self-consistency (decoder state == encoder state) and closeness to the
+  pinned forward are tested in tests/test_cpu_parity.py.
+
+* the reference's pure-PyTorch training forward (`forward_one_frame`,
 /root/reference/src/models/video_model_ld.py:308-343, with `forward_prior_2x`,
 /root/reference/src/models/common_model.py:212-229 and the 2-step checkerboard masks of
 common_model.py:157-172), restated functionally over a plain state_dict and PINNED against
@@ -15,7 +25,11 @@ import torch
 import torch.nn.functional as F
 
 from . import ops_ref
-from .hts_oracle import HtsOracle
+from .dmci_oracle import _pad_to
+from .hts_oracle import HtsOracle, _h
+
+LD_CH_Y = 128
+LD_CH_Z = 128
 
 
 def mask_2x(step: int, C: int, H: int, W: int) -> np.ndarray:
@@ -126,3 +140,123 @@ class LdOracle(HtsOracle):
             self.feature_p = f
         return {"x_hat": x_hat, "y_q": y_q_0 + y_q_1, "z_hat": z_hat, "scales_hat": scales * m0 + scales * m1,
                 "y_hat": y_hat, "feature": feature}
+
+    # ---------------------------------------------------------------- proxy restatement (fp16 emulation)
+    def add_ref_feature_from_frame(self, frame, apply_adaptor=True):
+        """dmc_ld_proxy.cpp:407-418; frame: [1,3,Hp,Wp] (already padded reconstruction)"""
+        self.feature_i = self._canon(F.pixel_unshuffle(frame, 8))
+        if apply_adaptor:
+            self.memory = self.feature_adaptor_i(self.feature_i)
+            self.ctx = self.feature_extractor(self.memory)
+        self.memory_has_value = apply_adaptor
+
+    def _ld_params(self, z_hat, qp, H16, W16):
+        temporal = self.rbd(self.memory, "temporal_prior_encoder.conv.", False)
+        hyper = self.ld_hyper_dec(z_hat)[:, :, :H16, :W16]   # crop_hyper_params
+        q = self.r(self._w("q_feature")[qp]).view(1, -1, 1, 1)
+        t = self.seq(torch.cat((hyper, self.r(temporal * q)), 1), "y_prior_fusion.conv.", 3)
+        return self.r(ops_ref.conv1x1(t, self._w("y_prior_fusion.conv.3.weight"), self._w("y_prior_fusion.conv.3.bias")))
+
+    def _two_steps(self, common, y_np=None, decoded_dense=None):
+        """process_with_mask_no_scale + process_with_mask_no_scale_add_and_multiply (encoder, :444-449) resp.
+        restore_y + restore_y_and_add_multiply (decoder, :579-581): scales stay fixed, only the means are refined.
+        Encoder: y_np = y / clamp_min(q_dec, .5) [H,W,C] fp16 -> (y_hat, y_q, scales); decoder: decoded_dense = y_q."""
+        p_np = self._nhwc16(common)
+        q_dec, scales, means0 = p_np[..., :LD_CH_Y], p_np[..., LD_CH_Y:2 * LD_CH_Y], p_np[..., 2 * LD_CH_Y:]
+        H, W, C = scales.shape
+        thres = np.float32(np.float16(self.skip_thres))
+        acc = np.zeros((H, W, C), dtype=np.float16)
+        y_q_all = np.zeros((H, W, C), dtype=np.int32)
+        means = means0
+        for k in range(2):
+            if k == 1:
+                means = self._nhwc16(self.ld_spatial_prior(self._nchw32(acc), common))
+            m = np.transpose(mask_2x(k, C, H, W), (1, 2, 0)) > 0
+            means_hat = np.where(m, means, np.float16(0))
+            if y_np is not None:
+                res = np.where(m, _h(y_np.astype(np.float32) - means_hat.astype(np.float32)), np.float16(0)).astype(np.float32)
+                yq = np.sign(res) * np.floor(np.abs(res) + 0.5)
+                yq = np.where(np.where(m, scales, np.float16(0)).astype(np.float32) > thres, yq, 0.0)
+                yq = np.clip(yq, -128, 127)
+                y_q_all += yq.astype(np.int32)
+            else:
+                yq = np.where(m, decoded_dense, 0).astype(np.float32)
+            y_hat = np.where(m, _h(yq + means_hat.astype(np.float32)), np.float16(0))
+            acc = _h(acc.astype(np.float32) + y_hat.astype(np.float32))
+        qd = np.maximum(q_dec.astype(np.float32), np.float32(0.5))
+        return _h(acc.astype(np.float32) * qd), y_q_all, scales
+
+    @torch.inference_mode()
+    def compress(self, x, qp: int, reset_feature_memory: bool, padding_b: int, padding_r: int):
+        """x: [1,3,H,W] fp16-representable; memory / ctx were produced by add_ref_feature_from_frame or at the end of
+        the previous call (dmc_ld_proxy.cpp:420-486)."""
+        assert self.emu
+        _, _, H, W = x.shape
+        Hp, Wp = _pad_to(H, 16), _pad_to(W, 16)
+        H16, W16 = Hp // 16, Wp // 16
+        H16p, W16p = _pad_to(H16, 4), _pad_to(W16, 4)
+        xu = ops_ref.unshuffle8_pad(x, padding_b, padding_r)
+        y = self.ld_encoder(xu, self.ctx, qp)
+        y_pad = F.pad(y, (0, W16p - W16, 0, H16p - H16), mode="replicate")
+        z = self.ld_hyper_enc(y_pad)
+        z_hat = self._canon(torch.clamp(ops_ref.round_half_away(z), -64, 63))
+        z_i8 = z_hat[0].permute(1, 2, 0).contiguous().numpy().astype(np.int8).reshape(-1)
+        common = self._ld_params(z_hat, qp, H16, W16)
+        q_dec = self._nhwc16(common)[..., :LD_CH_Y]
+        rcp = _h(np.float32(1.0) / np.maximum(q_dec.astype(np.float32), np.float32(0.5)))
+        y_np = _h(self._nhwc16(y).astype(np.float32) * rcp.astype(np.float32))
+        y_hat, y_q, scales = self._two_steps(common, y_np=y_np)
+        keep = scales.astype(np.float32) > np.float32(np.float16(self.skip_thres))
+        idx = self.lut[scales.view(np.uint16)].astype(np.int32)
+        sym = ((y_q << 8) + idx).astype(np.int16).reshape(-1)[keep.reshape(-1)]
+        ec_parallel = max(1, min(8, len(sym) // 32768))
+        enc, _ = self._coder()
+        enc.reset()
+        enc.set_entropy_coder_parallel(ec_parallel)
+        enc.encode_y(np.ascontiguousarray(sym))
+        enc.encode_z(z_i8, qp * LD_CH_Z, LD_CH_Z)
+        enc.flush()
+        stream = bytes(np.asarray(enc.get_encoded_stream()).tobytes())
+        # enc_1: decoder, then memory / context for the NEXT frame (:468-472, 639-649)
+        self.feature_p = self.ld_decoder(self._nchw32(y_hat), self.ctx, qp)
+        if reset_feature_memory:
+            self.memory = self.feature_adaptor_i(self.ld_recon_head(self.feature_p, for_reset=True))
+        else:
+            self.memory = self.feature_adaptor_m(self.memory, self.feature_p)
+        self.ctx = self.feature_extractor(self.memory)
+        return {"bit_stream": stream, "ec_parallel": ec_parallel, "symbols": sym, "z_i8": z_i8, "y_hat": y_hat}
+
+    @torch.inference_mode()
+    def decompress(self, bit_stream: bytes, qp: int, height: int, width: int, ec_parallel: int,
+                   reset_feature_memory: bool):
+        """dmc_ld_proxy.cpp:488-593: the memory update of the previous frame is applied lazily here (:512-516, 651-658)"""
+        assert self.emu
+        Hp, Wp = _pad_to(height, 16), _pad_to(width, 16)
+        H16, W16 = Hp // 16, Wp // 16
+        zh, zw = (height + 63) // 64, (width + 63) // 64
+        if self.memory_has_value:
+            self.memory = self.feature_adaptor_m(self.memory, self.feature_p)
+        else:
+            self.memory = self.feature_adaptor_i(self.feature_i)
+        _, dec = self._coder()
+        dec.set_entropy_coder_parallel(ec_parallel)
+        dec.set_stream(np.frombuffer(bit_stream, dtype=np.uint8))
+        n_z = LD_CH_Z * zh * zw
+        dec.decode_z(n_z, qp * LD_CH_Z, LD_CH_Z)
+        z_i8 = dec.get_decoded(n_z)
+        z_hat = self._canon(torch.from_numpy(z_i8.astype(np.float32)).view(zh, zw, LD_CH_Z).permute(2, 0, 1).unsqueeze(0))
+        common = self._ld_params(z_hat, qp, H16, W16)
+        scales = self._nhwc16(common)[..., LD_CH_Y:2 * LD_CH_Y]
+        keep = scales.astype(np.float32) > np.float32(np.float16(self.skip_thres))
+        idx = self.lut[scales.view(np.uint16)].reshape(-1)[keep.reshape(-1)]
+        dec.decode_y(np.ascontiguousarray(idx))
+        decoded = dec.get_decoded(len(idx))
+        self.ctx = self.feature_extractor(self.memory)
+        dense = np.zeros(scales.size, dtype=np.int32)
+        dense[keep.reshape(-1)] = decoded
+        y_hat, _, _ = self._two_steps(common, decoded_dense=dense.reshape(scales.shape))
+        self.feature_p = self.ld_decoder(self._nchw32(y_hat), self.ctx, qp)
+        head = self.ld_recon_head(self.feature_p, for_reset=True)
+        self.feature_i = head   # the head output doubles as the reset reference (:585-586)
+        self.memory_has_value = not reset_feature_memory
+        return {"x_hat": ops_ref.shuffle8_clamp(head, True), "y_hat": y_hat}

@@ -320,3 +320,26 @@ def test_ld_oracle_forward_pinned_to_reference():
         r = o.forward_one_frame(torch.from_numpy(g[f"x{c}"]), int(g[f"qp{c}"]), reset_feature_memory=reset)
         assert (r["x_hat"] - torch.from_numpy(g[f"x_hat{c}"])).abs().max().item() < 2e-5
         assert (o.feature_p - torch.from_numpy(g[f"ref_feature{c}"])).abs().max().item() < 2e-5
+
+
+def test_ld_oracle_compress_decompress_consistency():
+    """proxy-control-flow restatement of the low-delay codec (dmc_ld_proxy.cpp:407-593): the decoder reproduces the
+    encoder's latents and recurrent state over a 3-frame sequence with a feature-memory reset and ragged padding"""
+    from oracle.build_ref import import_ref_shim
+    if import_ref_shim() is None:
+        pytest.skip("oracle/_ref not built")
+    from dcvc_b200.spec import ld_spec, synth_state_dict
+    from oracle.ld_oracle import LdOracle
+    g = np.load(os.path.join(GOLD, "ld_forward_64x64.npz"))
+    sd = synth_state_dict(ld_spec(), 2)
+    enc, dec = LdOracle(sd, 0.15, True, threads=8), LdOracle(sd, 0.15, True, threads=8)
+    ref = torch.from_numpy(g["ref_frame"])
+    enc.add_ref_feature_from_frame(ref, True)        # encoder side of test_video.py:228-229
+    dec.add_ref_feature_from_frame(ref, False)       # decoder side of test_video.py:314-315
+    for c, reset in enumerate([False, True, False]):
+        x = torch.from_numpy(g[f"x{c}"])[:, :, :56, :60].contiguous()
+        e = enc.compress(x, 30 + c, reset, 8, 4)
+        d = dec.decompress(e["bit_stream"], 30 + c, 56, 60, e["ec_parallel"], reset)
+        assert np.array_equal(e["y_hat"].view(np.uint16), d["y_hat"].view(np.uint16)), f"frame {c}"
+        assert torch.equal(enc.feature_p, dec.feature_p), f"decoder state drifted at frame {c}"
+        assert d["x_hat"].shape == (1, 3, 64, 64)
