@@ -28,6 +28,7 @@ SOURCES = [
     "c_api_ops.cu",
     "codec.cu",
     "codec_hts.cu",
+    "codec_ld.cu",
 ]
 
 NVCC_FLAGS = [

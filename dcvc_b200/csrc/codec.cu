@@ -511,6 +511,13 @@ using dcvc::IntraCodec;
 namespace dcvc {
 // codec_hts.cu
 CodecBase* make_hts_codec(int device);
+CodecBase* make_ld_codec(int device);
+int ld_add_ref(CodecBase* c, const void* frame, int H, int W, int64_t sc, int64_t sh, int64_t sw, int apply,
+               cudaStream_t stream);
+int ld_compress(CodecBase* c, const void* x, int H, int W, int64_t sc, int64_t sh, int64_t sw, int qp, int reset,
+                int pad_b, int pad_r, cudaStream_t stream, const uint8_t** bs, int32_t* len, int32_t* ec);
+int ld_decompress(CodecBase* c, const uint8_t* bs, int len, int qp, int height, int width, int ec, int reset,
+                  cudaStream_t stream, void* const* x_hat_out);
 int hts_add_ref(CodecBase* c, const void* frame, int H, int W, int64_t sc, int64_t sh, int64_t sw, int apply,
                 cudaStream_t stream);
 int hts_compress(CodecBase* c, const void* x, int H, int W, int64_t sc, int64_t sh, int64_t sw, int qp, int reset,
@@ -546,8 +553,8 @@ extern "C" {
 
 int dcvc_create(int32_t kind, int32_t device, dcvc_codec** out)
 {
-    if (kind != DCVC_KIND_INTRA && kind != DCVC_KIND_HTS) {
-        dcvc::set_api_error("dcvc_create: only DCVC_KIND_INTRA and DCVC_KIND_HTS are implemented in this build");
+    if (kind != DCVC_KIND_INTRA && kind != DCVC_KIND_HTS && kind != DCVC_KIND_LD) {
+        dcvc::set_api_error("dcvc_create: DCVC_KIND_INTRA, DCVC_KIND_HTS and DCVC_KIND_LD are implemented in this build (HT-L is not)");
         return 1;
     }
     int n = 0;
@@ -560,6 +567,8 @@ int dcvc_create(int32_t kind, int32_t device, dcvc_codec** out)
     if (kind == DCVC_KIND_INTRA) {
         h->intra = new IntraCodec(device);
         h->base.reset(h->intra);
+    } else if (kind == DCVC_KIND_LD) {
+        h->base.reset(dcvc::make_ld_codec(device));
     } else {
         h->base.reset(dcvc::make_hts_codec(device));
     }
@@ -646,7 +655,9 @@ int dcvc_add_ref_feature_from_frame(dcvc_codec* h, const void* frame, int32_t H,
                                     int64_t sw, int32_t apply_adaptor, void* stream)
 {
     CODEC_TRY(h)
-    if (h->kind != DCVC_KIND_HTS) throw std::runtime_error("add_ref_feature_from_frame needs a chunk codec handle");
+    if (h->kind == DCVC_KIND_LD)
+        return dcvc::ld_add_ref(h->base.get(), frame, H, W, sc, sh, sw, apply_adaptor, static_cast<cudaStream_t>(stream));
+    if (h->kind != DCVC_KIND_HTS) throw std::runtime_error("add_ref_feature_from_frame needs a video codec handle");
     return dcvc::hts_add_ref(h->base.get(), frame, H, W, sc, sh, sw, apply_adaptor, static_cast<cudaStream_t>(stream));
     CODEC_CATCH(h)
 }
@@ -656,7 +667,10 @@ int dcvc_compress_chunk(dcvc_codec* h, const void* x, int32_t H, int32_t W, int6
                         const uint8_t** bit_stream, int32_t* bit_stream_len, int32_t* ec_parallel)
 {
     CODEC_TRY(h)
-    if (h->kind != DCVC_KIND_HTS) throw std::runtime_error("compress_chunk needs a chunk codec handle");
+    if (h->kind == DCVC_KIND_LD)
+        return dcvc::ld_compress(h->base.get(), x, H, W, sc, sh, sw, qp, reset_feature_memory, pad_b, pad_r,
+                                 static_cast<cudaStream_t>(stream), bit_stream, bit_stream_len, ec_parallel);
+    if (h->kind != DCVC_KIND_HTS) throw std::runtime_error("compress_chunk needs a video codec handle");
     return dcvc::hts_compress(h->base.get(), x, H, W, sc, sh, sw, qp, reset_feature_memory, pad_b, pad_r,
                               static_cast<cudaStream_t>(stream), bit_stream, bit_stream_len, ec_parallel);
     CODEC_CATCH(h)
@@ -667,7 +681,10 @@ int dcvc_decompress_chunk(dcvc_codec* h, const uint8_t* bit_stream, int32_t len,
                           void* const* x_hat_out)
 {
     CODEC_TRY(h)
-    if (h->kind != DCVC_KIND_HTS) throw std::runtime_error("decompress_chunk needs a chunk codec handle");
+    if (h->kind == DCVC_KIND_LD)
+        return dcvc::ld_decompress(h->base.get(), bit_stream, len, qp, height, width, ec_parallel, reset_feature_memory,
+                                   static_cast<cudaStream_t>(stream), x_hat_out);
+    if (h->kind != DCVC_KIND_HTS) throw std::runtime_error("decompress_chunk needs a video codec handle");
     return dcvc::hts_decompress(h->base.get(), bit_stream, len, qp, height, width, ec_parallel, reset_feature_memory,
                                 static_cast<cudaStream_t>(stream), x_hat_out);
     CODEC_CATCH(h)

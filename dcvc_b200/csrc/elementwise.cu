@@ -344,8 +344,16 @@ __device__ __forceinline__ int active_group(int step, int h, int w)
     return p ^ x;
 }
 
+// ng == 2: the two-step checkerboard of the low-delay model (get_mask_2x, common_model.py:157-172): the first
+// channel half is coded on the even checkerboard phase in step 0 and on the odd one in step 1, the second half the
+// other way round -> the active half of pixel (h, w) in step k is ((h + w) & 1) ^ k.
+__device__ __forceinline__ int active_group_n(int ng, int step, int h, int w)
+{
+    return ng == 2 ? (((h + w) & 1) ^ step) : active_group(step, h, w);
+}
+
 struct EntropyDev {
-    const __half* qdiv; int q_pitch; int m_pitch; int8_t* yq; int full;
+    const __half* qdiv; int q_pitch; int m_pitch; int8_t* yq; int full; int ng;
     int H, W, G, step;
     const __half* y; int y_pitch;
     const __half* q_enc;
@@ -360,7 +368,7 @@ static EntropyDev to_dev(const EntropyStepArgs& a)
 {
     EntropyDev d;
     d.qdiv = a.q_div; d.q_pitch = a.q_pitch; d.m_pitch = a.m_pitch ? a.m_pitch : a.p_pitch;
-    d.yq = a.yq_dense; d.full = a.full;
+    d.yq = a.yq_dense; d.full = a.full; d.ng = a.ng == 2 ? 2 : 4;
     d.H = a.H; d.W = a.W; d.G = a.G; d.step = a.step;
     d.y = a.y; d.y_pitch = a.y_pitch; d.q_enc = a.q_enc;
     d.scales = a.scales; d.means = a.means; d.p_pitch = a.p_pitch;
@@ -380,7 +388,7 @@ entropy_enc_step_kernel(const EntropyDev d)
     if (pix >= npix) return;
     const int w = static_cast<int>(pix % d.W);
     const int h = static_cast<int>(pix / d.W);
-    const int g = active_group(d.step, h, w);
+    const int g = active_group_n(d.ng, d.step, h, w);
     int count = 0;
     for (int c = lane * 2; c < d.G; c += 64) {
         const int ch = g * d.G + c;
@@ -410,7 +418,7 @@ entropy_enc_step_kernel(const EntropyDev d)
             char2 qq;
             qq.x = static_cast<signed char>(q0);
             qq.y = static_cast<signed char>(q1);
-            *reinterpret_cast<char2*>(d.yq + pix * (4 * d.G) + ch) = qq;
+            *reinterpret_cast<char2*>(d.yq + pix * (d.ng * d.G) + ch) = qq;
         }
         if (d.sym_raw) {
             const int i0 = d.lut[__half_as_ushort(__low2half(sv))];
@@ -425,7 +433,7 @@ entropy_enc_step_kernel(const EntropyDev d)
     if (d.step == 0) {
         // y_hat_so_far.copy_(y_hat): the three inactive groups start at zero (dmci_proxy.cpp:344)
         const __half2 z = __floats2half2_rn(0.f, 0.f);
-        for (int c = lane * 2; c < 4 * d.G; c += 64) {
+        for (int c = lane * 2; c < d.ng * d.G; c += 64) {
             if (c / d.G != g) *reinterpret_cast<__half2*>(d.acc + pix * d.acc_pitch + c) = z;
         }
     }
@@ -443,7 +451,7 @@ entropy_dec_index_kernel(const EntropyDev d)
     if (pix >= npix) return;
     const int w = static_cast<int>(pix % d.W);
     const int h = static_cast<int>(pix / d.W);
-    const int g = d.full ? 0 : active_group(d.step, h, w);
+    const int g = d.full ? 0 : active_group_n(d.ng, d.step, h, w);
     int count = 0;
     for (int c = lane * 2; c < d.G; c += 64) {
         const int ch = g * d.G + c;
@@ -483,7 +491,7 @@ compact_kernel(const EntropyDev d, const T* __restrict__ raw, const int32_t* __r
     if (pix >= npix) return;
     const int w = static_cast<int>(pix % d.W);
     const int h = static_cast<int>(pix / d.W);
-    const int g = d.full ? 0 : active_group(d.step, h, w);
+    const int g = d.full ? 0 : active_group_n(d.ng, d.step, h, w);
     int base = offsets[pix];
     for (int c0i = 0; c0i < d.G; c0i += 64) {
         const int c = c0i + lane * 2;
@@ -514,7 +522,7 @@ entropy_dec_restore_kernel(const EntropyDev d, const int32_t* __restrict__ offse
     if (pix >= npix) return;
     const int w = static_cast<int>(pix % d.W);
     const int h = static_cast<int>(pix / d.W);
-    const int g = active_group(d.step, h, w);
+    const int g = active_group_n(d.ng, d.step, h, w);
     int base = offsets[pix];
     for (int c0i = 0; c0i < d.G; c0i += 64) {
         const int c = c0i + lane * 2;
@@ -539,7 +547,7 @@ entropy_dec_restore_kernel(const EntropyDev d, const int32_t* __restrict__ offse
     }
     if (d.step == 0) {
         const __half2 z = __floats2half2_rn(0.f, 0.f);
-        for (int c = lane * 2; c < 4 * d.G; c += 64) {
+        for (int c = lane * 2; c < d.ng * d.G; c += 64) {
             if (c / d.G != g) *reinterpret_cast<__half2*>(d.acc + pix * d.acc_pitch + c) = z;
         }
     }
@@ -605,17 +613,17 @@ entropy_restore_dense_kernel(const EntropyDev d)
     if (pix >= static_cast<long long>(d.H) * d.W) return;
     const int w = static_cast<int>(pix % d.W);
     const int h = static_cast<int>(pix / d.W);
-    const int g = active_group(d.step, h, w);
+    const int g = active_group_n(d.ng, d.step, h, w);
     for (int c = lane * 2; c < d.G; c += 64) {
         const int ch = g * d.G + c;
-        const char2 qq = *reinterpret_cast<const char2*>(d.yq + pix * (4 * d.G) + ch);
+        const char2 qq = *reinterpret_cast<const char2*>(d.yq + pix * (d.ng * d.G) + ch);
         const __half2 mv = *reinterpret_cast<const __half2*>(d.means + pix * d.m_pitch + ch);
         const __half2 yh = __hadd2_rn(__floats2half2_rn(static_cast<float>(qq.x), static_cast<float>(qq.y)), mv);
         *reinterpret_cast<__half2*>(d.acc + pix * d.acc_pitch + ch) = yh;
     }
     if (d.step == 0) {
         const __half2 z = __floats2half2_rn(0.f, 0.f);
-        for (int c = lane * 2; c < 4 * d.G; c += 64) {
+        for (int c = lane * 2; c < d.ng * d.G; c += 64) {
             if (c / d.G != g) *reinterpret_cast<__half2*>(d.acc + pix * d.acc_pitch + c) = z;
         }
     }

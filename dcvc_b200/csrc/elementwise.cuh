@@ -54,6 +54,7 @@ struct EntropyStepArgs {
     int m_pitch = 0;                  // pitch of `means` (0: same as p_pitch)
     int8_t* yq_dense = nullptr;       // [H*W][4G] quantised latents, written (enc) / read (dec restore)
     int full = 0;                     // 1: index/compaction kernels run over all 4*G channels of a pixel
+    int ng = 4;                       // channel groups per pixel: 4 (4-step mask) or 2 (two-step checkerboard of the LD model, C = 2*G)
     // outputs, per pixel row of G entries
     int16_t* sym_raw = nullptr;       // encoder: (sym << 8) + idx, uncompacted [H*W][G]
     uint8_t* idx_raw = nullptr;       // decoder: idx, uncompacted [H*W][G]

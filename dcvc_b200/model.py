@@ -151,3 +151,29 @@ class DMC(DMCI):
         x_hat = self.proxy.decompress(np.frombuffer(bit_stream, dtype=np.uint8), qp, sps["height"], sps["width"],
                                       ec_part, reset_feature_memory)
         return {"x_hat": x_hat}
+
+
+class DMCLD(DMC):
+    """Host-side mirror of the reference's low-delay video model API (src/models/video_model_ld.py:191-306): the class
+    there is also called DMC; one frame per compress / decompress, `x_hat` is a single tensor."""
+
+    def __init__(self):
+        from .spec import ld_spec
+        self._spec = ld_spec()
+        self._sd = OrderedDict((k, torch.zeros(v)) for k, v in self._spec.items())
+        self.proxy = None
+        self.skip_thres = 0.0
+        self._cdf = None
+
+    @classmethod
+    def synthetic(cls, seed: int = 2) -> "DMCLD":
+        m = cls()
+        m.load_state_dict(synth_state_dict(m._spec, seed))
+        return m
+
+    def _ensure_proxy(self):
+        if self.proxy is None:
+            from inference_extensions_cuda import DMCLDProxy
+            sd = self.add_cdf_to_state_dict(self.state_dict())
+            self.proxy = DMCLDProxy()
+            self.proxy.set_param(sd, self.skip_thres)

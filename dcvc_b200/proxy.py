@@ -183,3 +183,19 @@ class DMCHTSProxy:
     profile_enable = DMCIProxy.profile_enable
     profile_get = DMCIProxy.profile_get
     debug_fetch = DMCIProxy.debug_fetch
+
+
+class DMCLDProxy(DMCHTSProxy):
+    """DCVC-UF low-delay codec proxy (reference: DMCLDProxy, dmc_ld_proxy.h; bind.cpp:32-38): one frame per call,
+    `decompress` returns ONE tensor."""
+
+    FRAMES = 1
+
+    def __init__(self):
+        self._hd = _CodecHandle(_lib.KIND_LD)
+        self._x_hat = None
+
+    def decompress(self, bit_stream: np.ndarray, qp: int, height: int, width: int, ec_parallel: int,
+                   reset_feature_memory: bool):
+        """-> fp16 channels_last tensor [1,3,H16p,W16p] (proxy-owned, reused by the next call)"""
+        return super().decompress(bit_stream, qp, height, width, ec_parallel, reset_feature_memory)[0]

@@ -186,7 +186,9 @@ int dcvc_decompress(dcvc_codec* h, const uint8_t* bit_stream, int32_t len, int32
                     int32_t height, int32_t width, int32_t ec_parallel, void* stream,
                     void* x_hat_out);
 
-/* Chunk codecs (DCVC_KIND_HTS): DMCHTSProxy::add_ref_feature_from_frame / compress / decompress
+/* Video codecs.  DCVC_KIND_LD (DMCLDProxy, dmc_ld_proxy.cpp:407-593; bind.cpp:32-38): the same three entry points with
+ * x = fp16 [1,3,H,W] (one frame) and x_hat_out = ONE caller-owned fp16 NHWC [Hp][Wp][3] buffer.
+ * Chunk codecs (DCVC_KIND_HTS): DMCHTSProxy::add_ref_feature_from_frame / compress / decompress
  * (dmc_hts_proxy.cpp:492-502, 504-585, 587-710; bind.cpp:24-31).
  * frame: fp16 [1,3,Hp,Wp] reconstruction (already padded to x16) with element strides;
  * x: fp16 [1,24,H,W] = 8 stacked YUV444 frames; x_hat_out: 8 caller-owned fp16 NHWC [Hp][Wp][3] buffers. */

@@ -4,9 +4,10 @@
 Put the repository root on PYTHONPATH and the reference's own
 `from inference_extensions_cuda import DMCIProxy` (src/models/image_model.py:197) /
 `from inference_extensions_cuda import DMCHTSProxy` (src/models/video_model_ht.py:420) resolve here.
-DMCHTLProxy / DMCLDProxy are not provided yet: importing them raises ImportError, which the reference
-turns into its NotImplementedError (video_model_ht.py:424-428, video_model_ld.py:280-284).
+`from inference_extensions_cuda import DMCLDProxy` (src/models/video_model_ld.py:279) too.
+DMCHTLProxy is not provided yet: importing it raises ImportError, which the reference turns into its
+NotImplementedError (video_model_ht.py:424-428).
 """
-from dcvc_b200.proxy import DMCHTSProxy, DMCIProxy  # noqa: F401
+from dcvc_b200.proxy import DMCHTSProxy, DMCIProxy, DMCLDProxy  # noqa: F401
 
-__all__ = ["DMCIProxy", "DMCHTSProxy"]
+__all__ = ["DMCIProxy", "DMCHTSProxy", "DMCLDProxy"]
