@@ -45,9 +45,9 @@ def depth_conv_block(spec, prefix, in_ch, out_ch, dcb2=False, force_adaptor=Fals
     _conv(spec, prefix + "ffn.2.", out_ch, out_ch // r)
 
 
-def residual_block_upsample(spec, prefix, in_ch, out_ch, dcb2=False):
-    """ResidualBlockUpsample (layers.py:162-173): SubpelConv2x(1x1, no bias) + DepthConvBlock"""
-    _conv(spec, prefix + "up.conv.0.", out_ch * 4, in_ch, bias=False)
+def residual_block_upsample(spec, prefix, in_ch, out_ch, dcb2=False, force_bias=False):
+    """ResidualBlockUpsample (layers.py:162-173): SubpelConv2x(1x1, bias only with force_bias) + DepthConvBlock"""
+    _conv(spec, prefix + "up.conv.0.", out_ch * 4, in_ch, bias=force_bias)
     depth_conv_block(spec, prefix + "conv.", out_ch, out_ch, dcb2=dcb2)
 
 
@@ -159,6 +159,56 @@ def hts_spec() -> "OrderedDict[str, tuple]":
     return s
 
 
+def htl_spec() -> "OrderedDict[str, tuple]":
+    """state_dict layout of DMC(ModelStructure.HTL) (src/models/video_model_ht.py: the `else` branches of :26-317).
+    Used by the oracle (oracle/htl_oracle.py) and its goldens; the CUDA proxy for this model is not built yet."""
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    s["bit_estimator_z.h"] = (QP_NUM, G_CH_Z, 4)
+    s["bit_estimator_z.b"] = (QP_NUM, G_CH_Z, 4)
+    s["bit_estimator_z.a"] = (QP_NUM, G_CH_Z, 3)
+    s["q_encoder"] = (QP_NUM, G_CH_D)
+    s["q_decoder"] = (QP_NUM, G_CH_D)
+    s["q_feature"] = (QP_NUM, G_CH_D)
+    depth_conv_block(s, "feature_adaptor_i.conv.0.", G_CH_SRC, G_CH_M)
+    for i in range(1, 3):
+        depth_conv_block(s, f"feature_adaptor_i.conv.{i}.", G_CH_M, G_CH_M)
+    depth_conv_block(s, "feature_adaptor_m.conv.0.", G_CH_M + G_CH_D, G_CH_M)
+    for i in range(1, 10):
+        depth_conv_block(s, f"feature_adaptor_m.conv.{i}.", G_CH_M, G_CH_M)
+    for i in range(2):
+        depth_conv_block(s, f"feature_extractor.conv.{i}.", G_CH_D, G_CH_D)
+    depth_conv_block(s, "encoder.conv1.0.", G_CH_SRC_D + G_CH_D, G_CH_D)
+    for i in range(1, 7):
+        depth_conv_block(s, f"encoder.conv1.{i}.", G_CH_D, G_CH_D)
+    _conv(s, "encoder.down.", G_CH_Y, G_CH_D, k=3)
+    depth_conv_block(s, "hyper_encoder.conv.0.", G_CH_Y, G_CH_Y)
+    residual_block_stride2(s, "hyper_encoder.conv.1.", G_CH_Y, G_CH_Y)
+    residual_block_stride2(s, "hyper_encoder.conv.2.", G_CH_Y, G_CH_Z)
+    residual_block_upsample(s, "hyper_decoder.conv.0.", G_CH_Z, G_CH_Y, force_bias=True)
+    residual_block_upsample(s, "hyper_decoder.conv.1.", G_CH_Y, G_CH_Y, force_bias=True)
+    depth_conv_block(s, "hyper_decoder.conv.2.", G_CH_Y, G_CH_Y)
+    residual_block_stride2(s, "temporal_prior_encoder.conv.", G_CH_D, G_CH_Y * 2)
+    for i in range(3):
+        depth_conv_block(s, f"y_prior_fusion.conv.{i}.", G_CH_Y * 3, G_CH_Y * 3)
+    _conv(s, "y_prior_fusion.conv.3.", G_CH_Y * 3, G_CH_Y * 3)
+    _conv(s, "y_spatial_prior_reduction.", G_CH_Y, G_CH_Y * 3)
+    for i in (1, 2, 3):
+        depth_conv_block(s, f"y_spatial_prior_adaptor_{i}.", G_CH_Y * 2, G_CH_Y * 2, force_adaptor=True)
+    for i in range(3):
+        depth_conv_block(s, f"y_spatial_prior.conv.{i}.", G_CH_Y * 2, G_CH_Y * 2)
+    _conv(s, "y_spatial_prior.conv.3.", G_CH_Y * 2, G_CH_Y * 2)   # (scales, means)
+    _conv(s, "decoder.up.conv.0.", G_CH_D * 4, G_CH_Y, k=3)      # 3x3 SubpelConv2x with bias
+    depth_conv_block(s, "decoder.conv1.0.", G_CH_D * 2, G_CH_D)
+    for i in range(1, 11):
+        depth_conv_block(s, f"decoder.conv1.{i}.", G_CH_D, G_CH_D)
+    for i in range(G_FRAME_DELAY):
+        depth_conv_block(s, f"recon_head.conv.{i}.0.", G_CH_D, G_CH_RECON)
+        for j in range(1, 5):
+            depth_conv_block(s, f"recon_head.conv.{i}.{j}.", G_CH_RECON, G_CH_RECON)
+        _conv(s, f"recon_head.conv.{i}.5.", G_CH_SRC, G_CH_RECON)
+    return s
+
+
 # DCVC-UF low-delay model constants (src/models/video_model_ld.py:16-21)
 LD_CH_SRC_D = 3 * 8 * 8
 LD_CH_Y = 128
@@ -237,6 +287,7 @@ _WEIGHT_GAIN = {
 }
 for _i in range(G_FRAME_DELAY):
     _WEIGHT_GAIN[f"recon_head.conv2.{_i}.3.weight"] = 0.5
+    _WEIGHT_GAIN[f"recon_head.conv.{_i}.5.weight"] = 0.5   # HT-L
 
 
 def synth_state_dict(spec, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":

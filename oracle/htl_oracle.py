@@ -1,0 +1,115 @@
+"""CPU oracle for the DCVC-UF HT-L chunk model (DMC(ModelStructure.HTL) of src/models/video_model_ht.py).
+TEST INFRASTRUCTURE ONLY.
+
+Round-1 scope: the reference's pure-PyTorch training forward (`forward_one_frame`,
+/root/reference/src/models/video_model_ht.py:452-496 with the `else` (non-HTS) branches of :26-317 and
+`forward_prior_4x(..., spatial_prior_has_scales=True)`, /root/reference/src/models/common_model.py:231-282), restated
+functionally over a plain state_dict and PINNED against tests/golden/htl_forward_64x64.npz (minted by importing the
+reference modules, tests/golden/make_golden.py).  The CUDA proxy for this model (dmc_htl_proxy.cpp) is not built yet
+(SURVEY.md §8 f3); it additionally needs a 3x3 / stride-1 SubpelConv with bias (`decoder.up`) in pw_gemm.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import ops_ref
+from .hts_oracle import G, HtsOracle
+
+
+class HtlOracle(HtsOracle):
+    # ---------------------------------------------------------------- sub-networks (video_model_ht.py, non-HTS branches)
+    def rbu_bias(self, x, p, shortcut):
+        """ResidualBlockUpsample with force_bias (layers.py:92-103,162-173): 1x1 conv + bias, pixel_shuffle(2), block"""
+        t = F.conv2d(x, self._w(p + "up.conv.0.weight"), self._w(p + "up.conv.0.bias"))
+        return self.dcb(self.r(F.pixel_shuffle(t, 2)), p + "conv.", shortcut=shortcut)
+
+    def feature_adaptor_i(self, f):
+        return self.seq(f, "feature_adaptor_i.conv.", 3)
+
+    def feature_adaptor_m(self, memory, feature):
+        return self.seq(torch.cat((memory, feature), 1), "feature_adaptor_m.conv.", 10)
+
+    def feature_extractor(self, memory):
+        return self.seq(memory, "feature_extractor.conv.", 2)
+
+    def v_encoder(self, x_unshuffled, ctx, qp):
+        q = self.r(self._w("q_encoder")[qp])
+        t = self.seq(torch.cat((x_unshuffled, ctx), 1), "encoder.conv1.", 7, q_last=q)
+        return self.r(ops_ref.conv3x3_s2(t, self._w("encoder.down.weight"), self._w("encoder.down.bias")))
+
+    def v_hyper_enc(self, y):
+        t = self.dcb(y, "hyper_encoder.conv.0.")
+        t = self.rbd(t, "hyper_encoder.conv.1.", True)
+        return self.rbd(t, "hyper_encoder.conv.2.", True)
+
+    def v_hyper_dec(self, z_hat):
+        t = self.rbu_bias(z_hat, "hyper_decoder.conv.0.", True)
+        t = self.rbu_bias(t, "hyper_decoder.conv.1.", True)
+        return self.dcb(t, "hyper_decoder.conv.2.")
+
+    def temporal_prior(self, memory, qp):
+        q = self.r(self._w("q_feature")[qp])
+        t = self.r(memory * q.view(1, -1, 1, 1))
+        return self.rbd(t, "temporal_prior_encoder.conv.", True)
+
+    def v_spatial_prior_sm(self, y_hat_so_far, reduced, k):
+        """adaptor_k(cat(y_hat_so_far, common)) -> 3 blocks -> 1x1: (scales, means)"""
+        t = self.dcb(torch.cat((y_hat_so_far, reduced), 1), f"y_spatial_prior_adaptor_{k}.")
+        t = self.seq(t, "y_spatial_prior.conv.", 3)
+        return self.r(ops_ref.conv1x1(t, self._w("y_spatial_prior.conv.3.weight"), self._w("y_spatial_prior.conv.3.bias")))
+
+    def v_decoder(self, y_hat, ctx, qp):
+        """Decoder (:41-60): 3x3 SubpelConv2x with bias, 11 blocks on cat(feature, ctx), * quant_step"""
+        up = F.conv2d(y_hat, self._w("decoder.up.conv.0.weight"), self._w("decoder.up.conv.0.bias"), padding=1)
+        up = self.r(F.pixel_shuffle(up, 2))
+        q = self.r(self._w("q_decoder")[qp])
+        return self.seq(torch.cat((up, ctx), 1), "decoder.conv1.", 11, q_last=q)
+
+    def recon_head_one(self, feature, i, common=None):
+        t = self.seq(feature, f"recon_head.conv.{i}.", 5)
+        return self.r(ops_ref.conv1x1(t, self._w(f"recon_head.conv.{i}.5.weight"), self._w(f"recon_head.conv.{i}.5.bias"))), None
+
+    def recon_head(self, feature):
+        return [self.recon_head_one(feature, i)[0] for i in range(G)]
+
+    # ---------------------------------------------------------------- reference training forward (fp32)
+    @torch.inference_mode()
+    def forward_one_frame(self, x, qp: int, reset_feature_memory=False):
+        """video_model_ht.py:452-496 with spatial_prior_has_scales=True; state as the reference"""
+        assert not self.emu
+        if self.memory is None:
+            self.memory = self.feature_adaptor_i(self.feature_p)
+        else:
+            self.memory = self.feature_adaptor_m(self.memory, self.feature_p)
+        self.ctx = self.feature_extractor(self.memory)
+        y = self.v_encoder(F.pixel_unshuffle(x, 8), self.ctx, qp)
+        z = self.v_hyper_enc(y)
+        z_hat = torch.round(z)
+        params = self.v_prior_fusion(self.v_hyper_dec(z_hat), self.temporal_prior(self.memory, qp))
+        quant_step, scales, means = params.chunk(3, 1)
+        quant_step = torch.clamp_min(quant_step, 0.5)
+        y = y * (1.0 / quant_step)
+        reduced = ops_ref.conv1x1(params, self._w("y_spatial_prior_reduction.weight"), self._w("y_spatial_prior_reduction.bias"))
+        B, C, H, W = y.shape
+        y_hat_so_far = None
+        y_q_tot = torch.zeros_like(y)
+        for k in range(4):
+            mask = torch.from_numpy(ops_ref.mask_4x(k, C, H, W))[None]
+            if k > 0:
+                scales, means = self.v_spatial_prior_sm(y_hat_so_far, reduced, k).chunk(2, 1)
+            means_hat = means * mask
+            y_q = torch.round((y - means_hat) * mask)
+            y_hat = y_q + means_hat
+            y_hat_so_far = y_hat if k == 0 else y_hat_so_far + y_hat
+            y_q_tot = y_q_tot + y_q
+        y_hat = y_hat_so_far * quant_step
+        feature = self.v_decoder(y_hat, self.ctx, qp)
+        x_hat = [F.pixel_shuffle(h, 8) for h in self.recon_head(feature)]
+        self.feature_p = feature
+        if reset_feature_memory:          # set_ref_feature (:406-411): recon_head(feature, for_reset=True) = last head
+            head, _ = self.recon_head_one(feature, G - 1)
+            self.memory = None
+            self.ctx = None
+            self.feature_p = head
+        return {"x_hat": x_hat, "y_q": y_q_tot, "z_hat": z_hat, "y": y, "feature": feature}

@@ -66,9 +66,39 @@ def make_ld():
     np.savez_compressed(os.path.join(HERE, "ld_forward_64x64.npz"), **out)
 
 
+def make_htl():
+    """7. HT-L: layout + a 3-chunk forward sequence (state carried, reset on chunk 1), seed 3"""
+    from src.models.video_model_ht import DMC as DMC_HT
+    from src.utils.common import ModelStructure
+    from dcvc_b200.spec import htl_spec
+    p = DMC_HT(ModelStructure.HTL)
+    with open(os.path.join(HERE, "htl_state_dict_layout.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in p.state_dict().items()}, f, indent=0, sort_keys=True)
+    p.load_state_dict(synth_state_dict(htl_spec(), 3), strict=True)
+    p.eval()
+    ref0 = synth_frame(64, 64, 710)
+    out = {"ref_frame": ref0.numpy()}
+    with torch.inference_mode():
+        p.clear_dpb()
+        p.ref_feature = torch.nn.functional.pixel_unshuffle(ref0, 8)
+        for c, reset in enumerate([False, True, False]):
+            x = synth_frame(64, 64, 810 + c, channels=24)
+            qp = 12 + 20 * c
+            r = p.forward_one_frame(x, torch.tensor([qp]), reset_feature_memory=reset)
+            out[f"x{c}"] = x.numpy()
+            out[f"qp{c}"] = np.int32(qp)
+            out[f"x_hat{c}"] = torch.cat(r["x_hat"], 1).numpy()
+            out[f"ref_feature{c}"] = p.ref_feature.numpy()
+    np.savez_compressed(os.path.join(HERE, "htl_forward_64x64.npz"), **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if "--only-htl" in sys.argv:   # adds the HT-L fixtures without regenerating the others
+        make_htl()
+        print("HT-L golden fixtures written to", HERE)
+        return
     if "--only-ld" in sys.argv:   # adds the LD fixtures without regenerating the others
         make_ld()
         print("LD golden fixtures written to", HERE)
@@ -169,6 +199,7 @@ def main():
             out[f"ref_feature{c}"] = p.ref_feature.numpy()
     np.savez_compressed(os.path.join(HERE, "hts_forward_64x64.npz"), **out)
     make_ld()
+    make_htl()
     print("golden fixtures written to", HERE)
 
 

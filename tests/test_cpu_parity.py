@@ -343,3 +343,26 @@ def test_ld_oracle_compress_decompress_consistency():
         assert np.array_equal(e["y_hat"].view(np.uint16), d["y_hat"].view(np.uint16)), f"frame {c}"
         assert torch.equal(enc.feature_p, dec.feature_p), f"decoder state drifted at frame {c}"
         assert d["x_hat"].shape == (1, 3, 64, 64)
+
+
+def test_htl_spec_matches_reference_layout():
+    """dcvc_b200.spec.htl_spec vs the state_dict of the reference's DMC(ModelStructure.HTL)"""
+    import json
+    from dcvc_b200.spec import htl_spec
+    ref = json.load(open(os.path.join(GOLD, "htl_state_dict_layout.json")))
+    assert {k: list(v) for k, v in htl_spec().items()} == ref
+
+
+def test_htl_oracle_forward_pinned_to_reference():
+    """oracle/htl_oracle.py (the non-HTS branches of video_model_ht.py + forward_prior_4x with scale updates) vs the
+    reference's own modules on a 3-chunk sequence with a feature-memory reset (seed-3 synthetic checkpoint)"""
+    from dcvc_b200.spec import htl_spec, synth_state_dict
+    from oracle.htl_oracle import HtlOracle
+    g = np.load(os.path.join(GOLD, "htl_forward_64x64.npz"))
+    o = HtlOracle(synth_state_dict(htl_spec(), 3), emulate_fp16=False, threads=8)
+    o.clear_dpb()
+    o.feature_p = torch.nn.functional.pixel_unshuffle(torch.from_numpy(g["ref_frame"]), 8)
+    for c, reset in enumerate([False, True, False]):
+        r = o.forward_one_frame(torch.from_numpy(g[f"x{c}"]), int(g[f"qp{c}"]), reset_feature_memory=reset)
+        assert (torch.cat(r["x_hat"], 1) - torch.from_numpy(g[f"x_hat{c}"])).abs().max().item() < 5e-5
+        assert (o.feature_p - torch.from_numpy(g[f"ref_feature{c}"])).abs().max().item() < 5e-5
