@@ -371,7 +371,7 @@ protected:
         // 5.71 ms) — see DESIGN.md "experiments"
         const char* ch = getenv("DCVC_B200_GEMM_CHAIN");
         chain_enabled_ = ch && ch[0] == '1';
-        if (!flags_base_) {
+        if (chain_enabled_ && !flags_base_) {
             flags_cap_ = (8u << 20) / sizeof(int);
             CK(cudaMalloc(&flags_base_, flags_cap_ * sizeof(int)));
         }
