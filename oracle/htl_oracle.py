@@ -1,7 +1,16 @@
 """CPU oracle for the DCVC-UF HT-L chunk model (DMC(ModelStructure.HTL) of src/models/video_model_ht.py).
 TEST INFRASTRUCTURE ONLY.
 
-Round-1 scope: the reference's pure-PyTorch training forward (`forward_one_frame`,
+Two restatements:
+
+* `compress` / `decompress` / `add_ref_feature_from_frame` — the control flow of the reference's CUDA proxy,
+  /root/reference/src/layers/extensions/inference/dmc_htl_proxy.cpp:583-594, 596-717 (compress: four
+  process_with_mask steps with scale updates, one symbol run per step, y / clamp_min(q_dec, .5) first, final
+  add_and_multiply_with_clamp_min), :719-915 (decompress: z, then four index / decode / restore round trips),
+  with the half arithmetic of elementwise/stream.cu (oracle/ops_ref.py) and the reference's own rANS coder.
+  PARITY UNPINNED at the NN-output level; encoder/decoder state identity is tested in tests/test_cpu_parity.py.
+
+* the reference's pure-PyTorch training forward (`forward_one_frame`,
 /root/reference/src/models/video_model_ht.py:452-496 with the `else` (non-HTS) branches of :26-317 and
 `forward_prior_4x(..., spatial_prior_has_scales=True)`, /root/reference/src/models/common_model.py:231-282), restated
 functionally over a plain state_dict and PINNED against tests/golden/htl_forward_64x64.npz (minted by importing the
@@ -10,11 +19,13 @@ reference modules, tests/golden/make_golden.py).  The CUDA proxy for this model 
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
 from . import ops_ref
-from .hts_oracle import G, HtsOracle
+from .dmci_oracle import CH_Y, CH_Z, _pad_to
+from .hts_oracle import G, HtsOracle, _h
 
 
 class HtlOracle(HtsOracle):
@@ -113,3 +124,104 @@ class HtlOracle(HtsOracle):
             self.ctx = None
             self.feature_p = head
         return {"x_hat": x_hat, "y_q": y_q_tot, "z_hat": z_hat, "y": y, "feature": feature}
+
+    # ---------------------------------------------------------------- proxy restatement (fp16 emulation)
+    # add_ref_feature_from_frame: HtsOracle's (dmc_htl_proxy.cpp:583-594 == dmc_hts_proxy.cpp:492-502)
+
+    def _sp_np(self, acc, red_np, k):
+        cat = np.concatenate([acc, red_np], axis=2)
+        t = self._nchw32(cat)
+        return self._nhwc16(self.v_spatial_prior_sm(t[:, :CH_Y], t[:, CH_Y:], k))
+
+    @torch.inference_mode()
+    def compress(self, x, qp: int, reset_feature_memory: bool, padding_b: int, padding_r: int):
+        """x: [1,24,H,W] fp16-representable (dmc_htl_proxy.cpp:596-717)"""
+        assert self.emu
+        _, _, H, W = x.shape
+        Hp, Wp = _pad_to(H, 16), _pad_to(W, 16)
+        H16, W16 = Hp // 16, Wp // 16
+        H16p, W16p = _pad_to(H16, 4), _pad_to(W16, 4)
+        xu = ops_ref.unshuffle8_pad(x, padding_b, padding_r)
+        y = self.v_encoder(xu, self.ctx, qp)
+        y_pad = F.pad(y, (0, W16p - W16, 0, H16p - H16), mode="replicate")
+        z = self.v_hyper_enc(y_pad)
+        z_hat = self._canon(torch.clamp(ops_ref.round_half_away(z), -64, 63))
+        z_i8 = z_hat[0].permute(1, 2, 0).contiguous().numpy().astype(np.int8).reshape(-1)
+        common = self._params(z_hat, qp, H16, W16)
+        p_np = self._nhwc16(common)
+        q_dec, scales, means = p_np[..., :CH_Y], p_np[..., CH_Y:2 * CH_Y], p_np[..., 2 * CH_Y:]
+        rcp = _h(np.float32(1.0) / np.maximum(q_dec.astype(np.float32), np.float32(0.5)))
+        y_np = _h(self._nhwc16(y).astype(np.float32) * rcp.astype(np.float32))   # divide_with_clamp_min_inplace
+        red_np = self._nhwc16(self.r(ops_ref.conv1x1(common, self._w("y_spatial_prior_reduction.weight"),
+                                                      self._w("y_spatial_prior_reduction.bias"))))
+        acc = np.zeros((H16, W16, CH_Y), dtype=np.float16)
+        symbols = []
+        for k in range(4):
+            if k > 0:
+                sm = self._sp_np(acc, red_np, k)
+                scales, means = sm[..., :CH_Y], sm[..., CH_Y:]
+            y_hat_k, sym_k, _ = ops_ref.entropy_enc_step_np(k, y_np, None, scales, means, self.skip_thres, self.lut)
+            acc = _h(acc.astype(np.float32) + y_hat_k.astype(np.float32))
+            symbols.append(sym_k)
+        y_hat = _h(acc.astype(np.float32) * np.maximum(q_dec.astype(np.float32), np.float32(0.5)))
+        total = sum(len(v) for v in symbols)
+        ec_parallel = max(1, min(8, total // 32768))
+        enc, _ = self._coder()
+        enc.reset()
+        enc.set_entropy_coder_parallel(ec_parallel)
+        for k in (3, 2, 1, 0):
+            enc.encode_y(np.ascontiguousarray(symbols[k]))
+        enc.encode_z(z_i8, qp * CH_Z, CH_Z)
+        enc.flush()
+        stream = bytes(np.asarray(enc.get_encoded_stream()).tobytes())
+        # enc_1: decoder, then memory / context for the NEXT chunk
+        self.feature_p = self.v_decoder(self._nchw32(y_hat), self.ctx, qp)
+        if reset_feature_memory:
+            head, _ = self.recon_head_one(self.feature_p, G - 1)
+            self.memory = self.feature_adaptor_i(head)
+        else:
+            self.memory = self.feature_adaptor_m(self.memory, self.feature_p)
+        self.ctx = self.feature_extractor(self.memory)
+        return {"bit_stream": stream, "ec_parallel": ec_parallel, "symbols": symbols, "z_i8": z_i8, "y_hat": y_hat}
+
+    @torch.inference_mode()
+    def decompress(self, bit_stream: bytes, qp: int, height: int, width: int, ec_parallel: int,
+                   reset_feature_memory: bool):
+        """dmc_htl_proxy.cpp:719-915"""
+        assert self.emu
+        Hp, Wp = _pad_to(height, 16), _pad_to(width, 16)
+        H16, W16 = Hp // 16, Wp // 16
+        zh, zw = (height + 63) // 64, (width + 63) // 64
+        if self.memory_has_value:
+            self.memory = self.feature_adaptor_m(self.memory, self.feature_p)
+        else:
+            self.memory = self.feature_adaptor_i(self.feature_i)
+        _, dec = self._coder()
+        dec.set_entropy_coder_parallel(ec_parallel)
+        dec.set_stream(np.frombuffer(bit_stream, dtype=np.uint8))
+        n_z = CH_Z * zh * zw
+        dec.decode_z(n_z, qp * CH_Z, CH_Z)
+        z_i8 = dec.get_decoded(n_z)
+        z_hat = self._canon(torch.from_numpy(z_i8.astype(np.float32)).view(zh, zw, CH_Z).permute(2, 0, 1).unsqueeze(0))
+        common = self._params(z_hat, qp, H16, W16)
+        p_np = self._nhwc16(common)
+        q_dec, scales, means = p_np[..., :CH_Y], p_np[..., CH_Y:2 * CH_Y], p_np[..., 2 * CH_Y:]
+        red_np = self._nhwc16(self.r(ops_ref.conv1x1(common, self._w("y_spatial_prior_reduction.weight"),
+                                                      self._w("y_spatial_prior_reduction.bias"))))
+        self.ctx = self.feature_extractor(self.memory)
+        acc = np.zeros((H16, W16, CH_Y), dtype=np.float16)
+        for k in range(4):
+            if k > 0:
+                sm = self._sp_np(acc, red_np, k)
+                scales, means = sm[..., :CH_Y], sm[..., CH_Y:]
+            idx, _ = ops_ref.entropy_dec_index_np(k, scales, self.skip_thres, self.lut)
+            dec.decode_y(np.ascontiguousarray(idx))
+            decoded = dec.get_decoded(len(idx))
+            y_hat_k = ops_ref.entropy_dec_restore_np(k, scales, means, self.skip_thres, decoded)
+            acc = _h(acc.astype(np.float32) + y_hat_k.astype(np.float32))
+        y_hat = _h(acc.astype(np.float32) * np.maximum(q_dec.astype(np.float32), np.float32(0.5)))
+        self.feature_p = self.v_decoder(self._nchw32(y_hat), self.ctx, qp)
+        heads = self.recon_head(self.feature_p)
+        self.feature_i = heads[G - 1]
+        self.memory_has_value = not reset_feature_memory
+        return {"x_hat": [ops_ref.shuffle8_clamp(h, True) for h in heads], "y_hat": y_hat}

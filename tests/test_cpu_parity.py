@@ -366,3 +366,26 @@ def test_htl_oracle_forward_pinned_to_reference():
         r = o.forward_one_frame(torch.from_numpy(g[f"x{c}"]), int(g[f"qp{c}"]), reset_feature_memory=reset)
         assert (torch.cat(r["x_hat"], 1) - torch.from_numpy(g[f"x_hat{c}"])).abs().max().item() < 5e-5
         assert (o.feature_p - torch.from_numpy(g[f"ref_feature{c}"])).abs().max().item() < 5e-5
+
+
+def test_htl_oracle_compress_decompress_consistency():
+    """proxy-control-flow restatement of the HT-L chunk codec (dmc_htl_proxy.cpp:583-915): four symbol runs per chunk
+    with scale updates; the decoder reproduces the encoder's latents and recurrent state (reset + ragged padding)"""
+    from oracle.build_ref import import_ref_shim
+    if import_ref_shim() is None:
+        pytest.skip("oracle/_ref not built")
+    from dcvc_b200.spec import htl_spec, synth_state_dict
+    from oracle.htl_oracle import HtlOracle
+    g = np.load(os.path.join(GOLD, "htl_forward_64x64.npz"))
+    sd = synth_state_dict(htl_spec(), 3)
+    enc, dec = HtlOracle(sd, 0.15, True, threads=8), HtlOracle(sd, 0.15, True, threads=8)
+    ref = torch.from_numpy(g["ref_frame"])
+    enc.add_ref_feature_from_frame(ref, True)
+    dec.add_ref_feature_from_frame(ref, False)
+    for c, reset in enumerate([False, True]):
+        x = torch.from_numpy(g[f"x{c}"])[:, :, :56, :60].contiguous()
+        e = enc.compress(x, 30 + c, reset, 8, 4)
+        d = dec.decompress(e["bit_stream"], 30 + c, 56, 60, e["ec_parallel"], reset)
+        assert np.array_equal(e["y_hat"].view(np.uint16), d["y_hat"].view(np.uint16)), f"chunk {c}"
+        assert torch.equal(enc.feature_p, dec.feature_p), f"decoder state drifted at chunk {c}"
+        assert len(d["x_hat"]) == 8 and d["x_hat"][0].shape == (1, 3, 64, 64)
