@@ -36,7 +36,7 @@ class EntropyStep(C.Structure):
                 ("decoded", C.c_void_p)]
 
 
-GEMM_PW, GEMM_CONV3X3_S2, GEMM_CONV2X2_S2, GEMM_TCONV2X2 = 0, 1, 2, 3
+GEMM_PW, GEMM_CONV3X3_S2, GEMM_CONV2X2_S2, GEMM_TCONV2X2, GEMM_CONV3X3_PS2 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_WSILU, ACT_GDN, ACT_IGDN = 0, 1, 2, 3
 KIND_INTRA, KIND_HTS, KIND_HTL, KIND_LD = 0, 1, 2, 3
 DTYPE_F16, DTYPE_I32, DTYPE_F32 = 0, 1, 2

@@ -29,6 +29,7 @@ SOURCES = [
     "codec.cu",
     "codec_hts.cu",
     "codec_ld.cu",
+    "codec_htl.cu",
 ]
 
 NVCC_FLAGS = [

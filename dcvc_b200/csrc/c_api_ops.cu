@@ -100,6 +100,18 @@ int dcvc_pack_weight(int32_t kind, const void* w_host, int32_t cout, int32_t cin
                        w + (static_cast<size_t>(co) * 4 + ph) * cin, static_cast<size_t>(cin) * 2);
         return 0;
     }
+    case DCVC_GEMM_CONV3X3_PS2: {
+        // 3x3 conv in front of pixel_shuffle(2): output channel = co*4 + phase -> GEMM row phase*Cout + co, [tap][c]
+        if (kh != 3 || kw != 3 || cout % 4) { set_api_error("pack_weight: conv3x3_ps2 needs [4Cout][C][3][3]"); return 1; }
+        const int co_n = cout / 4;
+        for (int co = 0; co < co_n; ++co)
+            for (int ph = 0; ph < 4; ++ph)
+                for (int c = 0; c < cin; ++c)
+                    for (int t = 0; t < 9; ++t)
+                        dst[((static_cast<size_t>(ph) * co_n + co) * 9 + t) * cin + c] =
+                            w[((static_cast<size_t>(co) * 4 + ph) * cin + c) * 9 + t];
+        return 0;
+    }
     }
     set_api_error("pack_weight: bad kind");
     return 1;

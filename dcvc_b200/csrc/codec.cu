@@ -518,6 +518,13 @@ int ld_compress(CodecBase* c, const void* x, int H, int W, int64_t sc, int64_t s
                 int pad_b, int pad_r, cudaStream_t stream, const uint8_t** bs, int32_t* len, int32_t* ec);
 int ld_decompress(CodecBase* c, const uint8_t* bs, int len, int qp, int height, int width, int ec, int reset,
                   cudaStream_t stream, void* const* x_hat_out);
+CodecBase* make_htl_codec(int device);
+int htl_add_ref(CodecBase* c, const void* frame, int H, int W, int64_t sc, int64_t sh, int64_t sw, int apply,
+                cudaStream_t stream);
+int htl_compress(CodecBase* c, const void* x, int H, int W, int64_t sc, int64_t sh, int64_t sw, int qp, int reset,
+                 int pad_b, int pad_r, cudaStream_t stream, const uint8_t** bs, int32_t* len, int32_t* ec);
+int htl_decompress(CodecBase* c, const uint8_t* bs, int len, int qp, int height, int width, int ec, int reset,
+                   cudaStream_t stream, void* const* x_hat_out);
 int hts_add_ref(CodecBase* c, const void* frame, int H, int W, int64_t sc, int64_t sh, int64_t sw, int apply,
                 cudaStream_t stream);
 int hts_compress(CodecBase* c, const void* x, int H, int W, int64_t sc, int64_t sh, int64_t sw, int qp, int reset,
@@ -553,8 +560,15 @@ extern "C" {
 
 int dcvc_create(int32_t kind, int32_t device, dcvc_codec** out)
 {
-    if (kind != DCVC_KIND_INTRA && kind != DCVC_KIND_HTS && kind != DCVC_KIND_LD) {
-        dcvc::set_api_error("dcvc_create: DCVC_KIND_INTRA, DCVC_KIND_HTS and DCVC_KIND_LD are implemented in this build (HT-L is not)");
+    if (kind == DCVC_KIND_HTL) {
+        // the HT-L codec has not been validated on a device yet: opt-in only
+        const char* e = getenv("DCVC_B200_EXPERIMENTAL_HTL");
+        if (!e || e[0] != '1') {
+            dcvc::set_api_error("dcvc_create: DCVC_KIND_HTL is experimental in this build (set DCVC_B200_EXPERIMENTAL_HTL=1)");
+            return 1;
+        }
+    } else if (kind != DCVC_KIND_INTRA && kind != DCVC_KIND_HTS && kind != DCVC_KIND_LD) {
+        dcvc::set_api_error("dcvc_create: unknown codec kind");
         return 1;
     }
     int n = 0;
@@ -569,6 +583,8 @@ int dcvc_create(int32_t kind, int32_t device, dcvc_codec** out)
         h->base.reset(h->intra);
     } else if (kind == DCVC_KIND_LD) {
         h->base.reset(dcvc::make_ld_codec(device));
+    } else if (kind == DCVC_KIND_HTL) {
+        h->base.reset(dcvc::make_htl_codec(device));
     } else {
         h->base.reset(dcvc::make_hts_codec(device));
     }
@@ -657,6 +673,8 @@ int dcvc_add_ref_feature_from_frame(dcvc_codec* h, const void* frame, int32_t H,
     CODEC_TRY(h)
     if (h->kind == DCVC_KIND_LD)
         return dcvc::ld_add_ref(h->base.get(), frame, H, W, sc, sh, sw, apply_adaptor, static_cast<cudaStream_t>(stream));
+    if (h->kind == DCVC_KIND_HTL)
+        return dcvc::htl_add_ref(h->base.get(), frame, H, W, sc, sh, sw, apply_adaptor, static_cast<cudaStream_t>(stream));
     if (h->kind != DCVC_KIND_HTS) throw std::runtime_error("add_ref_feature_from_frame needs a video codec handle");
     return dcvc::hts_add_ref(h->base.get(), frame, H, W, sc, sh, sw, apply_adaptor, static_cast<cudaStream_t>(stream));
     CODEC_CATCH(h)
@@ -670,6 +688,9 @@ int dcvc_compress_chunk(dcvc_codec* h, const void* x, int32_t H, int32_t W, int6
     if (h->kind == DCVC_KIND_LD)
         return dcvc::ld_compress(h->base.get(), x, H, W, sc, sh, sw, qp, reset_feature_memory, pad_b, pad_r,
                                  static_cast<cudaStream_t>(stream), bit_stream, bit_stream_len, ec_parallel);
+    if (h->kind == DCVC_KIND_HTL)
+        return dcvc::htl_compress(h->base.get(), x, H, W, sc, sh, sw, qp, reset_feature_memory, pad_b, pad_r,
+                                  static_cast<cudaStream_t>(stream), bit_stream, bit_stream_len, ec_parallel);
     if (h->kind != DCVC_KIND_HTS) throw std::runtime_error("compress_chunk needs a video codec handle");
     return dcvc::hts_compress(h->base.get(), x, H, W, sc, sh, sw, qp, reset_feature_memory, pad_b, pad_r,
                               static_cast<cudaStream_t>(stream), bit_stream, bit_stream_len, ec_parallel);
@@ -684,6 +705,9 @@ int dcvc_decompress_chunk(dcvc_codec* h, const uint8_t* bit_stream, int32_t len,
     if (h->kind == DCVC_KIND_LD)
         return dcvc::ld_decompress(h->base.get(), bit_stream, len, qp, height, width, ec_parallel, reset_feature_memory,
                                    static_cast<cudaStream_t>(stream), x_hat_out);
+    if (h->kind == DCVC_KIND_HTL)
+        return dcvc::htl_decompress(h->base.get(), bit_stream, len, qp, height, width, ec_parallel, reset_feature_memory,
+                                    static_cast<cudaStream_t>(stream), x_hat_out);
     if (h->kind != DCVC_KIND_HTS) throw std::runtime_error("decompress_chunk needs a video codec handle");
     return dcvc::hts_decompress(h->base.get(), bit_stream, len, qp, height, width, ec_parallel, reset_feature_memory,
                                 static_cast<cudaStream_t>(stream), x_hat_out);

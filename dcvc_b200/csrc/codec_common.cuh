@@ -322,7 +322,18 @@ protected:
         if (dcvc_pack_weight(kind, src.data(), cout, cin, kh, kw, dst.data()))
             throw std::runtime_error("pack_weight failed for " + p);
         c.w = upload(dst);
-        if (has_param(p + "bias")) c.b = upload_param(p + "bias");
+        if (has_param(p + "bias")) {
+            std::vector<__half> b = param_f16(p + "bias");
+            if (kind == DCVC_GEMM_TCONV2X2 || kind == DCVC_GEMM_CONV3X3_PS2) {
+                // GEMM columns of the pixel-shuffle kinds are phase-major: column ph * Cout + co <- channel co * 4 + ph
+                std::vector<__half> r(b.size());
+                const int co_n = cout / 4;
+                for (int co = 0; co < co_n; ++co)
+                    for (int ph = 0; ph < 4; ++ph) r[static_cast<size_t>(ph) * co_n + co] = b[static_cast<size_t>(co) * 4 + ph];
+                b.swap(r);
+            }
+            c.b = upload(b);
+        }
         c.cout = cout;
         c.cin = cin;
         return c;
@@ -443,11 +454,11 @@ protected:
             s.notes.back() = buf;
         }
         const double px_in = static_cast<double>(in.W) * in.H, px_out = static_cast<double>(out.W) * out.H;
-        const int taps = (kind == GEMM_CONV3X3_S2) ? 9 : (kind == GEMM_CONV2X2_S2 ? 4 : 1);
+        const int taps = (kind == GEMM_CONV3X3_S2 || kind == GEMM_CONV3X3_PS2) ? 9 : (kind == GEMM_CONV2X2_S2 ? 4 : 1);
         double bytes = px_in * in.C * 2 + px_out * out.C * 2;
         if (r1) bytes += px_out * out.C * 2;
         if (r2) bytes += px_out * out.C * 2;
-        const double m_px = (kind == GEMM_TCONV2X2) ? px_in : px_out;
+        const double m_px = (kind == GEMM_TCONV2X2 || kind == GEMM_CONV3X3_PS2) ? px_in : px_out;
         s.annotate(OP_GEMM, bytes, 2.0 * m_px * N * taps * in.C);
     }
     void conv1x1(Segment& s, const ActView& in, const ActView& out, const ConvW& c)

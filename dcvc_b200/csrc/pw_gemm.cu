@@ -579,6 +579,17 @@ int gemm_plan(GemmOp& op)
         taps = 1;
         p.tap_px[0] = p.tap_py[0] = p.tap_dx[0] = p.tap_dy[0] = 0;
         break;
+    case GEMM_CONV3X3_PS2:
+        taps = 9;
+        for (int ky = 0; ky < 3; ++ky) {
+            for (int kx = 0; kx < 3; ++kx) {
+                const int t = ky * 3 + kx;
+                p.tap_px[t] = p.tap_py[t] = 0;   // unsplit view: the tap is a pure shift, OOB = zero padding
+                p.tap_dx[t] = static_cast<int8_t>(kx - 1);
+                p.tap_dy[t] = static_cast<int8_t>(ky - 1);
+            }
+        }
+        break;
     default:
         g_err = "gemm_plan: bad kind";
         return 1;
@@ -589,15 +600,16 @@ int gemm_plan(GemmOp& op)
             return 1;
         }
     }
-    if (op.kind == GEMM_TCONV2X2) {
+    const bool upsamples = (op.kind == GEMM_TCONV2X2 || op.kind == GEMM_CONV3X3_PS2);  // N = 4 phases x out.C
+    if (upsamples) {
         if (op.out.W != op.in.W * 2 || op.out.H != op.in.H * 2 || op.N != op.out.C * 4) {
             g_err = "gemm_plan: tconv geometry mismatch";
             return 1;
         }
     }
     // pixel tile geometry (over the GEMM-M pixel grid = output grid, except tconv = input grid)
-    const int gw = (op.kind == GEMM_TCONV2X2) ? op.in.W : op.out.W;
-    const int gh = (op.kind == GEMM_TCONV2X2) ? op.in.H : op.out.H;
+    const int gw = upsamples ? op.in.W : op.out.W;
+    const int gh = upsamples ? op.in.H : op.out.H;
     long long m_tiles;
     int tiles_x, tiles_y;
     if (linear) {
@@ -611,7 +623,7 @@ int gemm_plan(GemmOp& op)
     }
     m_tiles = static_cast<long long>(tiles_x) * tiles_y;
 
-    const int n_unit = (op.kind == GEMM_TCONV2X2) ? op.out.C : op.N;
+    const int n_unit = upsamples ? op.out.C : op.N;
     int num_sms = 148;
     {
         int dev = 0;
@@ -622,7 +634,7 @@ int gemm_plan(GemmOp& op)
     }
     {
         // geometry checks shared by both kernels
-        const int out_c = op.chunk_add ? op.N / 4 : (op.kind == GEMM_TCONV2X2 ? op.N / 4 : op.N);
+        const int out_c = op.chunk_add ? op.N / 4 : (upsamples ? op.N / 4 : op.N);
         if (op.out.C != out_c) { g_err = "gemm_plan: out.C does not match N"; return 1; }
         if (op.res2.ptr && !op.res1.ptr) { g_err = "gemm_plan: res2 without res1"; return 1; }
         if (op.act >= ACT_GDN && (!op.res1.ptr || op.res2.ptr || op.chunk_add || op.kind != GEMM_PW)) {
@@ -630,7 +642,7 @@ int gemm_plan(GemmOp& op)
             return 1;
         }
         if (op.res1.ptr) {
-            if (op.kind == GEMM_TCONV2X2) { g_err = "gemm_plan: tconv takes no residual"; return 1; }
+            if (upsamples) { g_err = "gemm_plan: tconv takes no residual"; return 1; }
             const ActView* rs[2] = { &op.res1, &op.res2 };
             for (int i = 0; i < (op.res2.ptr ? 2 : 1); ++i) {
                 if (rs[i]->W != op.out.W || rs[i]->H != op.out.H || rs[i]->C != op.out.C || (rs[i]->pitch % 8) ||
@@ -653,7 +665,7 @@ int gemm_plan(GemmOp& op)
     const TilePlan tp = pick_tile_plan(n_unit, op.N, op.chunk_add != 0, m_tiles, taps * C / 64, num_sms);
     const int bn = tp.bn;
     if (bn == 0 || op.N % bn != 0) { g_err = "gemm_plan: unsupported N"; return 1; }
-    const int out_c_expected = op.chunk_add ? op.N / 4 : (op.kind == GEMM_TCONV2X2 ? op.N / 4 : op.N);
+    const int out_c_expected = op.chunk_add ? op.N / 4 : (upsamples ? op.N / 4 : op.N);
     if (op.out.C != out_c_expected) { g_err = "gemm_plan: out.C does not match N"; return 1; }
     op.block_n = bn;
 
@@ -663,7 +675,7 @@ int gemm_plan(GemmOp& op)
     p.chunk_add = op.chunk_add;
     p.bias = op.bias;
     p.qscale = op.qscale;
-    p.phase_c = (op.kind == GEMM_TCONV2X2) ? op.out.C : 0;
+    p.phase_c = upsamples ? op.out.C : 0;
     p.n_res = (op.res1.ptr ? 1 : 0) + (op.res2.ptr ? 1 : 0);
     if (op.res2.ptr && !op.res1.ptr) { g_err = "gemm_plan: res2 without res1"; return 1; }
     if (linear) {
@@ -683,12 +695,12 @@ int gemm_plan(GemmOp& op)
         uint32_t box[2] = { 64, static_cast<uint32_t>(bn) };
         if (encode_map(&p.tm_b, op.weight, 2, dims, st, box)) return 1;
     }
-    const bool out_split = (op.kind == GEMM_TCONV2X2);
+    const bool out_split = upsamples;
     // store box of one epilogue warp: 32 pixels (rows 32q .. 32q+31 of the tile) x 32 channels, SWIZZLE_64B
     p.epi_rows_y = linear ? 1 : 32 / p.bw;
     if (encode_act_map(&p.tm_c, op.out, out_split, linear, lin2d, linear ? 32 : p.bw, linear ? 1 : 32 / p.bw, 32)) return 1;
     if (op.res1.ptr) {
-        if (op.kind == GEMM_TCONV2X2) { g_err = "gemm_plan: tconv takes no residual"; return 1; }
+        if (upsamples) { g_err = "gemm_plan: tconv takes no residual"; return 1; }
         const ActView* rs[2] = { &op.res1, &op.res2 };
         for (int i = 0; i < p.n_res; ++i) {
             if (rs[i]->W != op.out.W || rs[i]->H != op.out.H || rs[i]->C != op.out.C || (rs[i]->pitch % 8) ||

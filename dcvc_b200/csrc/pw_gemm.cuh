@@ -29,6 +29,8 @@ enum GemmKind : int {
     GEMM_CONV3X3_S2 = 1, // 3x3, stride 2, pad 1     (reference conv_bias, image_model.py:62)
     GEMM_CONV2X2_S2 = 2, // pixel_unshuffle(2)+1x1   (reference conv_bias, layers_proxy.cpp:260-266)
     GEMM_TCONV2X2 = 3,   // 1x1 + pixel_shuffle(2)   (reference transposed_conv, layers_proxy.cpp:314-323)
+    GEMM_CONV3X3_PS2 = 4, // 3x3, stride 1, pad 1 + pixel_shuffle(2): the HT-L SubpelConv2x (video_model_ht.py:41,
+                          // layers_proxy.cpp:271-275); experimental: not validated on hardware yet
 };
 
 // ACT_GDN / ACT_IGDN: out = res1 * rsqrt(acc + bias) resp. res1 * sqrt(acc + bias) — generalised divisive normalisation

@@ -177,3 +177,29 @@ class DMCLD(DMC):
             sd = self.add_cdf_to_state_dict(self.state_dict())
             self.proxy = DMCLDProxy()
             self.proxy.set_param(sd, self.skip_thres)
+
+
+class DMCHTL(DMC):
+    """DMC(ModelStructure.HTL) of src/models/video_model_ht.py:320-450 (same API as the HT-S model).  EXPERIMENTAL,
+    needs DCVC_B200_EXPERIMENTAL_HTL=1 (see proxy.DMCHTLProxy)."""
+
+    def __init__(self):
+        from .spec import htl_spec
+        self._spec = htl_spec()
+        self._sd = OrderedDict((k, torch.zeros(v)) for k, v in self._spec.items())
+        self.proxy = None
+        self.skip_thres = 0.0
+        self._cdf = None
+
+    @classmethod
+    def synthetic(cls, seed: int = 3) -> "DMCHTL":
+        m = cls()
+        m.load_state_dict(synth_state_dict(m._spec, seed))
+        return m
+
+    def _ensure_proxy(self):
+        if self.proxy is None:
+            from inference_extensions_cuda import DMCHTLProxy
+            sd = self.add_cdf_to_state_dict(self.state_dict())
+            self.proxy = DMCHTLProxy()
+            self.proxy.set_param(sd, self.skip_thres)

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (ACT_GDN, ACT_IGDN, ACT_NONE, ACT_WSILU, GEMM_CONV2X2_S2, GEMM_CONV3X3_S2, GEMM_PW, GEMM_TCONV2X2,
+from ._lib import (ACT_GDN, ACT_IGDN, ACT_NONE, ACT_WSILU, GEMM_CONV2X2_S2, GEMM_CONV3X3_PS2, GEMM_CONV3X3_S2, GEMM_PW, GEMM_TCONV2X2,
                    EntropyStep, GemmDesc, View)
 
 

@@ -199,3 +199,13 @@ class DMCLDProxy(DMCHTSProxy):
                    reset_feature_memory: bool):
         """-> fp16 channels_last tensor [1,3,H16p,W16p] (proxy-owned, reused by the next call)"""
         return super().decompress(bit_stream, qp, height, width, ec_parallel, reset_feature_memory)[0]
+
+
+class DMCHTLProxy(DMCHTSProxy):
+    """DCVC-UF HT-L chunk codec proxy (reference: DMCHTLProxy, dmc_htl_proxy.h; bind.cpp).  EXPERIMENTAL: the CUDA codec
+    behind it (csrc/codec_htl.cu) has not been validated on a device, so the handle can only be created with
+    DCVC_B200_EXPERIMENTAL_HTL=1 and `inference_extensions_cuda` does not export this class otherwise."""
+
+    def __init__(self):
+        self._hd = _CodecHandle(_lib.KIND_HTL)
+        self._x_hat = None

@@ -37,7 +37,9 @@ typedef struct dcvc_view {
     int32_t C, pitch, W, H;
 } dcvc_view;
 
-enum { DCVC_GEMM_PW = 0, DCVC_GEMM_CONV3X3_S2 = 1, DCVC_GEMM_CONV2X2_S2 = 2, DCVC_GEMM_TCONV2X2 = 3 };
+/* DCVC_GEMM_CONV3X3_PS2 (3x3 / stride 1 / pad 1 + pixel_shuffle(2), the HT-L SubpelConv2x) is experimental: it is not
+ * validated on hardware yet. */
+enum { DCVC_GEMM_PW = 0, DCVC_GEMM_CONV3X3_S2 = 1, DCVC_GEMM_CONV2X2_S2 = 2, DCVC_GEMM_TCONV2X2 = 3, DCVC_GEMM_CONV3X3_PS2 = 4 };
 /* GDN / IGDN: out = res1 * rsqrt(acc + bias) / res1 * sqrt(acc + bias) (DCVC-family/DCVC/src/layers/gdn.py:52-67) */
 enum { DCVC_ACT_NONE = 0, DCVC_ACT_WSILU = 1, DCVC_ACT_GDN = 2, DCVC_ACT_IGDN = 3 };
 

@@ -54,6 +54,12 @@ def tconv2x2(x, w, b=None):
     return F.pixel_shuffle(F.conv2d(x, w, b), 2)
 
 
+def conv3x3_ps2(x, w, b):
+    """SubpelConv2x with a 3x3 kernel (/root/reference/src/layers/layers.py:92-103, HT-L decoder.up,
+    video_model_ht.py:41): conv2d(pad 1) + bias, then pixel_shuffle(2)"""
+    return F.pixel_shuffle(F.conv2d(x, w, b, padding=1), 2)
+
+
 def dw3x3(x, w, b=None):
     return F.conv2d(x, w, b, padding=1, groups=x.shape[1])
 

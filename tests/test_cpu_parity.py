@@ -389,3 +389,37 @@ def test_htl_oracle_compress_decompress_consistency():
         assert np.array_equal(e["y_hat"].view(np.uint16), d["y_hat"].view(np.uint16)), f"chunk {c}"
         assert torch.equal(enc.feature_p, dec.feature_p), f"decoder state drifted at chunk {c}"
         assert len(d["x_hat"]) == 8 and d["x_hat"][0].shape == (1, 3, 64, 64)
+
+
+@pytest.mark.parametrize("kind_name", ["TCONV2X2", "CONV3X3_PS2"])
+def test_pack_weight_of_pixel_shuffle_kinds_as_a_plain_gemm(lib, kind_name):
+    """host half of the pixel-shuffle GEMM kinds, no device: the packed operand [phase*Cout + co][tap][c], fed to a
+    plain numpy GEMM over shifted (zero-padded) views and scattered phase-major, must equal conv + pixel_shuffle(2)
+    (layers.py:92-103 SubpelConv2x); guards the layout contract between dcvc_pack_weight, the tap table of gemm_plan
+    and the phase-major bias of CodecBase::load_conv."""
+    import torch.nn.functional as F
+
+    from dcvc_b200 import _lib
+    kind = getattr(_lib, "GEMM_" + kind_name)
+    k = 3 if kind_name == "CONV3X3_PS2" else 1
+    cin, cout, H, W = 8, 6, 5, 7
+    g = torch.Generator().manual_seed(11)
+    w = (torch.randn(4 * cout, cin, k, k, generator=g) * 0.2).half()
+    b = (torch.randn(4 * cout, generator=g) * 0.2).half()
+    x = torch.randn(1, cin, H, W, generator=g).half()
+    want = F.pixel_shuffle(F.conv2d(x.float(), w.float(), b.float(), padding=k // 2), 2)
+    packed = torch.empty(w.numel(), dtype=torch.float16)
+    assert lib.dcvc_pack_weight(kind, w.contiguous().data_ptr(), 4 * cout, cin, k, k, packed.data_ptr()) == 0
+    B = packed.float().view(4 * cout, k * k, cin)                       # [n][tap][c]
+    xp = F.pad(x.float(), (k // 2,) * 4)[0]                              # zero padding = TMA out-of-bounds fill
+    acc = torch.zeros(H, W, 4 * cout)
+    for t in range(k * k):
+        dy, dx = (t // 3 - 1, t % 3 - 1) if k == 3 else (0, 0)          # gemm_plan's tap table
+        a = xp[:, k // 2 + dy:k // 2 + dy + H, k // 2 + dx:k // 2 + dx + W].permute(1, 2, 0)   # [H][W][c]
+        acc += a @ B[:, t, :].T
+    bias_pm = b.float().view(cout, 4).T.reshape(-1)                      # load_conv: column ph*Cout+co <- channel co*4+ph
+    acc += bias_pm
+    out = torch.zeros(1, cout, 2 * H, 2 * W)
+    for ph in range(4):                                                  # epilogue: phase ph -> pixel (2y + ph//2, 2x + ph%2)
+        out[0, :, ph // 2::2, ph % 2::2] = acc[:, :, ph * cout:(ph + 1) * cout].permute(2, 0, 1)
+    assert torch.allclose(out, want, atol=1e-5)

@@ -333,3 +333,47 @@ def test_gdn(H, W, C, inverse):
     ops.gdn(_nhwc(x), gamma, beta, out, inverse=inverse)
     torch.cuda.synchronize()
     _close(_nchw(out), ref, rel=6e-3, abs_=2e-3)
+
+
+# ---------------------------------------------------------------- HT-L groundwork, not validated on hardware yet
+import os  # noqa: E402
+
+_HTL = pytest.mark.skipif(os.environ.get("DCVC_B200_EXPERIMENTAL_HTL") != "1",
+                          reason="HT-L pieces are experimental: set DCVC_B200_EXPERIMENTAL_HTL=1 to run them")
+
+
+@_HTL
+@pytest.mark.parametrize("H,W,Cin,Cout", [(16, 16, 64, 64), (17, 30, 128, 128), (68, 120, 256, 512)])
+def test_conv3x3_ps2(H, W, Cin, Cout):
+    """3x3 / stride 1 / pad 1 conv + bias + pixel_shuffle(2) as a 9-tap pw_gemm with phase-major columns"""
+    from dcvc_b200 import ops
+    from oracle import ops_ref
+    gen = torch.Generator().manual_seed(23 + H)
+    x = _rand(gen, 1, Cin, H, W)
+    w = _rand(gen, Cout * 4, Cin, 3, 3, scale=(9 * Cin) ** -0.5)
+    b = _rand(gen, Cout * 4, scale=0.1)
+    ref = ops_ref.conv3x3_ps2(x, w, b)
+    out = torch.zeros(H * 2, W * 2, Cout, dtype=torch.float16, device="cuda")
+    b_packed = b.view(Cout, 4).t().contiguous().view(-1)    # GEMM column ph * Cout + co <- channel co * 4 + ph
+    ops.gemm(ops.GEMM_CONV3X3_PS2, _nhwc(x), ops.pack_weight(ops.GEMM_CONV3X3_PS2, w), Cout * 4, out,
+             bias=b_packed.half().cuda())
+    torch.cuda.synchronize()
+    _close(_nchw(out), ref)
+
+
+@_HTL
+def test_tconv2x2_with_bias():
+    """ResidualBlockUpsample(force_bias=True) of the HT-L hyper decoder: 1x1 conv + bias + pixel_shuffle(2)"""
+    from dcvc_b200 import ops
+    from oracle import ops_ref
+    gen = torch.Generator().manual_seed(29)
+    H, W, Cin, Cout = 17, 30, 128, 256
+    x = _rand(gen, 1, Cin, H, W)
+    w = _rand(gen, Cout * 4, Cin, 1, 1, scale=Cin ** -0.5)
+    b = _rand(gen, Cout * 4, scale=0.1)
+    ref = torch.nn.functional.pixel_shuffle(torch.nn.functional.conv2d(x, w, b), 2)
+    out = torch.zeros(H * 2, W * 2, Cout, dtype=torch.float16, device="cuda")
+    b_packed = b.view(Cout, 4).t().contiguous().view(-1)
+    ops.gemm(ops.GEMM_TCONV2X2, _nhwc(x), ops.pack_weight(ops.GEMM_TCONV2X2, w), Cout * 4, out, bias=b_packed.half().cuda())
+    torch.cuda.synchronize()
+    _close(_nchw(out), ref)

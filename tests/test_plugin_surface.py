@@ -3,10 +3,11 @@ reference's pybind module defines (src/layers/extensions/inference/bind.cpp:11-3
 the reference's call sites (image_model.py:194-217, video_model_ht.py:413-450, video_model_ld.py:273-306).
 No device needed: the classes are only inspected, never constructed."""
 import inspect
+import os
 
 import pytest
 
-# bind.cpp:13-38 — class -> methods; DMCHTLProxy is not built yet (SURVEY.md §8 f3)
+# bind.cpp:13-38 — class -> methods; DMCHTLProxy is experimental and hidden unless DCVC_B200_EXPERIMENTAL_HTL=1 (SURVEY.md §8 f3)
 REFERENCE_SURFACE = {
     "DMCIProxy": ["set_param", "compress", "decompress"],
     "DMCHTSProxy": ["set_param", "add_ref_feature_from_frame", "compress", "decompress"],
@@ -32,9 +33,24 @@ def test_plugin_exports_reference_classes_and_methods():
         cls = getattr(ext, cls_name)
         for m in methods:
             assert callable(getattr(cls, m)), f"{cls_name}.{m} missing"
-    assert not hasattr(ext, "DMCHTLProxy"), "HT-L is not built: the reference must get its ImportError -> NotImplementedError"
+    if os.environ.get("DCVC_B200_EXPERIMENTAL_HTL") == "1":
+        assert callable(ext.DMCHTLProxy.compress)
+        return
+    assert not hasattr(ext, "DMCHTLProxy"), "HT-L is opt-in: the reference must get its ImportError -> NotImplementedError"
     with pytest.raises(ImportError):
         from inference_extensions_cuda import DMCHTLProxy  # noqa: F401
+
+
+def test_htl_handle_is_opt_in():
+    """dcvc_create(DCVC_KIND_HTL) is refused (before any device is touched) unless the experimental switch is set"""
+    import ctypes as C
+
+    from dcvc_b200 import _lib
+    if os.environ.get("DCVC_B200_EXPERIMENTAL_HTL") == "1":
+        pytest.skip("experimental HT-L enabled")
+    h = C.c_void_p()
+    assert _lib.load().dcvc_create(_lib.KIND_HTL, 0, C.byref(h)) != 0
+    assert b"EXPERIMENTAL_HTL" in _lib.load().dcvc_last_error()
 
 
 @pytest.mark.parametrize("key", sorted(CALL_SIGNATURES))
