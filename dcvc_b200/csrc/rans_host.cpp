@@ -94,14 +94,29 @@ inline void enc_symbol(uint32_t& x, BackWriter& w, int32_t sym, const int32_t* c
     enc_put(x, w, start, freq);
 }
 
+// Bytes of zero padding behind every decoder stream, and the number of symbols the unchecked decode loop handles
+// between two bounds checks: one symbol reads at most kMaxBytesPerSymbol bytes (2 renormalisation bytes + one per
+// 2-bit escape digit; an escape has at most 3 * 6 + 16 digits for a 32-bit remainder).
+constexpr int kMaxBytesPerSymbol = 48;
+constexpr int kDecBlock = 64;
+constexpr int kDecPad = kMaxBytesPerSymbol * kDecBlock + 8;
+
+// Reader with a bounds check per byte: reads behind the stream return zero (as the reference's does).  Only used
+// for the (at most kDecBlock) symbols decoded after a stream has run past its end, i.e. for corrupt streams.
 struct ByteReader {
     const uint8_t* p;
     size_t pos;
     size_t size;
     inline uint8_t next() { return pos < size ? p[pos++] : (++pos, 0); }
 };
+// Reader without checks: the caller guarantees kMaxBytesPerSymbol readable bytes per symbol.
+struct FastReader {
+    const uint8_t* p;
+    inline uint8_t next() { return *p++; }
+};
 
-inline uint32_t dec_bits(uint32_t& x, ByteReader& r)
+template <class R>
+inline uint32_t dec_bits(uint32_t& x, R& r)
 {
     const uint32_t val = x & ((1u << kBypassBits) - 1);
     x >>= kBypassBits;
@@ -109,7 +124,8 @@ inline uint32_t dec_bits(uint32_t& x, ByteReader& r)
     return val;
 }
 
-inline int8_t dec_symbol(uint32_t& x, ByteReader& r, const int32_t* cdf_row, int maxv)
+template <class R>
+inline int8_t dec_symbol(uint32_t& x, R& r, const int32_t* cdf_row, int maxv)
 {
     const int32_t cum = static_cast<int32_t>(x & kProbMask);
     int s = 1;
@@ -121,21 +137,52 @@ inline int8_t dec_symbol(uint32_t& x, ByteReader& r, const int32_t* cdf_row, int
     while (x < kStateLow) x = (x << 8) | r.next();
 
     int32_t value = s;
-    if (value == maxv) {
+    if (__builtin_expect(value == maxv, 0)) {
         int32_t v = static_cast<int32_t>(dec_bits(x, r));
         int32_t n_digits = v;
-        while (v == kBypassMax) {
+        while (v == kBypassMax && n_digits < 30) {
             v = static_cast<int32_t>(dec_bits(x, r));
             n_digits += v;
         }
-        int32_t raw = 0;
+        uint32_t raw = 0;
         for (int j = 0; j < n_digits; ++j) {
             v = static_cast<int32_t>(dec_bits(x, r));
-            raw |= v << (j * kBypassBits);
+            if (j < 16) raw |= static_cast<uint32_t>(v) << (j * kBypassBits);
         }
-        value = raw + maxv;
+        value = static_cast<int32_t>((raw + static_cast<uint32_t>(maxv)) & 0x3fffffffu);
     }
     return static_cast<int8_t>((value & 1) ? (value + 1) / 2 : -((value + 1) / 2));
+}
+
+// Decodes symbols [off, off + len) of one stream.  row_of(k) -> CDF row of symbol k.  Blocks of kDecBlock symbols
+// run without per-byte bounds checks while the read position leaves kDecPad - 8 bytes of the (zero-padded) buffer.
+template <class RowOf>
+inline void decode_run(int8_t* __restrict out, int off, int len, const int32_t* __restrict cdf, int width,
+                       const int8_t* __restrict max_value, const uint8_t* __restrict bytes, size_t size_padded,
+                       uint32_t& state, size_t& pos, RowOf row_of)
+{
+    uint32_t x = state;
+    int k = off;
+    const int end = off + len;
+    while (k < end) {
+        const int stop = std::min(end, k + kDecBlock);
+        if (pos + static_cast<size_t>(kMaxBytesPerSymbol) * kDecBlock <= size_padded) {
+            FastReader r{ bytes + pos };
+            for (; k < stop; ++k) {
+                const int row = row_of(k);
+                out[k] = dec_symbol(x, r, cdf + static_cast<size_t>(row) * width, max_value[row]);
+            }
+            pos = static_cast<size_t>(r.p - bytes);
+        } else {
+            ByteReader r{ bytes, pos, size_padded };
+            for (; k < stop; ++k) {
+                const int row = row_of(k);
+                out[k] = dec_symbol(x, r, cdf + static_cast<size_t>(row) * width, max_value[row]);
+            }
+            pos = r.pos;
+        }
+    }
+    state = x;
 }
 
 // Trailing bytes two streams may share when the second is stored reversed behind the first
@@ -366,7 +413,7 @@ void RansCodec::set_stream(const uint8_t* data, int size, int n_parallel)
     dec_n_ = n;
     auto load = [&](int i, const uint8_t* p, int len, bool reversed) {
         DecStream& d = dec_[i];
-        d.bytes.resize(static_cast<size_t>(std::max(len, 0)) + 8);
+        d.bytes.resize(static_cast<size_t>(std::max(len, 0)) + kDecPad);
         if (reversed) std::reverse_copy(p, p + len, d.bytes.begin());
         else std::copy(p, p + len, d.bytes.begin());
         std::fill(d.bytes.begin() + len, d.bytes.end(), 0);
@@ -420,14 +467,8 @@ void RansCodec::decode_z(int8_t* out, int total, int cdf_offset, int ch)
         int off, len;
         split_range(total, n, i, off, len);
         DecStream& d = dec_[i];
-        ByteReader r{ d.bytes.data(), d.pos, d.bytes.size() };
-        uint32_t x = d.state;
-        for (int k = off; k < off + len; ++k) {
-            const int row = (k % ch) + cdf_offset;
-            out[k] = dec_symbol(x, r, cs.cdf.data() + static_cast<size_t>(row) * cs.width, cs.max_value[row]);
-        }
-        d.state = x;
-        d.pos = r.pos;
+        decode_run(out, off, len, cs.cdf.data(), cs.width, cs.max_value.data(), d.bytes.data(), d.bytes.size(), d.state,
+                   d.pos, [=](int k) { return (k % ch) + cdf_offset; });
     };
     pool_.run(n, body);
 }
@@ -440,14 +481,8 @@ void RansCodec::decode_y(int8_t* out, const uint8_t* cdf_rows, int total)
         int off, len;
         split_range(total, n, i, off, len);
         DecStream& d = dec_[i];
-        ByteReader r{ d.bytes.data(), d.pos, d.bytes.size() };
-        uint32_t x = d.state;
-        for (int k = off; k < off + len; ++k) {
-            const int row = cdf_rows[k];
-            out[k] = dec_symbol(x, r, cs.cdf.data() + static_cast<size_t>(row) * cs.width, cs.max_value[row]);
-        }
-        d.state = x;
-        d.pos = r.pos;
+        decode_run(out, off, len, cs.cdf.data(), cs.width, cs.max_value.data(), d.bytes.data(), d.bytes.size(), d.state,
+                   d.pos, [=](int k) { return static_cast<int>(cdf_rows[k]); });
     };
     pool_.run(n, body);
 }

@@ -174,6 +174,42 @@ def test_rans_live_against_reference_build(lib, tables):
         assert np.array_equal(dec.get_decoded(z.size), z)
         dz, dys = r.decode(ref_stream, ys, z.size, qp, n_par)
         assert np.array_equal(dz, z)
+        for k in range(4):   # includes escape-coded magnitudes (sigma 30 on narrow rows)
+            assert np.array_equal(dys[k], (ys[k] >> 8).astype(np.int8)), (n_par, k)
+
+
+def test_rans_decoder_survives_truncated_and_garbage_streams(lib, tables):
+    """a damaged stream must decode to *something* without reading outside the stream buffer: the decoder runs
+    unchecked blocks only while a zero-padded margin remains and falls back to a bounds-checked reader behind it
+    (csrc/rans_host.cpp decode_run); reads behind the end return zero, as in the reference (rans.cpp byte reader)"""
+    r = _Rans(lib, *tables)
+    rng = np.random.default_rng(5)
+    n = 40000
+    sym = np.clip(np.rint(rng.standard_normal(n) * 2), -128, 127).astype(np.int32)
+    ys = [((sym << 8) + rng.integers(0, 128, n)).astype(np.int16) for _ in range(4)]
+    z = np.zeros(128 * 4, dtype=np.int8)
+    for n_par in (1, 2, 5, 8):
+        good = r.encode(ys, z, 10, n_par)
+        header = 0 if n_par <= 2 else 4 * (n_par // 2 - 1 + n_par % 2)
+        def damaged(stream):
+            st = np.ascontiguousarray(stream, dtype=np.uint8)
+            if lib.dcvc_rans_dec_set_stream(r.h, st.ctypes.data, st.size, n_par) != 0:
+                return                                                   # rejected loudly (group offsets out of range)
+            zz = np.zeros(z.size, dtype=np.int8)
+            assert lib.dcvc_rans_dec_z(r.h, zz.ctypes.data, z.size, 10 * 128, 128) == 0
+            for k in range(4):
+                rows = np.ascontiguousarray((ys[k] & 0xff).astype(np.uint8))
+                o = np.zeros(n, dtype=np.int8)
+                assert lib.dcvc_rans_dec_y(r.h, o.ctypes.data, rows.ctypes.data, n) == 0
+
+        for cut in (good.size // 2, good.size - 3, header + 16, header + 4):
+            damaged(good[:cut])
+        junk = rng.integers(0, 256, good.size, dtype=np.uint8)
+        junk[:header] = good[:header]                                    # keep the group offsets valid
+        damaged(junk)
+        # and the intact stream still round-trips afterwards on the same handle
+        dz, dys = r.decode(good, ys, z.size, 10, n_par)
+        assert all(np.array_equal(dys[k], (ys[k] >> 8).astype(np.int8)) for k in range(4))
 
 
 def test_pmf_to_quantized_cdf_against_reference(lib):
