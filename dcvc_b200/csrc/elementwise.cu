@@ -352,18 +352,6 @@ __device__ __forceinline__ int active_group_n(int ng, int step, int h, int w)
     return ng == 2 ? (((h + w) & 1) ^ step) : active_group(step, h, w);
 }
 
-struct EntropyDev {
-    const __half* qdiv; int q_pitch; int m_pitch; int8_t* yq; int full; int ng;
-    int H, W, G, step;
-    const __half* y; int y_pitch;
-    const __half* q_enc;
-    const __half* scales; const __half* means; int p_pitch;
-    __half* acc; int acc_pitch;
-    __half thres;
-    const uint8_t* lut;
-    int16_t* sym_raw; uint8_t* idx_raw; int32_t* counts;
-};
-
 static EntropyDev to_dev(const EntropyStepArgs& a)
 {
     EntropyDev d;

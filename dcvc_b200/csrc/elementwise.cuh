@@ -61,6 +61,20 @@ struct EntropyStepArgs {
     int32_t* counts = nullptr;        // [H*W] number of coded (non-skipped) entries
 };
 
+// Parameter block of the entropy kernels as it is passed to the device (built from EntropyStepArgs by the launchers;
+// declared here because the host-side kernel emulation of tests/cpp reads the same block).
+struct EntropyDev {
+    const __half* qdiv; int q_pitch; int m_pitch; int8_t* yq; int full; int ng;
+    int H, W, G, step;
+    const __half* y; int y_pitch;
+    const __half* q_enc;
+    const __half* scales; const __half* means; int p_pitch;
+    __half* acc; int acc_pitch;
+    __half thres;
+    const uint8_t* lut;
+    int16_t* sym_raw; uint8_t* idx_raw; int32_t* counts;
+};
+
 // encoder step: process_with_mask + 4->1 fold + build_index_enc + per-pixel count
 // (stream.cu:548-630, 931-949, 130-161)
 int launch_entropy_enc_step(const EntropyStepArgs& a, cudaStream_t s);

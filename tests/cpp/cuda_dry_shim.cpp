@@ -1,0 +1,260 @@
+// cuda_dry_shim.cpp — TEST INFRASTRUCTURE ONLY (tests/test_host_dry_run.py).
+//
+// A stand-in for the handful of CUDA runtime entry points libdcvc_b200 uses, LD_PRELOADed in front of a copy of the
+// library that the test relinks against the *shared* runtime (the shipped library links the static one and cannot be
+// interposed).  "Device" memory is zeroed host memory, copies are memcpy, streams are synchronous, a captured graph
+// is the list of its launches.  A kernel launch is handed to the host-side restatement of that kernel in
+// cuda_emu_kernels.cpp (DRY_SHIM_EMULATE=1), or only counted (default: nothing is computed).  The point is to drive
+// the host side of the codecs — parameter loading and weight repacking, arena sizing, the plan of every GEMM (geometry
+// checks, tile plans, tensor-map encoding with the driver's documented argument rules), operand wiring, segment
+// building, the compress / decompress control flow and the rANS hand-off — on a machine without a GPU, so that shape
+// and wiring mistakes surface in the CPU test tier.  A launch of a kernel the emulation does not know fails loudly.
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+// cuda_emu_kernels.cpp
+extern "C" int emu_lookup(const char* name);
+extern "C" int emu_num_args(int k);
+extern "C" int emu_arg_size(int k, int i);
+extern "C" int emu_run(int k, void** args);
+extern "C" unsigned long long emu_map_magic();
+
+extern "C" {
+
+typedef int cudaError_t;
+typedef struct CUstream_st* cudaStream_t;
+typedef struct CUevent_st* cudaEvent_t;
+typedef struct CUgraph_st* cudaGraph_t;
+typedef struct CUgraphExec_st* cudaGraphExec_t;
+struct dim3 { unsigned x, y, z; };
+
+static std::atomic<long long> g_launches{0}, g_graph_launches{0}, g_maps{0}, g_bytes{0};
+static int g_fail_map = 0;
+
+long long dry_shim_launches() { return g_launches.load(); }
+long long dry_shim_graph_launches() { return g_graph_launches.load(); }
+long long dry_shim_tensor_maps() { return g_maps.load(); }
+long long dry_shim_bytes() { return g_bytes.load(); }
+
+// ---- fat binary registration (no driver is ever touched) --------------------------------------------------------
+void** __cudaRegisterFatBinary(void*) { static void* h[4]; return h; }
+void __cudaRegisterFatBinaryEnd(void**) {}
+void __cudaUnregisterFatBinary(void**) {}
+static std::map<const void*, std::string>& kernel_names() { static std::map<const void*, std::string> m; return m; }
+void __cudaRegisterFunction(void**, const char* host_fun, char*, const char* device_name, int, void*, void*, void*, void*, int*)
+{
+    kernel_names()[host_fun] = device_name;
+}
+void __cudaRegisterVar(void**, char*, char*, const char*, int, size_t, int, int) {}
+
+static thread_local struct { dim3 g, b; size_t smem; void* st; } t_cfg;
+unsigned __cudaPushCallConfiguration(dim3 g, dim3 b, size_t smem, void* st) { t_cfg = { g, b, smem, st }; return 0; }
+cudaError_t __cudaPopCallConfiguration(dim3* g, dim3* b, size_t* smem, void* st)
+{
+    *g = t_cfg.g; *b = t_cfg.b; *smem = t_cfg.smem; *static_cast<void**>(st) = t_cfg.st;
+    return 0;
+}
+
+// ---- device / memory ---------------------------------------------------------------------------------------------
+cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
+cudaError_t cudaSetDevice(int) { return 0; }
+cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
+cudaError_t cudaDeviceGetAttribute(int* v, int attr, int)
+{
+    *v = (attr == 16 /* cudaDevAttrMultiProcessorCount */) ? 148 : 0;
+    return 0;
+}
+cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = -1; return 0; }
+cudaError_t cudaDeviceSynchronize() { return 0; }
+cudaError_t cudaGetLastError() { return 0; }
+const char* cudaGetErrorString(cudaError_t) { return "dry-run shim"; }
+
+static cudaError_t alloc_zeroed(void** p, size_t n)
+{
+    void* q = nullptr;
+    if (posix_memalign(&q, 1024, n ? n : 1)) return 2;
+    memset(q, 0, n);
+    g_bytes += static_cast<long long>(n);
+    *p = q;
+    return 0;
+}
+cudaError_t cudaMalloc(void** p, size_t n) { return alloc_zeroed(p, n); }
+cudaError_t cudaFree(void* p) { free(p); return 0; }
+cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return alloc_zeroed(p, n); }
+cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { memmove(d, s, n); return 0; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memmove(d, s, n); return 0; }
+cudaError_t dry_memset_async(void* d, int v, size_t n, cudaStream_t st);
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st) { return dry_memset_async(d, v, n, st); }
+
+// ---- streams / events / graphs -------------------------------------------------------------------------------------
+static void* token() { return malloc(8); }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = static_cast<cudaStream_t>(token()); return 0; }
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = static_cast<cudaStream_t>(token()); return 0; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return 0; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = static_cast<cudaEvent_t>(token()); return 0; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = static_cast<cudaEvent_t>(token()); return 0; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return 0; }
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
+// a captured graph = the launches (kernel + a private copy of its arguments) and memsets issued while capturing
+struct GraphOp {
+    int kernel = -1;                       // emulation table index, -1: memset
+    std::vector<std::shared_ptr<void>> args;   // 64-byte aligned private copies (PwGemmParams is alignas(64))
+    void* dst = nullptr; int value = 0; size_t bytes = 0;
+};
+struct Graph { std::vector<GraphOp> ops; };
+static std::map<cudaStream_t, Graph*>& capturing() { static std::map<cudaStream_t, Graph*> m; return m; }
+static const bool g_emulate = []() { const char* e = getenv("DRY_SHIM_EMULATE"); return e && e[0] == '1'; }();
+
+static cudaError_t run_op(const GraphOp& op)
+{
+    if (op.kernel < 0) { memset(op.dst, op.value, op.bytes); return 0; }
+    if (!g_emulate) return 0;
+    std::vector<void*> ptrs(op.args.size());
+    for (size_t i = 0; i < op.args.size(); ++i) ptrs[i] = op.args[i].get();
+    return emu_run(op.kernel, ptrs.data()) ? 719 /* launch failure */ : 0;
+}
+static cudaError_t submit_kernel(const void* fn, void** args, cudaStream_t st)
+{
+    ++g_launches;
+    auto it = kernel_names().find(fn);
+    if (it == kernel_names().end()) { fprintf(stderr, "dry shim: launch of an unregistered kernel\n"); return 98; }
+    const int k = emu_lookup(it->second.c_str());
+    if (k < 0) {
+        if (!g_emulate) return 0;
+        fprintf(stderr, "dry shim: no host restatement of kernel %s\n", it->second.c_str());
+        return 98;  // invalid device function
+    }
+    GraphOp op;
+    op.kernel = k;
+    for (int i = 0; i < emu_num_args(k); ++i) {
+        const size_t n = static_cast<size_t>(emu_arg_size(k, i));
+        void* q = nullptr;
+        if (posix_memalign(&q, 64, (n + 63) & ~static_cast<size_t>(63))) return 2;
+        memcpy(q, args[i], n);
+        op.args.emplace_back(q, free);
+    }
+    auto cap = capturing().find(st);
+    if (cap != capturing().end()) { cap->second->ops.push_back(std::move(op)); return 0; }
+    return run_op(op);
+}
+
+cudaError_t cudaStreamBeginCapture(cudaStream_t s, int)
+{
+    if (capturing().count(s)) return 900;
+    capturing()[s] = new Graph();
+    return 0;
+}
+cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t* g)
+{
+    auto it = capturing().find(s);
+    if (it == capturing().end()) return 901;
+    *g = reinterpret_cast<cudaGraph_t>(it->second);
+    capturing().erase(it);
+    return 0;
+}
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long)
+{
+    *e = reinterpret_cast<cudaGraphExec_t>(new Graph(*reinterpret_cast<Graph*>(g)));
+    return 0;
+}
+cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t)
+{
+    ++g_graph_launches;
+    for (const GraphOp& op : reinterpret_cast<Graph*>(e)->ops) {
+        const cudaError_t r = run_op(op);
+        if (r) return r;
+    }
+    return 0;
+}
+cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete reinterpret_cast<Graph*>(g); return 0; }
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { delete reinterpret_cast<Graph*>(e); return 0; }
+
+// ---- launches ------------------------------------------------------------------------------------------------------
+struct LaunchConfigHead { dim3 grid, block; size_t smem; cudaStream_t stream; void* attrs; unsigned num_attrs; };
+static cudaError_t check_dims(const dim3& g, const dim3& b, size_t smem)
+{
+    if (g.x == 0 || g.y == 0 || g.z == 0 || b.x == 0 || b.y == 0 || b.z == 0) return 9;       // invalid configuration
+    if (static_cast<unsigned long long>(b.x) * b.y * b.z > 1024 || smem > 232448) return 9;
+    if (g.y > 65535 || g.z > 65535) return 9;
+    return 0;
+}
+cudaError_t dry_memset_async(void* d, int v, size_t n, cudaStream_t st)
+{
+    auto cap = capturing().find(st);
+    if (cap == capturing().end()) { memset(d, v, n); return 0; }
+    GraphOp op;
+    op.dst = d; op.value = v; op.bytes = n;
+    cap->second->ops.push_back(op);
+    return 0;
+}
+cudaError_t cudaLaunchKernel(const void* fn, dim3 g, dim3 b, void** args, size_t smem, cudaStream_t st)
+{
+    const cudaError_t e = check_dims(g, b, smem);
+    return e ? e : submit_kernel(fn, args, st);
+}
+cudaError_t cudaLaunchKernelExC(const void* cfg, const void* fn, void** args)
+{
+    const LaunchConfigHead* c = static_cast<const LaunchConfigHead*>(cfg);
+    const cudaError_t e = check_dims(c->grid, c->block, c->smem);
+    return e ? e : submit_kernel(fn, args, c->stream);
+}
+cudaError_t cudaFuncSetAttribute(const void*, int, int) { return 0; }
+cudaError_t cudaOccupancyMaxActiveClusters(int* n, const void*, const void*)
+{
+    *n = 0;
+    return 1;   // "not available": the library falls back to num_sms / cluster size
+}
+
+// ---- cuTensorMapEncodeTiled with the argument rules of the driver API documentation ------------------------------------
+static int fake_encode_tiled(void* map, int dtype, unsigned rank, void* addr, const uint64_t* dims, const uint64_t* strides,
+                             const uint32_t* box, const uint32_t* estr, int interleave, int swizzle, int, int)
+{
+    ++g_maps;
+    if (g_fail_map) return 1;
+    if (!map || rank < 1 || rank > 5) return 1;
+    if (reinterpret_cast<uintptr_t>(addr) & 15) return 1;
+    const int esize = (dtype == 6 /* FLOAT16 */) ? 2 : 0;
+    if (!esize || interleave != 0) return 1;
+    for (unsigned i = 0; i < rank; ++i) {
+        if (dims[i] == 0 || dims[i] > (1ull << 32)) return 1;
+        if (box[i] == 0 || box[i] > 256) return 1;
+        if (estr[i] == 0 || estr[i] > 8) return 1;
+    }
+    for (unsigned i = 0; i + 1 < rank; ++i)
+        if ((strides[i] & 15) || strides[i] >= (1ull << 40)) return 1;
+    const uint64_t inner = static_cast<uint64_t>(box[0]) * esize;
+    if (inner & 15) return 1;
+    const uint64_t span = swizzle == 1 ? 32 : swizzle == 2 ? 64 : swizzle == 3 ? 128 : (1ull << 40);
+    if (inner > span) return 1;
+    // transparent map for the host restatement of the kernels (FakeMap in cuda_emu_kernels.cpp)
+    struct { uint64_t magic; const void* ptr; uint32_t rank, swz; uint64_t dims[5]; uint64_t strides[4]; uint32_t box[5]; } f;
+    memset(&f, 0, sizeof(f));
+    f.magic = emu_map_magic(); f.ptr = addr; f.rank = rank; f.swz = static_cast<uint32_t>(swizzle);
+    for (unsigned i = 0; i < rank; ++i) { f.dims[i] = dims[i]; f.box[i] = box[i]; }
+    for (unsigned i = 0; i + 1 < rank; ++i) f.strides[i] = strides[i];
+    memset(map, 0, 128);
+    memcpy(map, &f, sizeof(f));
+    return 0;
+}
+cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, unsigned long long, int* qres)
+{
+    if (strcmp(name, "cuTensorMapEncodeTiled") != 0) { *fn = nullptr; if (qres) *qres = 1; return 0; }
+    *fn = reinterpret_cast<void*>(&fake_encode_tiled);
+    if (qres) *qres = 0;
+    return 0;
+}
+
+}  // extern "C"
