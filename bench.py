@@ -236,6 +236,14 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001 — reported in the JSON line instead of failing the bench
             ld = {"error": f"{type(e).__name__}: {e}"}
 
+    # ---- HT-L (experimental codec, opt-in): same leg with the large model, failure-isolated like LD
+    htl = None
+    if not args.no_hts and world == 1 and os.environ.get("DCVC_B200_EXPERIMENTAL_HTL") == "1":
+        try:
+            htl = bench_hts(model, device, world, rank, args, timed, reduce_max, large=True)
+        except Exception as e:  # noqa: BLE001
+            htl = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- CPU baseline: the oracle port on the host cores (rank 0, N=1 only), bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -265,26 +273,31 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
             "hts": hts,
             "ld": ld,
+            "htl": htl,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def bench_hts(i_net, device, world, rank, args, timed, reduce_max):
+def bench_hts(i_net, device, world, rank, args, timed, reduce_max, large=False):
     """DCVC-UF HT-S 1080p chunk (8 frames) encode / decode after one intra frame (configs[2]); published B200
-    numbers of the reference's CUTLASS build: 1415.1 / 945.8 FPS."""
+    numbers of the reference's CUTLASS build: 1415.1 / 945.8 FPS.  large=True: the HT-L model
+    (experimental codec, DCVC_B200_EXPERIMENTAL_HTL=1; published 811.7 / 551.6 FPS)."""
     import torch.distributed as dist
     from util_frames import psnr, synth_frame
-    from dcvc_b200.model import DMC
+    from dcvc_b200.model import DMC, DMCHTL
     from dcvc_b200.shard import broadcast_state_dict
-    from dcvc_b200.spec import hts_spec, synth_state_dict
-    spec = hts_spec()
+    from dcvc_b200.spec import htl_spec, hts_spec, synth_state_dict
+    spec = htl_spec() if large else hts_spec()
+    seed = 3 if large else 1
+    published = {"encode": 811.7, "decode": 551.6} if large else {"encode": 1415.1, "decode": 945.8}
+    alg_bytes_decode = 17.33e9 if large else 14.09e9     # SURVEY.md §8d, per chunk
     if world == 1:
-        sd = synth_state_dict(spec, 1)
+        sd = synth_state_dict(spec, seed)
     else:
-        sd = broadcast_state_dict(synth_state_dict(spec, 1) if rank == 0 else None, spec, 0, device)
-    p_net = DMC()
+        sd = broadcast_state_dict(synth_state_dict(spec, seed) if rank == 0 else None, spec, 0, device)
+    p_net = DMCHTL() if large else DMC()
     p_net.load_state_dict(sd)
     p_net.update(SKIP)
     p_net = p_net.half().to(device)
@@ -327,7 +340,7 @@ def bench_hts(i_net, device, world, rank, args, timed, reduce_max):
     last = (args.warmup + args.steps - 1) % len(chunks)
     src = chunks[last][:, 0:3].float().cpu()
     out = {
-        "workload": "DCVC-UF HT-S 1080p, 8-frame chunks after one intra frame, q_index 32, skip_thres 0.15 (configs[2])",
+        "workload": f"DCVC-UF {'HT-L' if large else 'HT-S'} 1080p, 8-frame chunks after one intra frame, q_index 32, skip_thres 0.15 (configs[2])",
         "decode_fps": round(world * 8 * args.steps / (tot_dec * 1e-3), 1),
         "encode_fps": round(world * 8 * args.steps / (tot_enc * 1e-3), 1),
         "ms_per_chunk_decode": round(tot_dec / args.steps, 3), "ms_per_chunk_encode": round(tot_enc / args.steps, 3),
@@ -335,9 +348,9 @@ def bench_hts(i_net, device, world, rank, args, timed, reduce_max):
         "gpu_launches_per_chunk_decode": int((l1 - l0) // args.steps),
         "bytes_per_chunk": int(np.mean([len(s[0]) for s in streams])),
         "psnr_db_frame0": round(psnr(state["x_hat"][0].float().cpu()[:, :, :H, :W], src), 3),
-        "published_b200_reference_fps": {"encode": 1415.1, "decode": 945.8, "source": "BASELINE.md (assets/complexity.png)"},
-        "decode_vs_published": round(world * 8 * args.steps / (tot_dec * 1e-3) / 945.8, 3),
-        "alg_gbs_decode": round(14.09e9 / (gpu_ms * 1e-3) / 1e9, 1),
+        "published_b200_reference_fps": dict(published, source="BASELINE.md (assets/complexity.png)"),
+        "decode_vs_published": round(world * 8 * args.steps / (tot_dec * 1e-3) / published["decode"], 3),
+        "alg_gbs_decode": round(alg_bytes_decode / (gpu_ms * 1e-3) / 1e9, 1),
     }
     del p_net
     return out

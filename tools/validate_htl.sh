@@ -11,3 +11,5 @@ timeout 600 python -m pytest tests/test_htl_gpu.py -q -x -k "64-64 or oracle" > 
 echo "small rc=$?"; tail -3 gpurun_out/htl_small.log
 timeout 900 python -m pytest tests/test_htl_gpu.py -q > gpurun_out/htl_all.log 2>&1
 echo "all rc=$?"; tail -5 gpurun_out/htl_all.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/htl_bench.json 2> gpurun_out/htl_bench.err
+echo "bench rc=$?"; python -c "import json;d=json.loads(open('gpurun_out/htl_bench.json').read().strip().splitlines()[-1]);print(d.get('htl'))"
