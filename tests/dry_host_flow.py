@@ -74,6 +74,19 @@ class Handle:
         self.chk(self.lib.dcvc_debug_fetch(self.h, name.encode(), buf.ctypes.data, nbytes, C.byref(n)), "debug_fetch " + name)
         return buf[: n.value].view(dtype).copy()
 
+    def profiled(self, fn):
+        """algorithmic bytes / FLOPs the codec books for the launches of fn() (Segment annotations: bench.py's roofline
+        numerators); kinds 0 = pw_gemm, 1 = dw3x3, 2 = elementwise / entropy"""
+        self.lib.dcvc_profile_enable(self.h, 1)
+        out = fn()
+        acc = {"bytes": 0.0, "flops": 0.0, "launches": 0}
+        for kind in range(3):
+            ms, n, b, f = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+            self.lib.dcvc_profile_get(self.h, kind, C.byref(ms), C.byref(n), C.byref(b), C.byref(f))
+            acc["bytes"] += b.value; acc["flops"] += f.value; acc["launches"] += n.value
+        self.lib.dcvc_profile_enable(self.h, 0)
+        return out, acc
+
     def close(self):
         self.lib.dcvc_destroy(self.h)
 
@@ -116,8 +129,9 @@ def run_intra(lib, mode, sizes):
         Hp, Wp = pads(H, W)
         xt = synth_frame(H, W, 1234) if mode == "check" else torch.zeros(1, 3, H, W)
         stream, ec, xh_enc = intra_compress(hd, f16(xt), 32)
-        xh_dec = intra_decompress(hd, stream, 32, H, W, ec)
-        rec = {"size": [H, W], "bytes": len(stream), "ec": ec}
+        xh_dec, acc = hd.profiled(lambda: intra_decompress(hd, stream, 32, H, W, ec))
+        rec = {"size": [H, W], "bytes": len(stream), "ec": ec, "decode_alg_gb": acc["bytes"] / 1e9,
+               "decode_gmac": acc["flops"] / 2e9, "decode_launches": acc["launches"]}
         if mode == "check":
             from oracle.dmci_oracle import DmciOracle
             assert np.array_equal(xh_enc.view(np.uint16), xh_dec.view(np.uint16)), "decoder reconstruction differs from the encoder's"
@@ -179,8 +193,11 @@ def run_video(lib, mode, which, sizes):
         p8 = (Hp // 8) * (Wp // 8)
         enc_state = hd.fetch("cat_fam", np.uint16, p8 * fam_c * 2) if mode == "check" else None
         video_add_ref(hd, f16(ref_frame), False)
-        recon = [video_decompress(hd, s, 25, H, W, ec, r, frames) for (s, ec), r in zip(streams, resets)]
-        rec = {"size": [H, W], "bytes": [len(s[0]) for s in streams]}
+        recon = [video_decompress(hd, s, 25, H, W, ec, r, frames) for (s, ec), r in zip(streams[:-1], resets[:-1])]
+        last, acc = hd.profiled(lambda: video_decompress(hd, streams[-1][0], 25, H, W, streams[-1][1], resets[-1], frames))
+        recon.append(last)
+        rec = {"size": [H, W], "bytes": [len(s[0]) for s in streams], "decode_alg_gb": acc["bytes"] / 1e9,
+               "decode_gmac": acc["flops"] / 2e9, "decode_launches": acc["launches"]}
         if mode == "check":
             dec_state = hd.fetch("cat_fam", np.uint16, p8 * fam_c * 2)
             half = fam_c // 2

@@ -60,6 +60,11 @@ def _run(dry, mode, codec, sizes, timeout=900):
     return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
 
 
+# decode-side algorithmic GB and GMAC per picture (Intra, LD) / per 8-frame chunk (HT-S, HT-L) at 1088x1920, measured on
+# the reference's own modules with forward hooks: the numerators of bench.py's roofline
+REFERENCE_DECODE_WORK = {"intra": (5.89, 701.2), "hts": (14.09, 1483.4), "ld": (2.80, 147.8), "htl": (17.33, 2001.8)}
+
+
 @pytest.mark.parametrize("codec", ["intra", "hts", "ld", "htl"])
 def test_host_flow_plans_and_runs_at_all_sizes(dry, codec):
     res = _run(dry, "plan", codec, ["64x64", "200x328", "1080x1920"])
@@ -67,6 +72,11 @@ def test_host_flow_plans_and_runs_at_all_sizes(dry, codec):
     for run in res["runs"]:
         sizes = run["bytes"] if isinstance(run["bytes"], list) else [run["bytes"]]
         assert all(s > 4 for s in sizes)            # an all-skipped picture still carries z
+    # the launches of one 1080p decode book exactly the reference network's work: no op missing, none counted twice
+    gb, gmac = REFERENCE_DECODE_WORK[codec]
+    full = res["runs"][2]
+    assert abs(full["decode_alg_gb"] - gb) <= 0.005 * gb + 0.005, (codec, full["decode_alg_gb"], gb)
+    assert abs(full["decode_gmac"] - gmac) <= 0.002 * gmac, (codec, full["decode_gmac"], gmac)
 
 
 @pytest.mark.parametrize("codec,sizes", [("intra", ["64x64", "72x104"]), ("hts", ["72x104"]), ("ld", ["72x104"]),
