@@ -92,9 +92,49 @@ def make_htl():
     np.savez_compressed(os.path.join(HERE, "htl_forward_64x64.npz"), **out)
 
 
+def container_payload(n, seed):
+    return np.random.default_rng(seed).integers(0, 256, n, dtype=np.uint8).tobytes()
+
+
+def container_script(seed):
+    """a deterministic series of container writes shared by the golden and the test: ["sps", id, h, w] and
+    ["ip", is_i, sps_id, qp, ec_parallel, reset, payload_len, payload_seed]; lengths sit on the varint boundaries"""
+    rng = np.random.default_rng(seed)
+    ops = []
+    sizes = [(1080, 1920), (64, 64), (2160, 3840), (120, 17000)]
+    lengths = [0, 1, 100, 127, 128, 16383, 16384, 70000]
+    for i, (h, w) in enumerate(sizes):
+        ops.append(["sps", i, h, w])
+        for j in range(4):
+            ops.append(["ip", bool(rng.integers(0, 2)), i, int(rng.integers(0, 64)), int(rng.integers(1, 9)),
+                        int(rng.integers(0, 2)), lengths[(2 * i + j) % len(lengths)], 100 * i + j])
+    return ops
+
+
+def make_stream():
+    """byte stream the reference's own container helpers produce for container_script(7): length, sha256, head"""
+    import hashlib
+    import io
+    from src.utils.stream_helper import write_ip, write_sps  # reference
+    ops = container_script(7)
+    f = io.BytesIO()
+    for op in ops:
+        if op[0] == "sps":
+            write_sps(f, {"sps_id": op[1], "height": op[2], "width": op[3]})
+        else:
+            write_ip(f, op[1], op[2], op[3], op[4], op[5], container_payload(op[6], op[7]))
+    data = f.getvalue()
+    with open(os.path.join(HERE, "stream_container.json"), "w") as out:
+        json.dump({"ops": ops, "length": len(data), "sha256": hashlib.sha256(data).hexdigest(), "head_hex": data[:512].hex()}, out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if "--only-stream" in sys.argv:   # adds the bitstream-container fixture without regenerating the others
+        make_stream()
+        print("container golden fixture written to", HERE)
+        return
     if "--only-htl" in sys.argv:   # adds the HT-L fixtures without regenerating the others
         make_htl()
         print("HT-L golden fixtures written to", HERE)
