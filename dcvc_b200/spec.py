@@ -161,7 +161,7 @@ def hts_spec() -> "OrderedDict[str, tuple]":
 
 def htl_spec() -> "OrderedDict[str, tuple]":
     """state_dict layout of DMC(ModelStructure.HTL) (src/models/video_model_ht.py: the `else` branches of :26-317).
-    Used by the oracle (oracle/htl_oracle.py) and its goldens; the CUDA proxy for this model is not built yet."""
+    Used by the experimental HT-L codec (csrc/codec_htl.cu, opt-in), the oracle (oracle/htl_oracle.py) and its goldens."""
     s: "OrderedDict[str, tuple]" = OrderedDict()
     s["bit_estimator_z.h"] = (QP_NUM, G_CH_Z, 4)
     s["bit_estimator_z.b"] = (QP_NUM, G_CH_Z, 4)
@@ -219,7 +219,7 @@ LD_CH_M = 256
 
 def ld_spec() -> "OrderedDict[str, tuple]":
     """state_dict layout of the low-delay DMC (src/models/video_model_ld.py:24-211).  Used by the oracle
-    (oracle/ld_oracle.py) and its goldens; the CUDA proxy for this model is not built yet."""
+    (oracle/ld_oracle.py), its goldens and the LD codec (csrc/codec_ld.cu)."""
     s: "OrderedDict[str, tuple]" = OrderedDict()
     s["bit_estimator_z.h"] = (QP_NUM, LD_CH_Z, 4)
     s["bit_estimator_z.b"] = (QP_NUM, LD_CH_Z, 4)

@@ -14,8 +14,9 @@ Two restatements:
 /root/reference/src/models/video_model_ht.py:452-496 with the `else` (non-HTS) branches of :26-317 and
 `forward_prior_4x(..., spatial_prior_has_scales=True)`, /root/reference/src/models/common_model.py:231-282), restated
 functionally over a plain state_dict and PINNED against tests/golden/htl_forward_64x64.npz (minted by importing the
-reference modules, tests/golden/make_golden.py).  The CUDA proxy for this model (dmc_htl_proxy.cpp) is not built yet
-(SURVEY.md §8 f3); it additionally needs a 3x3 / stride-1 SubpelConv with bias (`decoder.up`) in pw_gemm.
+reference modules, tests/golden/make_golden.py).  The product's counterpart of the CUDA proxy for this model
+(dmc_htl_proxy.cpp) is the experimental dcvc_b200/csrc/codec_htl.cu, compared with this oracle by
+tests/test_htl_gpu.py on a device and by tests/test_host_dry_run.py under kernel emulation.
 """
 from __future__ import annotations
 

@@ -15,8 +15,8 @@ Two restatements, both functional over a plain state_dict:
 /root/reference/src/models/common_model.py:212-229 and the 2-step checkerboard masks of
 common_model.py:157-172), restated functionally over a plain state_dict and PINNED against
 tests/golden/ld_forward_64x64.npz, which tests/golden/make_golden.py produced by importing the reference
-modules themselves.  The CUDA proxy for this model (dmc_ld_proxy.cpp) is not built yet (SURVEY.md §8 f3);
-this oracle and dcvc_b200.spec.ld_spec are the groundwork its parity tests will stand on.
+modules themselves.  The product's counterpart of the CUDA proxy for this model (dmc_ld_proxy.cpp) is
+dcvc_b200/csrc/codec_ld.cu; tests/test_ld_gpu.py compares it with this oracle.
 """
 from __future__ import annotations
 
