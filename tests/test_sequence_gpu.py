@@ -40,14 +40,14 @@ def nets():
     return nets
 
 
-@pytest.mark.parametrize("which,delay,n_frames", [("hts", 8, 19), ("ld", 1, 6)])
-def test_sequence_driver_matches_the_hand_driven_api(nets, which, delay, n_frames):
+@pytest.mark.parametrize("which,delay,n_frames,reset_interval", [("hts", 8, 19, 16), ("ld", 1, 6, 4)])
+def test_sequence_driver_matches_the_hand_driven_api(nets, which, delay, n_frames, reset_interval):
     from dcvc_b200 import stream
     from dcvc_b200.frame_io import frame_to_yuv420, yuv420_to_frame
     from dcvc_b200.sequence import SequenceDecoder, SequenceEncoder, frame_schedule
     i_net, p_net = nets["i"], nets[which]
     frames = _planes(n_frames, 5)
-    enc = SequenceEncoder(i_net, p_net, H, W, qp_i=30, qp_p=25, frame_delay=delay, reset_interval=8)
+    enc = SequenceEncoder(i_net, p_net, H, W, qp_i=30, qp_p=25, frame_delay=delay, reset_interval=reset_interval)
     data = enc.encode(frames)
     dec = [tuple(p.clone() for p in planes) for planes in SequenceDecoder(i_net, p_net, frame_delay=delay).decode(data, n_frames)]
     torch.cuda.synchronize()
@@ -60,7 +60,7 @@ def test_sequence_driver_matches_the_hand_driven_api(nets, which, delay, n_frame
     sps = {"sps_id": 0, "height": H, "width": W}
     out = io.BytesIO()
     stream.write_sps(out, sps)
-    for unit in frame_schedule(n_frames, delay, -1, 8):
+    for unit in frame_schedule(n_frames, delay, -1, reset_interval):
         group = frames[unit.first:unit.first + unit.count]
         group = group + [group[-1]] * ((1 if unit.is_intra else delay) - len(group))
         x = torch.cat([yuv420_to_frame(*g) for g in group], dim=1).contiguous(memory_format=torch.channels_last)
