@@ -74,7 +74,8 @@ cudaError_t cudaDeviceGetAttribute(int* v, int attr, int)
 }
 cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = -1; return 0; }
 cudaError_t cudaDeviceSynchronize() { return 0; }
-cudaError_t cudaGetLastError() { return 0; }
+static thread_local cudaError_t t_last_error = 0;
+cudaError_t cudaGetLastError() { const cudaError_t e = t_last_error; t_last_error = 0; return e; }
 const char* cudaGetErrorString(cudaError_t) { return "dry-run shim"; }
 
 static cudaError_t alloc_zeroed(void** p, size_t n)
@@ -202,14 +203,18 @@ cudaError_t dry_memset_async(void* d, int v, size_t n, cudaStream_t st)
 }
 cudaError_t cudaLaunchKernel(const void* fn, dim3 g, dim3 b, void** args, size_t smem, cudaStream_t st)
 {
-    const cudaError_t e = check_dims(g, b, smem);
-    return e ? e : submit_kernel(fn, args, st);
+    cudaError_t e = check_dims(g, b, smem);
+    if (!e) e = submit_kernel(fn, args, st);
+    if (e) t_last_error = e;      // a failed launch is also what cudaGetLastError() reports next (<<< >>> launches)
+    return e;
 }
 cudaError_t cudaLaunchKernelExC(const void* cfg, const void* fn, void** args)
 {
     const LaunchConfigHead* c = static_cast<const LaunchConfigHead*>(cfg);
-    const cudaError_t e = check_dims(c->grid, c->block, c->smem);
-    return e ? e : submit_kernel(fn, args, c->stream);
+    cudaError_t e = check_dims(c->grid, c->block, c->smem);
+    if (!e) e = submit_kernel(fn, args, c->stream);
+    if (e) t_last_error = e;
+    return e;
 }
 cudaError_t cudaFuncSetAttribute(const void*, int, int) { return 0; }
 cudaError_t cudaOccupancyMaxActiveClusters(int* n, const void*, const void*)

@@ -253,6 +253,105 @@ static int emu_scan(void** g)
     return 0;
 }
 
+// ---- frame IO (csrc/frame_io.cu): every fp16 step rounded like the kernels (integer results are exact)
+static inline __half norm_u8(uint8_t v) { return f2h(h2f(f2h(static_cast<float>(v) / 255.0f)) - 0.5f); }
+static inline __half to_255(__half h) { return f2h(fminf(fmaxf(h2f(f2h(h2f(h) * 255.0f)), 0.f), 255.f)); }
+
+static int emu_yuv420_to_frame(void** g)
+{
+    const uint8_t *yp = arg<const uint8_t*>(g, 0), *up = arg<const uint8_t*>(g, 1), *vp = arg<const uint8_t*>(g, 2);
+    const int H = arg<int>(g, 3), W = arg<int>(g, 4);
+    __half* x = arg<__half*>(g, 5);
+    const long long sc = arg<long long>(g, 6), sh = arg<long long>(g, 7), sw = arg<long long>(g, 8);
+    const int Wc = W >> 1;
+    for (int yy = 0; yy < H; ++yy)
+        for (int xx = 0; xx < W; ++xx) {
+            __half* dst = x + yy * sh + xx * sw;
+            dst[0] = norm_u8(yp[static_cast<long long>(yy) * W + xx]);
+            dst[sc] = norm_u8(up[static_cast<long long>(yy >> 1) * Wc + (xx >> 1)]);
+            dst[2 * sc] = norm_u8(vp[static_cast<long long>(yy >> 1) * Wc + (xx >> 1)]);
+        }
+    return 0;
+}
+
+static int emu_frame_to_yuv420(void** g)
+{
+    const __half* x = arg<const __half*>(g, 0);
+    const long long sc = arg<long long>(g, 1), sh = arg<long long>(g, 2), sw = arg<long long>(g, 3);
+    const int H = arg<int>(g, 4), W = arg<int>(g, 5);
+    uint8_t *yp = arg<uint8_t*>(g, 6), *up = arg<uint8_t*>(g, 7), *vp = arg<uint8_t*>(g, 8);
+    const int Wc = W >> 1;
+    for (int by = 0; by < (H >> 1); ++by)
+        for (int bx = 0; bx < Wc; ++bx) {
+            float su = 0.f, sv = 0.f;
+            for (int r = 0; r < 2; ++r)
+                for (int c = 0; c < 2; ++c) {
+                    const int yy = 2 * by + r, xx = 2 * bx + c;
+                    const __half* src = x + yy * sh + xx * sw;
+                    yp[static_cast<long long>(yy) * W + xx] = static_cast<uint8_t>(rintf(h2f(to_255(f2h(h2f(src[0]) + 0.5f)))));
+                    su += h2f(f2h(h2f(src[sc]) + 0.5f));
+                    sv += h2f(f2h(h2f(src[2 * sc]) + 0.5f));
+                }
+            up[static_cast<long long>(by) * Wc + bx] = static_cast<uint8_t>(h2f(to_255(f2h(su / 4.f))));
+            vp[static_cast<long long>(by) * Wc + bx] = static_cast<uint8_t>(h2f(to_255(f2h(sv / 4.f))));
+        }
+    return 0;
+}
+
+static int emu_sse_u8(void** g)
+{
+    const uint8_t *a = arg<const uint8_t*>(g, 0), *b = arg<const uint8_t*>(g, 1);
+    const long long n = arg<long long>(g, 2);
+    unsigned long long* out = arg<unsigned long long*>(g, 3);
+    unsigned long long acc = 0;
+    for (long long i = 0; i < n; ++i) { const int d = static_cast<int>(a[i]) - static_cast<int>(b[i]); acc += static_cast<unsigned long long>(d * d); }
+    *out += acc;
+    return 0;
+}
+
+// ---- DCVC-family ops (csrc/family_ops.cu)
+static int emu_square(void** g)
+{
+    const __half* in = arg<const __half*>(g, 0); const int ip = arg<int>(g, 1);
+    __half* out = arg<__half*>(g, 2); const int op = arg<int>(g, 3); const long long npix = arg<long long>(g, 4); const int C = arg<int>(g, 5);
+    for (long long p = 0; p < npix; ++p)
+        for (int c = 0; c < C; ++c) out[p * op + c] = f2h(h2f(in[p * ip + c]) * h2f(in[p * ip + c]));
+    return 0;
+}
+
+// one rounding, like the device's HFMA: the product of two halfs and the sum are exact in double for all but
+// astronomically separated exponents
+static inline __half hfma(__half a, __half b, __half c)
+{
+    return __double2half(static_cast<double>(h2f(a)) * static_cast<double>(h2f(b)) + static_cast<double>(h2f(c)));
+}
+
+static int emu_warp_bilinear(void** g)
+{
+    const __half* im = arg<const __half*>(g, 0); const int ip = arg<int>(g, 1); const __half* flow = arg<const __half*>(g, 2);
+    const long long fc = arg<long long>(g, 3), fh = arg<long long>(g, 4), fw = arg<long long>(g, 5);
+    __half* out = arg<__half*>(g, 6); const int op = arg<int>(g, 7), W = arg<int>(g, 8), H = arg<int>(g, 9), C = arg<int>(g, 10);
+    for (int h = 0; h < H; ++h)
+        for (int w = 0; w < W; ++w) {
+            float x_pos = h2f(flow[h * fh + w * fw]) + static_cast<float>(w);
+            float y_pos = h2f(flow[fc + h * fh + w * fw]) + static_cast<float>(h);
+            x_pos = fminf(fmaxf(x_pos, 0.f), static_cast<float>(W - 1));
+            y_pos = fminf(fmaxf(y_pos, 0.f), static_cast<float>(H - 1));
+            const int x0 = static_cast<int>(floorf(x_pos)), y0 = static_cast<int>(floorf(y_pos));
+            const int x1 = x0 + 1 < W ? x0 + 1 : W - 1, y1 = y0 + 1 < H ? y0 + 1 : H - 1;
+            const float w_r = x_pos - static_cast<float>(x0), w_l = 1.f - w_r, w_b = y_pos - static_cast<float>(y0), w_t = 1.f - w_b;
+            const __half wa = f2h(w_l * w_t), wb = f2h(w_l * w_b), wc = f2h(w_r * w_t), wd = f2h(w_r * w_b);
+            for (int c = 0; c < C; ++c) {
+                __half r = hfma(im[(static_cast<long long>(y0) * W + x0) * ip + c], wa, f2h(0.f));
+                r = hfma(im[(static_cast<long long>(y1) * W + x0) * ip + c], wb, r);
+                r = hfma(im[(static_cast<long long>(y0) * W + x1) * ip + c], wc, r);
+                r = hfma(im[(static_cast<long long>(y1) * W + x1) * ip + c], wd, r);
+                out[(static_cast<long long>(h) * W + w) * op + c] = r;
+            }
+        }
+    return 0;
+}
+
 // ---- entropy-parameter kernels: one latent pixel at a time, channels in ascending order (the order the warp-ballot
 //      compaction produces)
 static inline int active_group(const EntropyDev& d, int h, int w)
@@ -428,6 +527,11 @@ static const KernelEntry kTable[] = {
     { "entropy_build_symbols_full_kernel", 1, { static_cast<int>(sizeof(EntropyDev)) }, emu_build_symbols_full },
     { "entropy_recover_dense_kernel", 3, { static_cast<int>(sizeof(EntropyDev)), 8, 8 }, emu_recover_dense },
     { "entropy_restore_dense_kernel", 1, { static_cast<int>(sizeof(EntropyDev)) }, emu_restore_dense },
+    { "yuv420_to_frame_kernel", 9, { 8, 8, 8, 4, 4, 8, 8, 8, 8 }, emu_yuv420_to_frame },
+    { "frame_to_yuv420_kernel", 9, { 8, 8, 8, 8, 4, 4, 8, 8, 8 }, emu_frame_to_yuv420 },
+    { "sse_u8_kernel", 4, { 8, 8, 8, 8 }, emu_sse_u8 },
+    { "square_kernel", 6, { 8, 4, 8, 4, 8, 4 }, emu_square },
+    { "warp_bilinear_kernel", 11, { 8, 4, 8, 8, 8, 8, 8, 4, 4, 4, 4 }, emu_warp_bilinear },
 };
 
 extern "C" {

@@ -12,6 +12,11 @@ points are replaced by tests/cpp/cuda_dry_shim.cpp (LD_PRELOAD):
   numbers; they are compared with the CPU oracle of each codec with the tolerances of the GPU parity tests
   (bytes within 2 %, PSNR within 0.1 dB) plus encoder/decoder state identity.
 
+* the `-m gpu` test files themselves, unmodified, in the same emulated process (tests/dry_pytest_runner.py +
+  tests/dry_torch_patch.py answer torch's `cuda` idioms with host memory): model mirrors -> inference_extensions_cuda
+  -> proxies -> C ABI -> emulated kernels.  By default the op-level file and one sequence-driver case; with
+  DCVC_B200_DRY_FULL=1 also the small cases of every codec file (~10 more minutes).
+
 This is test infrastructure: nothing under dcvc_b200/ can reach the shim, and the kernels themselves (tcgen05 / TMA
 code) are only exercised by the `-m gpu` tests.  HT-L (experimental, never run on a device) is covered here too."""
 import json
@@ -92,3 +97,34 @@ def test_emulated_codec_matches_its_oracle(dry, codec, sizes):
         if "symbols" in run:
             for n, n_ref in zip(run["symbols"], run["ref_symbols"]):
                 assert abs(n - n_ref) <= 0.01 * n_ref + 4
+
+
+def _pytest_under_emulation(dry, args, timeout=3000):
+    lib, shim = dry
+    env = dict(os.environ)
+    env.update({"LD_PRELOAD": shim, "LD_LIBRARY_PATH": CUDA_LIB + ":" + env.get("LD_LIBRARY_PATH", ""),
+                "DCVC_B200_EXPERIMENTAL_HTL": "1", "DCVC_B200_RANS_SPIN_US": "0", "DRY_SHIM_EMULATE": "1"})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests/dry_pytest_runner.py"), lib] + args + ["-q", "-x"],
+                       env=env, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    tail = r.stdout[-3000:] + r.stderr[-2000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and " failed" not in r.stdout and " error" not in r.stdout.lower().replace("errors=", ""), tail
+
+
+FULL = os.environ.get("DCVC_B200_DRY_FULL") == "1"
+GPU_FILES_UNDER_EMULATION = [
+    ("ops", ["tests/test_ops_gpu.py"], True),
+    ("sequence-ld", ["tests/test_sequence_gpu.py", "-k", "ld"], True),
+    ("sequence-hts", ["tests/test_sequence_gpu.py", "-k", "hts"], False),
+    ("htl", ["tests/test_htl_gpu.py", "-k", "64-64 or oracle or bit_identical"], False),
+    ("hts", ["tests/test_hts_gpu.py", "-k", "64-64 or oracle or bit_identical"], False),
+    ("ld", ["tests/test_ld_gpu.py", "-k", "64-64 or oracle or bit_identical"], False),
+    ("intra", ["tests/test_codec_gpu.py", "-k", "bit_exact and (256-256-32 or 64-64-0 or 200-328-63) or oracle"], False),
+]
+
+
+@pytest.mark.parametrize("name,args,default", GPU_FILES_UNDER_EMULATION, ids=[g[0] for g in GPU_FILES_UNDER_EMULATION])
+def test_gpu_test_files_run_under_emulation(dry, name, args, default):
+    if not default and not FULL:
+        pytest.skip("set DCVC_B200_DRY_FULL=1 for the long emulated runs")
+    _pytest_under_emulation(dry, args)
