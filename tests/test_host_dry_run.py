@@ -128,3 +128,14 @@ def test_gpu_test_files_run_under_emulation(dry, name, args, default):
     if not default and not FULL:
         pytest.skip("set DCVC_B200_DRY_FULL=1 for the long emulated runs")
     _pytest_under_emulation(dry, args)
+
+
+def test_smoke_entry_under_emulation(dry):
+    """__graft_entry__.smoke() (the first thing the GPU box runs) end to end on the emulated runtime"""
+    lib, shim = dry
+    env = dict(os.environ)
+    env.update({"LD_PRELOAD": shim, "LD_LIBRARY_PATH": CUDA_LIB + ":" + env.get("LD_LIBRARY_PATH", ""),
+                "DCVC_B200_RANS_SPIN_US": "0", "DRY_SHIM_EMULATE": "1"})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests/dry_smoke_runner.py"), lib], env=env, capture_output=True,
+                       text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and "smoke-under-emulation ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
