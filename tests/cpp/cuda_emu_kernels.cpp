@@ -79,6 +79,31 @@ static int emu_pw_gemm(void** args)
     const int n_out = p.chunk_add ? N / 4 : N;
     const int out_c = up ? p.phase_c : n_out;
     if (static_cast<int>(Cm->dims[0]) != out_c) { fprintf(stderr, "emu pw_gemm: C channels %d != %d\n", (int)Cm->dims[0], out_c); return 1; }
+    // hazards the sequential restatement would hide: a kernel whose tiles run concurrently must not write where another
+    // tile still reads.  Spatial taps / pixel-shuffle outputs may not overlap the input at all; a 1x1 may only overlap
+    // it pixel for pixel (same base and pitch), and then must not widen or narrow the row
+    {
+        auto extent = [](const FakeMap* m) {
+            size_t e = m->dims[0] * 2;
+            for (uint32_t d = 1; d < m->rank; ++d) e += (m->dims[d] - 1) * m->strides[d - 1];
+            return e;
+        };
+        const uint8_t *a0 = A->ptr, *a1 = A->ptr + extent(A), *c0 = Cm->ptr, *c1 = Cm->ptr + extent(Cm);
+        const bool overlap = a0 < c1 && c0 < a1;
+        if (overlap) {
+            const bool same_rows = !up && taps == 1 && A->rank == Cm->rank && A->strides[A->rank == 2 ? 0 : 1] == Cm->strides[Cm->rank == 2 ? 0 : 1];
+            // channel windows of one cat buffer (same pitch, disjoint channel ranges) are fine for any kind
+            const size_t pitch = A->strides[A->rank == 2 ? 0 : 1];
+            const size_t a_off = static_cast<size_t>(a0 - (a0 < c0 ? a0 : c0)) % pitch, c_off = static_cast<size_t>(c0 - (a0 < c0 ? a0 : c0)) % pitch;
+            const bool disjoint_channels = pitch == Cm->strides[Cm->rank == 2 ? 0 : 1] &&
+                                           (a_off + A->dims[0] * 2 <= c_off || c_off + Cm->dims[0] * 2 <= a_off) &&
+                                           A->dims[0] * 2 + Cm->dims[0] * 2 <= pitch;
+            if (!disjoint_channels && !(same_rows && a0 == c0)) {
+                fprintf(stderr, "emu pw_gemm: output overlaps the input (taps %d, upsample %d)\n", taps, up ? 1 : 0);
+                return 1;
+            }
+        }
+    }
     // weights as float [N][Ktot]
     std::vector<float> W(static_cast<size_t>(N) * Ktot);
     {
