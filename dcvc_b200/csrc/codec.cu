@@ -32,6 +32,7 @@ public:
     void decompress(const uint8_t* bs, int len, int qp, int height, int width, int ec_parallel,
                     cudaStream_t stream, void* x_hat_out);
     int debug_fetch(const char* name, void* dst, int64_t max_bytes, int64_t* written) override;
+    int arena_overflow_blocks() const override { return arena_.overflow_blocks(); }
 
 private:
 
@@ -718,6 +719,14 @@ int dcvc_debug_fetch(dcvc_codec* h, const char* name, void* host_dst, int64_t ma
                      int64_t* bytes_written)
 {
     CODEC_TRY(h)
+    if (strcmp(name, "arena_overflow_blocks") == 0) {
+        // how many times the activation arena had to grow beyond the plan's estimate (0 when the estimate is right)
+        if (max_bytes < 4) throw std::runtime_error("debug_fetch: buffer too small");
+        const int32_t n = h->base->arena_overflow_blocks();
+        memcpy(host_dst, &n, 4);
+        *bytes_written = 4;
+        return 0;
+    }
     return h->base->debug_fetch(name, host_dst, max_bytes, bytes_written);
     CODEC_CATCH(h)
 }

@@ -65,35 +65,51 @@ static __global__ void view_checksum_kernel(const uint16_t* __restrict__ p, int 
 }
 
 // bump allocator over one cudaMalloc block
+// Device arena of one plan: one cudaMalloc sized from the plan's estimate, carved with 1 KB alignment.  If the estimate
+// turns out short (a size / padding combination the formula missed), further blocks are added instead of failing:
+// pointers already handed out stay valid, and `overflow_blocks()` tells the tests that the estimate needs fixing.
 class Arena {
 public:
     ~Arena() { release(); }
     void release()
     {
         if (base_) cudaFree(base_);
-        base_ = nullptr;
+        for (void* p : extra_) cudaFree(p);
+        extra_.clear();
+        base_ = cur_ = nullptr;
         cap_ = used_ = 0;
     }
     void reserve(size_t bytes)
     {
         release();
         CK(cudaMalloc(&base_, bytes));
+        cur_ = base_;
         cap_ = bytes;
         used_ = 0;
     }
     void* alloc(size_t bytes)
     {
-        const size_t off = (used_ + 1023) & ~static_cast<size_t>(1023);
-        if (off + bytes > cap_) throw std::runtime_error("device arena exhausted");
+        size_t off = (used_ + 1023) & ~static_cast<size_t>(1023);
+        if (off + bytes > cap_) {
+            const size_t block = std::max(bytes + 1024, static_cast<size_t>(32) << 20);
+            void* p = nullptr;
+            CK(cudaMalloc(&p, block));
+            extra_.push_back(p);
+            cur_ = p;
+            cap_ = block;
+            off = 0;
+        }
         used_ = off + bytes;
-        return static_cast<uint8_t*>(base_) + off;
+        return static_cast<uint8_t*>(cur_) + off;
     }
     __half* halves(size_t n) { return static_cast<__half*>(alloc(n * 2)); }
-    size_t used() const { return used_; }
     void* base() const { return base_; }
+    int overflow_blocks() const { return static_cast<int>(extra_.size()); }
 
 private:
-    void* base_ = nullptr;
+    void* base_ = nullptr;   // first block (the estimate)
+    void* cur_ = nullptr;    // block being carved
+    std::vector<void*> extra_;
     size_t cap_ = 0, used_ = 0;
 };
 
@@ -201,6 +217,7 @@ public:
 
     virtual void finalize(float skip_thres) = 0;
     virtual int debug_fetch(const char* name, void* dst, int64_t max_bytes, int64_t* written) = 0;
+    virtual int arena_overflow_blocks() const { return 0; }   // > 0: the plan's arena estimate was short (tests)
 
     void set_param(const char* name, const void* data, int dtype, int ndim, const int64_t* shape, int on_device)
     {

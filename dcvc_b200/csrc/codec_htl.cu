@@ -24,6 +24,7 @@ public:
 
     void finalize(float skip_thres) override;
     int debug_fetch(const char* name, void* dst, int64_t max_bytes, int64_t* written) override;
+    int arena_overflow_blocks() const override { return arena_.overflow_blocks(); }
 
     void add_ref(const void* frame, int H, int W, int64_t sc, int64_t sh, int64_t sw, int apply, cudaStream_t stream);
     void compress(const void* x, int H, int W, int64_t sc, int64_t sh, int64_t sw, int qp, int reset, int pad_b,

@@ -23,6 +23,7 @@ public:
 
     void finalize(float skip_thres) override;
     int debug_fetch(const char* name, void* dst, int64_t max_bytes, int64_t* written) override;
+    int arena_overflow_blocks() const override { return arena_.overflow_blocks(); }
 
     void add_ref(const void* frame, int H, int W, int64_t sc, int64_t sh, int64_t sw, int apply, cudaStream_t stream);
     void compress(const void* x, int H, int W, int64_t sc, int64_t sh, int64_t sw, int qp, int reset, int pad_b,
@@ -172,7 +173,7 @@ void HtsCodec::plan(int height, int width)
     const bool padded = (H16p_ != H16_) || (W16p_ != W16_);
 
     size_t bytes = p8 * 2 * (2048 + 1024 + 192 + 512 + 512 + 192 * kG + 4 * 512);
-    bytes += p16p * 2 * (4 * 768 + 256 + 256 + 768 + 768 + 512 + 256 + 256);
+    bytes += p16p * 2 * (4 * 768 + 256 + 256 + 768 + 256 + 768 + 512 + 256 + 256);  // l16 x4, y, ypad, cat_pf, hyp_p, common, cat_sp, means, yhat
     bytes += p32 * 2 * 4 * 256 + p64 * 2 * 4 * 256 + p64 * kZ * 3;
     bytes += n_lat_ * (1 + 2 + 2 + 1 + 1 + 1) + p16 * 8 + (2u << 20) + 64 * 4096;
     arena_.reserve(bytes);

@@ -143,6 +143,7 @@ def run_intra(lib, mode, sizes):
             totals = hd.fetch("totals", np.int32, 16)
             rec["symbols"] = [int(v) for v in totals]
             rec["ref_symbols"] = [len(s) for s in ref["symbols"]]
+        rec["arena_overflow_blocks"] = int(hd.fetch("arena_overflow_blocks", np.int32, 4)[0])
         out.append(rec)
     hd.close()
     return out
@@ -218,6 +219,7 @@ def run_video(lib, mode, which, sizes):
                     src = x[:, 3 * f:3 * f + 3]
                     rec["psnr"].append(psnr(nhwc_to_tensor(recon[c][f])[:, :, :H, :W], src))
                     rec["ref_psnr"].append(psnr(ref_hats[f][:, :, :H, :W], src))
+        rec["arena_overflow_blocks"] = int(hd.fetch("arena_overflow_blocks", np.int32, 4)[0])
         out.append(rec)
     hd.close()
     return out

@@ -72,11 +72,13 @@ REFERENCE_DECODE_WORK = {"intra": (5.89, 701.2), "hts": (14.09, 1483.4), "ld": (
 
 @pytest.mark.parametrize("codec", ["intra", "hts", "ld", "htl"])
 def test_host_flow_plans_and_runs_at_all_sizes(dry, codec):
-    res = _run(dry, "plan", codec, ["64x64", "200x328", "1080x1920"])
-    assert len(res["runs"]) == 3 and res["launches"] > 100 and res["tensor_maps"] > 100
+    res = _run(dry, "plan", codec, ["64x64", "200x328", "1080x1920", "2160x3840", "1096x1928"])
+    assert len(res["runs"]) == 5 and res["launches"] > 100 and res["tensor_maps"] > 100
     for run in res["runs"]:
         sizes = run["bytes"] if isinstance(run["bytes"], list) else [run["bytes"]]
         assert all(s > 4 for s in sizes)            # an all-skipped picture still carries z
+        # the arena estimate of the plan covered every buffer (HT-S at 4K once did not: hyper-prior padding buffer)
+        assert run["arena_overflow_blocks"] == 0, (codec, run["size"])
     # the launches of one 1080p decode book exactly the reference network's work: no op missing, none counted twice
     gb, gmac = REFERENCE_DECODE_WORK[codec]
     full = res["runs"][2]

@@ -63,7 +63,8 @@ def _run(i_net, p_net, h, w, n_chunks, qp_i, qp_p, reset_at, seed=300):
     return frames, streams, recon, enc_feature, dec_feature
 
 
-@pytest.mark.parametrize("h,w,n_chunks,reset_at", [(64, 64, 3, (1,)), (200, 328, 2, ()), (1080, 1920, 3, (1,))])
+@pytest.mark.parametrize("h,w,n_chunks,reset_at", [(64, 64, 3, (1,)), (200, 328, 2, ()), (1080, 1920, 3, (1,)),
+                                                   (2160, 3840, 1, ())])   # 4K: configs[4]; hyper path padded 135 -> 136 rows
 def test_chunk_roundtrip_state_consistency(nets, h, w, n_chunks, reset_at):
     """size-independent property: after decoding the stream, the decoder holds bit-identical feature_p
     (the state the next chunk conditions on) to what the encoder derived — i.e. no encoder/decoder drift —

@@ -51,7 +51,8 @@ def _run(i_net, p_net, h, w, n_frames, qp_i, qp_p, reset_at, seed=300):
     return frames, streams, recon, enc_state, dec_state
 
 
-@pytest.mark.parametrize("h,w,n_frames,reset_at", [(64, 64, 4, (1,)), (200, 328, 3, ()), (1080, 1920, 3, (1,))])
+@pytest.mark.parametrize("h,w,n_frames,reset_at", [(64, 64, 4, (1,)), (200, 328, 3, ()), (1080, 1920, 3, (1,)),
+                                                   (2160, 3840, 2, ())])
 def test_frame_roundtrip_state_consistency(nets, h, w, n_frames, reset_at):
     """after decoding everything the decoder holds the feature_p the encoder holds (bit for bit): the two state
     machines (eager memory update in compress, lazy in decompress) agree, and every frame decodes to a sane picture"""
