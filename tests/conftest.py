@@ -12,7 +12,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
 
 
+# Device cases that were written after the round's GPU budget ran out and have only run under the CPU tier's
+# kernel emulation so far.  The driver runs `pytest -x`: they go last, so a surprise in one of them cannot hide the
+# results of the device-validated cases behind it.  Remove an entry once its first device run is green.
+FIRST_DEVICE_RUN = ("test_sequence_gpu.py", "test_hts_gpu.py::test_chunk_roundtrip_state_consistency[2160-3840",
+                    "test_ld_gpu.py::test_frame_roundtrip_state_consistency[2160-3840")
+
+
 def pytest_collection_modifyitems(config, items):
+    items.sort(key=lambda it: any(tag in it.nodeid for tag in FIRST_DEVICE_RUN))  # stable: order kept otherwise
     try:
         import torch
         has_gpu = torch.cuda.is_available()
