@@ -135,7 +135,7 @@ def run_intra(lib, mode, sizes):
         if mode == "check":
             from oracle.dmci_oracle import DmciOracle
             assert np.array_equal(xh_enc.view(np.uint16), xh_dec.view(np.uint16)), "decoder reconstruction differs from the encoder's"
-            o = DmciOracle(synth_state_dict(dmci_spec(), 0), skip_thres=SKIP, emulate_fp16=True, threads=8)
+            o = DmciOracle(synth_state_dict(dmci_spec(), 0), skip_thres=SKIP, emulate_fp16=True, threads=int(os.environ.get("DCVC_DRY_THREADS", "8")))
             ref = o.compress(xt, 32, Hp - H, Wp - W)
             rec["ref_bytes"] = len(ref["bit_stream"])
             rec["psnr"] = psnr(nhwc_to_tensor(xh_enc)[:, :, :H, :W], xt)
@@ -205,8 +205,8 @@ def run_video(lib, mode, which, sizes):
             e, d = enc_state.reshape(-1, fam_c)[:, half:], dec_state.reshape(-1, fam_c)[:, half:]
             assert np.array_equal(e, d), "decoder feature_p differs from the encoder's"
             mod = __import__(oracle_cls[0], fromlist=[oracle_cls[1]])
-            oe = getattr(mod, oracle_cls[1])(synth_state_dict(spec, seed), SKIP, True, threads=8)
-            od = getattr(mod, oracle_cls[1])(synth_state_dict(spec, seed), SKIP, True, threads=8)
+            oe = getattr(mod, oracle_cls[1])(synth_state_dict(spec, seed), SKIP, True, threads=int(os.environ.get("DCVC_DRY_THREADS", "8")))
+            od = getattr(mod, oracle_cls[1])(synth_state_dict(spec, seed), SKIP, True, threads=int(os.environ.get("DCVC_DRY_THREADS", "8")))
             oe.add_ref_feature_from_frame(ref_frame, True)
             od.add_ref_feature_from_frame(ref_frame, False)
             rec["ref_bytes"], rec["psnr"], rec["ref_psnr"] = [], [], []

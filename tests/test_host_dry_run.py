@@ -24,6 +24,7 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 import pytest
 
@@ -48,19 +49,65 @@ def dry(tmp_path_factory):
     subprocess.run([gxx, "-O2", "-shared", "-fPIC", "-std=c++17", "-I/usr/local/cuda/include",
                     os.path.join(ROOT, "tests/cpp/cuda_dry_shim.cpp"), os.path.join(ROOT, "tests/cpp/cuda_emu_kernels.cpp"),
                     "-o", shim], check=True, capture_output=True)
-    return lib, shim
+    return _Dry(lib, shim)
 
 
-def _run(dry, mode, codec, sizes, timeout=900):
-    lib, shim = dry
-    env = dict(os.environ)
-    env.update({"LD_PRELOAD": shim, "LD_LIBRARY_PATH": CUDA_LIB + ":" + env.get("LD_LIBRARY_PATH", ""),
-                "DCVC_B200_EXPERIMENTAL_HTL": "1", "DCVC_B200_RANS_SPIN_US": "0"})
-    env.pop("DRY_SHIM_EMULATE", None)
-    if mode == "check":
-        env["DRY_SHIM_EMULATE"] = "1"
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests/dry_host_flow.py"), lib, shim, mode, codec] + sizes,
-                       env=env, capture_output=True, text=True, timeout=timeout)
+class _Dry:
+    """The emulated runs are independent subprocesses (each mostly one busy thread): every default job of this file is
+    started when the first test asks for one and they run side by side; a test then only waits for its own job.
+    Serially the file took ~7 minutes of the CPU suite."""
+
+    def __init__(self, lib, shim):
+        self.lib, self.shim = lib, shim
+        self.pool = ThreadPoolExecutor(max_workers=max(2, min(6, (os.cpu_count() or 2) - 2)))
+        self.jobs = {}
+
+    def env(self, emulate, htl=True):
+        env = dict(os.environ)
+        env.update({"LD_PRELOAD": self.shim, "LD_LIBRARY_PATH": CUDA_LIB + ":" + env.get("LD_LIBRARY_PATH", ""),
+                    "DCVC_B200_RANS_SPIN_US": "0", "OMP_NUM_THREADS": "2", "MKL_NUM_THREADS": "2", "DCVC_DRY_THREADS": "2"})
+        if htl:
+            env["DCVC_B200_EXPERIMENTAL_HTL"] = "1"
+        env.pop("DRY_SHIM_EMULATE", None)
+        if emulate:
+            env["DRY_SHIM_EMULATE"] = "1"
+        return env
+
+    def submit(self, key, cmd, env, timeout):
+        if key not in self.jobs:
+            self.jobs[key] = self.pool.submit(subprocess.run, cmd, env=env, capture_output=True, text=True,
+                                              timeout=timeout, cwd=ROOT)
+
+    def start_defaults(self):
+        for codec, sizes in PLAN_JOBS:
+            self.submit_flow("plan", codec, sizes)
+        for codec, sizes in CHECK_JOBS:
+            self.submit_flow("check", codec, sizes)
+        for name, args, default in GPU_FILES_UNDER_EMULATION:
+            if default or FULL:
+                self.submit_pytest(name, args)
+        self.submit_smoke()
+
+    def submit_flow(self, mode, codec, sizes):
+        self.submit((mode, codec), [sys.executable, os.path.join(ROOT, "tests/dry_host_flow.py"), self.lib, self.shim, mode,
+                                    codec] + sizes, self.env(mode == "check"), 1800)
+
+    def submit_pytest(self, name, args):
+        self.submit(("pytest", name), [sys.executable, os.path.join(ROOT, "tests/dry_pytest_runner.py"), self.lib] + args +
+                    ["-q", "-x"], self.env(True), 3000)
+
+    def submit_smoke(self):
+        self.submit(("smoke",), [sys.executable, os.path.join(ROOT, "tests/dry_smoke_runner.py"), self.lib],
+                    self.env(True, htl=False), 900)
+
+    def result(self, key):
+        self.start_defaults()
+        return self.jobs[key].result()
+
+
+def _run(dry, mode, codec, sizes):
+    dry.submit_flow(mode, codec, sizes)
+    r = dry.result((mode, codec))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
 
@@ -70,9 +117,14 @@ def _run(dry, mode, codec, sizes, timeout=900):
 REFERENCE_DECODE_WORK = {"intra": (5.89, 701.2), "hts": (14.09, 1483.4), "ld": (2.80, 147.8), "htl": (17.33, 2001.8)}
 
 
+PLAN_SIZES = ["64x64", "200x328", "1080x1920", "2160x3840", "1096x1928"]
+PLAN_JOBS = [(c, PLAN_SIZES) for c in ("intra", "hts", "ld", "htl")]
+CHECK_JOBS = [("intra", ["64x64", "72x104"]), ("hts", ["72x104"]), ("ld", ["72x104"]), ("htl", ["72x104"])]
+
+
 @pytest.mark.parametrize("codec", ["intra", "hts", "ld", "htl"])
 def test_host_flow_plans_and_runs_at_all_sizes(dry, codec):
-    res = _run(dry, "plan", codec, ["64x64", "200x328", "1080x1920", "2160x3840", "1096x1928"])
+    res = _run(dry, "plan", codec, PLAN_SIZES)
     assert len(res["runs"]) == 5 and res["launches"] > 100 and res["tensor_maps"] > 100
     for run in res["runs"]:
         sizes = run["bytes"] if isinstance(run["bytes"], list) else [run["bytes"]]
@@ -86,10 +138,9 @@ def test_host_flow_plans_and_runs_at_all_sizes(dry, codec):
     assert abs(full["decode_gmac"] - gmac) <= 0.002 * gmac, (codec, full["decode_gmac"], gmac)
 
 
-@pytest.mark.parametrize("codec,sizes", [("intra", ["64x64", "72x104"]), ("hts", ["72x104"]), ("ld", ["72x104"]),
-                                         ("htl", ["72x104"])])
+@pytest.mark.parametrize("codec,sizes", CHECK_JOBS)
 def test_emulated_codec_matches_its_oracle(dry, codec, sizes):
-    res = _run(dry, "check", codec, sizes, timeout=1800)
+    res = _run(dry, "check", codec, sizes)
     for run in res["runs"]:
         as_list = lambda v: v if isinstance(v, list) else [v]  # noqa: E731
         for n, n_ref in zip(as_list(run["bytes"]), as_list(run["ref_bytes"])):
@@ -101,13 +152,9 @@ def test_emulated_codec_matches_its_oracle(dry, codec, sizes):
                 assert abs(n - n_ref) <= 0.01 * n_ref + 4
 
 
-def _pytest_under_emulation(dry, args, timeout=3000):
-    lib, shim = dry
-    env = dict(os.environ)
-    env.update({"LD_PRELOAD": shim, "LD_LIBRARY_PATH": CUDA_LIB + ":" + env.get("LD_LIBRARY_PATH", ""),
-                "DCVC_B200_EXPERIMENTAL_HTL": "1", "DCVC_B200_RANS_SPIN_US": "0", "DRY_SHIM_EMULATE": "1"})
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests/dry_pytest_runner.py"), lib] + args + ["-q", "-x"],
-                       env=env, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+def _pytest_under_emulation(dry, name, args):
+    dry.submit_pytest(name, args)
+    r = dry.result(("pytest", name))
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and " failed" not in r.stdout and " error" not in r.stdout.lower().replace("errors=", ""), tail
@@ -129,15 +176,11 @@ GPU_FILES_UNDER_EMULATION = [
 def test_gpu_test_files_run_under_emulation(dry, name, args, default):
     if not default and not FULL:
         pytest.skip("set DCVC_B200_DRY_FULL=1 for the long emulated runs")
-    _pytest_under_emulation(dry, args)
+    _pytest_under_emulation(dry, name, args)
 
 
 def test_smoke_entry_under_emulation(dry):
     """__graft_entry__.smoke() (the first thing the GPU box runs) end to end on the emulated runtime"""
-    lib, shim = dry
-    env = dict(os.environ)
-    env.update({"LD_PRELOAD": shim, "LD_LIBRARY_PATH": CUDA_LIB + ":" + env.get("LD_LIBRARY_PATH", ""),
-                "DCVC_B200_RANS_SPIN_US": "0", "DRY_SHIM_EMULATE": "1"})
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests/dry_smoke_runner.py"), lib], env=env, capture_output=True,
-                       text=True, timeout=900, cwd=ROOT)
+    dry.submit_smoke()
+    r = dry.result(("smoke",))
     assert r.returncode == 0 and "smoke-under-emulation ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
