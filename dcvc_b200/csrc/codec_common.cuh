@@ -146,6 +146,12 @@ struct Segment {
     std::vector<double> flops;
     std::vector<ActView> out_views; // output view per op where known (DCVC_B200_OPSUM debugging)
     std::vector<std::string> notes;
+    // capture lane per op.  Lane 0 is the caller's stream; ops of other lanes are captured on side streams that fork
+    // from the segment's start and join at its end, i.e. the lanes become parallel branches of the graph (only for
+    // op groups that share no buffers: the 8 recon heads of the chunk codecs).  Outside graphs everything runs in list
+    // order on one stream.
+    std::vector<int> lanes;
+    int cur_lane = 0, n_lanes = 1;
     cudaGraphExec_t exec = nullptr;
     int launches = 0;
     // tile-level chaining of consecutive 1x1 GEMMs (pw_gemm.cuh: done_flags / wait_a): the flag words of this
@@ -163,7 +169,15 @@ struct Segment {
             kinds.push_back(kind);
             alg_bytes.push_back(bytes);
             flops.push_back(fl);
+            lanes.push_back(cur_lane);
         }
+    }
+    void set_lane(int l)
+    {
+        annotate(OP_ELEM, 0, 0);  // ops pushed so far keep the lane they were pushed under
+        break_chain();
+        cur_lane = l;
+        if (l + 1 > n_lanes) n_lanes = l + 1;
     }
     void elem(OpFn f)
     {
@@ -181,7 +195,8 @@ struct Segment {
     {
         if (exec) cudaGraphExecDestroy(exec);
         exec = nullptr;
-        ops.clear(); kinds.clear(); alg_bytes.clear(); flops.clear();
+        ops.clear(); kinds.clear(); alg_bytes.clear(); flops.clear(); lanes.clear();
+        cur_lane = 0; n_lanes = 1;
         launches = 0;
         flag_begin = nullptr;
         flag_words = 0;
@@ -211,6 +226,9 @@ public:
         if (own_stream_) cudaStreamDestroy(own_stream_);
         if (ev_hop_) cudaEventDestroy(ev_hop_);
         if (ev_y_) cudaEventDestroy(ev_y_);
+        if (ev_fork_) cudaEventDestroy(ev_fork_);
+        for (auto& st : lane_streams_) cudaStreamDestroy(st);
+        for (auto& e : lane_events_) cudaEventDestroy(e);
         for (auto& e : tev_) cudaEventDestroy(e);
         for (auto& e : prof_events_) cudaEventDestroy(e);
     }
@@ -585,17 +603,46 @@ protected:
         if (use_graphs_) {
             if (!s.exec) {
                 cudaGraph_t graph = nullptr;
+                const int n_lanes = s.n_lanes;
+                if (n_lanes > 1) {  // side streams / events exist before the capture starts
+                    if (!ev_fork_) CK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+                    while (static_cast<int>(lane_streams_.size()) < n_lanes - 1) {
+                        cudaStream_t st = nullptr;
+                        cudaEvent_t ev = nullptr;
+                        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+                        lane_streams_.push_back(st);
+                        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                        lane_events_.push_back(ev);
+                    }
+                }
                 CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
                 if (s.flag_words) cudaMemsetAsync(s.flag_begin, 0, s.flag_words * sizeof(int), stream);
                 int rc = 0;
-                for (auto& op : s.ops) {
-                    rc = op(stream);
-                    if (rc) break;
+                std::string lane_err;
+                if (n_lanes > 1) {  // fork: every lane starts where the segment starts
+                    if (cudaEventRecord(ev_fork_, stream) != cudaSuccess) rc = 1;
+                    for (int l = 1; l < n_lanes && !rc; ++l)
+                        if (cudaStreamWaitEvent(lane_streams_[l - 1], ev_fork_, 0) != cudaSuccess) rc = 1;
+                    if (rc) lane_err = "fork of the capture lanes failed";
+                }
+                for (size_t i = 0; i < s.ops.size() && !rc; ++i) {
+                    const int l = (n_lanes > 1 && i < s.lanes.size()) ? s.lanes[i] : 0;
+                    rc = s.ops[i](l == 0 ? stream : lane_streams_[l - 1]);
+                }
+                if (n_lanes > 1) {  // join (also after a failed op: an unjoined capture cannot be ended)
+                    for (int l = 1; l < n_lanes; ++l) {
+                        if (cudaEventRecord(lane_events_[l - 1], lane_streams_[l - 1]) != cudaSuccess ||
+                            cudaStreamWaitEvent(stream, lane_events_[l - 1], 0) != cudaSuccess) {
+                            if (!rc) lane_err = "join of the capture lanes failed";
+                            rc = 1;
+                        }
+                    }
                 }
                 cudaError_t e = cudaStreamEndCapture(stream, &graph);
                 if (rc || e != cudaSuccess) {
                     if (graph) cudaGraphDestroy(graph);
-                    throw std::runtime_error(std::string("graph capture failed: ") + (rc ? gemm_last_error() : cudaGetErrorString(e)));
+                    throw std::runtime_error(std::string("graph capture failed: ") +
+                                             (!lane_err.empty() ? lane_err.c_str() : rc ? gemm_last_error() : cudaGetErrorString(e)));
                 }
                 e = cudaGraphInstantiate(&s.exec, graph, 0);
                 cudaGraphDestroy(graph);
@@ -665,7 +712,9 @@ protected:
     uint8_t* lut_ = nullptr;
     RansCodec rans_;
     cudaStream_t copy_stream_ = nullptr, own_stream_ = nullptr;
-    cudaEvent_t ev_hop_ = nullptr, ev_y_ = nullptr;
+    cudaEvent_t ev_hop_ = nullptr, ev_y_ = nullptr, ev_fork_ = nullptr;
+    std::vector<cudaStream_t> lane_streams_;   // side streams of multi-lane segments (graph capture only)
+    std::vector<cudaEvent_t> lane_events_;
     std::vector<cudaEvent_t> tev_;
     std::vector<cudaEvent_t> prof_events_;
     int tev_n_ = 0;

@@ -48,6 +48,13 @@ private:
     int H8_ = 0, W8_ = 0, H16_ = 0, W16_ = 0, H16p_ = 0, W16p_ = 0, H64_ = 0, W64_ = 0;
     Arena arena_;
     Level l8_, l16_, l32_, l64_;
+    // recon-head lanes (DCVC_B200_HEAD_LANES = 1 | 2 | 4, default 1): the four head pairs share nothing but their
+    // read-only input, so with n lanes pair j runs on lane j % n as a parallel branch of the recon graph, each lane
+    // with its own ping-pong level and its own shared-block output — one persistent GEMM's tail and drain then overlap
+    // the next branch's work instead of idling the SMs.  Measurement switch: not validated on hardware yet.
+    int head_lanes_ = 1;
+    Level lane_l8_[3];
+    __half* lane_common8_[3] = { nullptr, nullptr, nullptr };
     __half *cat_enc_ = nullptr, *cat_fam_ = nullptr, *feature_i_ = nullptr, *temporal_in_ = nullptr, *common8_ = nullptr,
            *head_out_ = nullptr;
     __half *y_ = nullptr, *ypad_ = nullptr, *hyp_p_ = nullptr, *cat_pf_ = nullptr, *common_ = nullptr, *cat_sp_ = nullptr,
@@ -172,7 +179,13 @@ void HtsCodec::plan(int height, int width)
     n_lat_ = p16 * kY;
     const bool padded = (H16p_ != H16_) || (W16p_ != W16_);
 
+    {
+        const char* e = getenv("DCVC_B200_HEAD_LANES");
+        const int n = e ? atoi(e) : 1;
+        head_lanes_ = (n == 2 || n == 4) ? n : 1;
+    }
     size_t bytes = p8 * 2 * (2048 + 1024 + 192 + 512 + 512 + 192 * kG + 4 * 512);
+    bytes += static_cast<size_t>(head_lanes_ - 1) * (p8 * 2 * (4 * 512 + 512) + 5 * 4096);
     bytes += p16p * 2 * (4 * 768 + 256 + 256 + 768 + 256 + 768 + 512 + 256 + 256);  // l16 x4, y, ypad, cat_pf, hyp_p, common, cat_sp, means, yhat
     bytes += p32 * 2 * 4 * 256 + p64 * 2 * 4 * 256 + p64 * kZ * 3;
     bytes += n_lat_ * (1 + 2 + 2 + 1 + 1 + 1) + p16 * 8 + (2u << 20) + 64 * 4096;
@@ -189,6 +202,13 @@ void HtsCodec::plan(int height, int width)
     l8_.H = H8; l8_.W = W8;
     l8_.A = arena_.halves(p8 * 512); l8_.B = arena_.halves(p8 * 512);
     l8_.T1 = arena_.halves(p8 * 512); l8_.T2 = arena_.halves(p8 * 512);
+    for (int l = 0; l + 1 < head_lanes_; ++l) {
+        Level& L = lane_l8_[l];
+        L.H = H8; L.W = W8;
+        L.A = arena_.halves(p8 * 512); L.B = arena_.halves(p8 * 512);
+        L.T1 = arena_.halves(p8 * 512); L.T2 = arena_.halves(p8 * 512);
+        lane_common8_[l] = arena_.halves(p8 * kD);
+    }
     l16_.H = H16p_; l16_.W = W16p_;
     l16_.A = arena_.halves(p16p * 768); l16_.B = arena_.halves(p16p * 768);
     l16_.T1 = arena_.halves(p16p * 768); l16_.T2 = arena_.halves(p16p * 768);
@@ -387,13 +407,17 @@ void HtsCodec::plan(int height, int width)
         // recon head: 4 shared blocks + 8 x (3 blocks + 1x1); head i lands in head_out_[i], head 7 in feature_i
         // (the reset reference, dmc_hts_proxy.cpp:336-338)
         Segment& s = s_recon_;
-        const ActView common = make_view(common8_, kD, kD, W8, H8);
         for (int i = 0; i < kG; ++i) {
-            if (i % 2 == 0) dcb(s, l8_, v_feature_p, rh1_[i / 2], false, nullptr, &common);
-            ActView t = chain(s, l8_, common, rh2_[i], 3, nullptr, nullptr);
+            const int lane = (i / 2) % head_lanes_;
+            if (head_lanes_ > 1) s.set_lane(lane);
+            Level& L = lane == 0 ? l8_ : lane_l8_[lane - 1];
+            const ActView common = make_view(lane == 0 ? common8_ : lane_common8_[lane - 1], kD, kD, W8, H8);
+            if (i % 2 == 0) dcb(s, L, v_feature_p, rh1_[i / 2], false, nullptr, &common);
+            ActView t = chain(s, L, common, rh2_[i], 3, nullptr, nullptr);
             const ActView ho = (i == kG - 1) ? v_feature_i : make_view(head_out_ + static_cast<size_t>(i) * p8 * kSrcI, kSrcI, kSrcI, W8, H8);
             conv1x1(s, t, ho, rh_out_[i]);
         }
+        if (head_lanes_ > 1) s.set_lane(0);
     }
     Segment* segs[] = { &s_enc0_, &s_decoder_, &s_reset_head_, &s_fa_i_, &s_fa_m_, &s_fe_, &s_temporal_, &s_dec1_, &s_dec3_, &s_recon_ };
     for (Segment* s : segs) s->seal();

@@ -15,12 +15,15 @@ def pytest_configure(config):
 # Device cases that were written after the round's GPU budget ran out and have only run under the CPU tier's
 # kernel emulation so far.  The driver runs `pytest -x`: they go last, so a surprise in one of them cannot hide the
 # results of the device-validated cases behind it.  Remove an entry once its first device run is green.
-FIRST_DEVICE_RUN = ("test_sequence_gpu.py", "test_hts_gpu.py::test_chunk_roundtrip_state_consistency[2160-3840",
-                    "test_ld_gpu.py::test_frame_roundtrip_state_consistency[2160-3840")
+FIRST_DEVICE_RUN = ("test_hts_gpu.py::test_chunk_roundtrip_state_consistency[2160-3840",
+                    "test_ld_gpu.py::test_frame_roundtrip_state_consistency[2160-3840", "test_sequence_gpu.py",
+                    "test_hts_gpu.py::test_recon_head_lanes_bit_identical")   # in the order they run
 
 
 def pytest_collection_modifyitems(config, items):
-    items.sort(key=lambda it: any(tag in it.nodeid for tag in FIRST_DEVICE_RUN))  # stable: order kept otherwise
+    def rank(it):
+        return max((i + 1 for i, tag in enumerate(FIRST_DEVICE_RUN) if tag in it.nodeid), default=0)
+    items.sort(key=rank)  # stable: the collection order is kept otherwise
     try:
         import torch
         has_gpu = torch.cuda.is_available()

@@ -36,11 +36,12 @@ typedef struct CUgraph_st* cudaGraph_t;
 typedef struct CUgraphExec_st* cudaGraphExec_t;
 struct dim3 { unsigned x, y, z; };
 
-static std::atomic<long long> g_launches{0}, g_graph_launches{0}, g_maps{0}, g_bytes{0};
+static std::atomic<long long> g_launches{0}, g_graph_launches{0}, g_maps{0}, g_bytes{0}, g_forks{0};
 static int g_fail_map = 0;
 
 long long dry_shim_launches() { return g_launches.load(); }
 long long dry_shim_graph_launches() { return g_graph_launches.load(); }
+long long dry_shim_capture_forks() { return g_forks.load(); }   // streams that joined a capture by waiting for its event
 long long dry_shim_tensor_maps() { return g_maps.load(); }
 long long dry_shim_bytes() { return g_bytes.load(); }
 
@@ -102,11 +103,9 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = static_c
 cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = static_cast<cudaStream_t>(token()); return 0; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return 0; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = static_cast<cudaEvent_t>(token()); return 0; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = static_cast<cudaEvent_t>(token()); return 0; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return 0; }
-cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
 // a captured graph = the launches (kernel + a private copy of its arguments) and memsets issued while capturing
@@ -117,6 +116,38 @@ struct GraphOp {
 };
 struct Graph { std::vector<GraphOp> ops; };
 static std::map<cudaStream_t, Graph*>& capturing() { static std::map<cudaStream_t, Graph*> m; return m; }
+// Cross-stream capture (fork / join), as the runtime does it: an event recorded on a capturing stream carries the
+// capture; a stream that waits for it joins the capture (its launches land in the same graph); every forked stream must
+// have been joined back into the origin stream (record on the fork, wait on the origin) when the capture ends
+// (cudaErrorStreamCaptureUnjoined otherwise).
+struct CaptureState { cudaStream_t origin; std::map<cudaStream_t, bool> forks; /* stream -> joined */ };
+static std::map<Graph*, CaptureState>& capture_state() { static std::map<Graph*, CaptureState> m; return m; }
+static std::map<cudaEvent_t, std::pair<Graph*, cudaStream_t>>& event_capture() { static std::map<cudaEvent_t, std::pair<Graph*, cudaStream_t>> m; return m; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st)
+{
+    auto cap = capturing().find(st);
+    if (cap == capturing().end()) { event_capture().erase(e); return 0; }
+    event_capture()[e] = { cap->second, st };
+    return 0;
+}
+cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t e, unsigned)
+{
+    auto ev = event_capture().find(e);
+    if (ev == event_capture().end()) return 0;
+    Graph* g = ev->second.first;
+    auto cs = capture_state().find(g);
+    if (cs == capture_state().end()) return 0;               // capture already over: a plain (completed) event
+    auto cap = capturing().find(st);
+    if (cap == capturing().end()) {                           // fork
+        capturing()[st] = g;
+        cs->second.forks[st] = false;
+        ++g_forks;
+        return 0;
+    }
+    if (cap->second != g) return 905;                         // cudaErrorStreamCaptureMerge
+    if (st == cs->second.origin && cs->second.forks.count(ev->second.second)) cs->second.forks[ev->second.second] = true;  // join
+    return 0;
+}
 static const bool g_emulate = []() { const char* e = getenv("DRY_SHIM_EMULATE"); return e && e[0] == '1'; }();
 
 static cudaError_t run_op(const GraphOp& op)
@@ -155,15 +186,27 @@ static cudaError_t submit_kernel(const void* fn, void** args, cudaStream_t st)
 cudaError_t cudaStreamBeginCapture(cudaStream_t s, int)
 {
     if (capturing().count(s)) return 900;
-    capturing()[s] = new Graph();
+    Graph* g = new Graph();
+    capturing()[s] = g;
+    capture_state()[g] = CaptureState{ s, {} };
     return 0;
 }
 cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t* g)
 {
     auto it = capturing().find(s);
     if (it == capturing().end()) return 901;
-    *g = reinterpret_cast<cudaGraph_t>(it->second);
+    Graph* gr = it->second;
+    auto cs = capture_state().find(gr);
+    if (cs == capture_state().end() || cs->second.origin != s) return 902;   // cudaErrorStreamCaptureUnmatched
+    bool unjoined = false;
+    for (auto& f : cs->second.forks) {
+        unjoined = unjoined || !f.second;
+        capturing().erase(f.first);
+    }
+    capture_state().erase(cs);
     capturing().erase(it);
+    if (unjoined) { delete gr; *g = nullptr; fprintf(stderr, "dry shim: capture ended with an unjoined forked stream\n"); return 904; }
+    *g = reinterpret_cast<cudaGraph_t>(gr);
     return 0;
 }
 cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long)

@@ -228,7 +228,7 @@ def run_video(lib, mode, which, sizes):
 def main():
     lib = load(sys.argv[1])
     shim = C.CDLL(sys.argv[2])
-    for f in ("dry_shim_launches", "dry_shim_graph_launches", "dry_shim_tensor_maps", "dry_shim_bytes"):
+    for f in ("dry_shim_launches", "dry_shim_graph_launches", "dry_shim_tensor_maps", "dry_shim_bytes", "dry_shim_capture_forks"):
         getattr(shim, f).restype = C.c_longlong
     mode, which = sys.argv[3], sys.argv[4]
     if (mode == "check") != (os.environ.get("DRY_SHIM_EMULATE") == "1"):
@@ -237,7 +237,7 @@ def main():
     res = run_intra(lib, mode, sizes) if which == "intra" else run_video(lib, mode, which, sizes)
     print(json.dumps({"codec": which, "mode": mode, "runs": res, "launches": shim.dry_shim_launches(),
                       "graph_launches": shim.dry_shim_graph_launches(), "tensor_maps": shim.dry_shim_tensor_maps(),
-                      "device_bytes": shim.dry_shim_bytes()}))
+                      "device_bytes": shim.dry_shim_bytes(), "capture_forks": shim.dry_shim_capture_forks()}))
 
 
 if __name__ == "__main__":

@@ -178,6 +178,60 @@ def test_rans_live_against_reference_build(lib, tables):
             assert np.array_equal(dys[k], (ys[k] >> 8).astype(np.int8)), (n_par, k)
 
 
+def test_rans_edge_cases_against_reference_build(lib, tables):
+    """the corners of the symbol format, byte for byte against the reference coder: empty steps (an all-skipped
+    picture still carries z), a single symbol, fewer symbols than streams, the clamp limits -128 / 127 on the
+    narrowest and the widest table rows (escape-coded magnitudes), z at its limits -64 / 63 on every qp row"""
+    from oracle.build_ref import import_ref_shim
+    ref = import_ref_shim()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    zc, zl, yc, yl = tables
+    enc, dec = ref.RansEncoder(), ref.RansDecoder()
+    for c in (enc, dec):
+        c.set_cdf(zc, zl, 0)
+        c.set_cdf(yc, yl, 1)
+    r = _Rans(lib, *tables)
+    rng = np.random.default_rng(11)
+
+    def pack(sym, rows):
+        return ((np.asarray(sym, dtype=np.int32) << 8) + np.asarray(rows, dtype=np.int32)).astype(np.int16)
+
+    e = np.zeros(0, dtype=np.int16)
+    limits = np.array([-128, 127] * 64, dtype=np.int32)
+    cases = {
+        "all steps empty": [e, e, e, e],
+        "only step 2": [e, e, pack(rng.integers(-3, 4, 777), rng.integers(0, 128, 777)), e],
+        "single symbol": [pack([5], [17]), e, e, e],
+        "fewer symbols than streams": [pack([1, -1, 0], [0, 64, 127]), pack([2], [3]), e, pack([-7, 7], [100, 5])],
+        "clamp limits on every row": [pack(limits, np.arange(128)), pack(limits[::-1], np.arange(128)),
+                                      pack(np.full(128, -128), np.zeros(128, dtype=np.int32)),
+                                      pack(np.full(128, 127), np.full(128, 127))],
+    }
+    z_cases = [np.zeros(128, dtype=np.int8), np.tile(np.array([-64, 63], dtype=np.int8), 64 * 3),
+               rng.integers(-64, 64, 128 * 5).astype(np.int8)]
+    n_checked = 0
+    for name, ys in cases.items():
+        for z in z_cases:
+            for n_par in (1, 2, 5, 8):
+                for qp in (0, 63):
+                    enc.reset()
+                    enc.set_entropy_coder_parallel(n_par)
+                    for k in (3, 2, 1, 0):
+                        enc.encode_y(ys[k])
+                    enc.encode_z(z, qp * 128, 128)
+                    enc.flush()
+                    ref_stream = np.asarray(enc.get_encoded_stream()).copy()
+                    mine = r.encode(ys, z, qp, n_par)
+                    assert np.array_equal(mine, ref_stream), (name, n_par, qp)
+                    dz, dys = r.decode(ref_stream, ys, z.size, qp, n_par)
+                    assert np.array_equal(dz, z), (name, n_par, qp)
+                    for k in range(4):
+                        assert np.array_equal(dys[k], (ys[k] >> 8).astype(np.int8)), (name, n_par, qp, k)
+                    n_checked += 1
+    assert n_checked == len(cases) * len(z_cases) * 4 * 2
+
+
 def test_rans_decoder_survives_truncated_and_garbage_streams(lib, tables):
     """a damaged stream must decode to *something* without reading outside the stream buffer: the decoder runs
     unchecked blocks only while a zero-padded margin remains and falls back to a bounds-checked reader behind it

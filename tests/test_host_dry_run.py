@@ -83,14 +83,19 @@ class _Dry:
             self.submit_flow("plan", codec, sizes)
         for codec, sizes in CHECK_JOBS:
             self.submit_flow("check", codec, sizes)
+        self.submit_flow("check", "hts", ["72x104"], {"DCVC_B200_HEAD_LANES": "4"}, tag="lanes4")
+        self.submit_flow("plan", "hts", ["1080x1920", "2160x3840"], {"DCVC_B200_HEAD_LANES": "2"}, tag="lanes2")
         for name, args, default in GPU_FILES_UNDER_EMULATION:
             if default or FULL:
                 self.submit_pytest(name, args)
         self.submit_smoke()
 
-    def submit_flow(self, mode, codec, sizes):
-        self.submit((mode, codec), [sys.executable, os.path.join(ROOT, "tests/dry_host_flow.py"), self.lib, self.shim, mode,
-                                    codec] + sizes, self.env(mode == "check"), 1800)
+    def submit_flow(self, mode, codec, sizes, extra_env=None, tag=None):
+        env = self.env(mode == "check")
+        env.update(extra_env or {})
+        self.submit((mode, codec) if tag is None else (mode, codec, tag),
+                    [sys.executable, os.path.join(ROOT, "tests/dry_host_flow.py"), self.lib, self.shim, mode, codec] + sizes,
+                    env, 1800)
 
     def submit_pytest(self, name, args):
         self.submit(("pytest", name), [sys.executable, os.path.join(ROOT, "tests/dry_pytest_runner.py"), self.lib] + args +
@@ -150,6 +155,25 @@ def test_emulated_codec_matches_its_oracle(dry, codec, sizes):
         if "symbols" in run:
             for n, n_ref in zip(run["symbols"], run["ref_symbols"]):
                 assert abs(n - n_ref) <= 0.01 * n_ref + 4
+
+
+def test_recon_head_lanes_change_nothing_but_the_graph_shape(dry):
+    """DCVC_B200_HEAD_LANES (measurement switch, off by default): the four recon-head pairs of the HT-S decoder become
+    parallel branches of the recon graph, each on its own scratch level.  Under emulation the result must be the one of
+    the single-lane run bit for bit (the branches share nothing but their read-only input), the capture must really fork
+    (and join: the shim ends an unjoined capture with cudaErrorStreamCaptureUnjoined, like the runtime), and the arena
+    estimate must cover the extra scratch levels at 1080p and 4K."""
+    def last_json(r):
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    base = last_json(dry.result(("check", "hts")))
+    lanes = last_json(dry.result(("check", "hts", "lanes4")))
+    assert base["capture_forks"] == 0 and lanes["capture_forks"] >= 3
+    assert lanes["runs"][0]["bytes"] == base["runs"][0]["bytes"]
+    assert lanes["runs"][0]["psnr"] == base["runs"][0]["psnr"]
+    plan = last_json(dry.result(("plan", "hts", "lanes2")))
+    assert plan["capture_forks"] >= 1
+    assert all(run["arena_overflow_blocks"] == 0 for run in plan["runs"])
 
 
 def _pytest_under_emulation(dry, name, args):

@@ -165,3 +165,28 @@ def test_hts_stream_bit_identical_to_reference_coder(nets):
     r.encode_z(z, 40 * 128, 128)
     r.flush()
     assert np.asarray(r.get_encoded_stream()).tobytes() == e["bit_stream"]
+
+
+@pytest.mark.parametrize("lanes", ["2", "4"])
+def test_recon_head_lanes_bit_identical(nets, lanes, monkeypatch):
+    """DCVC_B200_HEAD_LANES (measurement switch, default off): the four recon-head pairs run as parallel branches of the
+    recon graph, each on its own scratch level, so that one persistent GEMM's tail overlaps the next branch's work.  The
+    branches share nothing but their read-only input: streams, every decoded frame and the carried state must equal
+    the single-lane run bit for bit (the CPU tier checks the same under emulation and that the capture forks / joins)."""
+    from dcvc_b200.model import DMC
+    i_net, p_net = nets
+    h, w = 136, 200                                        # ragged: pads to 144 x 208
+    _, streams0, recon0, _, dec0 = _run(i_net, p_net, h, w, 2, 20, 33, ())
+    monkeypatch.setenv("DCVC_B200_HEAD_LANES", lanes)      # read when the codec plans a resolution
+    p2 = DMC.synthetic(1)
+    p2.update(SKIP)
+    p2 = p2.half().to("cuda")
+    _, streams1, recon1, enc1, dec1 = _run(i_net, p2, h, w, 2, 20, 33, ())
+    for a, b in zip(streams0, streams1):
+        assert np.array_equal(np.asarray(a[1]), np.asarray(b[1])) and a[2] == b[2]
+    for a, b in zip(recon0[1:], recon1[1:]):
+        for fa, fb in zip(a, b):
+            assert torch.equal(fa, fb)
+    assert np.array_equal(dec0.view(np.uint16), dec1.view(np.uint16))
+    # feature_p half of the state: encoder and decoder agree (the memory half is updated lazily on the decoder side)
+    assert np.array_equal(enc1.reshape(-1, 1024)[:, 512:].view(np.uint16), dec1.reshape(-1, 1024)[:, 512:].view(np.uint16))

@@ -1,0 +1,65 @@
+#!/bin/bash
+# The first gpurun call of the next round, in one script (about 35 minutes of box time on one B200):
+#   /usr/local/graft/bin/gpurun --timeout 2700 -- 'bash tools/round2_first_call.sh'
+# Every step runs under its own timeout and writes to gpurun_out/r2_*.{log,json,csv}, so a hang costs one step and
+# whatever finished before it comes back.  What it answers (DESIGN.md §0, round-2 plan):
+#   1. are the device cases that only ran under emulation green (4K HT-S / LD, sequence driver, recon-head lanes)?
+#   2. does the experimental HT-L path pass its first device run (tools/validate_htl.sh)?
+#   3. do parallel recon-head branches (DCVC_B200_HEAD_LANES) pay on the HT-S decode?
+#   4. what is the throughput of two concurrent Intra decodes per GPU (bench.py --pipelined)?
+#   5. where does the steady state of the N = K = 384 GEMM go: operand ingest, tensor pipe or epilogue
+#      (DCVC_B200_GEMM_DBG 0 / 1 / 2 / 3 on the streaming, A-resident and CTA-pair kernels)?
+#   6. the round's ncu evidence (tools/profile_round.sh).
+cd ${GRAFT_REPO_ROOT:-.}
+mkdir -p gpurun_out
+O=gpurun_out
+
+echo "== 1. pytest -m gpu"
+timeout 1200 python -m pytest tests -m gpu -q -x > $O/r2_pytest_gpu.log 2>&1
+echo "rc=$?"; tail -3 $O/r2_pytest_gpu.log
+
+echo "== 2. HT-L first device run"
+timeout 1500 bash tools/validate_htl.sh > $O/r2_validate_htl.log 2>&1
+tail -12 $O/r2_validate_htl.log
+
+echo "== 3. recon-head lanes on the HT-S leg"
+for L in 1 2 4; do
+    DCVC_B200_HEAD_LANES=$L timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $O/r2_bench_lanes$L.json 2> $O/r2_bench_lanes$L.err
+    python - <<EOF
+import json
+try:
+    d = json.loads(open("$O/r2_bench_lanes$L.json").read().strip().splitlines()[-1])
+    h = d["hts"]
+    print("lanes $L: hts decode %.1f FPS  gpu-only %.3f ms/chunk  encode %.1f FPS | intra decode %.1f FPS" %
+          (h["decode_fps"], h["gpu_only_ms_per_chunk_decode"], h["encode_fps"], d["value"]))
+except Exception as e:
+    print("lanes $L: no result (%s)" % e)
+EOF
+done
+
+echo "== 4. two concurrent Intra decodes"
+timeout 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-hts --pipelined > $O/r2_bench_pipelined.json 2> $O/r2_bench_pipelined.err
+python -c "
+import json
+d = json.loads(open('$O/r2_bench_pipelined.json').read().strip().splitlines()[-1])
+print('single', d['value'], 'FPS; pipelined', d.get('pipelined'))" 2>&1 | tail -1
+
+echo "== 5. where the steady state of the 384x384 GEMM goes (us per launch, M = 32640)"
+for variant in "ARES=0" "ARES=1 PAIR=0" "ARES=1 PAIR=1"; do
+    for dbg in 0 1 2 3; do
+        envs="DCVC_B200_GEMM_DBG=$dbg"
+        for kv in $variant; do envs="$envs DCVC_B200_GEMM_$kv"; done
+        echo -n "[$variant dbg=$dbg] "
+        env $envs timeout 120 python tools/gemm_micro.py 136 240 384 384 0 0 1 2>&1 | tail -1
+    done
+done | tee $O/r2_gemm_steady_state.log
+for shape in "136 240 384 1536 1 1 0" "136 240 512 256 0 0 1" "68 120 512 512 1 0 0"; do
+    for dbg in 0 3; do
+        echo -n "[stream dbg=$dbg] "
+        DCVC_B200_GEMM_DBG=$dbg timeout 120 python tools/gemm_micro.py $shape 2>&1 | tail -1
+    done
+done | tee -a $O/r2_gemm_steady_state.log
+
+echo "== 6. ncu evidence"
+timeout 1500 bash tools/profile_round.sh r2a > $O/r2_profile_round.log 2>&1
+tail -8 $O/r2_profile_round.log
