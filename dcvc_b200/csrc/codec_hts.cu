@@ -410,8 +410,11 @@ void HtsCodec::plan(int height, int width)
         for (int i = 0; i < kG; ++i) {
             const int lane = (i / 2) % head_lanes_;
             if (head_lanes_ > 1) s.set_lane(lane);
-            Level& L = lane == 0 ? l8_ : lane_l8_[lane - 1];
-            const ActView common = make_view(lane == 0 ? common8_ : lane_common8_[lane - 1], kD, kD, W8, H8);
+            // fault injection for the CPU tier's lane race check (tests/cpp/cuda_dry_shim.cpp): every lane on lane 0's scratch
+            static const bool alias_scratch = []() { const char* e = getenv("DCVC_B200_TEST_ALIAS_LANE_SCRATCH"); return e && e[0] == '1'; }();
+            const bool own = lane != 0 && !alias_scratch;
+            Level& L = own ? lane_l8_[lane - 1] : l8_;
+            const ActView common = make_view(own ? lane_common8_[lane - 1] : common8_, kD, kD, W8, H8);
             if (i % 2 == 0) dcb(s, L, v_feature_p, rh1_[i / 2], false, nullptr, &common);
             ActView t = chain(s, L, common, rh2_[i], 3, nullptr, nullptr);
             const ActView ho = (i == kG - 1) ? v_feature_i : make_view(head_out_ + static_cast<size_t>(i) * p8 * kSrcI, kSrcI, kSrcI, W8, H8);

@@ -25,6 +25,8 @@ extern "C" int emu_lookup(const char* name);
 extern "C" int emu_num_args(int k);
 extern "C" int emu_arg_size(int k, int i);
 extern "C" int emu_run(int k, void** args);
+extern "C" void (*emu_access_hook)(const void* lo, const void* hi, int is_write);
+extern "C" int emu_reported;
 extern "C" unsigned long long emu_map_magic();
 
 extern "C" {
@@ -113,8 +115,9 @@ struct GraphOp {
     int kernel = -1;                       // emulation table index, -1: memset
     std::vector<std::shared_ptr<void>> args;   // 64-byte aligned private copies (PwGemmParams is alignas(64))
     void* dst = nullptr; int value = 0; size_t bytes = 0;
+    cudaStream_t lane = nullptr;           // the stream the op was captured on (parallel branch of the graph)
 };
-struct Graph { std::vector<GraphOp> ops; };
+struct Graph { std::vector<GraphOp> ops; bool multi_lane = false, lanes_checked = false; };
 static std::map<cudaStream_t, Graph*>& capturing() { static std::map<cudaStream_t, Graph*> m; return m; }
 // Cross-stream capture (fork / join), as the runtime does it: an event recorded on a capturing stream carries the
 // capture; a stream that waits for it joins the capture (its launches land in the same graph); every forked stream must
@@ -179,8 +182,55 @@ static cudaError_t submit_kernel(const void* fn, void** args, cudaStream_t st)
         op.args.emplace_back(q, free);
     }
     auto cap = capturing().find(st);
-    if (cap != capturing().end()) { cap->second->ops.push_back(std::move(op)); return 0; }
+    if (cap != capturing().end()) { op.lane = st; cap->second->ops.push_back(std::move(op)); return 0; }
     return run_op(op);
+}
+
+// Lane race check.  The library's multi-lane segments fork every lane at the segment's start and join at its end, so
+// ops captured on different streams of one graph may run concurrently on the device, while this shim runs them one
+// after the other.  On the first (emulated) launch of such a graph every kernel reports the byte ranges it reads and
+// writes; a range written on one lane that overlaps any range touched on another lane fails the launch.
+struct Access { const uint8_t *lo, *hi; int write; cudaStream_t lane; };
+static std::vector<Access>* g_collect = nullptr;
+static cudaStream_t g_collect_lane = nullptr;
+static void collect_access(const void* lo, const void* hi, int is_write)
+{
+    if (g_collect) g_collect->push_back({ static_cast<const uint8_t*>(lo), static_cast<const uint8_t*>(hi), is_write, g_collect_lane });
+}
+static cudaError_t run_graph_checked(Graph* g)
+{
+    std::vector<Access> acc;
+    g_collect = &acc;
+    emu_access_hook = collect_access;
+    cudaError_t rc = 0;
+    for (const GraphOp& op : g->ops) {
+        g_collect_lane = op.lane;
+        emu_reported = 0;
+        rc = run_op(op);
+        if (rc) break;
+        if (op.kernel >= 0 && !emu_reported) {
+            fprintf(stderr, "dry shim: a kernel of a multi-lane graph does not report its accesses (no race check possible)\n");
+            rc = 719;
+            break;
+        }
+        if (op.kernel < 0) acc.push_back({ static_cast<const uint8_t*>(op.dst), static_cast<const uint8_t*>(op.dst) + op.bytes, 1, op.lane });
+    }
+    emu_access_hook = nullptr;
+    g_collect = nullptr;
+    if (rc) return rc;
+    for (size_t i = 0; i < acc.size(); ++i) {
+        if (!acc[i].write) continue;
+        for (size_t j = 0; j < acc.size(); ++j) {
+            if (acc[j].lane == acc[i].lane) continue;
+            if (acc[i].lo < acc[j].hi && acc[j].lo < acc[i].hi) {
+                fprintf(stderr, "dry shim: lane race: [%p, %p) written on one branch of the graph overlaps [%p, %p) %s on another\n",
+                        (const void*)acc[i].lo, (const void*)acc[i].hi, (const void*)acc[j].lo, (const void*)acc[j].hi,
+                        acc[j].write ? "written" : "read");
+                return 719;
+            }
+        }
+    }
+    return 0;
 }
 
 cudaError_t cudaStreamBeginCapture(cudaStream_t s, int)
@@ -199,6 +249,7 @@ cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t* g)
     auto cs = capture_state().find(gr);
     if (cs == capture_state().end() || cs->second.origin != s) return 902;   // cudaErrorStreamCaptureUnmatched
     bool unjoined = false;
+    gr->multi_lane = !cs->second.forks.empty();
     for (auto& f : cs->second.forks) {
         unjoined = unjoined || !f.second;
         capturing().erase(f.first);
@@ -217,7 +268,12 @@ cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned lon
 cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t)
 {
     ++g_graph_launches;
-    for (const GraphOp& op : reinterpret_cast<Graph*>(e)->ops) {
+    Graph* gr = reinterpret_cast<Graph*>(e);
+    if (g_emulate && gr->multi_lane && !gr->lanes_checked) {
+        gr->lanes_checked = true;
+        return run_graph_checked(gr);
+    }
+    for (const GraphOp& op : gr->ops) {
         const cudaError_t r = run_op(op);
         if (r) return r;
     }
@@ -240,7 +296,7 @@ cudaError_t dry_memset_async(void* d, int v, size_t n, cudaStream_t st)
     auto cap = capturing().find(st);
     if (cap == capturing().end()) { memset(d, v, n); return 0; }
     GraphOp op;
-    op.dst = d; op.value = v; op.bytes = n;
+    op.dst = d; op.value = v; op.bytes = n; op.lane = st;
     cap->second->ops.push_back(op);
     return 0;
 }

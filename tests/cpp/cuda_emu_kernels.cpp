@@ -52,6 +52,22 @@ static const uint8_t* map_at(const FakeMap* m, long long c, long long i1, long l
     return p;
 }
 
+// Access reports for the shim's lane race check (cuda_dry_shim.cpp): kernels that may run in parallel graph branches
+// report the byte ranges they read and write (conservative: first to last byte of a view, pitch gaps included).
+// A kernel without reports in a multi-lane graph fails that graph's launch.
+extern "C" { void (*emu_access_hook)(const void* lo, const void* hi, int is_write) = nullptr; int emu_reported = 0; }
+static void report(const void* lo, size_t bytes, int is_write)
+{
+    emu_reported = 1;
+    if (emu_access_hook && lo && bytes) emu_access_hook(lo, static_cast<const uint8_t*>(lo) + bytes, is_write);
+}
+static size_t map_extent(const FakeMap* m)
+{
+    size_t e = m->dims[0] * 2;
+    for (uint32_t d = 1; d < m->rank; ++d) e += (m->dims[d] - 1) * m->strides[d - 1];
+    return e;
+}
+
 static inline float wsilu(float x)
 {
     const float h = 0.5f * x;
@@ -103,6 +119,14 @@ static int emu_pw_gemm(void** args)
                 return 1;
             }
         }
+    }
+    report(A->ptr, map_extent(A), 0);
+    report(B->ptr, map_extent(B), 0);
+    report(Cm->ptr, map_extent(Cm), 1);
+    {
+        const size_t px = static_cast<size_t>(gw) * gh;
+        if (p.n_res > 0 && px) report(p.r1, ((px - 1) * p.r1_pitch + n_out) * 2, 0);
+        if (p.n_res > 1 && px) report(p.r2, ((px - 1) * p.r2_pitch + n_out) * 2, 0);
     }
     // weights as float [N][Ktot]
     std::vector<float> W(static_cast<size_t>(N) * Ktot);
@@ -171,6 +195,12 @@ static int emu_dw3x3(void** g)
     __half* out = arg<__half*>(g, 2); const int op = arg<int>(g, 3);
     const __half* w = arg<const __half*>(g, 4); const int C = arg<int>(g, 5), W = arg<int>(g, 6), H = arg<int>(g, 7);
     if (in == out) { fprintf(stderr, "emu dw3x3: in-place\n"); return 1; }
+    if (W > 0 && H > 0) {
+        const size_t px = static_cast<size_t>(W) * H;
+        report(in, ((px - 1) * ip + C) * 2, 0);
+        report(w, static_cast<size_t>(9) * C * 2, 0);
+        report(out, ((px - 1) * op + C) * 2, 1);
+    }
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x)
             for (int c = 0; c < C; ++c) {

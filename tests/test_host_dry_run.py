@@ -85,6 +85,8 @@ class _Dry:
             self.submit_flow("check", codec, sizes)
         self.submit_flow("check", "hts", ["72x104"], {"DCVC_B200_HEAD_LANES": "4"}, tag="lanes4")
         self.submit_flow("plan", "hts", ["1080x1920", "2160x3840"], {"DCVC_B200_HEAD_LANES": "2"}, tag="lanes2")
+        self.submit_flow("check", "hts", ["64x64"], {"DCVC_B200_HEAD_LANES": "2", "DCVC_B200_TEST_ALIAS_LANE_SCRATCH": "1"},
+                         tag="lanes-racy")
         for name, args, default in GPU_FILES_UNDER_EMULATION:
             if default or FULL:
                 self.submit_pytest(name, args)
@@ -174,6 +176,12 @@ def test_recon_head_lanes_change_nothing_but_the_graph_shape(dry):
     plan = last_json(dry.result(("plan", "hts", "lanes2")))
     assert plan["capture_forks"] >= 1
     assert all(run["arena_overflow_blocks"] == 0 for run in plan["runs"])
+    # Emulation runs the branches one after the other, so equal results say nothing about races.  The shim therefore
+    # collects what every kernel of a multi-lane graph reads and writes and fails the launch when a range written on
+    # one branch overlaps a range touched on another: the run above passed that check, and a deliberately broken
+    # wiring (all lanes on lane 0's scratch, a test-only switch) must trip it.
+    racy = dry.result(("check", "hts", "lanes-racy"))
+    assert racy.returncode != 0 and "lane race" in racy.stderr, racy.stderr[-1500:]
 
 
 def _pytest_under_emulation(dry, name, args):
