@@ -104,6 +104,10 @@ def run_ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    numa = None
+    if os.environ.get("DCVC_B200_NUMA_PIN") == "1":     # opt-in until measured: host threads on the GPU's socket
+        from dcvc_b200.shard import pin_to_gpu_numa_node
+        numa = pin_to_gpu_numa_node(local)
     model = make_model(device, world, rank)
     stream = torch.cuda.Stream(device)
     torch.cuda.set_stream(stream)  # a non-default stream, like test_video.py:423-425
@@ -283,6 +287,7 @@ def run_ours(args):
             "ld": ld,
             "htl": htl,
             "pipelined": pipelined,
+            "host": {"cpus": os.cpu_count(), "numa_pinned_cpus": (len(numa) if numa else None)},
         }
         print(json.dumps(out))
     if world > 1:

@@ -44,3 +44,54 @@ def gather_results(local_results, dst: int = 0):
     for part in gathered:
         merged.extend(part)
     return merged
+
+
+# ---------------------------------------------------------------------------------------------- host placement
+def _parse_cpulist(text: str):
+    """'0-3,8,10-11' -> {0, 1, 2, 3, 8, 10, 11} (the kernel's cpulist format)."""
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_cpus(pci_bus_id: str, sysfs_root: str = "/sys"):
+    """CPUs of the NUMA node the GPU at `pci_bus_id` ('0000:1b:00.0') hangs off, or None when the platform does not
+    say (numa_node -1: single node or a virtualised topology)."""
+    import os
+    dev = os.path.join(sysfs_root, "bus", "pci", "devices", pci_bus_id.lower())
+    try:
+        node = int(open(os.path.join(dev, "numa_node")).read().strip())
+        if node < 0:
+            return None
+        return _parse_cpulist(open(os.path.join(sysfs_root, "devices", "system", "node", f"node{node}", "cpulist")).read()) or None
+    except (OSError, ValueError):
+        return None
+
+
+def pin_to_gpu_numa_node(device_index: int, sysfs_root: str = "/sys"):
+    """One process per GPU on a two-socket box: keep this process — and every thread it starts afterwards: the rANS
+    fork-join pool is created with the codec handle, pinned host buffers are placed by first touch — on the socket the
+    GPU is attached to, so the symbol hand-off (D2H indexes -> host rANS -> H2D symbols, five times per picture) never
+    crosses the inter-socket link.  Call it before the first proxy is created.  Returns the CPU set applied, or None
+    when nothing was changed (no topology information, no permission, or the set would be empty)."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bus = f"{getattr(p, 'pci_domain_id'):04x}:{getattr(p, 'pci_bus_id'):02x}:{getattr(p, 'pci_device_id'):02x}.0"
+    except Exception:  # noqa: BLE001 — older torch without the pci_* properties, or no device
+        return None
+    cpus = gpu_numa_cpus(bus, sysfs_root)
+    if not cpus:
+        return None
+    try:
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except OSError:
+        return None

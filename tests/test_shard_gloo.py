@@ -50,3 +50,21 @@ def test_broadcast_and_sharding_world2():
     assert all(r[0] for r in res), "broadcast checkpoint differs"
     assert all(r[1] for r in res), "job shards do not cover the job list exactly once"
     assert sorted(r[2] for r in res) == [10, 10]
+
+
+def test_gpu_numa_cpu_set_from_a_sysfs_tree(tmp_path):
+    """host placement helper (opt-in in bench.py: DCVC_B200_NUMA_PIN=1): the CPUs of the GPU's NUMA node come from
+    sysfs; a platform that does not say (numa_node -1, missing files) changes nothing"""
+    from dcvc_b200.shard import _parse_cpulist, gpu_numa_cpus
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    dev = tmp_path / "bus" / "pci" / "devices" / "0000:1b:00.0"
+    dev.mkdir(parents=True)
+    node = tmp_path / "devices" / "system" / "node" / "node1"
+    node.mkdir(parents=True)
+    (node / "cpulist").write_text("32-63,96-127\n")
+    (dev / "numa_node").write_text("1\n")
+    cpus = gpu_numa_cpus("0000:1B:00.0", str(tmp_path))
+    assert cpus == set(range(32, 64)) | set(range(96, 128))
+    (dev / "numa_node").write_text("-1\n")
+    assert gpu_numa_cpus("0000:1b:00.0", str(tmp_path)) is None
+    assert gpu_numa_cpus("0000:ff:00.0", str(tmp_path)) is None

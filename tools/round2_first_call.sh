@@ -44,6 +44,13 @@ import json
 d = json.loads(open('$O/r2_bench_pipelined.json').read().strip().splitlines()[-1])
 print('single', d['value'], 'FPS; pipelined', d.get('pipelined'))" 2>&1 | tail -1
 
+echo "== 4b. host threads pinned to the GPU's NUMA node"
+DCVC_B200_NUMA_PIN=1 timeout 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-hts > $O/r2_bench_numa.json 2> $O/r2_bench_numa.err
+python -c "
+import json
+d = json.loads(open('$O/r2_bench_numa.json').read().strip().splitlines()[-1])
+print('numa-pinned: decode', d['value'], 'e2e', d['e2e']['value'], 'encode', d['encode_fps'], d.get('host'))" 2>&1 | tail -1
+
 echo "== 5. where the steady state of the 384x384 GEMM goes (us per launch, M = 32640)"
 for variant in "ARES=0" "ARES=1 PAIR=0" "ARES=1 PAIR=1"; do
     for dbg in 0 1 2 3; do
