@@ -109,7 +109,7 @@ cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = static_cast<cudaEvent_t>(toke
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = static_cast<cudaEvent_t>(token()); return 0; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return 0; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
-cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.25f; return 0; }   // a made-up, non-zero interval
 // a captured graph = the launches (kernel + a private copy of its arguments) and memsets issued while capturing
 struct GraphOp {
     int kernel = -1;                       // emulation table index, -1: memset

@@ -91,6 +91,13 @@ class _Dry:
             if default or FULL:
                 self.submit_pytest(name, args)
         self.submit_smoke()
+        self.submit_bench()
+
+    def submit_bench(self):
+        env = self.env(True, htl=False)
+        env["DCVC_B200_BENCH_TEST_SIZE"] = "64x64"
+        self.submit(("bench",), [sys.executable, os.path.join(ROOT, "tests/dry_bench_runner.py"), self.lib, "--steps", "1",
+                                 "--warmup", "3", "--no-cpu-baseline"], env, 1200)
 
     def submit_flow(self, mode, codec, sizes, extra_env=None, tag=None):
         env = self.env(mode == "check")
@@ -216,3 +223,31 @@ def test_smoke_entry_under_emulation(dry):
     dry.submit_smoke()
     r = dry.result(("smoke",))
     assert r.returncode == 0 and "smoke-under-emulation ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_bench_control_flow_and_json_contract_under_emulation(dry):
+    """bench.py is run unattended by the driver at round end: its whole control flow (decode / e2e / encode legs, the
+    per-family profile, the HT-S and LD legs) runs here on the emulated runtime at a tiny size with made-up timings,
+    and the JSON line must carry every key of the contract.  The line says it is invalid as a measurement."""
+    dry.submit_bench()
+    r = dry.result(("bench",))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, "bench.py must print exactly one JSON line"
+    d = json.loads(lines[0])
+    assert d["INVALID_test_size_override"] == "64x64"
+    for key, typ in (("metric", str), ("value", float), ("unit", str), ("n_gpus", int), ("steps", int), ("warmup", int),
+                     ("ms_per_step", float), ("higher_is_better", bool), ("scaling", str), ("dtype", str), ("data", str),
+                     ("config", dict), ("e2e", dict), ("gpu_launches", int), ("clocks", dict), ("roofline", dict)):
+        assert isinstance(d[key], typ), (key, d.get(key))
+    assert "vs_baseline" in d and d["vs_baseline"] is None           # BASELINE.md publishes nothing for this exact metric
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 3 and d["scaling"] == "weak" and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
+    assert d["roofline"]["bound"] == "hbm" and d["roofline"]["unit"] == "GB/s"
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
+    assert d["gpu_launches"] > 100
+    for leg in ("hts", "ld"):
+        assert "error" not in d[leg] and d[leg]["decode_fps"] > 0 and d[leg]["encode_fps"] > 0, d[leg]
