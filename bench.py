@@ -253,6 +253,15 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             htl = {"error": f"{type(e).__name__}: {e}"}
 
+    # ---- opt-in (--hts-size HxW, e.g. 2160x3840 = configs[4]): the HT-S leg again at another picture size
+    hts_extra = None
+    if args.hts_size and world == 1:
+        try:
+            eh, ew = (int(v) for v in args.hts_size.lower().split("x"))
+            hts_extra = bench_hts(model, device, world, rank, args, timed, reduce_max, hw=(eh, ew))
+        except Exception as e:  # noqa: BLE001
+            hts_extra = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- opt-in (--pipelined): two independent decodes in flight per GPU (two proxies, two streams, two host threads)
     pipelined = None
     if args.pipelined and world == 1:
@@ -292,6 +301,7 @@ def run_ours(args):
             "ld": ld,
             "htl": htl,
             "pipelined": pipelined,
+            "hts_extra": hts_extra,
             "host": {"cpus": os.cpu_count(), "numa_pinned_cpus": (len(numa) if numa else None)},
         }
         if _SIZE_OVERRIDE:
@@ -368,7 +378,7 @@ def bench_pipelined(model, device, bs, sps, ec, args, ways=2):
             "protocol": "throughput of concurrent independent decodes on one GPU (not the reference's per-call FPS protocol)"}
 
 
-def bench_hts(i_net, device, world, rank, args, timed, reduce_max, large=False):
+def bench_hts(i_net, device, world, rank, args, timed, reduce_max, large=False, hw=None):
     """DCVC-UF HT-S 1080p chunk (8 frames) encode / decode after one intra frame (configs[2]); published B200
     numbers of the reference's CUTLASS build: 1415.1 / 945.8 FPS.  large=True: the HT-L model
     (experimental codec, DCVC_B200_EXPERIMENTAL_HTL=1; published 811.7 / 551.6 FPS)."""
@@ -377,10 +387,17 @@ def bench_hts(i_net, device, world, rank, args, timed, reduce_max, large=False):
     from dcvc_b200.model import DMC, DMCHTL
     from dcvc_b200.shard import broadcast_state_dict
     from dcvc_b200.spec import htl_spec, hts_spec, synth_state_dict
+    h, w = hw or (H, W)
     spec = htl_spec() if large else hts_spec()
     seed = 3 if large else 1
     published = {"encode": 811.7, "decode": 551.6} if large else {"encode": 1415.1, "decode": 945.8}
-    alg_bytes_decode = 17.33e9 if large else 14.09e9     # SURVEY.md §8d, per chunk
+    if (h, w) == (2160, 3840):                           # BASELINE.md, assets/complexity.png table (d)
+        published = {"encode": 237.9, "decode": 177.2} if large else {"encode": 424.0, "decode": 289.5}
+    elif (h, w) != (1080, 1920):
+        published = None
+    # SURVEY.md §8d, per chunk at 1088x1920; scaled by the padded area for other sizes
+    area = ((h + 15) // 16 * 16) * ((w + 15) // 16 * 16) / float(1088 * 1920)
+    alg_bytes_decode = (17.33e9 if large else 14.09e9) * area
     if world == 1:
         sd = synth_state_dict(spec, seed)
     else:
@@ -389,11 +406,11 @@ def bench_hts(i_net, device, world, rank, args, timed, reduce_max, large=False):
     p_net.load_state_dict(sd)
     p_net.update(SKIP)
     p_net = p_net.half().to(device)
-    pad_r, pad_b = i_net.get_padding_size(H, W, 16)
-    sps = {"height": H, "width": W}
-    x0 = synth_frame(H, W, 4000 + rank).half().to(device).contiguous(memory_format=torch.channels_last)
+    pad_r, pad_b = i_net.get_padding_size(h, w, 16)
+    sps = {"height": h, "width": w}
+    x0 = synth_frame(h, w, 4000 + rank).half().to(device).contiguous(memory_format=torch.channels_last)
     n_chunks = args.steps + args.warmup
-    chunks = [synth_frame(H, W, 4100 + 10 * rank + (c % 3), channels=24).half().to(device)
+    chunks = [synth_frame(h, w, 4100 + 10 * rank + (c % 3), channels=24).half().to(device)
               .contiguous(memory_format=torch.channels_last) for c in range(min(n_chunks, 3))]
     enc = i_net.compress(x0, QP, pad_b, pad_r)
     p_net.add_ref_feature_from_frame(enc["x_hat"])
@@ -428,17 +445,18 @@ def bench_hts(i_net, device, world, rank, args, timed, reduce_max, large=False):
     last = (args.warmup + args.steps - 1) % len(chunks)
     src = chunks[last][:, 0:3].float().cpu()
     out = {
-        "workload": f"DCVC-UF {'HT-L' if large else 'HT-S'} 1080p, 8-frame chunks after one intra frame, q_index 32, skip_thres 0.15 (configs[2])",
+        "workload": f"DCVC-UF {'HT-L' if large else 'HT-S'} {w}x{h}, 8-frame chunks after one intra frame, q_index 32, skip_thres 0.15 (configs[2])",
         "decode_fps": round(world * 8 * args.steps / (tot_dec * 1e-3), 1),
         "encode_fps": round(world * 8 * args.steps / (tot_enc * 1e-3), 1),
         "ms_per_chunk_decode": round(tot_dec / args.steps, 3), "ms_per_chunk_encode": round(tot_enc / args.steps, 3),
         "gpu_only_ms_per_chunk_decode": round(gpu_ms, 3),
         "gpu_launches_per_chunk_decode": int((l1 - l0) // args.steps),
         "bytes_per_chunk": int(np.mean([len(s[0]) for s in streams])),
-        "psnr_db_frame0": round(psnr(state["x_hat"][0].float().cpu()[:, :, :H, :W], src), 3),
-        "published_b200_reference_fps": dict(published, source="BASELINE.md (assets/complexity.png)"),
-        "decode_vs_published": round(world * 8 * args.steps / (tot_dec * 1e-3) / published["decode"], 3),
+        "psnr_db_frame0": round(psnr(state["x_hat"][0].float().cpu()[:, :, :h, :w], src), 3),
+        "published_b200_reference_fps": dict(published, source="BASELINE.md (assets/complexity.png)") if published else None,
+        "decode_vs_published": round(world * 8 * args.steps / (tot_dec * 1e-3) / published["decode"], 3) if published else None,
         "alg_gbs_decode": round(alg_bytes_decode / (gpu_ms * 1e-3) / 1e9, 1),
+        "hbm_frac_decode": round(alg_bytes_decode / (gpu_ms * 1e-3) / 1e9 / _peaks()[0], 4),
     }
     del p_net
     return out
@@ -583,6 +601,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hts", action="store_true")
+    ap.add_argument("--hts-size", default=None, help="also run the HT-S leg at HxW, e.g. 2160x3840 (opt-in, single GPU)")
     ap.add_argument("--pipelined", action="store_true", help="also measure two concurrent decodes per GPU (opt-in)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

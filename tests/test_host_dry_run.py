@@ -97,7 +97,7 @@ class _Dry:
         env = self.env(True, htl=False)
         env["DCVC_B200_BENCH_TEST_SIZE"] = "64x64"
         self.submit(("bench",), [sys.executable, os.path.join(ROOT, "tests/dry_bench_runner.py"), self.lib, "--steps", "1",
-                                 "--warmup", "3", "--no-cpu-baseline"], env, 1200)
+                                 "--warmup", "3", "--no-cpu-baseline", "--hts-size", "64x128"], env, 1200)
 
     def submit_flow(self, mode, codec, sizes, extra_env=None, tag=None):
         env = self.env(mode == "check")
@@ -249,5 +249,6 @@ def test_bench_control_flow_and_json_contract_under_emulation(dry):
     assert d["roofline"]["bound"] == "hbm" and d["roofline"]["unit"] == "GB/s"
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
     assert d["gpu_launches"] > 100
-    for leg in ("hts", "ld"):
+    assert d["hts_extra"]["published_b200_reference_fps"] is None          # an unpublished size
+    for leg in ("hts", "ld", "hts_extra"):
         assert "error" not in d[leg] and d[leg]["decode_fps"] > 0 and d[leg]["encode_fps"] > 0, d[leg]

@@ -37,6 +37,13 @@ except Exception as e:
 EOF
 done
 
+echo "== 3b. HT-S at 4K (configs[4]; published reference CUTLASS build on B200: 424.0 / 289.5 FPS)"
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --hts-size 2160x3840 > $O/r2_bench_4k.json 2> $O/r2_bench_4k.err
+python -c "
+import json
+d = json.loads(open('$O/r2_bench_4k.json').read().strip().splitlines()[-1])
+print('hts 4K:', d.get('hts_extra'))" 2>&1 | tail -1
+
 echo "== 4. two concurrent Intra decodes"
 timeout 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-hts --pipelined > $O/r2_bench_pipelined.json 2> $O/r2_bench_pipelined.err
 python -c "
