@@ -23,8 +23,12 @@ timeout 1500 bash tools/validate_htl.sh > $O/r2_validate_htl.log 2>&1
 tail -12 $O/r2_validate_htl.log
 
 echo "== 3. recon-head lanes on the HT-S leg"
-for L in 1 2 4; do
-    DCVC_B200_HEAD_LANES=$L timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $O/r2_bench_lanes$L.json 2> $O/r2_bench_lanes$L.err
+# PDL matters here: a dependent kernel that was launched early sits in griddepcontrol.wait ON an SM — it may take the SMs a
+# finished CTA frees before the other branch's ready CTAs get them.  So every lane count is measured with PDL on and off.
+for L in 1 2 4 2nopdl 4nopdl; do
+    LN=${L%nopdl}
+    PDL=1; [ "$L" != "$LN" ] && PDL=0
+    DCVC_B200_PDL=$PDL DCVC_B200_HEAD_LANES=$LN timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $O/r2_bench_lanes$L.json 2> $O/r2_bench_lanes$L.err
     python - <<EOF
 import json
 try:
