@@ -356,10 +356,12 @@ void IntraCodec::build_synthesis(Segment& s)
     const ActView yh = make_view(yhat_, kChY, kChY, W16_, H16_);
     ActView t = make_view(l8_.A, kChEncDec, kChEncDec, W8_, H8_);
     add_gemm(s, GEMM_TCONV2X2, yh, t, dec_up_.w, nullptr, 4 * kChEncDec, ACT_NONE, 0, nullptr, nullptr, nullptr);
+    begin_split(s);  // the 14 P8 blocks of the synthesis transform: half-picture lanes when DCVC_B200_SPLIT_P8=1
     t = dcb(s, l8_, t, dec1_[0], true, nullptr, nullptr);
     for (int i = 1; i < 13; ++i) t = dcb(s, l8_, t, dec1_[i], false, (i == 12) ? q_dec_ : nullptr, nullptr);
     const ActView out = make_view(dec_out_, kChSrc, kChSrc, W8_, H8_);
     dcb(s, l8_, t, dec2_, false, nullptr, &out);
+    end_split(s);
 }
 
 void IntraCodec::stage_qp(int qp, cudaStream_t stream)

@@ -152,6 +152,12 @@ struct Segment {
     // order on one stream.
     std::vector<int> lanes;
     int cur_lane = 0, n_lanes = 1;
+    // cross-lane edges: before op `at` is captured, lane `to` waits for everything captured on lane `from` so far
+    // (an event record / wait pair inside the capture).  The list order of the ops is always a valid serial order.
+    struct LaneSync { size_t at; int from, to; };
+    std::vector<LaneSync> syncs;
+    bool split_open = false;  // inside a half-picture region (CodecBase::begin_split / end_split)
+    int split_c = 0, split_inner = 0, split_in_pitch = 0;  // channel widths of the previous split block (byte layout of the halves)
     cudaGraphExec_t exec = nullptr;
     int launches = 0;
     // tile-level chaining of consecutive 1x1 GEMMs (pw_gemm.cuh: done_flags / wait_a): the flag words of this
@@ -171,6 +177,14 @@ struct Segment {
             flops.push_back(fl);
             lanes.push_back(cur_lane);
         }
+    }
+    void lane_sync(int from, int to)
+    {
+        annotate(OP_ELEM, 0, 0);
+        break_chain();
+        syncs.push_back(LaneSync{ ops.size(), from, to });
+        const int hi = (from > to ? from : to) + 1;
+        if (hi > n_lanes) n_lanes = hi;
     }
     void set_lane(int l)
     {
@@ -195,8 +209,9 @@ struct Segment {
     {
         if (exec) cudaGraphExecDestroy(exec);
         exec = nullptr;
-        ops.clear(); kinds.clear(); alg_bytes.clear(); flops.clear(); lanes.clear();
-        cur_lane = 0; n_lanes = 1;
+        ops.clear(); kinds.clear(); alg_bytes.clear(); flops.clear(); lanes.clear(); syncs.clear();
+        cur_lane = 0; n_lanes = 1; split_open = false;
+        split_c = split_inner = split_in_pitch = 0;
         launches = 0;
         flag_begin = nullptr;
         flag_words = 0;
@@ -229,6 +244,7 @@ public:
         if (ev_fork_) cudaEventDestroy(ev_fork_);
         for (auto& st : lane_streams_) cudaStreamDestroy(st);
         for (auto& e : lane_events_) cudaEventDestroy(e);
+        for (auto& e : sync_events_) cudaEventDestroy(e);
         for (auto& e : tev_) cudaEventDestroy(e);
         for (auto& e : prof_events_) cudaEventDestroy(e);
     }
@@ -417,6 +433,12 @@ protected:
         // 5.71 ms) — see DESIGN.md "experiments"
         const char* ch = getenv("DCVC_B200_GEMM_CHAIN");
         chain_enabled_ = ch && ch[0] == '1';
+        {
+            const char* sp = getenv("DCVC_B200_SPLIT_P8");
+            split_enabled_ = sp && sp[0] == '1';
+            const char* dr = getenv("DCVC_B200_TEST_DROP_LANE_SYNC");
+            test_drop_sync_ = dr && dr[0] == '1';
+        }
         if (chain_enabled_ && !flags_base_) {
             flags_cap_ = (8u << 20) / sizeof(int);
             CK(cudaMalloc(&flags_base_, flags_cap_ * sizeof(int)));
@@ -501,6 +523,57 @@ protected:
         add_gemm(s, GEMM_PW, in, out, c.w, c.b, c.cout, ACT_NONE, 0, nullptr, nullptr, nullptr);
     }
 
+    // ------------------------------------------------------------------ half-picture lanes (DCVC_B200_SPLIT_P8=1)
+    // Measurement switch, off by default.  Every pw_gemm launch is one persistent wave that ends in a ragged tail and a
+    // drain, and the next launch of the same chain cannot start before it has ended.  Inside a split region every 1x1
+    // GEMM of a DepthConvBlock is issued twice — upper half of the picture on lane 0, lower half on lane 1 (pixel-local
+    // ops: the halves are independent) — as two parallel branches of the graph, so one half's tail and fill overlap the
+    // other half's steady state.  Only the depthwise 3x3 needs rows of both halves: it stays one full-picture launch on
+    // lane 0 between two cross-lane edges.  Results are bit-identical to the unsplit path (a pixel's value does not
+    // depend on the tile it is computed in).
+    static ActView half_view(const ActView& v, int part)
+    {
+        const int ht = v.H / 2;
+        ActView h = v;
+        if (part == 0) {
+            h.H = ht;
+        } else {
+            h.ptr = static_cast<const __half*>(v.ptr) + static_cast<size_t>(ht) * v.W * v.pitch;
+            h.H = v.H - ht;
+        }
+        return h;
+    }
+    void begin_split(Segment& s)
+    {
+        if (!split_enabled_ || s.split_open) return;
+        s.lane_sync(0, 1);  // lane 1 starts behind everything lane 0 has done so far in this segment
+        s.split_open = true;
+        s.split_c = s.split_inner = s.split_in_pitch = 0;
+    }
+    void end_split(Segment& s)
+    {
+        if (!s.split_open) return;
+        s.lane_sync(1, 0);
+        s.set_lane(0);
+        s.split_open = false;
+    }
+    void gemm_1x1(Segment& s, const ActView& in, const ActView& out, const __half* w, const __half* bias, int N, int act,
+                  int chunk, const ActView* r1, const ActView* r2, const __half* q)
+    {
+        if (!s.split_open || in.H < 2) {
+            add_gemm(s, GEMM_PW, in, out, w, bias, N, act, chunk, r1, r2, q, true);
+            return;
+        }
+        for (int part = 0; part < 2; ++part) {
+            s.set_lane(part);
+            const ActView hi = half_view(in, part), ho = half_view(out, part);
+            ActView h1, h2;
+            if (r1) h1 = half_view(*r1, part);
+            if (r2) h2 = half_view(*r2, part);
+            add_gemm(s, GEMM_PW, hi, ho, w, bias, N, act, chunk, r1 ? &h1 : nullptr, r2 ? &h2 : nullptr, q, true);
+        }
+    }
+
     // DepthConvBlock (layers.py:152-159 == layers_proxy.cpp:71-101): returns the view holding the output.
     // The block input is overwritten in place unless `out` redirects the last GEMM.  `in` may live in one
     // of the level's ping-pong buffers or outside of it (then, without an adaptor, `out` is mandatory
@@ -509,12 +582,24 @@ protected:
                 const ActView* out)
     {
         const int H = in.H, W = in.W;
+        if (s.split_open) {
+            // The ping-pong buffers are reused from block to block.  While every block has the same channel widths, "upper
+            // half" and "lower half" are the same byte ranges in every tensor that lives in a buffer, so each lane only ever
+            // touches its own half.  When the widths change (adaptor, narrower inner width, another input pitch) the byte
+            // ranges of the halves shift: both lanes meet before such a block.
+            const bool same = (s.split_c == w.c && s.split_inner == w.inner && s.split_in_pitch == in.pitch && !w.adaptor);
+            if (s.split_c != 0 && !same) {
+                s.lane_sync(0, 1);
+                s.lane_sync(1, 0);
+            }
+            s.split_c = w.c; s.split_inner = w.inner; s.split_in_pitch = w.adaptor ? w.c : in.pitch;
+        }
         __half* bufX;
         ActView x;
         if (w.adaptor) {
             bufX = (in.ptr == L.A) ? L.B : L.A;
             x = make_view(bufX, w.c, w.c, W, H);
-            add_gemm(s, GEMM_PW, in, x, w.wa, w.ba, w.c, ACT_NONE, 0, nullptr, nullptr, nullptr, true);
+            gemm_1x1(s, in, x, w.wa, w.ba, w.c, ACT_NONE, 0, nullptr, nullptr, nullptr);
         } else {
             x = in;
             bufX = static_cast<__half*>(const_cast<void*>(in.ptr));
@@ -526,20 +611,26 @@ protected:
         const ActView t1 = make_view(L.T1, w.inner, w.inner, W, H);
         const ActView t2 = make_view(L.T2, w.inner, w.inner, W, H);
         const ActView o = make_view(bufO, w.c, w.c, W, H);
-        add_gemm(s, GEMM_PW, x, t1, w.w0, w.b0, w.inner, ACT_WSILU, 0, nullptr, nullptr, nullptr, true);
+        gemm_1x1(s, x, t1, w.w0, w.b0, w.inner, ACT_WSILU, 0, nullptr, nullptr, nullptr);
         {
             const __half* wdw = w.wdw;
             s.break_chain();  // 3x3 neighbourhoods: full-grid dependency on both sides
+            if (s.split_open) {
+                // the full-picture depthwise conv reads dc.0 rows of both halves and writes rows both halves' dc.3 read
+                if (!test_drop_sync_) s.lane_sync(1, 0);
+                s.set_lane(0);
+            }
             s.annotate(OP_ELEM, 0, 0);
             s.ops.push_back([t1, t2, wdw](cudaStream_t st) { return launch_dw3x3(t1, t2, wdw, st); });
             s.out_views.resize(s.ops.size());
             s.out_views.back() = t2;
             s.annotate(OP_DW, 2.0 * 2 * W * H * w.inner, 2.0 * 9 * W * H * w.inner);
+            if (s.split_open) s.lane_sync(0, 1);
         }
-        add_gemm(s, GEMM_PW, t2, o, w.w3, w.b3, w.c, ACT_NONE, 0, &x, nullptr, nullptr, true);
-        add_gemm(s, GEMM_PW, o, t1, w.wf0, w.bf0, 4 * w.inner, ACT_WSILU, 1, nullptr, nullptr, nullptr, true);
+        gemm_1x1(s, t2, o, w.w3, w.b3, w.c, ACT_NONE, 0, &x, nullptr, nullptr);
+        gemm_1x1(s, o, t1, w.wf0, w.bf0, 4 * w.inner, ACT_WSILU, 1, nullptr, nullptr, nullptr);
         const ActView dst = out ? *out : x;
-        add_gemm(s, GEMM_PW, t1, dst, w.wf2, w.bf2, w.c, ACT_NONE, 0, &o, shortcut ? &x : nullptr, qscale, true);
+        gemm_1x1(s, t1, dst, w.wf2, w.bf2, w.c, ACT_NONE, 0, &o, shortcut ? &x : nullptr, qscale);
         return dst;
     }
 
@@ -614,6 +705,11 @@ protected:
                         CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
                         lane_events_.push_back(ev);
                     }
+                    while (sync_events_.size() < s.syncs.size()) {
+                        cudaEvent_t ev = nullptr;
+                        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                        sync_events_.push_back(ev);
+                    }
                 }
                 CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
                 if (s.flag_words) cudaMemsetAsync(s.flag_begin, 0, s.flag_words * sizeof(int), stream);
@@ -625,10 +721,25 @@ protected:
                         if (cudaStreamWaitEvent(lane_streams_[l - 1], ev_fork_, 0) != cudaSuccess) rc = 1;
                     if (rc) lane_err = "fork of the capture lanes failed";
                 }
+                auto lane_stream = [&](int l) { return l == 0 ? stream : lane_streams_[l - 1]; };
+                size_t next_sync = 0;
+                auto do_syncs = [&](size_t at) {  // cross-lane edges that precede op `at`
+                    for (; n_lanes > 1 && next_sync < s.syncs.size() && s.syncs[next_sync].at <= at && !rc; ++next_sync) {
+                        const Segment::LaneSync& y = s.syncs[next_sync];
+                        if (cudaEventRecord(sync_events_[next_sync], lane_stream(y.from)) != cudaSuccess ||
+                            cudaStreamWaitEvent(lane_stream(y.to), sync_events_[next_sync], 0) != cudaSuccess) {
+                            lane_err = "cross-lane edge of the capture failed";
+                            rc = 1;
+                        }
+                    }
+                };
                 for (size_t i = 0; i < s.ops.size() && !rc; ++i) {
+                    do_syncs(i);
+                    if (rc) break;
                     const int l = (n_lanes > 1 && i < s.lanes.size()) ? s.lanes[i] : 0;
-                    rc = s.ops[i](l == 0 ? stream : lane_streams_[l - 1]);
+                    rc = s.ops[i](lane_stream(l));
                 }
+                if (!rc) do_syncs(s.ops.size());
                 if (n_lanes > 1) {  // join (also after a failed op: an unjoined capture cannot be ended)
                     for (int l = 1; l < n_lanes; ++l) {
                         if (cudaEventRecord(lane_events_[l - 1], lane_streams_[l - 1]) != cudaSuccess ||
@@ -715,6 +826,9 @@ protected:
     cudaEvent_t ev_hop_ = nullptr, ev_y_ = nullptr, ev_fork_ = nullptr;
     std::vector<cudaStream_t> lane_streams_;   // side streams of multi-lane segments (graph capture only)
     std::vector<cudaEvent_t> lane_events_;
+    std::vector<cudaEvent_t> sync_events_;     // one per cross-lane edge of the largest multi-lane segment
+    bool split_enabled_ = false;               // DCVC_B200_SPLIT_P8=1 (read in finalize)
+    bool test_drop_sync_ = false;              // DCVC_B200_TEST_DROP_LANE_SYNC=1: fault injection for the CPU tier's race check
     std::vector<cudaEvent_t> tev_;
     std::vector<cudaEvent_t> prof_events_;
     int tev_n_ = 0;

@@ -116,6 +116,8 @@ struct GraphOp {
     std::vector<std::shared_ptr<void>> args;   // 64-byte aligned private copies (PwGemmParams is alignas(64))
     void* dst = nullptr; int value = 0; size_t bytes = 0;
     cudaStream_t lane = nullptr;           // the stream the op was captured on (parallel branch of the graph)
+    int lane_i = 0;                        // its index in the capture (0 = origin stream)
+    std::vector<int> vc;                   // vector clock of the op (happens-before between branches)
 };
 struct Graph { std::vector<GraphOp> ops; bool multi_lane = false, lanes_checked = false; };
 static std::map<cudaStream_t, Graph*>& capturing() { static std::map<cudaStream_t, Graph*> m; return m; }
@@ -123,32 +125,59 @@ static std::map<cudaStream_t, Graph*>& capturing() { static std::map<cudaStream_
 // capture; a stream that waits for it joins the capture (its launches land in the same graph); every forked stream must
 // have been joined back into the origin stream (record on the fork, wait on the origin) when the capture ends
 // (cudaErrorStreamCaptureUnjoined otherwise).
-struct CaptureState { cudaStream_t origin; std::map<cudaStream_t, bool> forks; /* stream -> joined */ };
+struct CaptureState {
+    cudaStream_t origin;
+    std::map<cudaStream_t, int> lane_idx;      // origin = 0, forks in the order they joined the capture
+    std::vector<std::vector<int>> vc;          // vector clock per lane: what of every lane's work it has seen
+};
+struct EventSnap { Graph* g; cudaStream_t st; std::vector<int> vc; };
 static std::map<Graph*, CaptureState>& capture_state() { static std::map<Graph*, CaptureState> m; return m; }
-static std::map<cudaEvent_t, std::pair<Graph*, cudaStream_t>>& event_capture() { static std::map<cudaEvent_t, std::pair<Graph*, cudaStream_t>> m; return m; }
+static std::map<cudaEvent_t, EventSnap>& event_capture() { static std::map<cudaEvent_t, EventSnap> m; return m; }
+static int vc_get(const std::vector<int>& v, int i) { return i < static_cast<int>(v.size()) ? v[i] : 0; }
+static void vc_merge(std::vector<int>& into, const std::vector<int>& from)
+{
+    if (into.size() < from.size()) into.resize(from.size(), 0);
+    for (size_t i = 0; i < from.size(); ++i) if (from[i] > into[i]) into[i] = from[i];
+}
+// stamps an op captured on `st` (a kernel or a memset) with its lane and clock
+static void stamp_op(Graph* g, cudaStream_t st, GraphOp& op)
+{
+    CaptureState& cs = capture_state()[g];
+    const int l = cs.lane_idx[st];
+    std::vector<int>& v = cs.vc[l];
+    if (static_cast<int>(v.size()) <= l) v.resize(l + 1, 0);
+    ++v[l];
+    op.lane = st;
+    op.lane_i = l;
+    op.vc = v;
+}
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st)
 {
     auto cap = capturing().find(st);
     if (cap == capturing().end()) { event_capture().erase(e); return 0; }
-    event_capture()[e] = { cap->second, st };
+    CaptureState& cs = capture_state()[cap->second];
+    event_capture()[e] = EventSnap{ cap->second, st, cs.vc[cs.lane_idx[st]] };
     return 0;
 }
 cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t e, unsigned)
 {
     auto ev = event_capture().find(e);
     if (ev == event_capture().end()) return 0;
-    Graph* g = ev->second.first;
-    auto cs = capture_state().find(g);
-    if (cs == capture_state().end()) return 0;               // capture already over: a plain (completed) event
+    Graph* g = ev->second.g;
+    auto csi = capture_state().find(g);
+    if (csi == capture_state().end()) return 0;               // capture already over: a plain (completed) event
+    CaptureState& cs = csi->second;
     auto cap = capturing().find(st);
-    if (cap == capturing().end()) {                           // fork
+    if (cap == capturing().end()) {                           // fork: the stream joins the capture behind the event
         capturing()[st] = g;
-        cs->second.forks[st] = false;
+        const int l = static_cast<int>(cs.vc.size());
+        cs.lane_idx[st] = l;
+        cs.vc.push_back(ev->second.vc);
         ++g_forks;
         return 0;
     }
     if (cap->second != g) return 905;                         // cudaErrorStreamCaptureMerge
-    if (st == cs->second.origin && cs->second.forks.count(ev->second.second)) cs->second.forks[ev->second.second] = true;  // join
+    vc_merge(cs.vc[cs.lane_idx[st]], ev->second.vc);          // st now runs behind everything the event had seen
     return 0;
 }
 static const bool g_emulate = []() { const char* e = getenv("DRY_SHIM_EMULATE"); return e && e[0] == '1'; }();
@@ -182,7 +211,7 @@ static cudaError_t submit_kernel(const void* fn, void** args, cudaStream_t st)
         op.args.emplace_back(q, free);
     }
     auto cap = capturing().find(st);
-    if (cap != capturing().end()) { op.lane = st; cap->second->ops.push_back(std::move(op)); return 0; }
+    if (cap != capturing().end()) { stamp_op(cap->second, st, op); cap->second->ops.push_back(std::move(op)); return 0; }
     return run_op(op);
 }
 
@@ -190,44 +219,59 @@ static cudaError_t submit_kernel(const void* fn, void** args, cudaStream_t st)
 // ops captured on different streams of one graph may run concurrently on the device, while this shim runs them one
 // after the other.  On the first (emulated) launch of such a graph every kernel reports the byte ranges it reads and
 // writes; a range written on one lane that overlaps any range touched on another lane fails the launch.
-struct Access { const uint8_t *lo, *hi; int write; cudaStream_t lane; };
+struct Access { const uint8_t *lo, *hi; int write; size_t op; };
 static std::vector<Access>* g_collect = nullptr;
-static cudaStream_t g_collect_lane = nullptr;
+static size_t g_collect_op = 0;
 static void collect_access(const void* lo, const void* hi, int is_write)
 {
-    if (g_collect) g_collect->push_back({ static_cast<const uint8_t*>(lo), static_cast<const uint8_t*>(hi), is_write, g_collect_lane });
+    if (g_collect) g_collect->push_back({ static_cast<const uint8_t*>(lo), static_cast<const uint8_t*>(hi), is_write, g_collect_op });
 }
+static bool happens_before(const GraphOp& a, const GraphOp& b) { return vc_get(a.vc, a.lane_i) <= vc_get(b.vc, a.lane_i); }
 static cudaError_t run_graph_checked(Graph* g)
 {
     std::vector<Access> acc;
+    std::vector<size_t> silent;  // kernels whose restatement reports no accesses
     g_collect = &acc;
     emu_access_hook = collect_access;
     cudaError_t rc = 0;
-    for (const GraphOp& op : g->ops) {
-        g_collect_lane = op.lane;
+    for (size_t i = 0; i < g->ops.size(); ++i) {
+        const GraphOp& op = g->ops[i];
+        g_collect_op = i;
         emu_reported = 0;
         rc = run_op(op);
         if (rc) break;
-        if (op.kernel >= 0 && !emu_reported) {
-            fprintf(stderr, "dry shim: a kernel of a multi-lane graph does not report its accesses (no race check possible)\n");
-            rc = 719;
-            break;
-        }
-        if (op.kernel < 0) acc.push_back({ static_cast<const uint8_t*>(op.dst), static_cast<const uint8_t*>(op.dst) + op.bytes, 1, op.lane });
+        if (op.kernel >= 0 && !emu_reported) silent.push_back(i);
+        if (op.kernel < 0) acc.push_back({ static_cast<const uint8_t*>(op.dst), static_cast<const uint8_t*>(op.dst) + op.bytes, 1, i });
     }
     emu_access_hook = nullptr;
     g_collect = nullptr;
     if (rc) return rc;
+    // a kernel that reports nothing can only be vouched for when it cannot overlap another branch at all, i.e. when it is
+    // ordered against every op of every other lane (ops in front of the fork or behind the join)
+    for (size_t i : silent) {
+        const GraphOp& a = g->ops[i];
+        for (const GraphOp& b : g->ops) {
+            if (b.lane_i == a.lane_i || happens_before(a, b) || happens_before(b, a)) continue;
+            fprintf(stderr, "dry shim: op %zu of a multi-lane graph may run beside another branch but does not report its accesses "
+                            "(no race check possible)\n", i);
+            return 719;
+        }
+    }
+    // two ops race when their ranges overlap, at least one writes, they sit on different branches and neither is
+    // ordered behind the other by the capture's event edges
     for (size_t i = 0; i < acc.size(); ++i) {
         if (!acc[i].write) continue;
+        const GraphOp& a = g->ops[acc[i].op];
         for (size_t j = 0; j < acc.size(); ++j) {
-            if (acc[j].lane == acc[i].lane) continue;
-            if (acc[i].lo < acc[j].hi && acc[j].lo < acc[i].hi) {
-                fprintf(stderr, "dry shim: lane race: [%p, %p) written on one branch of the graph overlaps [%p, %p) %s on another\n",
-                        (const void*)acc[i].lo, (const void*)acc[i].hi, (const void*)acc[j].lo, (const void*)acc[j].hi,
-                        acc[j].write ? "written" : "read");
-                return 719;
-            }
+            if (acc[j].op == acc[i].op) continue;
+            const GraphOp& b = g->ops[acc[j].op];
+            if (a.lane_i == b.lane_i) continue;
+            if (!(acc[i].lo < acc[j].hi && acc[j].lo < acc[i].hi)) continue;
+            if (happens_before(a, b) || happens_before(b, a)) continue;
+            fprintf(stderr, "dry shim: lane race: op %zu (lane %d) writes [%p, %p), op %zu (lane %d) %s [%p, %p), and no event edge orders them\n",
+                    acc[i].op, a.lane_i, (const void*)acc[i].lo, (const void*)acc[i].hi, acc[j].op, b.lane_i,
+                    acc[j].write ? "writes" : "reads", (const void*)acc[j].lo, (const void*)acc[j].hi);
+            return 719;
         }
     }
     return 0;
@@ -238,7 +282,11 @@ cudaError_t cudaStreamBeginCapture(cudaStream_t s, int)
     if (capturing().count(s)) return 900;
     Graph* g = new Graph();
     capturing()[s] = g;
-    capture_state()[g] = CaptureState{ s, {} };
+    CaptureState cs;
+    cs.origin = s;
+    cs.lane_idx[s] = 0;
+    cs.vc.push_back(std::vector<int>(1, 0));
+    capture_state()[g] = cs;
     return 0;
 }
 cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t* g)
@@ -249,9 +297,12 @@ cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t* g)
     auto cs = capture_state().find(gr);
     if (cs == capture_state().end() || cs->second.origin != s) return 902;   // cudaErrorStreamCaptureUnmatched
     bool unjoined = false;
-    gr->multi_lane = !cs->second.forks.empty();
-    for (auto& f : cs->second.forks) {
-        unjoined = unjoined || !f.second;
+    gr->multi_lane = cs->second.lane_idx.size() > 1;
+    for (auto& f : cs->second.lane_idx) {
+        if (f.second == 0) continue;
+        // joined = the origin stream has seen all of the fork's work (record on the fork, wait on the origin)
+        const int own = vc_get(cs->second.vc[f.second], f.second);
+        unjoined = unjoined || vc_get(cs->second.vc[0], f.second) < own;
         capturing().erase(f.first);
     }
     capture_state().erase(cs);
@@ -296,7 +347,8 @@ cudaError_t dry_memset_async(void* d, int v, size_t n, cudaStream_t st)
     auto cap = capturing().find(st);
     if (cap == capturing().end()) { memset(d, v, n); return 0; }
     GraphOp op;
-    op.dst = d; op.value = v; op.bytes = n; op.lane = st;
+    op.dst = d; op.value = v; op.bytes = n;
+    stamp_op(cap->second, st, op);
     cap->second->ops.push_back(op);
     return 0;
 }

@@ -126,3 +126,22 @@ def test_against_cpu_oracle(model, h, w, qp):
         h_ref = np.bincount((s_ref >> 8).astype(np.int32) + 128, minlength=256)
         assert np.abs(h_gpu - h_ref).sum() <= 0.03 * len(s_ref) + 8, (k, np.abs(h_gpu - h_ref).sum())
 
+
+
+@pytest.mark.parametrize("h,w,qp", [(72, 104, 32), (200, 328, 63), (1080, 1920, 32)])
+def test_half_picture_lanes_bit_identical(model, h, w, qp, monkeypatch):
+    """DCVC_B200_SPLIT_P8=1 (measurement switch, default off): inside the synthesis transform every 1x1 GEMM of a
+    DepthConvBlock runs twice — upper half of the picture on one capture lane, lower half on another — as parallel
+    branches of the graph, with one cross-lane edge pair per block around the full-picture depthwise conv.  A pixel's
+    value does not depend on the tile it is computed in: the stream and the reconstruction must equal the default
+    path bit for bit (72x104 has an odd number of P8 rows: 9 = 4 + 5).  The CPU tier checks the same under emulation,
+    plus that no branch writes what another touches without an event edge between them."""
+    from dcvc_b200.model import DMCI
+    x, enc0, xh0, dec0 = _roundtrip(model, h, w, qp)
+    monkeypatch.setenv("DCVC_B200_SPLIT_P8", "1")          # read when the codec finalises its parameters
+    m2 = DMCI.synthetic(0)
+    m2.update(SKIP)
+    m2 = m2.half().to("cuda")
+    x, enc1, xh1, dec1 = _roundtrip(m2, h, w, qp)
+    assert np.array_equal(np.asarray(enc0["bit_stream"]), np.asarray(enc1["bit_stream"]))
+    assert torch.equal(xh0, xh1) and torch.equal(dec0, dec1) and torch.equal(xh1, dec1)

@@ -87,6 +87,10 @@ class _Dry:
         self.submit_flow("plan", "hts", ["1080x1920", "2160x3840"], {"DCVC_B200_HEAD_LANES": "2"}, tag="lanes2")
         self.submit_flow("check", "hts", ["64x64"], {"DCVC_B200_HEAD_LANES": "2", "DCVC_B200_TEST_ALIAS_LANE_SCRATCH": "1"},
                          tag="lanes-racy")
+        self.submit_flow("check", "intra", ["64x64", "72x104"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
+        self.submit_flow("check", "intra", ["64x64"], {"DCVC_B200_SPLIT_P8": "1", "DCVC_B200_TEST_DROP_LANE_SYNC": "1"},
+                         tag="split-racy")
+        self.submit_flow("plan", "intra", ["1080x1920", "2160x3840", "1096x1928"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
         for name, args, default in GPU_FILES_UNDER_EMULATION:
             if default or FULL:
                 self.submit_pytest(name, args)
@@ -191,6 +195,30 @@ def test_recon_head_lanes_change_nothing_but_the_graph_shape(dry):
     assert racy.returncode != 0 and "lane race" in racy.stderr, racy.stderr[-1500:]
 
 
+def test_half_picture_lanes_change_nothing_but_the_graph_shape(dry):
+    """DCVC_B200_SPLIT_P8 (measurement switch, off by default): the 1x1 GEMMs of the synthesis transform's blocks run as
+    upper / lower half-picture branches of the graph with cross-lane event edges around the full-picture depthwise
+    conv.  Same results as the default path bit for bit (both sizes; 72x104 has 9 P8 rows = 4 + 5), the same booked
+    algorithmic work, a capture that forks, and a clean race check — which is not vacuous: the first version of the
+    split raced where a block changes the channel width (the halves' byte ranges shift inside the reused buffers; found
+    by this check, fixed by a two-way edge before such blocks), and dropping the edge in front of the depthwise conv
+    (test-only switch) must trip it.  Plan mode: every half-picture GEMM plans at 1080p, 4K and a padded size."""
+    def last_json(r):
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    base = last_json(dry.result(("check", "intra")))
+    split = last_json(dry.result(("check", "intra", "split")))
+    assert base["capture_forks"] == 0 and split["capture_forks"] >= 1
+    for a, b in zip(base["runs"], split["runs"]):
+        assert a["bytes"] == b["bytes"] and a["psnr"] == b["psnr"] and a["symbols"] == b["symbols"]
+        assert abs(a["decode_alg_gb"] - b["decode_alg_gb"]) < 1e-9 and abs(a["decode_gmac"] - b["decode_gmac"]) < 1e-9
+        assert b["decode_launches"] > a["decode_launches"]
+    racy = dry.result(("check", "intra", "split-racy"))
+    assert racy.returncode != 0 and "lane race" in racy.stderr, racy.stderr[-1500:]
+    plan = last_json(dry.result(("plan", "intra", "split")))
+    assert plan["capture_forks"] >= 1 and len(plan["runs"]) == 3
+
+
 def _pytest_under_emulation(dry, name, args):
     dry.submit_pytest(name, args)
     r = dry.result(("pytest", name))
@@ -203,6 +231,7 @@ FULL = os.environ.get("DCVC_B200_DRY_FULL") == "1"
 GPU_FILES_UNDER_EMULATION = [
     ("ops", ["tests/test_ops_gpu.py"], True),
     ("sequence-ld", ["tests/test_sequence_gpu.py", "-k", "ld"], True),
+    ("split-lanes", ["tests/test_codec_gpu.py", "-k", "half_picture and 72-104"], True),
     ("sequence-hts", ["tests/test_sequence_gpu.py", "-k", "hts"], False),
     ("htl", ["tests/test_htl_gpu.py", "-k", "64-64 or oracle or bit_identical"], False),
     ("hts", ["tests/test_hts_gpu.py", "-k", "64-64 or oracle or bit_identical"], False),
