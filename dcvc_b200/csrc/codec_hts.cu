@@ -139,6 +139,10 @@ ActView HtsCodec::chain(Segment& s, Level& L, ActView in, const DcbW* blocks, in
 {
     // n DepthConvBlocks in sequence; the first may take an external input (then it lands in L.B unless it has an
     // adaptor), the last is redirected to `out` when given and carries the fused per-channel quant scale.
+    // P8 chains run as half-picture lanes when DCVC_B200_SPLIT_P8=1 (codec_common.cuh); a region per chain, so whatever
+    // follows the chain (1x1 head convolutions, the next segment) sees both halves
+    const bool split = (&L == &l8_);
+    if (split) begin_split(s);
     ActView t = in;
     for (int i = 0; i < n; ++i) {
         const bool last = (i == n - 1);
@@ -148,6 +152,7 @@ ActView HtsCodec::chain(Segment& s, Level& L, ActView in, const DcbW* blocks, in
         if (!o && external && !blocks[i].adaptor) o = &first_out;
         t = dcb(s, L, t, blocks[i], false, last ? q_last : nullptr, o);
     }
+    if (split) end_split(s);
     return t;
 }
 
@@ -183,6 +188,8 @@ void HtsCodec::plan(int height, int width)
         const char* e = getenv("DCVC_B200_HEAD_LANES");
         const int n = e ? atoi(e) : 1;
         head_lanes_ = (n == 2 || n == 4) ? n : 1;
+        if (head_lanes_ > 1 && split_enabled_)
+            throw std::runtime_error("DCVC_B200_HEAD_LANES and DCVC_B200_SPLIT_P8 are alternatives (both use the capture lanes)");
     }
     size_t bytes = p8 * 2 * (2048 + 1024 + 192 + 512 + 512 + 192 * kG + 4 * 512);
     bytes += static_cast<size_t>(head_lanes_ - 1) * (p8 * 2 * (4 * 512 + 512) + 5 * 4096);

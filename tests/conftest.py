@@ -17,7 +17,7 @@ def pytest_configure(config):
 # results of the device-validated cases behind it.  Remove an entry once its first device run is green.
 FIRST_DEVICE_RUN = ("test_hts_gpu.py::test_chunk_roundtrip_state_consistency[2160-3840",
                     "test_ld_gpu.py::test_frame_roundtrip_state_consistency[2160-3840", "test_sequence_gpu.py",
-                    "test_hts_gpu.py::test_recon_head_lanes_bit_identical",
+                    "test_hts_gpu.py::test_capture_lanes_bit_identical",
                     "test_codec_gpu.py::test_half_picture_lanes_bit_identical")   # in the order they run
 
 

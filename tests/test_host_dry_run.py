@@ -91,6 +91,7 @@ class _Dry:
         self.submit_flow("check", "intra", ["64x64"], {"DCVC_B200_SPLIT_P8": "1", "DCVC_B200_TEST_DROP_LANE_SYNC": "1"},
                          tag="split-racy")
         self.submit_flow("plan", "intra", ["1080x1920", "2160x3840", "1096x1928"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
+        self.submit_flow("check", "hts", ["72x104"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
         for name, args, default in GPU_FILES_UNDER_EMULATION:
             if default or FULL:
                 self.submit_pytest(name, args)
@@ -217,6 +218,12 @@ def test_half_picture_lanes_change_nothing_but_the_graph_shape(dry):
     assert racy.returncode != 0 and "lane race" in racy.stderr, racy.stderr[-1500:]
     plan = last_json(dry.result(("plan", "intra", "split")))
     assert plan["capture_forks"] >= 1 and len(plan["runs"]) == 3
+    # the chunk codec: every P8 chain (encoder, decoder, memory update, context, recon heads) as a split region
+    hbase = last_json(dry.result(("check", "hts")))
+    hsplit = last_json(dry.result(("check", "hts", "split")))
+    assert hsplit["capture_forks"] >= 3
+    assert hsplit["runs"][0]["bytes"] == hbase["runs"][0]["bytes"] and hsplit["runs"][0]["psnr"] == hbase["runs"][0]["psnr"]
+    assert abs(hsplit["runs"][0]["decode_alg_gb"] - hbase["runs"][0]["decode_alg_gb"]) < 1e-9
 
 
 def _pytest_under_emulation(dry, name, args):

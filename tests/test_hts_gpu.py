@@ -167,17 +167,20 @@ def test_hts_stream_bit_identical_to_reference_coder(nets):
     assert np.asarray(r.get_encoded_stream()).tobytes() == e["bit_stream"]
 
 
-@pytest.mark.parametrize("lanes", ["2", "4"])
-def test_recon_head_lanes_bit_identical(nets, lanes, monkeypatch):
-    """DCVC_B200_HEAD_LANES (measurement switch, default off): the four recon-head pairs run as parallel branches of the
-    recon graph, each on its own scratch level, so that one persistent GEMM's tail overlaps the next branch's work.  The
-    branches share nothing but their read-only input: streams, every decoded frame and the carried state must equal
-    the single-lane run bit for bit (the CPU tier checks the same under emulation and that the capture forks / joins)."""
+@pytest.mark.parametrize("switch,value", [("DCVC_B200_HEAD_LANES", "2"), ("DCVC_B200_HEAD_LANES", "4"),
+                                          ("DCVC_B200_SPLIT_P8", "1")])
+def test_capture_lanes_bit_identical(nets, switch, value, monkeypatch):
+    """The two capture-lane switches (measurement switches, default off).  DCVC_B200_HEAD_LANES: the four recon-head pairs
+    run as parallel branches of the recon graph, each on its own scratch level.  DCVC_B200_SPLIT_P8: inside every P8
+    chain the 1x1 GEMMs run as upper / lower half-picture branches with cross-lane edges around the depthwise conv.
+    Either way one persistent GEMM's tail overlaps another branch's work, and nothing else changes: streams, every
+    decoded frame and the carried state must equal the default run bit for bit (the CPU tier checks the same under
+    emulation, that the captures fork / join, and that no branch races another)."""
     from dcvc_b200.model import DMC
     i_net, p_net = nets
     h, w = 136, 200                                        # ragged: pads to 144 x 208
     _, streams0, recon0, _, dec0 = _run(i_net, p_net, h, w, 2, 20, 33, ())
-    monkeypatch.setenv("DCVC_B200_HEAD_LANES", lanes)      # read when the codec plans a resolution
+    monkeypatch.setenv(switch, value)                      # read when the codec finalises its parameters / plans a resolution
     p2 = DMC.synthetic(1)
     p2.update(SKIP)
     p2 = p2.half().to("cuda")
