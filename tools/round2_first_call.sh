@@ -1,11 +1,12 @@
 #!/bin/bash
-# The first gpurun call of the next round, in one script (about 35 minutes of box time on one B200):
-#   /usr/local/graft/bin/gpurun --timeout 2700 -- 'bash tools/round2_first_call.sh'
+# The first gpurun call of the next round, in one script (about 50 minutes of box time on one B200; the steps are
+# independent — cut the list when the budget is tight):
+#   /usr/local/graft/bin/gpurun --timeout 3600 -- 'bash tools/round2_first_call.sh'
 # Every step runs under its own timeout and writes to gpurun_out/r2_*.{log,json,csv}, so a hang costs one step and
 # whatever finished before it comes back.  What it answers (DESIGN.md §0, round-2 plan):
 #   1. are the device cases that only ran under emulation green (4K HT-S / LD, sequence driver, recon-head lanes)?
 #   2. does the experimental HT-L path pass its first device run (tools/validate_htl.sh)?
-#   3. do parallel recon-head branches (DCVC_B200_HEAD_LANES) pay on the HT-S decode?
+#   3. do parallel graph branches pay: recon-head lanes (DCVC_B200_HEAD_LANES) and half-picture lanes (DCVC_B200_SPLIT_P8)?
 #   4. what is the throughput of two concurrent Intra decodes per GPU (bench.py --pipelined)?
 #   5. where does the steady state of the N = K = 384 GEMM go: operand ingest, tensor pipe or epilogue
 #      (DCVC_B200_GEMM_DBG 0 / 1 / 2 / 3 on the streaming, A-resident and CTA-pair kernels)?
@@ -22,22 +23,22 @@ echo "== 2. HT-L first device run"
 timeout 1500 bash tools/validate_htl.sh > $O/r2_validate_htl.log 2>&1
 tail -12 $O/r2_validate_htl.log
 
-echo "== 3. recon-head lanes on the HT-S leg"
+echo "== 3. capture lanes: recon-head branches (HT-S) and half-picture branches (Intra synthesis, HT-S P8 chains)"
 # PDL matters here: a dependent kernel that was launched early sits in griddepcontrol.wait ON an SM — it may take the SMs a
 # finished CTA frees before the other branch's ready CTAs get them.  So every lane count is measured with PDL on and off.
-for L in 1 2 4 2nopdl 4nopdl; do
-    LN=${L%nopdl}
-    PDL=1; [ "$L" != "$LN" ] && PDL=0
-    DCVC_B200_PDL=$PDL DCVC_B200_HEAD_LANES=$LN timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $O/r2_bench_lanes$L.json 2> $O/r2_bench_lanes$L.err
+for V in "lanes1:1:0:1" "lanes2:2:0:1" "lanes4:4:0:1" "lanes2nopdl:2:0:0" "lanes4nopdl:4:0:0" "split:1:1:1" "splitnopdl:1:1:0"; do
+    IFS=: read NAME LN SP PDL <<< "$V"
+    DCVC_B200_PDL=$PDL DCVC_B200_HEAD_LANES=$LN DCVC_B200_SPLIT_P8=$SP timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline \
+        > $O/r2_bench_$NAME.json 2> $O/r2_bench_$NAME.err
     python - <<EOF
 import json
 try:
-    d = json.loads(open("$O/r2_bench_lanes$L.json").read().strip().splitlines()[-1])
+    d = json.loads(open("$O/r2_bench_$NAME.json").read().strip().splitlines()[-1])
     h = d["hts"]
-    print("lanes $L: hts decode %.1f FPS  gpu-only %.3f ms/chunk  encode %.1f FPS | intra decode %.1f FPS" %
-          (h["decode_fps"], h["gpu_only_ms_per_chunk_decode"], h["encode_fps"], d["value"]))
+    print("$NAME: hts decode %.1f FPS gpu-only %.3f ms/chunk encode %.1f FPS | intra decode %.1f FPS gpu-only %.3f ms encode %.1f FPS" %
+          (h["decode_fps"], h["gpu_only_ms_per_chunk_decode"], h["encode_fps"], d["value"], d["gpu_only_ms_per_decode"], d["encode_fps"]))
 except Exception as e:
-    print("lanes $L: no result (%s)" % e)
+    print("$NAME: no result (%s)" % e)
 EOF
 done
 
