@@ -211,8 +211,10 @@ void IntraCodec::plan(int height, int width)
     // ------------------------------------------------------------------ enc_0 (dmci_proxy.cpp:308-394)
     {
         Segment& s = enc0_;
+        begin_split(s);  // the 7 P8 blocks of the analysis transform: half-picture lanes when DCVC_B200_SPLIT_P8=1
         ActView t = dcb(s, l8_, v_in8, enc1_, false, q_enc_, nullptr);     // enc_1, then * q_enc
         for (int i = 0; i < 6; ++i) t = dcb(s, l8_, t, enc2_[i], false, nullptr, nullptr);
+        end_split(s);
         add_gemm(s, GEMM_CONV3X3_S2, t, v_y, enc_down_.w, enc_down_.b, kChY, ACT_NONE, 0, nullptr, nullptr, nullptr);
         if (padded) s.ops.push_back([v_y, v_ypad](cudaStream_t st) { return launch_pad_crop(v_y, v_ypad, st); });
         // hyper encoder

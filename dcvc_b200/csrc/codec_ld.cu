@@ -127,6 +127,9 @@ ActView LdCodec::chain(Segment& s, Level& L, ActView in, const DcbW* blocks, int
 {
     // n DepthConvBlocks in sequence; the first may take an external input (then it lands in L.B unless it has an
     // adaptor), the last is redirected to `out` when given and carries the fused per-channel quant scale.
+    // P8 chains run as half-picture lanes when DCVC_B200_SPLIT_P8=1 (codec_common.cuh), one region per chain.
+    const bool split = (&L == &l8_);
+    if (split) begin_split(s);
     ActView t = in;
     for (int i = 0; i < n; ++i) {
         const bool last = (i == n - 1);
@@ -136,6 +139,7 @@ ActView LdCodec::chain(Segment& s, Level& L, ActView in, const DcbW* blocks, int
         if (!o && external && !blocks[i].adaptor) o = &first_out;
         t = dcb(s, L, t, blocks[i], false, last ? q_last : nullptr, o);
     }
+    if (split) end_split(s);
     return t;
 }
 

@@ -92,6 +92,7 @@ class _Dry:
                          tag="split-racy")
         self.submit_flow("plan", "intra", ["1080x1920", "2160x3840", "1096x1928"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
         self.submit_flow("check", "hts", ["72x104"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
+        self.submit_flow("check", "ld", ["72x104"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
         for name, args, default in GPU_FILES_UNDER_EMULATION:
             if default or FULL:
                 self.submit_pytest(name, args)
@@ -224,6 +225,10 @@ def test_half_picture_lanes_change_nothing_but_the_graph_shape(dry):
     assert hsplit["capture_forks"] >= 3
     assert hsplit["runs"][0]["bytes"] == hbase["runs"][0]["bytes"] and hsplit["runs"][0]["psnr"] == hbase["runs"][0]["psnr"]
     assert abs(hsplit["runs"][0]["decode_alg_gb"] - hbase["runs"][0]["decode_alg_gb"]) < 1e-9
+    lbase = last_json(dry.result(("check", "ld")))
+    lsplit = last_json(dry.result(("check", "ld", "split")))
+    assert lsplit["capture_forks"] >= 1
+    assert lsplit["runs"][0]["bytes"] == lbase["runs"][0]["bytes"] and lsplit["runs"][0]["psnr"] == lbase["runs"][0]["psnr"]
 
 
 def _pytest_under_emulation(dry, name, args):

@@ -118,3 +118,23 @@ def test_ld_stream_bit_identical_to_reference_coder(nets):
     r.encode_z(z, 40 * 128, 128)
     r.flush()
     assert np.asarray(r.get_encoded_stream()).tobytes() == e["bit_stream"]
+
+
+def test_half_picture_lanes_bit_identical(nets, monkeypatch):
+    """DCVC_B200_SPLIT_P8=1 (measurement switch, default off; see tests/test_codec_gpu.py): every P8 chain of the LD codec
+    as upper / lower half-picture branches of its graph.  Streams, decoded frames and the carried state must equal the
+    default run bit for bit."""
+    from dcvc_b200.model import DMCLD
+    i_net, p_net = nets
+    h, w = 136, 200
+    _, streams0, recon0, _, dec0 = _run(i_net, p_net, h, w, 3, 20, 33, (1,))
+    monkeypatch.setenv("DCVC_B200_SPLIT_P8", "1")          # read when the codec finalises its parameters
+    p2 = DMCLD.synthetic(2)
+    p2.update(SKIP)
+    p2 = p2.half().to("cuda")
+    _, streams1, recon1, _, dec1 = _run(i_net, p2, h, w, 3, 20, 33, (1,))
+    for a, b in zip(streams0, streams1):
+        assert np.array_equal(np.asarray(a[1]), np.asarray(b[1])) and a[2] == b[2]
+    for a, b in zip(recon0, recon1):
+        assert torch.equal(a, b)
+    assert np.array_equal(np.asarray(dec0).view(np.uint16), np.asarray(dec1).view(np.uint16))
