@@ -157,6 +157,7 @@ struct Segment {
     struct LaneSync { size_t at; int from, to; };
     std::vector<LaneSync> syncs;
     bool split_open = false;  // inside a half-picture region (CodecBase::begin_split / end_split)
+    bool lanes_region = false;  // ops pushed now may run beside another lane's ops (split region, recon-head lanes)
     int split_c = 0, split_inner = 0, split_in_pitch = 0;  // channel widths of the previous split block (byte layout of the halves)
     cudaGraphExec_t exec = nullptr;
     int launches = 0;
@@ -210,7 +211,7 @@ struct Segment {
         if (exec) cudaGraphExecDestroy(exec);
         exec = nullptr;
         ops.clear(); kinds.clear(); alg_bytes.clear(); flops.clear(); lanes.clear(); syncs.clear();
-        cur_lane = 0; n_lanes = 1; split_open = false;
+        cur_lane = 0; n_lanes = 1; split_open = false; lanes_region = false;
         split_c = split_inner = split_in_pitch = 0;
         launches = 0;
         flag_begin = nullptr;
@@ -438,6 +439,8 @@ protected:
             split_enabled_ = sp && sp[0] == '1';
             const char* dr = getenv("DCVC_B200_TEST_DROP_LANE_SYNC");
             test_drop_sync_ = dr && dr[0] == '1';
+            const char* lp = getenv("DCVC_B200_LANES_PDL");
+            lanes_pdl_ = !(lp && lp[0] == '0');
         }
         if (chain_enabled_ && !flags_base_) {
             flags_cap_ = (8u << 20) / sizeof(int);
@@ -463,6 +466,9 @@ protected:
         op->N = N;
         op->act = act;
         op->chunk_add = chunk;
+        // a kernel launched with PDL sits ON an SM while it waits for its predecessor: beside another lane that could use
+        // the SM this can be counter-productive (DCVC_B200_LANES_PDL=0 launches the ops of lane regions without it)
+        op->pdl = lanes_pdl_ || !s.lanes_region;
         if (chain_enabled_ && in_dcb && kind == GEMM_PW && flags_base_) {
             // Tile-level chaining, only between the 1x1 GEMMs of DepthConvBlocks: the op reports completed 128-pixel
             // tiles; if the previous op of the segment was such a GEMM and wrote exactly this op's input view, the op
@@ -548,6 +554,7 @@ protected:
         if (!split_enabled_ || s.split_open) return;
         s.lane_sync(0, 1);  // lane 1 starts behind everything lane 0 has done so far in this segment
         s.split_open = true;
+        s.lanes_region = true;
         s.split_c = s.split_inner = s.split_in_pitch = 0;
     }
     void end_split(Segment& s)
@@ -556,6 +563,7 @@ protected:
         s.lane_sync(1, 0);
         s.set_lane(0);
         s.split_open = false;
+        s.lanes_region = false;
     }
     void gemm_1x1(Segment& s, const ActView& in, const ActView& out, const __half* w, const __half* bias, int N, int act,
                   int chunk, const ActView* r1, const ActView* r2, const __half* q)
@@ -621,7 +629,8 @@ protected:
                 s.set_lane(0);
             }
             s.annotate(OP_ELEM, 0, 0);
-            s.ops.push_back([t1, t2, wdw](cudaStream_t st) { return launch_dw3x3(t1, t2, wdw, st); });
+            const bool dw_pdl = lanes_pdl_ || !s.lanes_region;
+            s.ops.push_back([t1, t2, wdw, dw_pdl](cudaStream_t st) { return launch_dw3x3(t1, t2, wdw, st, dw_pdl); });
             s.out_views.resize(s.ops.size());
             s.out_views.back() = t2;
             s.annotate(OP_DW, 2.0 * 2 * W * H * w.inner, 2.0 * 9 * W * H * w.inner);
@@ -828,6 +837,7 @@ protected:
     std::vector<cudaEvent_t> lane_events_;
     std::vector<cudaEvent_t> sync_events_;     // one per cross-lane edge of the largest multi-lane segment
     bool split_enabled_ = false;               // DCVC_B200_SPLIT_P8=1 (read in finalize)
+    bool lanes_pdl_ = true;                    // DCVC_B200_LANES_PDL=0: no programmatic dependent launch inside lane regions
     bool test_drop_sync_ = false;              // DCVC_B200_TEST_DROP_LANE_SYNC=1: fault injection for the CPU tier's race check
     std::vector<cudaEvent_t> tev_;
     std::vector<cudaEvent_t> prof_events_;

@@ -414,6 +414,7 @@ void HtsCodec::plan(int height, int width)
         // recon head: 4 shared blocks + 8 x (3 blocks + 1x1); head i lands in head_out_[i], head 7 in feature_i
         // (the reset reference, dmc_hts_proxy.cpp:336-338)
         Segment& s = s_recon_;
+        if (head_lanes_ > 1) s.lanes_region = true;
         for (int i = 0; i < kG; ++i) {
             const int lane = (i / 2) % head_lanes_;
             if (head_lanes_ > 1) s.set_lane(lane);
@@ -427,7 +428,7 @@ void HtsCodec::plan(int height, int width)
             const ActView ho = (i == kG - 1) ? v_feature_i : make_view(head_out_ + static_cast<size_t>(i) * p8 * kSrcI, kSrcI, kSrcI, W8, H8);
             conv1x1(s, t, ho, rh_out_[i]);
         }
-        if (head_lanes_ > 1) s.set_lane(0);
+        if (head_lanes_ > 1) { s.set_lane(0); s.lanes_region = false; }
     }
     Segment* segs[] = { &s_enc0_, &s_decoder_, &s_reset_head_, &s_fa_i_, &s_fa_m_, &s_fe_, &s_temporal_, &s_dec1_, &s_dec3_, &s_recon_ };
     for (Segment* s : segs) s->seal();

@@ -109,7 +109,7 @@ dw3x3_kernel(const __half* __restrict__ in, int in_pitch, __half* __restrict__ o
 }
 
 template <int DW_TY>
-static int launch_dw3x3_ty(const ActView& in, const ActView& out, const __half* w, cudaStream_t s)
+static int launch_dw3x3_ty(const ActView& in, const ActView& out, const __half* w, cudaStream_t s, bool pdl)
 {
     const long long total = static_cast<long long>(in.W) * (in.C / 8) * ((in.H + DW_TY - 1) / DW_TY);
     cudaLaunchConfig_t cfg;
@@ -122,20 +122,20 @@ static int launch_dw3x3_ty(const ActView& in, const ActView& out, const __half* 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     const char* e = getenv("DCVC_B200_PDL");
-    cfg.numAttrs = (e && e[0] == '0') ? 0 : 1;
+    cfg.numAttrs = ((e && e[0] == '0') || !pdl) ? 0 : 1;
     cudaLaunchKernelEx(&cfg, dw3x3_kernel<DW_TY>, static_cast<const __half*>(in.ptr), in.pitch,
                        static_cast<__half*>(const_cast<void*>(out.ptr)), out.pitch, w, in.C, in.W, in.H);
     DCVC_LAUNCH_CHECK();
     return 0;
 }
 
-int launch_dw3x3(const ActView& in, const ActView& out, const __half* w, cudaStream_t s)
+int launch_dw3x3(const ActView& in, const ActView& out, const __half* w, cudaStream_t s, bool pdl)
 {
     // rows per thread: DCVC_B200_DW_TY = 2 | 4 | 8 (measurement switch; default 4)
     static const int ty = []() { const char* e = getenv("DCVC_B200_DW_TY"); return e ? atoi(e) : DW_TY_DEFAULT; }();
-    if (ty == 2) return launch_dw3x3_ty<2>(in, out, w, s);
-    if (ty == 8) return launch_dw3x3_ty<8>(in, out, w, s);
-    return launch_dw3x3_ty<4>(in, out, w, s);
+    if (ty == 2) return launch_dw3x3_ty<2>(in, out, w, s, pdl);
+    if (ty == 8) return launch_dw3x3_ty<8>(in, out, w, s, pdl);
+    return launch_dw3x3_ty<4>(in, out, w, s, pdl);
 }
 
 // ------------------------------------------------------------------------------- unshuffle8

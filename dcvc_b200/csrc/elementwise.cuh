@@ -12,7 +12,7 @@ namespace dcvc {
 
 // depthwise 3x3, pad 1, no bias (bias is folded into the next 1x1: layers_proxy.cpp:175-178).
 // w: [9][C] fp16 (tap-major).
-int launch_dw3x3(const ActView& in, const ActView& out, const __half* w, cudaStream_t s);
+int launch_dw3x3(const ActView& in, const ActView& out, const __half* w, cudaStream_t s, bool pdl = true);
 
 // replicate-pad to x8 + pixel_unshuffle(8): x[1,Cs,H,W] (element strides sc,sh,sw) -> [H8][W8][Cs*64]
 // (reference pad_and_unshuffle_8_kernel, cat_and_pad.cu:7-51)

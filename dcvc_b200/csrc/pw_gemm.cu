@@ -802,7 +802,7 @@ static cudaError_t launch_bn(const GemmOp& op, cudaStream_t stream)
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = g_pdl ? 2 : 1;
+    cfg.numAttrs = (g_pdl && op.pdl) ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, pw_gemm_kernel<BN, CHUNK>, op.p);
 }
 

@@ -104,6 +104,7 @@ struct GemmOp {
     const int* wait_a = nullptr;
     int wait_a_need = 0;
     bool no_grid_wait = false;
+    bool pdl = true;    // launch with the programmatic-dependent-launch attribute (when DCVC_B200_PDL allows it at all)
     // ---- derived by gemm_plan()
     PwGemmParams p;
     dim3 grid;

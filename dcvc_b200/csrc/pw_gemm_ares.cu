@@ -445,7 +445,7 @@ static cudaError_t ares_launch_bn(const GemmOp& op, cudaStream_t stream)
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = gemm_pdl_enabled() ? 2 : 1;
+    cfg.numAttrs = (gemm_pdl_enabled() && op.pdl) ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, pw_gemm_ares_kernel<BN, CHUNK, CTAS>, op.p);
 }
 
