@@ -134,7 +134,7 @@ def test_half_picture_lanes_bit_identical(model, h, w, qp, monkeypatch):
     DepthConvBlock runs twice — upper half of the picture on one capture lane, lower half on another — as parallel
     branches of the graph, with one cross-lane edge pair per block around the full-picture depthwise conv.  A pixel's
     value does not depend on the tile it is computed in: the stream and the reconstruction must equal the default
-    path bit for bit (72x104 has an odd number of P8 rows: 9 = 4 + 5).  The CPU tier checks the same under emulation,
+    path bit for bit.  The CPU tier checks the same under emulation,
     plus that no branch writes what another touches without an event edge between them."""
     from dcvc_b200.model import DMCI
     x, enc0, xh0, dec0 = _roundtrip(model, h, w, qp)

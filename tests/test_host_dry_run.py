@@ -200,7 +200,7 @@ def test_recon_head_lanes_change_nothing_but_the_graph_shape(dry):
 def test_half_picture_lanes_change_nothing_but_the_graph_shape(dry):
     """DCVC_B200_SPLIT_P8 (measurement switch, off by default): the 1x1 GEMMs of the synthesis transform's blocks run as
     upper / lower half-picture branches of the graph with cross-lane event edges around the full-picture depthwise
-    conv.  Same results as the default path bit for bit (both sizes; 72x104 has 9 P8 rows = 4 + 5), the same booked
+    conv.  Same results as the default path bit for bit (both sizes), the same booked
     algorithmic work, a capture that forks, and a clean race check — which is not vacuous: the first version of the
     split raced where a block changes the channel width (the halves' byte ranges shift inside the reused buffers; found
     by this check, fixed by a two-way edge before such blocks), and dropping the edge in front of the depthwise conv
