@@ -455,13 +455,20 @@ void IntraCodec::decompress(const uint8_t* bs, int len, int qp, int height, int 
         tick(stream);
         run(k == 0 ? dec0_ : dec_step_[k], stream);
         tock(stream);
+        // DCVC_B200_DECODE_ONE_SYNC=1 (measurement switch): the count and the whole index buffer travel together and the
+        // host waits once per step instead of twice (batched count path); costs copying quarter_ bytes
+        // instead of n
+        const bool one_sync = decode_one_sync_;
         CK(cudaMemcpyAsync(h_totals_ + k, totals_ + k, 4, cudaMemcpyDeviceToHost, stream));
+        if (one_sync) CK(cudaMemcpyAsync(h_idx_, idx_c_, quarter_, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         const int n = h_totals_[k];
         if (n < 0 || static_cast<size_t>(n) > quarter_) throw std::runtime_error("corrupt index count");
         if (n) {
-            CK(cudaMemcpyAsync(h_idx_, idx_c_, n, cudaMemcpyDeviceToHost, stream));
-            CK(cudaStreamSynchronize(stream));
+            if (!one_sync) {
+                CK(cudaMemcpyAsync(h_idx_, idx_c_, n, cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+            }
             rans_.decode_y(h_decoded_, h_idx_, n);
             CK(cudaMemcpyAsync(decoded_, h_decoded_, n, cudaMemcpyHostToDevice, stream));
         }

@@ -441,6 +441,8 @@ protected:
             test_drop_sync_ = dr && dr[0] == '1';
             const char* lp = getenv("DCVC_B200_LANES_PDL");
             lanes_pdl_ = !(lp && lp[0] == '0');
+            const char* os = getenv("DCVC_B200_DECODE_ONE_SYNC");
+            decode_one_sync_ = os && os[0] == '1';
         }
         if (chain_enabled_ && !flags_base_) {
             flags_cap_ = (8u << 20) / sizeof(int);
@@ -837,6 +839,7 @@ protected:
     std::vector<cudaEvent_t> lane_events_;
     std::vector<cudaEvent_t> sync_events_;     // one per cross-lane edge of the largest multi-lane segment
     bool split_enabled_ = false;               // DCVC_B200_SPLIT_P8=1 (read in finalize)
+    bool decode_one_sync_ = false;             // DCVC_B200_DECODE_ONE_SYNC=1: one host wait per prior step of the Intra decoder
     bool lanes_pdl_ = true;                    // DCVC_B200_LANES_PDL=0: no programmatic dependent launch inside lane regions
     bool test_drop_sync_ = false;              // DCVC_B200_TEST_DROP_LANE_SYNC=1: fault injection for the CPU tier's race check
     std::vector<cudaEvent_t> tev_;

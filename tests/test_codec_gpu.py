@@ -145,3 +145,20 @@ def test_half_picture_lanes_bit_identical(model, h, w, qp, monkeypatch):
     x, enc1, xh1, dec1 = _roundtrip(m2, h, w, qp)
     assert np.array_equal(np.asarray(enc0["bit_stream"]), np.asarray(enc1["bit_stream"]))
     assert torch.equal(xh0, xh1) and torch.equal(dec0, dec1) and torch.equal(xh1, dec1)
+
+
+@pytest.mark.parametrize("h,w", [(72, 104), (1080, 1920)])
+def test_decode_one_sync_bit_identical(model, h, w, monkeypatch):
+    """DCVC_B200_DECODE_ONE_SYNC=1 (measurement switch, default off; SURVEY.md 8 f1, batched count path): per prior step
+    the symbol count and the whole index buffer are copied together and the host waits once instead of twice."""
+    from dcvc_b200.model import DMCI
+    qp = 32
+    x, enc, xh_enc, dec0 = _roundtrip(model, h, w, qp)
+    monkeypatch.setenv("DCVC_B200_DECODE_ONE_SYNC", "1")     # read when the codec finalises its parameters
+    m2 = DMCI.synthetic(0)
+    m2.update(SKIP)
+    m2 = m2.half().to("cuda")
+    m2.compress(x, qp, *reversed(m2.get_padding_size(h, w, 16)))     # the proxy exists after the first compress
+    dec1 = m2.decompress(enc["bit_stream"], {"height": h, "width": w}, qp, enc["ec_parallel"])["x_hat"]
+    torch.cuda.synchronize()
+    assert torch.equal(dec0, dec1)

@@ -87,7 +87,8 @@ class _Dry:
         self.submit_flow("plan", "hts", ["1080x1920", "2160x3840"], {"DCVC_B200_HEAD_LANES": "2"}, tag="lanes2")
         self.submit_flow("check", "hts", ["64x64"], {"DCVC_B200_HEAD_LANES": "2", "DCVC_B200_TEST_ALIAS_LANE_SCRATCH": "1"},
                          tag="lanes-racy")
-        self.submit_flow("check", "intra", ["64x64", "72x104"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
+        self.submit_flow("check", "intra", ["64x64", "72x104"], {"DCVC_B200_SPLIT_P8": "1", "DCVC_B200_DECODE_ONE_SYNC": "1"},
+                         tag="split")   # + the one-wait-per-step decode hand-off: same results as well
         self.submit_flow("check", "intra", ["64x64"], {"DCVC_B200_SPLIT_P8": "1", "DCVC_B200_TEST_DROP_LANE_SYNC": "1"},
                          tag="split-racy")
         self.submit_flow("plan", "intra", ["1080x1920", "2160x3840", "1096x1928"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")

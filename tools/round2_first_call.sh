@@ -57,6 +57,13 @@ import json
 d = json.loads(open('$O/r2_bench_pipelined.json').read().strip().splitlines()[-1])
 print('single', d['value'], 'FPS; pipelined', d.get('pipelined'))" 2>&1 | tail -1
 
+echo "== 4a. one host wait per prior step in the Intra decoder"
+DCVC_B200_DECODE_ONE_SYNC=1 timeout 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-hts > $O/r2_bench_onesync.json 2> $O/r2_bench_onesync.err
+python -c "
+import json
+d = json.loads(open('$O/r2_bench_onesync.json').read().strip().splitlines()[-1])
+print('one-sync: decode', d['value'], 'e2e', d['e2e']['value'])" 2>&1 | tail -1
+
 echo "== 4b. host threads pinned to the GPU's NUMA node"
 DCVC_B200_NUMA_PIN=1 timeout 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-hts > $O/r2_bench_numa.json 2> $O/r2_bench_numa.err
 python -c "
