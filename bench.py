@@ -303,6 +303,8 @@ def run_ours(args):
             "pipelined": pipelined,
             "hts_extra": hts_extra,
             "host": {"cpus": os.cpu_count(), "numa_pinned_cpus": (len(numa) if numa else None)},
+            # every DCVC_B200_* switch of the environment (none in the driver's runs): an A/B line describes itself
+            "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("DCVC_B200_")},
         }
         if _SIZE_OVERRIDE:
             out["INVALID_test_size_override"] = _SIZE_OVERRIDE
