@@ -130,6 +130,9 @@ void HtlCodec::clear_plan()
 
 ActView HtlCodec::chain(Segment& s, Level& L, ActView in, const DcbW* blocks, int n, const __half* q_last, const ActView* out)
 {
+    // P8 chains run as half-picture lanes when DCVC_B200_SPLIT_P8=1 (codec_common.cuh), one region per chain
+    const bool split = (&L == &l8_);
+    if (split) begin_split(s);
     ActView t = in;
     for (int i = 0; i < n; ++i) {
         const bool last = (i == n - 1);
@@ -139,6 +142,7 @@ ActView HtlCodec::chain(Segment& s, Level& L, ActView in, const DcbW* blocks, in
         if (!o && external && !blocks[i].adaptor) o = &first_out;
         t = dcb(s, L, t, blocks[i], false, last ? q_last : nullptr, o);
     }
+    if (split) end_split(s);
     return t;
 }
 

@@ -94,7 +94,7 @@ class _Dry:
         self.submit_flow("plan", "intra", ["1080x1920", "2160x3840", "1096x1928"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
         self.submit_flow("check", "hts", ["72x104"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
         self.submit_flow("check", "ld", ["72x104"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
-        for codec in ("hts", "ld"):
+        for codec in ("hts", "ld", "htl"):
             self.submit_flow("plan", codec, ["1080x1920", "2160x3840", "200x328"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
         for name, args, default in GPU_FILES_UNDER_EMULATION:
             if default or FULL:
@@ -228,7 +228,7 @@ def test_half_picture_lanes_change_nothing_but_the_graph_shape(dry):
     assert hsplit["capture_forks"] >= 3
     assert hsplit["runs"][0]["bytes"] == hbase["runs"][0]["bytes"] and hsplit["runs"][0]["psnr"] == hbase["runs"][0]["psnr"]
     assert abs(hsplit["runs"][0]["decode_alg_gb"] - hbase["runs"][0]["decode_alg_gb"]) < 1e-9
-    for codec in ("hts", "ld"):   # every half-picture GEMM plans at 1080p / 4K / a ragged size and books the reference's work
+    for codec in ("hts", "ld", "htl"):   # every half-picture GEMM plans at 1080p / 4K / a ragged size and books the reference's work
         pl = last_json(dry.result(("plan", codec, "split")))
         gb, gmac = REFERENCE_DECODE_WORK[codec]
         assert abs(pl["runs"][0]["decode_alg_gb"] - gb) <= 0.005 * gb + 0.005 and abs(pl["runs"][0]["decode_gmac"] - gmac) <= 0.002 * gmac
