@@ -435,8 +435,10 @@ protected:
         const char* ch = getenv("DCVC_B200_GEMM_CHAIN");
         chain_enabled_ = ch && ch[0] == '1';
         {
-            const char* sp = getenv("DCVC_B200_SPLIT_P8");
-            split_enabled_ = sp && sp[0] == '1';
+            const char* sp = getenv("DCVC_B200_SPLIT_P8");   // 1 (= 2 bands) | 2 | 3 | 4
+            const int bands = sp ? atoi(sp) : 0;
+            split_enabled_ = bands >= 1 && bands <= 4;
+            split_parts_ = bands <= 1 ? 2 : bands;
             const char* dr = getenv("DCVC_B200_TEST_DROP_LANE_SYNC");
             test_drop_sync_ = dr && dr[0] == '1';
             const char* lp = getenv("DCVC_B200_LANES_PDL");
@@ -537,24 +539,24 @@ protected:
     // GEMM of a DepthConvBlock is issued twice — upper half of the picture on lane 0, lower half on lane 1 (pixel-local
     // ops: the halves are independent) — as two parallel branches of the graph, so one half's tail and fill overlap the
     // other half's steady state.  Only the depthwise 3x3 needs rows of both halves: it stays one full-picture launch on
-    // lane 0 between two cross-lane edges.  Results are bit-identical to the unsplit path (a pixel's value does not
+    // lane 0 between two cross-lane edges.  DCVC_B200_SPLIT_P8=3|4 cuts the picture into that many bands / lanes instead.  Results are bit-identical to the unsplit path (a pixel's value does not
     // depend on the tile it is computed in).
-    static ActView half_view(const ActView& v, int part)
+    // part `part` of `parts` horizontal bands of a view (the last band takes the remainder rows)
+    static ActView band_view(const ActView& v, int part, int parts)
     {
-        const int ht = v.H / 2;
+        const int hb = v.H / parts;
         ActView h = v;
-        if (part == 0) {
-            h.H = ht;
-        } else {
-            h.ptr = static_cast<const __half*>(v.ptr) + static_cast<size_t>(ht) * v.W * v.pitch;
-            h.H = v.H - ht;
-        }
+        h.ptr = static_cast<const __half*>(v.ptr) + static_cast<size_t>(part) * hb * v.W * v.pitch;
+        h.H = (part == parts - 1) ? v.H - hb * (parts - 1) : hb;
         return h;
     }
+    // lane 0 waits for every other lane / every other lane waits for lane 0
+    void gather_lanes(Segment& s) { for (int l = 1; l < split_parts_; ++l) s.lane_sync(l, 0); }
+    void scatter_lanes(Segment& s) { for (int l = 1; l < split_parts_; ++l) s.lane_sync(0, l); }
     void begin_split(Segment& s)
     {
         if (!split_enabled_ || s.split_open) return;
-        s.lane_sync(0, 1);  // lane 1 starts behind everything lane 0 has done so far in this segment
+        scatter_lanes(s);  // the other lanes start behind everything lane 0 has done so far in this segment
         s.split_open = true;
         s.lanes_region = true;
         s.split_c = s.split_inner = s.split_in_pitch = 0;
@@ -562,7 +564,7 @@ protected:
     void end_split(Segment& s)
     {
         if (!s.split_open) return;
-        s.lane_sync(1, 0);
+        gather_lanes(s);
         s.set_lane(0);
         s.split_open = false;
         s.lanes_region = false;
@@ -570,16 +572,16 @@ protected:
     void gemm_1x1(Segment& s, const ActView& in, const ActView& out, const __half* w, const __half* bias, int N, int act,
                   int chunk, const ActView* r1, const ActView* r2, const __half* q)
     {
-        if (!s.split_open || in.H < 2) {
+        if (!s.split_open || in.H < split_parts_) {
             add_gemm(s, GEMM_PW, in, out, w, bias, N, act, chunk, r1, r2, q, true);
             return;
         }
-        for (int part = 0; part < 2; ++part) {
+        for (int part = 0; part < split_parts_; ++part) {
             s.set_lane(part);
-            const ActView hi = half_view(in, part), ho = half_view(out, part);
+            const ActView hi = band_view(in, part, split_parts_), ho = band_view(out, part, split_parts_);
             ActView h1, h2;
-            if (r1) h1 = half_view(*r1, part);
-            if (r2) h2 = half_view(*r2, part);
+            if (r1) h1 = band_view(*r1, part, split_parts_);
+            if (r2) h2 = band_view(*r2, part, split_parts_);
             add_gemm(s, GEMM_PW, hi, ho, w, bias, N, act, chunk, r1 ? &h1 : nullptr, r2 ? &h2 : nullptr, q, true);
         }
     }
@@ -599,8 +601,8 @@ protected:
             // ranges of the halves shift: both lanes meet before such a block.
             const bool same = (s.split_c == w.c && s.split_inner == w.inner && s.split_in_pitch == in.pitch && !w.adaptor);
             if (s.split_c != 0 && !same) {
-                s.lane_sync(0, 1);
-                s.lane_sync(1, 0);
+                gather_lanes(s);
+                scatter_lanes(s);
             }
             s.split_c = w.c; s.split_inner = w.inner; s.split_in_pitch = w.adaptor ? w.c : in.pitch;
         }
@@ -627,7 +629,7 @@ protected:
             s.break_chain();  // 3x3 neighbourhoods: full-grid dependency on both sides
             if (s.split_open) {
                 // the full-picture depthwise conv reads dc.0 rows of both halves and writes rows both halves' dc.3 read
-                if (!test_drop_sync_) s.lane_sync(1, 0);
+                if (!test_drop_sync_) gather_lanes(s);
                 s.set_lane(0);
             }
             s.annotate(OP_ELEM, 0, 0);
@@ -636,7 +638,7 @@ protected:
             s.out_views.resize(s.ops.size());
             s.out_views.back() = t2;
             s.annotate(OP_DW, 2.0 * 2 * W * H * w.inner, 2.0 * 9 * W * H * w.inner);
-            if (s.split_open) s.lane_sync(0, 1);
+            if (s.split_open) scatter_lanes(s);
         }
         gemm_1x1(s, t2, o, w.w3, w.b3, w.c, ACT_NONE, 0, &x, nullptr, nullptr);
         gemm_1x1(s, o, t1, w.wf0, w.bf0, 4 * w.inner, ACT_WSILU, 1, nullptr, nullptr, nullptr);
@@ -838,7 +840,8 @@ protected:
     std::vector<cudaStream_t> lane_streams_;   // side streams of multi-lane segments (graph capture only)
     std::vector<cudaEvent_t> lane_events_;
     std::vector<cudaEvent_t> sync_events_;     // one per cross-lane edge of the largest multi-lane segment
-    bool split_enabled_ = false;               // DCVC_B200_SPLIT_P8=1 (read in finalize)
+    bool split_enabled_ = false;               // DCVC_B200_SPLIT_P8=1|2|3|4 (read in finalize)
+    int split_parts_ = 2;                      // horizontal bands = capture lanes of a split region
     bool decode_one_sync_ = false;             // DCVC_B200_DECODE_ONE_SYNC=1: one host wait per prior step of the Intra decoder
     bool lanes_pdl_ = true;                    // DCVC_B200_LANES_PDL=0: no programmatic dependent launch inside lane regions
     bool test_drop_sync_ = false;              // DCVC_B200_TEST_DROP_LANE_SYNC=1: fault injection for the CPU tier's race check

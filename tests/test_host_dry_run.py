@@ -92,7 +92,7 @@ class _Dry:
         self.submit_flow("check", "intra", ["64x64"], {"DCVC_B200_SPLIT_P8": "1", "DCVC_B200_TEST_DROP_LANE_SYNC": "1"},
                          tag="split-racy")
         self.submit_flow("plan", "intra", ["1080x1920", "2160x3840", "1096x1928"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
-        self.submit_flow("check", "hts", ["72x104"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
+        self.submit_flow("check", "hts", ["72x104"], {"DCVC_B200_SPLIT_P8": "4"}, tag="split")   # four bands / lanes
         self.submit_flow("check", "ld", ["72x104"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
         for codec in ("hts", "ld", "htl"):
             self.submit_flow("plan", codec, ["1080x1920", "2160x3840", "200x328"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")

@@ -168,11 +168,11 @@ def test_hts_stream_bit_identical_to_reference_coder(nets):
 
 
 @pytest.mark.parametrize("switch,value", [("DCVC_B200_HEAD_LANES", "2"), ("DCVC_B200_HEAD_LANES", "4"),
-                                          ("DCVC_B200_SPLIT_P8", "1")])
+                                          ("DCVC_B200_SPLIT_P8", "1"), ("DCVC_B200_SPLIT_P8", "4")])
 def test_capture_lanes_bit_identical(nets, switch, value, monkeypatch):
     """The two capture-lane switches (measurement switches, default off).  DCVC_B200_HEAD_LANES: the four recon-head pairs
     run as parallel branches of the recon graph, each on its own scratch level.  DCVC_B200_SPLIT_P8: inside every P8
-    chain the 1x1 GEMMs run as upper / lower half-picture branches with cross-lane edges around the depthwise conv.
+    chain the 1x1 GEMMs run as 2 (value 1 or 2), 3 or 4 horizontal-band branches with cross-lane edges around the depthwise conv.
     Either way one persistent GEMM's tail overlaps another branch's work, and nothing else changes: streams, every
     decoded frame and the carried state must equal the default run bit for bit (the CPU tier checks the same under
     emulation, that the captures fork / join, and that no branch races another)."""
