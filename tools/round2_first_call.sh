@@ -29,7 +29,7 @@ echo "== 3. capture lanes: recon-head branches (HT-S) and half-picture branches 
 # inside the lane regions (DCVC_B200_LANES_PDL; the serial parts of the graphs keep PDL either way).
 for V in "lanes1:1:0:1" "lanes2:2:0:1" "lanes4:4:0:1" "lanes2nopdl:2:0:0" "lanes4nopdl:4:0:0" "split:1:1:1" "splitnopdl:1:1:0" "split4:1:4:1" "split4nopdl:1:4:0"; do
     IFS=: read NAME LN SP PDL <<< "$V"
-    DCVC_B200_LANES_PDL=$PDL DCVC_B200_HEAD_LANES=$LN DCVC_B200_SPLIT_P8=$SP timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline \
+    DCVC_B200_LANES_PDL=$PDL DCVC_B200_HEAD_LANES=$LN DCVC_B200_SPLIT_P8=$SP timeout 400 python bench.py --steps 6 --warmup 3 --no-cpu-baseline \
         > $O/r2_bench_$NAME.json 2> $O/r2_bench_$NAME.err
     python - <<EOF
 import json
