@@ -14,7 +14,8 @@ def pytest_configure(config):
 
 # Device cases that were written after the round's GPU budget ran out and have only run under the CPU tier's
 # kernel emulation so far.  The driver runs `pytest -x`: they go last, so a surprise in one of them cannot hide the
-# results of the device-validated cases behind it.  Remove an entry once its first device run is green.
+# results of the device-validated cases behind it.  Remove an entry once its first device run is green.  (The capture-
+# lane cases are additionally gated: DCVC_B200_TEST_LANES=1, set by tools/round2_first_call.sh — see the test files.)
 FIRST_DEVICE_RUN = ("test_hts_gpu.py::test_chunk_roundtrip_state_consistency[2160-3840",
                     "test_ld_gpu.py::test_frame_roundtrip_state_consistency[2160-3840", "test_sequence_gpu.py",
                     "test_hts_gpu.py::test_capture_lanes_bit_identical",

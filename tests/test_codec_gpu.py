@@ -9,6 +9,8 @@ Checks, in the order of the contract (BASELINE.json north_star):
   3. reconstruction / rate agree with the CPU oracle (fp16-emulating restatement of the reference
      proxy) within the tolerances written below.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -16,6 +18,12 @@ import torch
 from util_frames import psnr, synth_frame
 
 pytestmark = pytest.mark.gpu
+
+# First device run of the capture-lane switches happens under tools/round2_first_call.sh (which sets this), not in the
+# driver's unattended round-end run: concurrent persistent kernels are the one kind of change that could hang a box on
+# a first run, and a hung box there would take the bench tier with it.  Remove the gate once they have run green.
+_LANES = pytest.mark.skipif(os.environ.get("DCVC_B200_TEST_LANES") != "1",
+                            reason="capture-lane switches: first device run is scripted (set DCVC_B200_TEST_LANES=1)")
 
 SKIP = 0.15  # test_compress_time.py:41
 
@@ -128,6 +136,8 @@ def test_against_cpu_oracle(model, h, w, qp):
 
 
 
+@_LANES
+@pytest.mark.timeout(300, method="thread")
 @pytest.mark.parametrize("h,w,qp", [(72, 104, 32), (200, 328, 63), (1080, 1920, 32)])
 def test_half_picture_lanes_bit_identical(model, h, w, qp, monkeypatch):
     """DCVC_B200_SPLIT_P8=1 (measurement switch, default off): inside the synthesis transform every 1x1 GEMM of a

@@ -1,6 +1,8 @@
 """HT-S chunk codec (configs[2-4]) on the GPU through the reference-facing API: intra frame -> 8-frame
 chunks with carried feature memory, exactly the call sequence of test_video.py:223-238 (encoder) and
 :312-317 (decoder)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -8,6 +10,12 @@ import torch
 from util_frames import psnr, synth_frame
 
 pytestmark = pytest.mark.gpu
+
+# First device run of the capture-lane switches happens under tools/round2_first_call.sh (which sets this), not in the
+# driver's unattended round-end run: concurrent persistent kernels are the one kind of change that could hang a box on
+# a first run, and a hung box there would take the bench tier with it.  Remove the gate once they have run green.
+_LANES = pytest.mark.skipif(os.environ.get("DCVC_B200_TEST_LANES") != "1",
+                            reason="capture-lane switches: first device run is scripted (set DCVC_B200_TEST_LANES=1)")
 SKIP = 0.15
 
 
@@ -167,6 +175,8 @@ def test_hts_stream_bit_identical_to_reference_coder(nets):
     assert np.asarray(r.get_encoded_stream()).tobytes() == e["bit_stream"]
 
 
+@_LANES
+@pytest.mark.timeout(300, method="thread")
 @pytest.mark.parametrize("switch,value", [("DCVC_B200_HEAD_LANES", "2"), ("DCVC_B200_HEAD_LANES", "4"),
                                           ("DCVC_B200_SPLIT_P8", "1"), ("DCVC_B200_SPLIT_P8", "4")])
 def test_capture_lanes_bit_identical(nets, switch, value, monkeypatch):

@@ -1,5 +1,7 @@
 """Low-delay codec (DCVC-UF LD, one frame per call) on the GPU through the reference-facing API: intra frame -> P frames
 with carried feature memory, the call sequence of test_video.py:223-238 (encoder) and :312-317 (decoder)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -7,6 +9,12 @@ import torch
 from util_frames import psnr, synth_frame
 
 pytestmark = pytest.mark.gpu
+
+# First device run of the capture-lane switches happens under tools/round2_first_call.sh (which sets this), not in the
+# driver's unattended round-end run: concurrent persistent kernels are the one kind of change that could hang a box on
+# a first run, and a hung box there would take the bench tier with it.  Remove the gate once they have run green.
+_LANES = pytest.mark.skipif(os.environ.get("DCVC_B200_TEST_LANES") != "1",
+                            reason="capture-lane switches: first device run is scripted (set DCVC_B200_TEST_LANES=1)")
 SKIP = 0.15
 
 
@@ -120,6 +128,8 @@ def test_ld_stream_bit_identical_to_reference_coder(nets):
     assert np.asarray(r.get_encoded_stream()).tobytes() == e["bit_stream"]
 
 
+@_LANES
+@pytest.mark.timeout(300, method="thread")
 def test_half_picture_lanes_bit_identical(nets, monkeypatch):
     """DCVC_B200_SPLIT_P8=1 (measurement switch, default off; see tests/test_codec_gpu.py): every P8 chain of the LD codec
     as upper / lower half-picture branches of its graph.  Streams, decoded frames and the carried state must equal the

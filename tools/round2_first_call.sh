@@ -16,7 +16,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 
 echo "== 1. pytest -m gpu"
-timeout 1200 python -m pytest tests -m gpu -q -x > $O/r2_pytest_gpu.log 2>&1
+DCVC_B200_TEST_LANES=1 timeout 1500 python -m pytest tests -m gpu -q -x > $O/r2_pytest_gpu.log 2>&1
 echo "rc=$?"; tail -3 $O/r2_pytest_gpu.log
 
 echo "== 2. HT-L first device run"
