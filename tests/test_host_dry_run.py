@@ -59,7 +59,7 @@ class _Dry:
 
     def __init__(self, lib, shim):
         self.lib, self.shim = lib, shim
-        self.pool = ThreadPoolExecutor(max_workers=max(2, min(6, (os.cpu_count() or 2) - 2)))
+        self.pool = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 2) - 1)))
         self.jobs = {}
 
     def env(self, emulate, htl=True):
