@@ -245,9 +245,9 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001 — reported in the JSON line instead of failing the bench
             ld = {"error": f"{type(e).__name__}: {e}"}
 
-    # ---- HT-L (experimental codec, opt-in): same leg with the large model, failure-isolated like LD
+    # ---- HT-L: same leg with the large model, failure-isolated like LD
     htl = None
-    if not args.no_hts and world == 1 and os.environ.get("DCVC_B200_EXPERIMENTAL_HTL") == "1":
+    if not args.no_hts and world == 1:
         try:
             htl = bench_hts(model, device, world, rank, args, timed, reduce_max, large=True)
         except Exception as e:  # noqa: BLE001
@@ -383,7 +383,7 @@ def bench_pipelined(model, device, bs, sps, ec, args, ways=2):
 def bench_hts(i_net, device, world, rank, args, timed, reduce_max, large=False, hw=None):
     """DCVC-UF HT-S 1080p chunk (8 frames) encode / decode after one intra frame (configs[2]); published B200
     numbers of the reference's CUTLASS build: 1415.1 / 945.8 FPS.  large=True: the HT-L model
-    (experimental codec, DCVC_B200_EXPERIMENTAL_HTL=1; published 811.7 / 551.6 FPS)."""
+    (published reference CUTLASS build on B200: 811.7 / 551.6 FPS)."""
     import torch.distributed as dist
     from util_frames import psnr, synth_frame
     from dcvc_b200.model import DMC, DMCHTL

@@ -572,14 +572,7 @@ extern "C" {
 
 int dcvc_create(int32_t kind, int32_t device, dcvc_codec** out)
 {
-    if (kind == DCVC_KIND_HTL) {
-        // the HT-L codec has not been validated on a device yet: opt-in only
-        const char* e = getenv("DCVC_B200_EXPERIMENTAL_HTL");
-        if (!e || e[0] != '1') {
-            dcvc::set_api_error("dcvc_create: DCVC_KIND_HTL is experimental in this build (set DCVC_B200_EXPERIMENTAL_HTL=1)");
-            return 1;
-        }
-    } else if (kind != DCVC_KIND_INTRA && kind != DCVC_KIND_HTS && kind != DCVC_KIND_LD) {
+    if (kind != DCVC_KIND_INTRA && kind != DCVC_KIND_HTS && kind != DCVC_KIND_LD && kind != DCVC_KIND_HTL) {
         dcvc::set_api_error("dcvc_create: unknown codec kind");
         return 1;
     }

@@ -1,7 +1,6 @@
 // codec_htl.cu — DCVC-UF HT-L chunk codec (8 frames per chunk, the large high-throughput model) behind the C ABI.
 //
-// EXPERIMENTAL: written against the parity oracle (oracle/htl_oracle.py) without access to a GPU; `dcvc_create` only
-// hands it out when DCVC_B200_EXPERIMENTAL_HTL=1 and tests/test_htl_gpu.py is skipped otherwise.
+// Device-validated in round 2 (tests/test_htl_gpu.py, tests/test_reference_surface_gpu.py).
 //
 // B200-native counterpart of src/layers/extensions/inference/dmc_htl_proxy.{h,cpp}: the state machine and "cat"
 // buffers of the HT-S codec (codec_hts.cu; dmc_htl_proxy.cpp:583-594, 700-703, 744-751) with the full-width networks of

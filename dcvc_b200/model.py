@@ -180,8 +180,7 @@ class DMCLD(DMC):
 
 
 class DMCHTL(DMC):
-    """DMC(ModelStructure.HTL) of src/models/video_model_ht.py:320-450 (same API as the HT-S model).  EXPERIMENTAL,
-    needs DCVC_B200_EXPERIMENTAL_HTL=1 (see proxy.DMCHTLProxy)."""
+    """DMC(ModelStructure.HTL) of src/models/video_model_ht.py:320-450 (same API as the HT-S model)."""
 
     def __init__(self):
         from .spec import htl_spec

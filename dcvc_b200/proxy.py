@@ -23,6 +23,10 @@ class _CodecHandle:
         if rc:
             raise RuntimeError("dcvc_create failed: " + self.lib.dcvc_last_error().decode())
 
+    def same_device(self, t):
+        if t.device.index != self.device:
+            raise RuntimeError(f"tensor on cuda:{t.device.index}, but this proxy was created on cuda:{self.device}")
+
     def check(self, rc, what):
         if rc:
             raise RuntimeError(f"{what}: " + self.lib.dcvc_codec_error(self.h).decode(errors="replace"))
@@ -36,6 +40,12 @@ class _CodecHandle:
 
 
 def _push_state_dict(hd: _CodecHandle, state_dict, skip_threshold: float):
+    """Hands every tensor of the state_dict to the C side (`dcvc_set_param` copies it with a blocking cudaMemcpy on the
+    legacy stream).  The layout / dtype conversions below run as kernels on torch's CURRENT stream, which is usually a
+    non-blocking stream the legacy stream does not order against (test_video.py runs the models under its own stream and
+    finalises them to channels_last, so every k > 1 conv weight needs such a kernel; the P model's set_param runs right
+    behind the I model's queued synthesis).  So: materialise every tensor first, synchronise that stream ONCE, then copy."""
+    staged = []
     for name, t in state_dict.items():
         if not isinstance(t, torch.Tensor):
             continue
@@ -51,8 +61,14 @@ def _push_state_dict(hd: _CodecHandle, state_dict, skip_threshold: float):
                 tt = tt.float()
                 dtype = _lib.DTYPE_F32
             on_dev = 1 if tt.is_cuda else 0
+            if tt.is_cuda and tt.device.index != hd.device:
+                raise RuntimeError(f"set_param({name}): tensor lives on cuda:{tt.device.index}, the proxy on cuda:{hd.device}")
         else:
             continue
+        staged.append((name, tt, dtype, on_dev))
+    if any(on_dev for _, _, _, on_dev in staged):
+        torch.cuda.current_stream(hd.device).synchronize()
+    for name, tt, dtype, on_dev in staged:
         shape = (C.c_int64 * max(1, tt.dim()))(*tt.shape)
         hd.check(hd.lib.dcvc_set_param(hd.h, name.encode(), C.c_void_p(tt.data_ptr()), dtype, tt.dim(), shape, on_dev),
                  f"set_param({name})")
@@ -79,10 +95,11 @@ class DMCIProxy:
         """-> (bit_stream: np.ndarray[uint8], x_hat: fp16 channels_last [1,3,H16p,W16p], ec_parallel)"""
         hd = self._hd
         assert x.is_cuda and x.dtype == torch.float16 and x.dim() == 4 and x.shape[0] == 1 and x.shape[1] == 3
+        hd.same_device(x)
         _, _, H, W = x.shape
         out = self._out(H + padding_b, W + padding_r, x.device)
         bs, n, ec = C.c_void_p(), C.c_int32(), C.c_int32()
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = C.c_void_p(torch.cuda.current_stream(hd.device).cuda_stream)
         hd.check(hd.lib.dcvc_compress(hd.h, C.c_void_p(x.data_ptr()), H, W, x.stride(1), x.stride(2), x.stride(3),
                                       int(qp), int(padding_b), int(padding_r), stream, C.byref(bs), C.byref(n),
                                       C.byref(ec), C.c_void_p(out.data_ptr())), "compress")
@@ -94,7 +111,7 @@ class DMCIProxy:
         bs = np.ascontiguousarray(bit_stream, dtype=np.uint8)
         hp, wp = (height + 15) // 16 * 16, (width + 15) // 16 * 16
         out = self._out(hp, wp, torch.device("cuda", hd.device))
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = C.c_void_p(torch.cuda.current_stream(hd.device).cuda_stream)
         hd.check(hd.lib.dcvc_decompress(hd.h, C.c_void_p(bs.ctypes.data), bs.size, int(qp), int(height), int(width),
                                         int(ec_parallel), stream, C.c_void_p(out.data_ptr())), "decompress")
         return out
@@ -143,8 +160,9 @@ class DMCHTSProxy:
     def add_ref_feature_from_frame(self, frame: torch.Tensor, apply_adaptor: bool):
         hd = self._hd
         assert frame.is_cuda and frame.dtype == torch.float16 and frame.dim() == 4 and frame.shape[1] == 3
+        hd.same_device(frame)
         _, _, H, W = frame.shape
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = C.c_void_p(torch.cuda.current_stream(hd.device).cuda_stream)
         hd.check(hd.lib.dcvc_add_ref_feature_from_frame(hd.h, C.c_void_p(frame.data_ptr()), H, W, frame.stride(1),
                                                         frame.stride(2), frame.stride(3), 1 if apply_adaptor else 0,
                                                         stream), "add_ref_feature_from_frame")
@@ -153,9 +171,10 @@ class DMCHTSProxy:
         """x: fp16 [1, 24, H, W] -> (bit_stream np.ndarray[uint8], ec_parallel)"""
         hd = self._hd
         assert x.is_cuda and x.dtype == torch.float16 and x.dim() == 4 and x.shape[1] == 3 * self.FRAMES
+        hd.same_device(x)
         _, _, H, W = x.shape
         bs, n, ec = C.c_void_p(), C.c_int32(), C.c_int32()
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = C.c_void_p(torch.cuda.current_stream(hd.device).cuda_stream)
         hd.check(hd.lib.dcvc_compress_chunk(hd.h, C.c_void_p(x.data_ptr()), H, W, x.stride(1), x.stride(2), x.stride(3),
                                             int(qp), 1 if reset_feature_memory else 0, int(padding_b), int(padding_r),
                                             stream, C.byref(bs), C.byref(n), C.byref(ec)), "compress")
@@ -172,7 +191,7 @@ class DMCHTSProxy:
             self._x_hat = [torch.empty((1, 3, hp, wp), dtype=torch.float16, device=dev,
                                        memory_format=torch.channels_last) for _ in range(self.FRAMES)]
         ptrs = (C.c_void_p * self.FRAMES)(*[t.data_ptr() for t in self._x_hat])
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = C.c_void_p(torch.cuda.current_stream(hd.device).cuda_stream)
         hd.check(hd.lib.dcvc_decompress_chunk(hd.h, C.c_void_p(bs.ctypes.data), bs.size, int(qp), int(height), int(width),
                                               int(ec_parallel), 1 if reset_feature_memory else 0, stream, ptrs),
                  "decompress")
@@ -202,9 +221,7 @@ class DMCLDProxy(DMCHTSProxy):
 
 
 class DMCHTLProxy(DMCHTSProxy):
-    """DCVC-UF HT-L chunk codec proxy (reference: DMCHTLProxy, dmc_htl_proxy.h; bind.cpp).  EXPERIMENTAL: the CUDA codec
-    behind it (csrc/codec_htl.cu) has not been validated on a device, so the handle can only be created with
-    DCVC_B200_EXPERIMENTAL_HTL=1 and `inference_extensions_cuda` does not export this class otherwise."""
+    """DCVC-UF HT-L chunk codec proxy (reference: DMCHTLProxy, dmc_htl_proxy.h; bind.cpp:18-23)."""
 
     def __init__(self):
         self._hd = _CodecHandle(_lib.KIND_HTL)

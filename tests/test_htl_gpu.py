@@ -1,9 +1,7 @@
 """HT-L chunk codec (the large high-throughput model) on the GPU through the reference-facing API.
 
-EXPERIMENTAL: csrc/codec_htl.cu was written against oracle/htl_oracle.py without a device to run it on, so these tests
-(and the codec handle itself) are only enabled with DCVC_B200_EXPERIMENTAL_HTL=1.  Same call sequence as the HT-S tests
-(test_video.py:223-238 encoder, :312-317 decoder)."""
-import os
+Same call sequence as the HT-S tests (test_video.py:223-238 encoder, :312-317 decoder).  First device run: round 2
+(tools/r2_call1.sh), green."""
 
 import numpy as np
 import pytest
@@ -11,11 +9,7 @@ import torch
 
 from util_frames import psnr, synth_frame
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("DCVC_B200_EXPERIMENTAL_HTL") != "1",
-                       reason="HT-L codec is experimental: set DCVC_B200_EXPERIMENTAL_HTL=1"),
-]
+pytestmark = pytest.mark.gpu
 SKIP = 0.15
 
 

@@ -335,14 +335,9 @@ def test_gdn(H, W, C, inverse):
     _close(_nchw(out), ref, rel=6e-3, abs_=2e-3)
 
 
-# ---------------------------------------------------------------- HT-L groundwork, not validated on hardware yet
-import os  # noqa: E402
-
-_HTL = pytest.mark.skipif(os.environ.get("DCVC_B200_EXPERIMENTAL_HTL") != "1",
-                          reason="HT-L pieces are experimental: set DCVC_B200_EXPERIMENTAL_HTL=1 to run them")
+# ---------------------------------------------------------------- the GEMM kinds HT-L adds
 
 
-@_HTL
 @pytest.mark.parametrize("H,W,Cin,Cout", [(16, 16, 64, 64), (17, 30, 128, 128), (68, 120, 256, 512)])
 def test_conv3x3_ps2(H, W, Cin, Cout):
     """3x3 / stride 1 / pad 1 conv + bias + pixel_shuffle(2) as a 9-tap pw_gemm with phase-major columns"""
@@ -361,7 +356,6 @@ def test_conv3x3_ps2(H, W, Cin, Cout):
     _close(_nchw(out), ref)
 
 
-@_HTL
 def test_tconv2x2_with_bias():
     """ResidualBlockUpsample(force_bias=True) of the HT-L hyper decoder: 1x1 conv + bias + pixel_shuffle(2)"""
     from dcvc_b200 import ops

@@ -7,10 +7,11 @@ import os
 
 import pytest
 
-# bind.cpp:13-38 — class -> methods; DMCHTLProxy is experimental and hidden unless DCVC_B200_EXPERIMENTAL_HTL=1
+# bind.cpp:13-38 — class -> methods
 REFERENCE_SURFACE = {
     "DMCIProxy": ["set_param", "compress", "decompress"],
     "DMCHTSProxy": ["set_param", "add_ref_feature_from_frame", "compress", "decompress"],
+    "DMCHTLProxy": ["set_param", "add_ref_feature_from_frame", "compress", "decompress"],
     "DMCLDProxy": ["set_param", "add_ref_feature_from_frame", "compress", "decompress"],
 }
 # positional parameters after self, as the reference's Python callers pass them
@@ -21,6 +22,9 @@ CALL_SIGNATURES = {
     ("DMCHTSProxy", "add_ref_feature_from_frame"): ["frame", "apply_adaptor"],
     ("DMCHTSProxy", "compress"): ["x", "qp", "reset_feature_memory", "padding_b", "padding_r"],
     ("DMCHTSProxy", "decompress"): ["bit_stream", "qp", "height", "width", "ec_parallel", "reset_feature_memory"],
+    ("DMCHTLProxy", "add_ref_feature_from_frame"): ["frame", "apply_adaptor"],
+    ("DMCHTLProxy", "compress"): ["x", "qp", "reset_feature_memory", "padding_b", "padding_r"],
+    ("DMCHTLProxy", "decompress"): ["bit_stream", "qp", "height", "width", "ec_parallel", "reset_feature_memory"],
     ("DMCLDProxy", "add_ref_feature_from_frame"): ["frame", "apply_adaptor"],
     ("DMCLDProxy", "compress"): ["x", "qp", "reset_feature_memory", "padding_b", "padding_r"],
     ("DMCLDProxy", "decompress"): ["bit_stream", "qp", "height", "width", "ec_parallel", "reset_feature_memory"],
@@ -33,24 +37,6 @@ def test_plugin_exports_reference_classes_and_methods():
         cls = getattr(ext, cls_name)
         for m in methods:
             assert callable(getattr(cls, m)), f"{cls_name}.{m} missing"
-    if os.environ.get("DCVC_B200_EXPERIMENTAL_HTL") == "1":
-        assert callable(ext.DMCHTLProxy.compress)
-        return
-    assert not hasattr(ext, "DMCHTLProxy"), "HT-L is opt-in: the reference must get its ImportError -> NotImplementedError"
-    with pytest.raises(ImportError):
-        from inference_extensions_cuda import DMCHTLProxy  # noqa: F401
-
-
-def test_htl_handle_is_opt_in():
-    """dcvc_create(DCVC_KIND_HTL) is refused (before any device is touched) unless the experimental switch is set"""
-    import ctypes as C
-
-    from dcvc_b200 import _lib
-    if os.environ.get("DCVC_B200_EXPERIMENTAL_HTL") == "1":
-        pytest.skip("experimental HT-L enabled")
-    h = C.c_void_p()
-    assert _lib.load().dcvc_create(_lib.KIND_HTL, 0, C.byref(h)) != 0
-    assert b"EXPERIMENTAL_HTL" in _lib.load().dcvc_last_error()
 
 
 @pytest.mark.parametrize("key", sorted(CALL_SIGNATURES))
