@@ -24,6 +24,13 @@ class GemmDesc(C.Structure):
                 ("N", C.c_int32), ("act", C.c_int32), ("chunk_add", C.c_int32)]
 
 
+class DcbTailDesc(C.Structure):
+    _fields_ = [("t2", View), ("x", View), ("y", View), ("t1n", View),
+                ("w3", C.c_void_p), ("b3", C.c_void_p), ("wf0", C.c_void_p), ("bf0", C.c_void_p),
+                ("wf2", C.c_void_p), ("bf2", C.c_void_p), ("w0n", C.c_void_p), ("b0n", C.c_void_p),
+                ("qscale", C.c_void_p), ("shortcut", C.c_int32)]
+
+
 class EntropyStep(C.Structure):
     _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("G", C.c_int32), ("step", C.c_int32),
                 ("y", C.c_void_p), ("y_pitch", C.c_int32),
@@ -50,6 +57,7 @@ SIGNATURES = {
     "dcvc_build_info": (C.c_char_p, []),
     "dcvc_abi_version": (C.c_int, []),
     "dcvc_op_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
+    "dcvc_op_dcb_tail": (C.c_int, [C.POINTER(DcbTailDesc), _P]),
     "dcvc_pack_weight": (C.c_int, [_I, _P, _I, _I, _I, _I, _P]),
     "dcvc_op_dw3x3": (C.c_int, [C.POINTER(View), C.POINTER(View), _P, _P]),
     "dcvc_op_unshuffle8_pad": (C.c_int, [_P, _I, _I, _I, _L, _L, _L, C.POINTER(View), _P]),

@@ -7,6 +7,7 @@
 
 #include "../../include/dcvc_b200.h"
 #include "elementwise.cuh"
+#include "dcb_tail.cuh"
 #include "pw_gemm.cuh"
 #include "rans_host.h"
 
@@ -59,6 +60,28 @@ int dcvc_op_gemm(const dcvc_gemm_desc* d, void* stream)
     op.chunk_add = d->chunk_add;
     if (gemm_plan(op)) { set_api_error(gemm_last_error()); return 1; }
     if (gemm_launch(op, static_cast<cudaStream_t>(stream))) { set_api_error(gemm_last_error()); return 1; }
+    return 0;
+    API_CATCH
+}
+
+int dcvc_op_dcb_tail(const dcvc_dcb_tail_desc* d, void* stream)
+{
+    API_TRY
+    DcbTailOp op;
+    op.t2 = to_view(d->t2);
+    op.x = to_view(d->x);
+    op.y = to_view(d->y);
+    op.t1n = to_view(d->t1n);
+    op.w3 = static_cast<const __half*>(d->w3);   op.b3 = static_cast<const __half*>(d->b3);
+    op.wf0 = static_cast<const __half*>(d->wf0); op.bf0 = static_cast<const __half*>(d->bf0);
+    op.wf2 = static_cast<const __half*>(d->wf2); op.bf2 = static_cast<const __half*>(d->bf2);
+    op.w0n = static_cast<const __half*>(d->w0n); op.b0n = static_cast<const __half*>(d->b0n);
+    op.qscale = static_cast<const __half*>(d->qscale);
+    op.shortcut = d->shortcut != 0;
+    const int r = dcb_tail_plan(op);
+    if (r == 1) { set_api_error("dcb_tail: not eligible"); return 2; }
+    if (r) { set_api_error(gemm_last_error()); return 1; }
+    if (dcb_tail_launch(op, static_cast<cudaStream_t>(stream))) { set_api_error(gemm_last_error()); return 1; }
     return 0;
     API_CATCH
 }

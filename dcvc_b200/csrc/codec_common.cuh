@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/dcvc_b200.h"
+#include "dcb_tail.cuh"
 #include "elementwise.cuh"
 #include "pw_gemm.cuh"
 #include "rans_host.h"
@@ -170,6 +171,10 @@ struct Segment {
     const void* last_out = nullptr;
     int last_W = 0, last_H = 0, last_C = 0, last_pitch = 0;
     void break_chain() { last_flags = nullptr; }
+    // the most recent fused DepthConvBlock tail (dcb_tail.cuh), kept so that the NEXT block can hang its dc.0 onto it as
+    // phase 4 — valid only while it is still the last op of the segment
+    std::shared_ptr<DcbTailOp> tail;
+    size_t tail_idx = 0;
     void annotate(int kind, double bytes, double fl)
     {
         while (kinds.size() < ops.size()) {
@@ -217,6 +222,7 @@ struct Segment {
         flag_begin = nullptr;
         flag_words = 0;
         break_chain();
+        tail.reset();
     }
 };
 
@@ -426,7 +432,7 @@ protected:
             tev_.resize(48);
             for (auto& e : tev_) CK(cudaEventCreate(&e));
         }
-        if (gemm_init()) throw std::runtime_error(gemm_last_error());
+        if (gemm_init() || dcb_tail_init()) throw std::runtime_error(gemm_last_error());
         const char* g = getenv("DCVC_B200_GRAPHS");
         use_graphs_ = !(g && g[0] == '0');
         // tile-level chaining of the DepthConvBlock GEMMs is an opt-in experiment (DCVC_B200_GEMM_CHAIN=1): parity-green,
@@ -434,6 +440,8 @@ protected:
         // 5.71 ms) — see DESIGN.md "experiments"
         const char* ch = getenv("DCVC_B200_GEMM_CHAIN");
         chain_enabled_ = ch && ch[0] == '1';
+        const char* ft = getenv("DCVC_B200_FUSE_TAIL");
+        fuse_tail_ = !(ft && ft[0] == '0');
         {
             const char* sp = getenv("DCVC_B200_SPLIT_P8");   // 1 (= 2 bands) | 2 | 3 | 4
             const int bands = sp ? atoi(sp) : 0;
@@ -623,7 +631,26 @@ protected:
         const ActView t1 = make_view(L.T1, w.inner, w.inner, W, H);
         const ActView t2 = make_view(L.T2, w.inner, w.inner, W, H);
         const ActView o = make_view(bufO, w.c, w.c, W, H);
-        gemm_1x1(s, x, t1, w.w0, w.b0, w.inner, ACT_WSILU, 0, nullptr, nullptr, nullptr);
+        // dc.0: when the previous op of the segment is the fused tail of the block that produced x, this GEMM rides along
+        // as that kernel's fourth phase (y is still in its tensor memory); otherwise it is a launch of its own
+        bool dc0_fused = false;
+        if (!w.adaptor && !s.split_open && s.tail && s.tail_idx + 1 == s.ops.size() && !s.tail->t1n.ptr &&
+            s.tail->y.ptr == x.ptr && s.tail->y.C == x.C && s.tail->y.pitch == x.pitch && s.tail->y.W == x.W && s.tail->y.H == x.H) {
+            DcbTailOp trial = *s.tail;
+            trial.t1n = t1;
+            trial.w0n = w.w0;
+            trial.b0n = w.b0;
+            if (dcb_tail_plan(trial) == 0) {
+                *s.tail = trial;
+                const double px = static_cast<double>(W) * H;
+                s.alg_bytes[s.tail_idx] += px * (x.C + w.inner) * 2;
+                s.flops[s.tail_idx] += 2.0 * px * w.inner * x.C;
+                s.notes[s.tail_idx] += " +dc0";
+                dc0_fused = true;
+            }
+        }
+        s.tail.reset();
+        if (!dc0_fused) gemm_1x1(s, x, t1, w.w0, w.b0, w.inner, ACT_WSILU, 0, nullptr, nullptr, nullptr);
         {
             const __half* wdw = w.wdw;
             s.break_chain();  // 3x3 neighbourhoods: full-grid dependency on both sides
@@ -640,9 +667,39 @@ protected:
             s.annotate(OP_DW, 2.0 * 2 * W * H * w.inner, 2.0 * 9 * W * H * w.inner);
             if (s.split_open) scatter_lanes(s);
         }
+        const ActView dst = out ? *out : x;
+        if (fuse_tail_ && !s.split_open) {
+            // dc.3 -> ffn.0 -> ffn.2 as one CTA-pair kernel: o and t1' stay on the SM (dcb_tail.cuh)
+            auto op = std::make_shared<DcbTailOp>();
+            op->t2 = t2; op->x = x; op->y = dst;
+            op->w3 = w.w3; op->b3 = w.b3; op->wf0 = w.wf0; op->bf0 = w.bf0; op->wf2 = w.wf2; op->bf2 = w.bf2;
+            op->qscale = qscale;
+            op->shortcut = shortcut;
+            const int r = dcb_tail_plan(*op);
+            if (r == 2) throw std::runtime_error(std::string("dcb_tail_plan: ") + gemm_last_error());
+            if (r == 0) {
+                s.break_chain();
+                s.annotate(OP_ELEM, 0, 0);
+                s.ops.push_back([op](cudaStream_t st) { return dcb_tail_launch(*op, st); });
+                s.out_views.resize(s.ops.size());
+                s.out_views.back() = dst;
+                char buf[200];
+                snprintf(buf, sizeof(buf), "dcb_tail %dx%d C=%d inner=%d shortcut=%d q=%d tiles=%d pairs=%d stages=%d", H, W, w.c, w.inner,
+                         shortcut ? 1 : 0, qscale ? 1 : 0, op->p.tiles, op->p.num_pairs, op->p.stages);
+                s.notes.resize(s.ops.size());
+                s.notes.back() = buf;
+                // algorithmic bytes / flops: the sum over the three ops it replaces (SURVEY.md 8d counts per op)
+                const double px = static_cast<double>(W) * H;
+                const double bytes = px * 2 * ((w.inner + w.c + w.c) + (w.c + w.inner) + (w.inner + w.c + w.c + (shortcut ? w.c : 0)));
+                const double fl = 2.0 * px * (static_cast<double>(w.c) * w.inner + 4.0 * w.inner * w.c + static_cast<double>(w.c) * w.inner);
+                s.annotate(OP_GEMM, bytes, fl);
+                s.tail = op;
+                s.tail_idx = s.ops.size() - 1;
+                return dst;
+            }
+        }
         gemm_1x1(s, t2, o, w.w3, w.b3, w.c, ACT_NONE, 0, &x, nullptr, nullptr);
         gemm_1x1(s, o, t1, w.wf0, w.bf0, 4 * w.inner, ACT_WSILU, 1, nullptr, nullptr, nullptr);
-        const ActView dst = out ? *out : x;
         gemm_1x1(s, t1, dst, w.wf2, w.bf2, w.c, ACT_NONE, 0, &o, shortcut ? &x : nullptr, qscale);
         return dst;
     }
@@ -825,6 +882,7 @@ protected:
     bool finalized_ = false;
     bool use_graphs_ = true;
     bool chain_enabled_ = true;
+    bool fuse_tail_ = true;                    // DCVC_B200_FUSE_TAIL=0: per-op kernels only (A/B runs, kernel emulation)
     int* flags_base_ = nullptr;
     size_t flags_cap_ = 0, flags_used_ = 0;
     void* dbg_base_ = nullptr;      // activation arena (DCVC_B200_OPSUM)

@@ -1,0 +1,571 @@
+// dcb_tail.cu — dc.3 -> ffn.0 -> ffn.2 (-> next dc.0) of a DepthConvBlock as one persistent CTA-pair kernel
+// (see dcb_tail.cuh for the what and why).  Hand-written for sm_100a: TMA, tcgen05.mma cta_group::2 with the A operand
+// from shared memory (phases 1, 3) or from tensor memory (phases 2, 4), tcgen05.ld / tcgen05.st epilogues.
+//
+// Per CTA (one SM), 18 warps:
+//   warp 0        TMA producer: the tile's t2 k-blocks into the resident buffer P, then the weight k-blocks of all four
+//                 GEMMs, in consumption order, through a ring of 8 KB stages (this CTA's 64 of a chunk's 128 columns)
+//   warp 1        TMEM allocator; in the leader CTA (cluster rank 0) the single thread that issues every tcgen05.mma
+//   warps 2..17   epilogue: warp (b, h, q) drains lane quarter q / column half h of the chunks that land in accumulator
+//                 buffer b (chunks alternate between the two 128-column buffers)
+// TMEM (512 columns): [0, C/2) = O: the tile's o, later y, as packed fp16 — the A operand of phases 2 and 4 and the
+//                     residual of phase 3;   [256, 384) and [384, 512) = the two fp32 accumulator buffers.
+// smem: P [inner/64 x 16 KB] (t2, later t1', UMMA K-major SWIZZLE_128B) | weight ring | 16 x 2 KB store slabs | barriers.
+//
+// Ordering between the phases needs no grid-wide or CTA-wide barrier: every hand-over is an mbarrier, and "all earlier
+// MMAs have completed" is implied by the tcgen05.commit that publishes a later chunk's accumulator (commits complete
+// in issue order), which is what makes the in-place reuse of P and O safe:
+//   P: TMA(t2) -> phase-1 MMAs -> phase-2 epilogue writes t1' -> phase-3 MMAs -> commit(p_empty) -> TMA(next t2)
+//   O: phase-1 epilogue writes o -> phase-2 MMAs -> phase-3 epilogue reads o, writes y -> phase-4 MMAs -> next tile
+#include "dcb_tail.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+
+#include "ptx.cuh"
+#include "pw_gemm_internal.cuh"
+
+namespace dcvc {
+
+static constexpr int DT_CHUNK_N = 128;                              // GEMM columns per accumulator chunk
+static constexpr int DT_B_STAGE = (DT_CHUNK_N / 2) * BLOCK_K * 2;   // 8 KB: this CTA's half of one weight k-block
+static constexpr int DT_MAX_STAGES = 16;
+static constexpr int DT_MAX_KB = 8;                                 // K <= 512
+static constexpr int DT_ACC_COL0 = 256;
+static constexpr int DT_TMEM_COLS = 512;
+static constexpr int DT_STAGING = EPI_WARPS * EPI_SLAB_BYTES;       // one 2 KB slab per epilogue warp
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* P = smem;
+    uint8_t* ring = P + p.p_bytes;
+    uint8_t* staging = ring + p.stages * DT_B_STAGE;
+    uint8_t* ctrl = smem + SMEM_USABLE;
+    uint64_t* p_full = reinterpret_cast<uint64_t*>(ctrl);   // [8]  leader: t2 k-block of both CTAs landed
+    uint64_t* p_ready = p_full + DT_MAX_KB;                 // [8]  leader: t1' k-block written by both CTAs' epilogues
+    uint64_t* b_full = p_ready + DT_MAX_KB;                 // [16] leader: both halves of a weight k-block landed
+    uint64_t* b_empty = b_full + DT_MAX_STAGES;             // [16] every CTA: ring slot consumed
+    uint64_t* acc_full = b_empty + DT_MAX_STAGES;           // [2]  every CTA: accumulator chunk complete
+    uint64_t* acc_empty = acc_full + 2;                     // [2]  leader: chunk drained by both CTAs' 8 warps
+    uint64_t* p_empty = acc_empty + 2;                      // [1]  every CTA: phase-3 MMAs done, P may be reloaded
+    uint64_t* o_ready = p_empty + 1;                        // [1]  leader: O holds the complete o (1st use) / y (2nd use per tile)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ctrl + 496);
+
+    const int rank = static_cast<int>(cluster_ctarank());
+    const int pair = static_cast<int>(blockIdx.x >> 1);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tm_a);
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tm_w[i]);
+        tma_prefetch_desc(&p.tm_y);
+        tma_prefetch_desc(&p.tm_t);
+        for (int i = 0; i < DT_MAX_KB; ++i) {
+            mbar_init(&p_full[i], 1);
+            mbar_init(&p_ready[i], 32);               // 2 chunks x 8 warps x 2 CTAs
+        }
+        for (int i = 0; i < DT_MAX_STAGES; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
+        }
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&acc_full[g], 1);
+            mbar_init(&acc_empty[g], 16);             // 8 warps x 2 CTAs
+        }
+        mbar_init(p_empty, 1);
+        mbar_init(o_ready, static_cast<uint32_t>(p.nch[0] * 16));   // every chunk of the phase: 8 warps x 2 CTAs
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_2cta(tmem_ptr_smem, DT_TMEM_COLS);
+        tmem_relinquish_2cta();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / commit multicast
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    griddep_launch_dependents();
+    griddep_wait();
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            // ------------------------------------------------------------ TMA producer (both CTAs)
+            auto load_tile = [&](int T, int i) {
+                mbar_wait(p_empty, static_cast<uint32_t>((i & 1) ^ 1));
+                const int row0 = T * 256 + rank * BLOCK_M;
+                for (int kb = 0; kb < p.nkb[0]; ++kb) {
+                    if (rank == 0) mbar_expect_tx(&p_full[kb], 2 * A_STAGE_BYTES);
+                    tma_load_2d_2sm(P + kb * A_STAGE_BYTES, &p.tm_a, mapa_u32(smem_u32(&p_full[kb]), 0), kb * BLOCK_K, row0);
+                }
+            };
+            int s = 0;
+            uint32_t bph = 0;
+            int i = 0;
+            int T = pair;
+            if (T < p.tiles) load_tile(T, 0);
+            // the next tile's t2 goes out once the ring is full of phase-4 weights: by then phase 3 has been issued
+            // completely, so the wait for p_empty is short and phase 4 starts on a full ring
+            const int total4 = p.nch[3] * p.nkb[3];
+            const int trigger = total4 < p.stages ? total4 : p.stages;
+            for (; T < p.tiles; T += p.num_pairs, ++i) {
+                const int Tn = T + p.num_pairs;
+                bool next_loaded = false;
+                for (int ph = 0; ph < 4; ++ph) {
+                    int cnt = 0;
+                    for (int n = 0; n < p.nch[ph]; ++n) {
+                        const int nrow = n * DT_CHUNK_N + rank * (DT_CHUNK_N / 2);
+                        for (int kb = 0; kb < p.nkb[ph]; ++kb) {
+                            mbar_wait(&b_empty[s], bph ^ 1);
+                            if (rank == 0) mbar_expect_tx(&b_full[s], 2 * DT_B_STAGE);
+                            tma_load_2d_2sm(ring + s * DT_B_STAGE, &p.tm_w[ph], mapa_u32(smem_u32(&b_full[s]), 0),
+                                            kb * BLOCK_K, nrow);
+                            if (++s == p.stages) { s = 0; bph ^= 1; }
+                            if (ph == 3 && !next_loaded && ++cnt == trigger) {
+                                if (Tn < p.tiles) load_tile(Tn, i + 1);
+                                next_loaded = true;
+                            }
+                        }
+                    }
+                }
+                if (!next_loaded && Tn < p.tiles) load_tile(Tn, i + 1);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (rank == 0 && elect_one_sync()) {
+            // ------------------------------------------------------------ MMA issuer (leader CTA only)
+            constexpr uint32_t idesc = make_idesc_f16_f32(BLOCK_M * 2, DT_CHUNK_N);
+            const bool do_mma = !(p.dbg & 1);
+            uint32_t t = 0;
+            int s = 0;
+            uint32_t bph = 0;
+            int i = 0;
+            for (int T = pair; T < p.tiles; T += p.num_pairs, ++i) {
+                const uint32_t tph = static_cast<uint32_t>(i & 1);
+                for (int ph = 0; ph < 4; ++ph) {
+                    if (p.nch[ph] == 0) continue;
+                    if (ph == 1 || ph == 3) {
+                        mbar_wait_cluster(o_ready, ph == 1 ? 0u : 1u);  // two uses per tile: o complete, y complete
+                        tcgen05_fence_after();
+                    }
+                    const bool a_tmem = (ph & 1) != 0;
+                    for (int n = 0; n < p.nch[ph]; ++n, ++t) {
+                        const int g = static_cast<int>(t & 1);
+                        mbar_wait_cluster(&acc_empty[g], ((t >> 1) & 1) ^ 1);  // both CTAs drained this buffer
+                        tcgen05_fence_after();
+                        const uint32_t acc = tmem_base + DT_ACC_COL0 + g * DT_CHUNK_N;
+                        for (int kb = 0; kb < p.nkb[ph]; ++kb) {
+                            if (n == 0 && ph == 0) mbar_wait(&p_full[kb], tph);
+                            if (n == 0 && ph == 2) mbar_wait_cluster(&p_ready[kb], tph);
+                            mbar_wait(&b_full[s], bph);
+                            tcgen05_fence_after();
+                            const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(ring + s * DT_B_STAGE));
+                            if (do_mma) {
+                                if (a_tmem) {
+                                    const uint32_t a_t = tmem_base + kb * (BLOCK_K / 2);
+#pragma unroll
+                                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                        umma_f16_ts_2cta(acc, a_t + k * (UMMA_K / 2), b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                                } else {
+                                    const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(P + kb * A_STAGE_BYTES));
+#pragma unroll
+                                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                        umma_f16_ss_2cta(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                                }
+                            }
+                            umma_commit_2cta_mc(&b_empty[s], 3);
+                            if (++s == p.stages) { s = 0; bph ^= 1; }
+                        }
+                        umma_commit_2cta_mc(&acc_full[g], 3);
+                    }
+                    if (ph == 2) umma_commit_2cta_mc(p_empty, 3);  // P is free for the next tile's t2
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------------------------------------------------------- epilogue (16 warps, both CTAs)
+        const int q = warp & 3;
+        const int b = ((warp - 2) >> 2) & 1;
+        const int h = (warp - 2) >> 3;
+        uint8_t* slab = staging + (warp - 2) * EPI_SLAB_BYTES;
+        const uint32_t slab_u = smem_u32(slab);
+        const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t acc = tmem_base + lane_off + DT_ACC_COL0 + b * DT_CHUNK_N + h * 64;  // this warp's 64 accumulator columns
+        const uint32_t o_base = tmem_base + lane_off;                                      // O, this warp's lanes
+        const uint32_t acc_empty_r = mapa_u32(smem_u32(&acc_empty[b]), 0);
+        const uint32_t o_ready_r = mapa_u32(smem_u32(o_ready), 0);
+        const uint32_t p_ready_r = mapa_u32(smem_u32(p_ready), 0);
+        const uint32_t P_u = smem_u32(P);
+        const uint32_t my_sw = static_cast<uint32_t>(lane * 64);
+        const uint32_t my_x = static_cast<uint32_t>((lane >> 1) & 3);
+        const uint16_t ONE = 0x3C00;
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        const bool skip_body = (p.dbg & 2) != 0;
+
+        auto hand_back = [&]() {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_r);
+        };
+        auto slab_free = [&]() {  // the TMA store that last read this warp's slab has finished reading it
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+        };
+        // coalesced fetch of a [32 rows][32 channels] piece of x into the slab (one LDGSTS = 8 rows x 64 B)
+        auto fetch_x = [&](int row_base, int c0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t rj = static_cast<uint32_t>((lane >> 2) + 8 * j);
+                long long gr = static_cast<long long>(row_base) + rj;
+                gr = gr < p.M ? gr : p.M - 1;
+                ldgsts16(slab_u + rj * 64 + ((static_cast<uint32_t>(lane & 3) ^ ((rj >> 1) & 3)) << 4),
+                         p.x + gr * p.x_pitch + c0 + (lane & 3) * 8);
+            }
+            cp_async_commit();
+        };
+        auto add_slab = [&](float (&tv)[32]) {  // tv += this thread's row of the slab
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+                const uint4 r = lds128(slab_u + my_sw + ((static_cast<uint32_t>(gq) ^ my_x) << 4));
+                const uint32_t* w1 = reinterpret_cast<const uint32_t*>(&r);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    tv[gq * 8 + 2 * e] = fma_f32_f16(static_cast<uint16_t>(w1[e] & 0xffffu), ONE, tv[gq * 8 + 2 * e]);
+                    tv[gq * 8 + 2 * e + 1] = fma_f32_f16(static_cast<uint16_t>(w1[e] >> 16), ONE, tv[gq * 8 + 2 * e + 1]);
+                }
+            }
+        };
+        auto add_bias = [&](const __half* bias, int c0, const uint32_t (&v)[32], float (&tv)[32]) {
+            uint4 cb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cb[j] = bias ? __ldg(reinterpret_cast<const uint4*>(bias + c0) + j) : zero4;
+            const uint32_t* bw = reinterpret_cast<const uint32_t*>(cb);
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+                tv[e] = fma_f32_f16(static_cast<uint16_t>(bw[e >> 1] & 0xffffu), ONE, __uint_as_float(v[e]));
+                tv[e + 1] = fma_f32_f16(static_cast<uint16_t>(bw[e >> 1] >> 16), ONE, __uint_as_float(v[e + 1]));
+            }
+        };
+        auto pack16 = [&](const float (&tv)[32], uint32_t (&w)[16]) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const __half2 h2 = __floats2half2_rn(tv[2 * j], tv[2 * j + 1]);
+                w[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+        };
+        // this thread's packed row -> its row of the slab -> one TMA store of [32 rows][32 channels]
+        auto store_slab = [&](const CUtensorMap* tm, const uint32_t (&w)[16], int c0, int row_base) {
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq)
+                sts128(slab_u + my_sw + ((static_cast<uint32_t>(gq) ^ my_x) << 4), make_uint4(w[4 * gq], w[4 * gq + 1], w[4 * gq + 2], w[4 * gq + 3]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(tm, slab, c0, row_base);
+                tma_store_commit();
+            }
+        };
+
+        uint32_t t = 0;
+        for (int T = pair; T < p.tiles; T += p.num_pairs) {
+            const int row_w = T * 256 + rank * BLOCK_M + q * 32;  // first pixel row of this warp
+            for (int ph = 0; ph < 4; ++ph) {
+                for (int n = 0; n < p.nch[ph]; ++n, ++t) {
+                    if (static_cast<int>(t & 1) != b) continue;
+                    mbar_wait(&acc_full[b], (t >> 1) & 1);
+                    tcgen05_fence_after();
+                    if (skip_body) {
+                        hand_back();
+                        if (ph == 0 || ph == 2) { if (lane == 0) mbar_arrive_cluster(o_ready_r); }
+                        if (ph == 1) { if (lane == 0) mbar_arrive_cluster(p_ready_r + (n >> 1) * 8); }
+                        continue;
+                    }
+                    if (ph == 0) {
+                        // ---------------- o = acc + b3 + x  ->  O (TMEM, packed fp16)
+#pragma unroll 1
+                        for (int a = 0; a < 2; ++a) {
+                            const int c0 = n * DT_CHUNK_N + h * 64 + a * 32;
+                            uint32_t v[32];
+                            tmem_ld_32x32b_x32(acc + a * 32, v);
+                            slab_free();
+                            fetch_x(row_w, c0);
+                            float tv[32];
+                            tmem_ld_wait();
+                            if (a == 1) hand_back();
+                            add_bias(p.bias[0], c0, v, tv);
+                            cp_async_wait_all();
+                            __syncwarp();
+                            add_slab(tv);
+                            uint32_t w[16];
+                            pack16(tv, w);
+                            tmem_st_32x32b_x16(o_base + (c0 >> 1), w);
+                            __syncwarp();  // every lane has read its slab row before the next LDGSTS overwrites it
+                        }
+                        tmem_st_wait();
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(o_ready_r);
+                    } else if (ph == 1) {
+                        // ---------------- t1' = fold4(wsilu(acc + bf0))  ->  P (smem, UMMA K-major SWIZZLE_128B)
+#pragma unroll 1
+                        for (int a = 0; a < 2; ++a) {
+                            const int col0 = n * DT_CHUNK_N + h * 64 + a * 32;  // GEMM column of accumulator column 0
+                            uint32_t v[32];
+                            tmem_ld_32x32b_x32(acc + a * 32, v);
+                            float tv[32];
+                            tmem_ld_wait();
+                            if (a == 1) hand_back();
+                            add_bias(p.bias[1], col0, v, tv);
+                            uint4 o4;
+                            uint32_t* ow = reinterpret_cast<uint32_t*>(&o4);
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                float o2[2];
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh) {
+                                    const int j = jj * 2 + hh;
+                                    float s4 = wsilu_f(tv[4 * j]);
+                                    s4 += wsilu_f(tv[4 * j + 1]);
+                                    s4 += wsilu_f(tv[4 * j + 2]);
+                                    s4 += wsilu_f(tv[4 * j + 3]);
+                                    o2[hh] = s4;
+                                }
+                                const __half2 h2 = __floats2half2_rn(o2[0], o2[1]);
+                                ow[jj] = *reinterpret_cast<const uint32_t*>(&h2);
+                            }
+                            // output channels 32 n + 16 h + 8 a .. + 8: k-block n / 2, 16-byte chunk 4 (n & 1) + 2 h + a of the row
+                            const uint32_t row = static_cast<uint32_t>(q * 32 + lane);
+                            sts128(P_u + (n >> 1) * A_STAGE_BYTES + sw128_offset(row, static_cast<uint32_t>((n & 1) * 4 + h * 2 + a)), o4);
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(p_ready_r + (n >> 1) * 8);
+                    } else if (ph == 2) {
+                        // ---------------- y = (acc + bf2 + o [+ x]) [* q]  ->  O (in place) and global
+#pragma unroll 1
+                        for (int a = 0; a < 2; ++a) {
+                            const int c0 = n * DT_CHUNK_N + h * 64 + a * 32;
+                            uint32_t v[32];
+                            tmem_ld_32x32b_x32(acc + a * 32, v);
+                            uint32_t ov[16];
+                            tmem_ld_32x32b_x16(o_base + (c0 >> 1), ov);
+                            slab_free();
+                            if (p.shortcut) fetch_x(row_w, c0);
+                            float tv[32];
+                            tmem_ld_wait();
+                            if (a == 1) hand_back();
+                            add_bias(p.bias[2], c0, v, tv);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                tv[2 * j] = fma_f32_f16(static_cast<uint16_t>(ov[j] & 0xffffu), ONE, tv[2 * j]);
+                                tv[2 * j + 1] = fma_f32_f16(static_cast<uint16_t>(ov[j] >> 16), ONE, tv[2 * j + 1]);
+                            }
+                            if (p.shortcut) {
+                                cp_async_wait_all();
+                                __syncwarp();
+                                add_slab(tv);
+                                __syncwarp();
+                            }
+                            if (p.qscale) {
+                                uint4 cq[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) cq[j] = __ldg(reinterpret_cast<const uint4*>(p.qscale + c0) + j);
+                                const uint32_t* qw = reinterpret_cast<const uint32_t*>(cq);
+#pragma unroll
+                                for (int e = 0; e < 32; e += 2) {
+                                    const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qw[e >> 1]));
+                                    tv[e] *= qf.x;
+                                    tv[e + 1] *= qf.y;
+                                }
+                            }
+                            uint32_t w[16];
+                            pack16(tv, w);
+                            tmem_st_32x32b_x16(o_base + (c0 >> 1), w);
+                            store_slab(&p.tm_y, w, c0, row_w);
+                        }
+                        tmem_st_wait();
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(o_ready_r);
+                    } else {
+                        // ---------------- t1n = wsilu(acc + b0n)  ->  global
+#pragma unroll 1
+                        for (int a = 0; a < 2; ++a) {
+                            const int c0 = n * DT_CHUNK_N + h * 64 + a * 32;
+                            uint32_t v[32];
+                            tmem_ld_32x32b_x32(acc + a * 32, v);
+                            float tv[32];
+                            tmem_ld_wait();
+                            if (a == 1) hand_back();
+                            add_bias(p.bias[3], c0, v, tv);
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) tv[e] = wsilu_f(tv[e]);
+                            uint32_t w[16];
+                            pack16(tv, w);
+                            slab_free();
+                            store_slab(&p.tm_t, w, c0, row_w);
+                        }
+                    }
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+    }
+
+    __syncthreads();
+    cluster_sync_all();  // no CTA exits (or frees TMEM) while its peer can still signal its barriers / read its smem
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc_2cta(tmem_base, DT_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------ host
+
+int dcb_tail_init()
+{
+    static bool done = false;
+    if (done) return 0;
+    cudaError_t e = cudaFuncSetAttribute(dcb_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e != cudaSuccess) {
+        gemm_set_error(std::string("cudaFuncSetAttribute(dcb_tail): ") + cudaGetErrorString(e));
+        return 1;
+    }
+    done = true;
+    return 0;
+}
+
+static int dt_max_pairs(int num_sms)
+{
+    static int cached = 0;
+    if (cached) return cached;
+    if (dcb_tail_init()) return num_sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * 64, 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SMEM_TOTAL;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, dcb_tail_kernel, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = num_sms / 2;
+    }
+    cached = n;
+    return n;
+}
+
+static bool view_ok(const ActView& v)
+{
+    return v.ptr && (v.pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0 && v.C <= v.pitch;
+}
+
+int dcb_tail_plan(DcbTailOp& op)
+{
+    op.planned = false;
+    static const bool enabled = []() { const char* e = getenv("DCVC_B200_FUSE_TAIL"); return !(e && e[0] == '0'); }();
+    if (!enabled) return 1;
+    const int C = op.x.C, inner = op.t2.C;
+    const int inner_n = op.t1n.ptr ? op.t1n.C : 0;
+    const long long M = static_cast<long long>(op.y.W) * op.y.H;
+    if (!view_ok(op.t2) || !view_ok(op.x) || !view_ok(op.y) || (op.t1n.ptr && !view_ok(op.t1n))) return 1;
+    if (op.y.C != C || C % DT_CHUNK_N || C > 512) return 1;
+    if (inner % 64 || inner > 512 || inner < 64) return 1;
+    if (inner_n % DT_CHUNK_N || inner_n > 512) return 1;
+    const ActView* vs[3] = { &op.t2, &op.x, &op.t1n };
+    for (int i = 0; i < (op.t1n.ptr ? 3 : 2); ++i)
+        if (static_cast<long long>(vs[i]->W) * vs[i]->H != M) return 1;
+    if (M < 1 || M > (1LL << 30)) return 1;
+    if (!op.w3 || !op.wf0 || !op.wf2 || (op.t1n.ptr && !op.w0n)) return 1;
+
+    int num_sms = 148;
+    {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) num_sms = v;
+    }
+    DcbTailParams& p = op.p;
+    memset(&p, 0, sizeof(p));
+    p.p_bytes = inner / 64 * A_STAGE_BYTES;
+    int stages = (SMEM_USABLE - p.p_bytes - DT_STAGING) / DT_B_STAGE;
+    if (stages > 12) stages = 12;
+    if (stages < 4) return 1;
+    p.stages = stages;
+    p.M = static_cast<int>(M);
+    p.C = C; p.inner = inner; p.inner_next = inner_n;
+    p.nkb[0] = inner / 64; p.nch[0] = C / DT_CHUNK_N;
+    p.nkb[1] = C / 64;     p.nch[1] = 4 * inner / DT_CHUNK_N;
+    p.nkb[2] = inner / 64; p.nch[2] = C / DT_CHUNK_N;
+    p.nkb[3] = C / 64;     p.nch[3] = inner_n / DT_CHUNK_N;
+    p.bias[0] = op.b3; p.bias[1] = op.bf0; p.bias[2] = op.bf2; p.bias[3] = op.b0n;
+    p.qscale = op.qscale;
+    p.x = static_cast<const __half*>(op.x.ptr);
+    p.x_pitch = op.x.pitch;
+    p.shortcut = op.shortcut ? 1 : 0;
+    p.tiles = static_cast<int>((M + 255) / 256);
+    const int max_pairs = dt_max_pairs(num_sms);
+    p.num_pairs = p.tiles < max_pairs ? p.tiles : max_pairs;
+    if (p.num_pairs < 1) return 1;
+
+    if (encode_act_map(&p.tm_a, op.t2, false, true, true, BLOCK_M, 1)) return 2;
+    const __half* ws[4] = { op.w3, op.wf0, op.wf2, op.w0n ? op.w0n : op.w3 };
+    const int Ns[4] = { C, 4 * inner, C, inner_n ? inner_n : C };
+    const int Ks[4] = { inner, C, inner, inner_n ? C : inner };
+    for (int i = 0; i < 4; ++i) {
+        uint64_t dims[2] = { static_cast<uint64_t>(Ks[i]), static_cast<uint64_t>(Ns[i]) };
+        uint64_t st[1] = { static_cast<uint64_t>(Ks[i]) * 2 };
+        uint32_t box[2] = { 64, DT_CHUNK_N / 2 };
+        if (encode_map(&p.tm_w[i], ws[i], 2, dims, st, box)) return 2;
+    }
+    if (encode_act_map(&p.tm_y, op.y, false, true, true, 32, 1, 32)) return 2;
+    if (encode_act_map(&p.tm_t, op.t1n.ptr ? op.t1n : op.y, false, true, true, 32, 1, 32)) return 2;
+    if (const char* d = getenv("DCVC_B200_GEMM_DBG")) p.dbg = atoi(d);
+    op.grid = dim3(2 * p.num_pairs, 1, 1);
+    op.planned = true;
+    return 0;
+}
+
+int dcb_tail_launch(const DcbTailOp& op, cudaStream_t stream)
+{
+    if (!op.planned) { gemm_set_error("dcb_tail_launch: op not planned"); return 1; }
+    if (dcb_tail_init()) return 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = op.grid;
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SMEM_TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (gemm_pdl_enabled() && op.pdl) ? 2 : 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, dcb_tail_kernel, op.p);
+    if (e != cudaSuccess) {
+        gemm_set_error(std::string("dcb_tail launch failed: ") + cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace dcvc

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_GDN, ACT_IGDN, ACT_NONE, ACT_WSILU, GEMM_CONV2X2_S2, GEMM_CONV3X3_PS2, GEMM_CONV3X3_S2, GEMM_PW, GEMM_TCONV2X2,
-                   EntropyStep, GemmDesc, View)
+                   DcbTailDesc, EntropyStep, GemmDesc, View)
 
 
 def _stream() -> C.c_void_p:
@@ -57,6 +57,23 @@ def gemm(kind, x, w_packed, N, out, bias=None, act=ACT_NONE, chunk_add=False, re
     d.chunk_add = 1 if chunk_add else 0
     _lib.check(lib.dcvc_op_gemm(C.byref(d), _stream()), "op_gemm")
     return out
+
+
+def dcb_tail(t2, x, y, w3, b3, wf0, bf0, wf2, bf2, t1n=None, w0n=None, b0n=None, qscale=None, shortcut=False):
+    """dc.3 -> ffn.0 -> ffn.2 (-> next block's dc.0) of a DepthConvBlock in one launch (include/dcvc_b200.h:
+    dcvc_op_dcb_tail).  Weights are [N, K] fp16 CUDA tensors.  Returns False when the shape is not eligible."""
+    lib = _lib.load()
+    d = DcbTailDesc()
+    d.t2, d.x, d.y, d.t1n = view_of(t2), view_of(x), view_of(y), view_of(t1n)
+    ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    d.w3, d.b3, d.wf0, d.bf0, d.wf2, d.bf2 = ptr(w3), ptr(b3), ptr(wf0), ptr(bf0), ptr(wf2), ptr(bf2)
+    d.w0n, d.b0n, d.qscale = ptr(w0n), ptr(b0n), ptr(qscale)
+    d.shortcut = 1 if shortcut else 0
+    rc = lib.dcvc_op_dcb_tail(C.byref(d), _stream())
+    if rc == 2:
+        return False
+    _lib.check(rc, "op_dcb_tail")
+    return True
 
 
 def dw3x3(x, w9c, out):

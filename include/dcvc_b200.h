@@ -63,6 +63,25 @@ typedef struct dcvc_gemm_desc {
 
 int dcvc_op_gemm(const dcvc_gemm_desc* d, void* stream);
 
+/*
+ * The pixel-local run of a DepthConvBlock (reference: DepthConvBlockProxy::forward, layers_proxy.cpp:71-101 — the four
+ * conv1x1_* calls behind the depthwise 3x3; layers.py:152-159) as ONE kernel:
+ *     o   = t2 . w3 + b3 + x                       (dc.3 + shortcut)
+ *     t1' = chunk_add4(wsilu(o . wf0 + bf0))       (ffn.0)
+ *     y   = (t1' . wf2 + bf2 + o [+ x]) [* qscale] (ffn.2 + shortcut [+ block shortcut] [* q])
+ *     t1n = wsilu(y . w0n + b0n)                   (the NEXT block's dc.0; t1n.ptr == NULL: absent)
+ * o and t1' never leave the SM.  Returns 2 (dcvc_last_error(): "not eligible") for shapes the fused kernel does not
+ * take (C % 128, inner % 64, > 512 channels); the codecs fall back to four dcvc_op_gemm-equivalent launches then.
+ */
+typedef struct dcvc_dcb_tail_desc {
+    dcvc_view t2, x, y, t1n;
+    const void *w3, *b3, *wf0, *bf0, *wf2, *bf2, *w0n, *b0n; /* fp16; weights [N][K] K-major */
+    const void* qscale;    /* fp16 [C] or NULL */
+    int32_t shortcut;      /* 1: y also adds x */
+} dcvc_dcb_tail_desc;
+
+int dcvc_op_dcb_tail(const dcvc_dcb_tail_desc* d, void* stream);
+
 /* Host helper: re-lay a PyTorch conv weight (fp16, contiguous [Cout][Cin][kh][kw] on the HOST)
  * into the packed layout of `kind` (layers_proxy.cpp:260-266, 314-323).  dst holds N*Ktot halves. */
 int dcvc_pack_weight(int32_t kind, const void* w_host, int32_t cout, int32_t cin, int32_t kh,

@@ -1,0 +1,145 @@
+"""dcb_tail — dc.3 -> ffn.0 -> ffn.2 (-> next dc.0) of a DepthConvBlock as one CTA-pair kernel — against
+(a) the fp32 oracle of the same four ops (oracle/ops_ref.py, the restatement of layers.py:152-159 that pins the per-op
+kernels) and (b) the per-op pw_gemm kernels on the device, which round to fp16 at exactly the same three places
+(o, t1', y): the fused kernel must agree with them to fp16 rounding of fp32 sums."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(gen, *shape, scale=1.0):
+    return ((torch.rand(*shape, generator=gen) - 0.5) * 2 * scale).half().float()
+
+
+def _nhwc(x):
+    return x[0].permute(1, 2, 0).contiguous().half().cuda()
+
+
+def _nchw(t):
+    return t.permute(2, 0, 1).unsqueeze(0)
+
+
+# (H, W, C, inner, inner_next, shortcut, q)
+CASES = [
+    (16, 16, 128, 128, 128, False, False),     # one pair tile, one chunk per phase
+    (16, 16, 384, 384, 384, False, False),     # the Intra P8 block shape, M = 256
+    (17, 30, 384, 384, 0, True, True),         # ragged M = 510 (second CTA's last rows out of range), no phase 4
+    (32, 40, 256, 128, 256, False, False),     # dcb2-style narrow inner width
+    (68, 120, 512, 512, 512, False, False),    # P16 prior blocks: O fills 256 TMEM columns, P = 128 KB
+    (136, 240, 384, 384, 384, True, False),    # 1080p P8: 128 pair tiles over 74 pairs (two tiles per pair, tail tile half empty)
+    (136, 240, 384, 384, 0, False, True),
+]
+
+
+def _make(gen, H, W, C, inner, inner_n):
+    d = {}
+    d["t2"] = _rand(gen, 1, inner, H, W)
+    d["x"] = _rand(gen, 1, C, H, W)
+    d["w3"] = _rand(gen, C, inner, 1, 1, scale=inner ** -0.5)
+    d["b3"] = _rand(gen, C, scale=0.1)
+    d["wf0"] = _rand(gen, 4 * inner, C, 1, 1, scale=C ** -0.5)
+    d["bf0"] = _rand(gen, 4 * inner, scale=0.1)
+    d["wf2"] = _rand(gen, C, inner, 1, 1, scale=inner ** -0.5)
+    d["bf2"] = _rand(gen, C, scale=0.1)
+    if inner_n:
+        d["w0n"] = _rand(gen, inner_n, C, 1, 1, scale=C ** -0.5)
+        d["b0n"] = _rand(gen, inner_n, scale=0.1)
+    return d
+
+
+def _oracle(d, shortcut, qs, inner_n):
+    from oracle import ops_ref
+    h16 = lambda t: t.half().float()  # noqa: E731  (the kernels store o, t1', y as fp16)
+    o = h16(ops_ref.conv1x1(d["t2"], d["w3"], d["b3"], res1=d["x"]))
+    t1 = h16(ops_ref.conv1x1(o, d["wf0"], d["bf0"], act=True, chunk_add=True))
+    y = h16(ops_ref.conv1x1(t1, d["wf2"], d["bf2"], res1=o, res2=d["x"] if shortcut else None, q=qs))
+    t1n = h16(ops_ref.conv1x1(y, d["w0n"], d["b0n"], act=True)) if inner_n else None
+    return y, t1n
+
+
+def _per_op(d, H, W, C, inner, inner_n, shortcut, qs):
+    from dcvc_b200 import ops
+    dev = dict(device="cuda", dtype=torch.float16)
+    x, t2 = _nhwc(d["x"]), _nhwc(d["t2"])
+    o = torch.zeros(H, W, C, **dev)
+    t1 = torch.zeros(H, W, inner, **dev)
+    y = torch.zeros(H, W, C, **dev)
+    pw = lambda w: ops.pack_weight(ops.GEMM_PW, w)  # noqa: E731
+    ops.gemm(ops.GEMM_PW, t2, pw(d["w3"]), C, o, bias=d["b3"].half().cuda(), res1=x)
+    ops.gemm(ops.GEMM_PW, o, pw(d["wf0"]), 4 * inner, t1, bias=d["bf0"].half().cuda(), act=ops.ACT_WSILU, chunk_add=True)
+    ops.gemm(ops.GEMM_PW, t1, pw(d["wf2"]), C, y, bias=d["bf2"].half().cuda(), res1=o, res2=x if shortcut else None,
+             qscale=qs.half().cuda() if qs is not None else None)
+    t1n = None
+    if inner_n:
+        t1n = torch.zeros(H, W, inner_n, **dev)
+        ops.gemm(ops.GEMM_PW, y, pw(d["w0n"]), inner_n, t1n, bias=d["b0n"].half().cuda(), act=ops.ACT_WSILU)
+    return y, t1n
+
+
+def _fused(d, H, W, C, inner, inner_n, shortcut, qs, y_out=None, t2_in=None):
+    from dcvc_b200 import ops
+    dev = dict(device="cuda", dtype=torch.float16)
+    g = lambda k: d[k].half().cuda().reshape(d[k].shape[0], -1).contiguous() if k in d else None  # noqa: E731
+    y = y_out if y_out is not None else torch.zeros(H, W, C, **dev)
+    t1n = torch.zeros(H, W, inner_n, **dev) if inner_n else None
+    ok = ops.dcb_tail(t2_in if t2_in is not None else _nhwc(d["t2"]), _nhwc(d["x"]), y, g("w3"), g("b3"), g("wf0"), g("bf0"),
+                      g("wf2"), g("bf2"), t1n=t1n, w0n=g("w0n"), b0n=g("b0n"),
+                      qscale=qs.half().cuda() if qs is not None else None, shortcut=shortcut)
+    assert ok, "shape must be eligible for the fused kernel"
+    torch.cuda.synchronize()
+    return y, t1n
+
+
+def _cmp(name, got, ref, rel, abs_):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err = (got - ref).abs()
+    bad = (err > abs_ + rel * ref.abs()).sum().item()
+    assert bad == 0, f"{name}: {bad} / {err.numel()} mismatches, max err {err.max().item():.5f}"
+
+
+@pytest.mark.parametrize("H,W,C,inner,inner_n,shortcut,q", CASES)
+def test_dcb_tail_matches_oracle_and_per_op_kernels(H, W, C, inner, inner_n, shortcut, q):
+    gen = torch.Generator().manual_seed(H * 131 + W * 7 + C + inner)
+    d = _make(gen, H, W, C, inner, inner_n)
+    qs = (torch.rand(C, generator=gen) + 0.5).half().float() if q else None
+    y_f, t_f = _fused(d, H, W, C, inner, inner_n, shortcut, qs)
+    y_o, t_o = _oracle(d, shortcut, qs, inner_n)
+    # three chained fp16 roundings: a flipped rounding of o or t1' moves y by ~1 fp16 ulp of its magnitude
+    _cmp("y vs oracle", _nchw(y_f), y_o, 6e-3, 4e-3)
+    if inner_n:
+        _cmp("t1n vs oracle", _nchw(t_f), t_o, 6e-3, 4e-3)
+    y_p, t_p = _per_op(d, H, W, C, inner, inner_n, shortcut, qs)
+    torch.cuda.synchronize()
+    _cmp("y vs per-op kernels", y_f, y_p, 2e-3, 2e-3)
+    if inner_n:
+        _cmp("t1n vs per-op kernels", t_f, t_p, 2e-3, 2e-3)
+    same = (y_f == y_p).float().mean().item()
+    print(f"[dcb_tail] {H}x{W} C={C} inner={inner}: y bit-identical to the per-op kernels in {100 * same:.3f} % of the elements")
+
+
+def test_dcb_tail_pitched_views_and_in_place_output():
+    """t2 is a channel slice of a wider buffer; y overwrites x in place (what CodecBase::dcb does: the block output lands in
+    the block input's buffer)."""
+    from dcvc_b200 import ops
+    H, W, C, inner = 24, 40, 256, 256
+    gen = torch.Generator().manual_seed(99)
+    d = _make(gen, H, W, C, inner, 0)
+    wide = torch.zeros(H, W, 2 * inner, device="cuda", dtype=torch.float16)
+    wide[..., inner:] = _nhwc(d["t2"])
+    xbuf = _nhwc(d["x"]).clone()
+    g = lambda k: d[k].half().cuda().reshape(d[k].shape[0], -1).contiguous()  # noqa: E731
+    assert ops.dcb_tail(wide[..., inner:], xbuf, xbuf, g("w3"), g("b3"), g("wf0"), g("bf0"), g("wf2"), g("bf2"), shortcut=True)
+    torch.cuda.synchronize()
+    y_o, _ = _oracle(d, True, None, 0)
+    _cmp("in-place y vs oracle", _nchw(xbuf), y_o, 6e-3, 4e-3)
+
+
+def test_dcb_tail_declines_unsupported_shapes():
+    from dcvc_b200 import ops
+    H, W, C, inner = 8, 8, 192, 192          # C % 128 != 0
+    gen = torch.Generator().manual_seed(5)
+    d = _make(gen, H, W, C, inner, 0)
+    g = lambda k: d[k].half().cuda().reshape(d[k].shape[0], -1).contiguous()  # noqa: E731
+    y = torch.zeros(H, W, C, device="cuda", dtype=torch.float16)
+    assert ops.dcb_tail(_nhwc(d["t2"]), _nhwc(d["x"]), y, g("w3"), g("b3"), g("wf0"), g("bf0"), g("wf2"), g("bf2")) is False

@@ -66,7 +66,8 @@ class _Dry:
         env = dict(os.environ)
         env.update({"LD_PRELOAD": self.shim, "LD_LIBRARY_PATH": CUDA_LIB + ":" + env.get("LD_LIBRARY_PATH", ""),
                     "DCVC_B200_RANS_SPIN_US": "0", "OMP_NUM_THREADS": "2", "MKL_NUM_THREADS": "2", "DCVC_DRY_THREADS": "2",
-                    "DCVC_B200_TEST_LANES": "1"})
+                    "DCVC_B200_TEST_LANES": "1",
+                    "DCVC_B200_FUSE_TAIL": "0"})   # the shim emulates the per-op kernels only
         env.pop("DRY_SHIM_EMULATE", None)
         if emulate:
             env["DRY_SHIM_EMULATE"] = "1"
