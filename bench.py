@@ -198,11 +198,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     prof = model.proxy.profile_get()
     model.proxy.profile_enable(False)
-    g = prof["pw_gemm"]
+    # the dominant kernel family of the step: the fused DepthConvBlock tail (dcb_tail_kernel) or, with it switched off,
+    # the per-op GEMM (pw_gemm_kernel)
+    fam = max(("pw_gemm", "dcb_tail"), key=lambda k: prof.get(k, {"ms": 0.0})["ms"])
+    g = prof[fam]
     roofline = None
     if g["launches"]:
         n_prof = 3
-        share = g["ms"] / max(1e-9, sum(v["ms"] for v in prof.values()))
+        total_ms = max(1e-9, sum(v["ms"] for v in prof.values()))
+        share = g["ms"] / total_ms
         # Duration of the dominant kernel inside the timed step: its share of the GPU time (CUDA events around every
         # launch, graphs off: those intervals include launch gaps and lose the PDL overlap, so they are reported
         # separately as *_isolated) x the GPU-only time of the timed, graph-launched decode (CUDA events around the
@@ -214,11 +218,11 @@ def run_ours(args):
         tfs = flops_per_step / (ms_in_step * 1e-3) / 1e12
         gbs_iso = g["alg_bytes"] / (g["ms"] * 1e-3) / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_pw_gemm.json")
+        tp = os.path.join(ROOT, "profiles", f"traffic_{fam}.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         launches_per_step = g["launches"] // n_prof
-        roofline = {"bound": "hbm", "kernel": "pw_gemm_kernel", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": fam + "_kernel", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(gbs / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "method": "algorithmic bytes of the kernel's launches in one step / (share_of_gpu_time x GPU-only ms of the timed step)",
                     "launches_per_step": launches_per_step,
@@ -229,6 +233,9 @@ def run_ours(args):
                     "achieved_isolated": round(gbs_iso, 1), "frac_isolated": round(gbs_iso / hbm_peak, 4),
                     "avg_launch_us_isolated": round(g["ms"] * 1e3 / g["launches"], 2),
                     "families_ms_per_step_isolated": {k: round(v["ms"] / n_prof, 3) for k, v in prof.items()},
+                    "families_launches_per_step": {k: int(v["launches"] // n_prof) for k, v in prof.items()},
+                    "families_alg_gbs_in_step": {k: round(v["alg_bytes"] / n_prof / max(1e-9, v["ms"] / total_ms * gpu_only_ms * 1e-3) / 1e9, 1)
+                                                 for k, v in prof.items() if v["alg_bytes"] > 0},
                     "whole_decode_alg_gbs": round(ALG_BYTES_DECODE / (gpu_only_ms * 1e-3) / 1e9, 1),
                     "whole_decode_frac": round(ALG_BYTES_DECODE / (gpu_only_ms * 1e-3) / 1e9 / hbm_peak, 4)}
 
@@ -253,9 +260,9 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             htl = {"error": f"{type(e).__name__}: {e}"}
 
-    # ---- opt-in (--hts-size HxW, e.g. 2160x3840 = configs[4]): the HT-S leg again at another picture size
+    # ---- configs[4]: the HT-S leg again at 4K (single-GPU runs; --hts-size HxW picks another size, "none" skips it)
     hts_extra = None
-    if args.hts_size and world == 1:
+    if args.hts_size.lower() != "none" and not args.no_hts and world == 1 and not (_SIZE_OVERRIDE and args.hts_size == "2160x3840"):
         try:
             eh, ew = (int(v) for v in args.hts_size.lower().split("x"))
             hts_extra = bench_hts(model, device, world, rank, args, timed, reduce_max, hw=(eh, ew))
@@ -270,10 +277,21 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             pipelined = {"error": f"{type(e).__name__}: {e}"}
 
+    # ---- the reference's own CUDA extension (CUTLASS, compiled for sm_100a by baseline/build_ref_cuda.py) under the
+    # reference's own models, same box, same checkpoints / frames / protocol, in its own process (rank 0, N=1 only)
+    reference_cuda = None
+    if rank == 0 and world == 1 and not args.no_reference_cuda and not _SIZE_OVERRIDE:
+        reference_cuda = run_reference_cuda(args)
+
     # ---- CPU baseline: the oracle port on the host cores (rank 0, N=1 only), bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_reference_sample(steps=1, sample_hw=(544, 960))
+        cpu_baseline = cpu_reference_sample(steps=1, sample_hw=(H, W))
+        try:  # what the reference's own driver pins (src/utils/common.py:264-272: torch.set_num_threads(1))
+            one = cpu_reference_sample(steps=1, sample_hw=(H, W), threads=1)
+            cpu_baseline["single_thread"] = {k: one[k] for k in ("value", "unit", "cores", "sample", "seconds_per_sample")}
+        except Exception as e:  # noqa: BLE001
+            cpu_baseline["single_thread"] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         fps = world * args.steps / (tot_dec * 1e-3)
@@ -302,10 +320,23 @@ def run_ours(args):
             "htl": htl,
             "pipelined": pipelined,
             "hts_extra": hts_extra,
+            "reference_cuda": reference_cuda,
             "host": {"cpus": os.cpu_count(), "numa_pinned_cpus": (len(numa) if numa else None)},
             # every DCVC_B200_* switch of the environment (none in the driver's runs): an A/B line describes itself
             "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("DCVC_B200_")},
         }
+        if reference_cuda and "intra" in reference_cuda:
+            # same frame, same checkpoint, same q_index: the product next to the reference's CUDA path
+            ri = reference_cuda["intra"]
+            out["parity"] = {"against": "reference CUDA extension, same box", "frame": "1080p synth seed 1234, q_index 32",
+                             "bytes": [len(bs), ri["bytes"]], "d_bpp": round(abs(len(bs) - ri["bytes"]) * 8 / (H * W), 6),
+                             "psnr_db": [out["psnr_db"], ri["psnr_db"]], "d_psnr_db": round(abs(out["psnr_db"] - ri["psnr_db"]), 5)}
+            sp = {"intra_decode": round(out["value"] / ri["decode_fps"], 3), "intra_encode": round(out["encode_fps"] / ri["encode_fps"], 3)}
+            for leg, name in ((hts, "hts"), (ld, "ld"), (htl, "htl")):
+                if leg and name in reference_cuda and "decode_fps" in leg:
+                    sp[name + "_decode"] = round(leg["decode_fps"] / reference_cuda[name]["decode_fps"], 3)
+                    sp[name + "_encode"] = round(leg["encode_fps"] / reference_cuda[name]["encode_fps"], 3)
+            out["speedup_vs_reference_cuda"] = sp
         if _SIZE_OVERRIDE:
             out["INVALID_test_size_override"] = _SIZE_OVERRIDE
         print(json.dumps(out))
@@ -532,10 +563,24 @@ def bench_ld(i_net, device, world, rank, args, timed, reduce_max):
     return out
 
 
+def run_reference_cuda(args):
+    """baseline/run_ref_cuda.py in a subprocess (the module name inference_extensions_cuda can only mean one thing per
+    process).  A missing build or a failing run is reported in the line, never raised."""
+    script = os.path.join(ROOT, "baseline", "run_ref_cuda.py")
+    try:
+        r = subprocess.run([sys.executable, script, "--steps", str(args.steps), "--warmup", str(args.warmup)],
+                           capture_output=True, text=True, timeout=900)
+        if r.returncode != 0:
+            return {"error": (r.stderr or r.stdout)[-600:]}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def cpu_reference_sample(steps, sample_hw, threads=None):
     """The reference's CPU path = oracle port (PyTorch fp32-accumulate restatement of the proxy control
     flow + the reference's own rANS coder from oracle/_ref), timed on the host cores on a bounded
-    sample; FPS is scaled to 1080p by pixel count."""
+    sample of whole frames at the bench's own picture size (no area scaling)."""
     from util_frames import synth_frame
     from dcvc_b200.spec import dmci_spec, synth_state_dict
     from oracle.dmci_oracle import DmciOracle
@@ -546,15 +591,30 @@ def cpu_reference_sample(steps, sample_hw, threads=None):
     o = DmciOracle(synth_state_dict(dmci_spec(), 0), skip_thres=SKIP, emulate_fp16=True, threads=cores)
     x = synth_frame(h, w, 1234)
     pad_b, pad_r = (16 - h % 16) % 16, (16 - w % 16) % 16
-    enc = o.compress(x, QP, pad_b, pad_r)
+    enc = _CPU_STREAM_CACHE.get((h, w))
+    if enc is None:
+        enc = _CPU_STREAM_CACHE[(h, w)] = o.compress(x, QP, pad_b, pad_r)
     t0 = time.perf_counter()
     for _ in range(steps):
         o.decompress(enc["bit_stream"], QP, h, w, enc["ec_parallel"])
     dt = (time.perf_counter() - t0) / steps
-    scale = (h * w) / float(H * W)
-    return {"value": round(scale / dt, 4), "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} decode(s) of a {h}x{w} crop-sized frame ({scale:.3f} of 1080p area), "
-                      f"{dt:.2f} s each, FPS scaled by area", "seconds_per_sample": round(dt, 3)}
+    return {"value": round(1.0 / dt, 4), "unit": "frames/s", "cores": cores, "kind": "port",
+            "cpu_model": _cpu_model(), "host_cpus": os.cpu_count(),
+            "sample": f"{steps} whole decode(s) of the bench's own {h}x{w} frame (q_index {QP}) with the oracle port + the reference's own "
+                      f"rANS coder on {cores} thread(s), {dt:.2f} s each", "seconds_per_sample": round(dt, 3)}
+
+
+_CPU_STREAM_CACHE = {}
+
+
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def run_reference(args):
@@ -563,33 +623,45 @@ def run_reference(args):
         return
     n = args.steps + args.warmup
     t0 = time.time()
-    # each step = one decode of a 272x480 sample (1/16 of the 1080p area) on all host cores
+    # each step = one whole decode of the product arm's own 1080p frame on the host cores (the same config: no sampling)
     from util_frames import synth_frame
     from dcvc_b200.spec import dmci_spec, synth_state_dict
     from oracle.dmci_oracle import DmciOracle
     cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
-    h, w = 272, 480
+    h, w = H, W
     o = DmciOracle(synth_state_dict(dmci_spec(), 0), skip_thres=SKIP, emulate_fp16=True, threads=cores)
     x = synth_frame(h, w, 1234)
-    enc = o.compress(x, QP, 0, 0)
+    enc = o.compress(x, QP, (16 - h % 16) % 16, (16 - w % 16) % 16)
+    # a step costs seconds here: the run is bounded to ~3 minutes of wall time, and the line says how many steps it timed
+    budget_s = 170.0
+    done_w = 0
     for _ in range(args.warmup):
+        if time.time() - t0 > budget_s * 0.25:
+            break
         o.decompress(enc["bit_stream"], QP, h, w, enc["ec_parallel"])
+        done_w += 1
     t1 = time.perf_counter()
+    done = 0
     for _ in range(args.steps):
         o.decompress(enc["bit_stream"], QP, h, w, enc["ec_parallel"])
+        done += 1
+        if time.time() - t0 > budget_s:
+            break
     dt = time.perf_counter() - t1
-    scale = (h * w) / float(H * W)
-    fps = args.steps / dt * scale
+    fps = done / dt
     out = {"impl": "reference", "metric": METRIC, "value": round(fps, 4), "unit": "frames/s",
-           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": done, "warmup": done_w,
+           "steps_requested": args.steps, "warmup_requested": args.warmup,
+           "ms_per_step": round(dt / done * 1e3, 2), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "DCVC-UF-Intra 1080p single-frame decode (configs[1]), q_index 32, skip_thres 0.15",
-                      "resolution": [H, W], "qp": QP},
+           "config": {"workload": "DCVC-UF-Intra 1080p single-frame decode (configs[1]), q_index 32, skip_thres 0.15, "
+                                  "one independent frame per GPU", "resolution": [H, W], "qp": QP,
+                      "l2": "n/a (CPU)", "weights": "seeded synthetic checkpoint (no checkpoints offline)"},
            "cpu_baseline": {"value": round(fps, 4), "unit": "frames/s", "cores": cores, "kind": "port",
-                            "sample": f"each step decodes a {h}x{w} frame ({scale:.4f} of the 1080p area) with the oracle "
-                                      f"port + the reference's own rANS coder; FPS scaled by area"},
+                            "cpu_model": _cpu_model(), "host_cpus": os.cpu_count(),
+                            "sample": f"each step = one whole decode of the {h}x{w} frame with the oracle port + the reference's own "
+                                      f"rANS coder on {cores} threads; {done} of {args.steps} requested steps fit the ~3 min bound"},
            "e2e": {"value": round(fps, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": round(time.time() - t0, 1)}
     print(json.dumps(out))
@@ -603,7 +675,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hts", action="store_true")
-    ap.add_argument("--hts-size", default=None, help="also run the HT-S leg at HxW, e.g. 2160x3840 (opt-in, single GPU)")
+    ap.add_argument("--hts-size", default="2160x3840", help="second HT-S leg at HxW (configs[4]: 4K; single GPU; 'none' skips it)")
+    ap.add_argument("--no-reference-cuda", action="store_true", help="skip the same-box run of the reference's own CUDA extension")
     ap.add_argument("--pipelined", action="store_true", help="also measure two concurrent decodes per GPU (opt-in)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

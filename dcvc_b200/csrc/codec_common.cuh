@@ -138,7 +138,7 @@ struct Level {  // one pyramid level: two ping-pong buffers + two scratch buffer
 
 using OpFn = std::function<int(cudaStream_t)>;
 
-enum OpKind { OP_GEMM = 0, OP_DW = 1, OP_ELEM = 2, OP_KINDS = 3 };
+enum OpKind { OP_GEMM = 0, OP_DW = 1, OP_ELEM = 2, OP_TAIL = 3, OP_KINDS = 4 };  // OP_TAIL: the fused dcb_tail kernel
 
 struct Segment {
     std::vector<OpFn> ops;
@@ -692,7 +692,7 @@ protected:
                 const double px = static_cast<double>(W) * H;
                 const double bytes = px * 2 * ((w.inner + w.c + w.c) + (w.c + w.inner) + (w.inner + w.c + w.c + (shortcut ? w.c : 0)));
                 const double fl = 2.0 * px * (static_cast<double>(w.c) * w.inner + 4.0 * w.inner * w.c + static_cast<double>(w.c) * w.inner);
-                s.annotate(OP_GEMM, bytes, fl);
+                s.annotate(OP_TAIL, bytes, fl);
                 s.tail = op;
                 s.tail_idx = s.ops.size() - 1;
                 return dst;

@@ -31,12 +31,22 @@
 namespace dcvc {
 
 static constexpr int DT_CHUNK_N = 128;                              // GEMM columns per accumulator chunk
-static constexpr int DT_B_STAGE = (DT_CHUNK_N / 2) * BLOCK_K * 2;   // 8 KB: this CTA's half of one weight k-block
+static constexpr int DT_KB_BYTES = (DT_CHUNK_N / 2) * BLOCK_K * 2;  // 8 KB: this CTA's half of one weight k-block
 static constexpr int DT_MAX_STAGES = 16;
 static constexpr int DT_MAX_KB = 8;                                 // K <= 512
 static constexpr int DT_ACC_COL0 = 256;
 static constexpr int DT_TMEM_COLS = 512;
 static constexpr int DT_STAGING = EPI_WARPS * EPI_SLAB_BYTES;       // one 2 KB slab per epilogue warp
+
+// timeline marks (tools/dcb_tail_trace.py): globaltimer into p.trace[slot], CTA `cta` only
+__device__ __forceinline__ void dt_mark(const DcbTailParams& p, int cta, int slot)
+{
+    if (p.trace && static_cast<int>(blockIdx.x) == cta && slot < 2048) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[slot] = t;
+    }
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
@@ -45,16 +55,17 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* P = smem;
     uint8_t* ring = P + p.p_bytes;
-    uint8_t* staging = ring + p.stages * DT_B_STAGE;
+    uint8_t* staging = ring + p.stages * p.stage_bytes;
     uint8_t* ctrl = smem + SMEM_USABLE;
     uint64_t* p_full = reinterpret_cast<uint64_t*>(ctrl);   // [8]  leader: t2 k-block of both CTAs landed
     uint64_t* p_ready = p_full + DT_MAX_KB;                 // [8]  leader: t1' k-block written by both CTAs' epilogues
-    uint64_t* b_full = p_ready + DT_MAX_KB;                 // [16] leader: both halves of a weight k-block landed
+    uint64_t* b_full = p_ready + DT_MAX_KB;                 // [16] leader: both halves of a weight stage landed
     uint64_t* b_empty = b_full + DT_MAX_STAGES;             // [16] every CTA: ring slot consumed
     uint64_t* acc_full = b_empty + DT_MAX_STAGES;           // [2]  every CTA: accumulator chunk complete
-    uint64_t* acc_empty = acc_full + 2;                     // [2]  leader: chunk drained by both CTAs' 8 warps
+    uint64_t* acc_empty = acc_full + 2;                     // [2]  leader: chunk drained by both CTAs' 16 warps
     uint64_t* p_empty = acc_empty + 2;                      // [1]  every CTA: phase-3 MMAs done, P may be reloaded
-    uint64_t* o_ready = p_empty + 1;                        // [1]  leader: O holds the complete o (1st use) / y (2nd use per tile)
+    uint64_t* o_ready = p_empty + 1;                        // [1]  leader: O holds the tile's complete o (both CTAs)
+    uint64_t* y_ready = o_ready + 1;                        // [1]  leader: O holds the tile's complete y; nobody reads o any more
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ctrl + 496);
 
     const int rank = static_cast<int>(cluster_ctarank());
@@ -69,7 +80,7 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
         tma_prefetch_desc(&p.tm_t);
         for (int i = 0; i < DT_MAX_KB; ++i) {
             mbar_init(&p_full[i], 1);
-            mbar_init(&p_ready[i], 32);               // 2 chunks x 8 warps x 2 CTAs
+            mbar_init(&p_ready[i], 64);               // 2 chunks x 16 warps x 2 CTAs
         }
         for (int i = 0; i < DT_MAX_STAGES; ++i) {
             mbar_init(&b_full[i], 1);
@@ -77,10 +88,11 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
         }
         for (int g = 0; g < 2; ++g) {
             mbar_init(&acc_full[g], 1);
-            mbar_init(&acc_empty[g], 16);             // 8 warps x 2 CTAs
+            mbar_init(&acc_empty[g], 32);             // 16 warps x 2 CTAs
         }
         mbar_init(p_empty, 1);
-        mbar_init(o_ready, static_cast<uint32_t>(p.nch[0] * 16));   // every chunk of the phase: 8 warps x 2 CTAs
+        mbar_init(o_ready, static_cast<uint32_t>(p.nch[0] * 32));   // every chunk of the phase: 16 warps x 2 CTAs
+        mbar_init(y_ready, static_cast<uint32_t>(p.nch[2] * 32));
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -96,7 +108,7 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
     griddep_wait();
 
     if (warp == 0) {
-        if (elect_one_sync()) {
+        if (!(p.dbg & 8) && elect_one_sync()) {
             // ------------------------------------------------------------ TMA producer (both CTAs)
             auto load_tile = [&](int T, int i) {
                 mbar_wait(p_empty, static_cast<uint32_t>((i & 1) ^ 1));
@@ -109,24 +121,36 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
             int s = 0;
             uint32_t bph = 0;
             int i = 0;
+            int issued = 0;
             int T = pair;
             if (T < p.tiles) load_tile(T, 0);
             // the next tile's t2 goes out once the ring is full of phase-4 weights: by then phase 3 has been issued
             // completely, so the wait for p_empty is short and phase 4 starts on a full ring
-            const int total4 = p.nch[3] * p.nkb[3];
+            const int total4 = p.nch[3] * p.nst[3];
             const int trigger = total4 < p.stages ? total4 : p.stages;
             for (; T < p.tiles; T += p.num_pairs, ++i) {
                 const int Tn = T + p.num_pairs;
                 bool next_loaded = false;
                 for (int ph = 0; ph < 4; ++ph) {
                     int cnt = 0;
+                    const int rot = p.rot ? pair % (p.nch[ph] > 0 ? p.nch[ph] : 1) : 0;
+                    const int rep_off = p.wrep > 1 ? (pair % p.wrep) * p.nch[ph] * DT_CHUNK_N : 0;   // timing experiments only
+                    const uint32_t tx = static_cast<uint32_t>(2 * p.kbs[ph] * DT_KB_BYTES);
                     for (int n = 0; n < p.nch[ph]; ++n) {
-                        const int nrow = n * DT_CHUNK_N + rank * (DT_CHUNK_N / 2);
-                        for (int kb = 0; kb < p.nkb[ph]; ++kb) {
+                        int nn = n + rot;
+                        if (nn >= p.nch[ph]) nn -= p.nch[ph];
+                        const int nrow = rep_off + nn * DT_CHUNK_N + rank * (DT_CHUNK_N / 2);
+                        for (int st = 0; st < p.nst[ph]; ++st) {
                             mbar_wait(&b_empty[s], bph ^ 1);
-                            if (rank == 0) mbar_expect_tx(&b_full[s], 2 * DT_B_STAGE);
-                            tma_load_2d_2sm(ring + s * DT_B_STAGE, &p.tm_w[ph], mapa_u32(smem_u32(&b_full[s]), 0),
-                                            kb * BLOCK_K, nrow);
+                            if (rank == 0) mbar_expect_tx(&b_full[s], tx);
+                            // a stage = kbs k-blocks of this CTA's 64 weight rows, one 2-D request each (rank-2 boxes stream
+                            // through the TMA unit; a rank-3 box {64, 64, kbs} was measured ~25 % slower), ONE barrier round trip
+                            const uint32_t bar = mapa_u32(smem_u32(&b_full[s]), 0);
+                            for (int j = 0; j < p.kbs[ph]; ++j)
+                                tma_load_2d_2sm(ring + s * p.stage_bytes + j * DT_KB_BYTES, &p.tm_w[ph], bar,
+                                                (st * p.kbs[ph] + j) * BLOCK_K, nrow);
+                            dt_mark(p, 0, 1024 + issued);
+                            ++issued;
                             if (++s == p.stages) { s = 0; bph ^= 1; }
                             if (ph == 3 && !next_loaded && ++cnt == trigger) {
                                 if (Tn < p.tiles) load_tile(Tn, i + 1);
@@ -144,6 +168,8 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
             // ------------------------------------------------------------ MMA issuer (leader CTA only)
             constexpr uint32_t idesc = make_idesc_f16_f32(BLOCK_M * 2, DT_CHUNK_N);
             const bool do_mma = !(p.dbg & 1);
+            const bool no_acc = (p.dbg & 4) != 0;   // timing experiments: no accumulator hand-off (the epilogue warps idle)
+            const bool no_tma = (p.dbg & 8) != 0;   // timing experiments: no loads (operands are whatever smem holds)
             uint32_t t = 0;
             int s = 0;
             uint32_t bph = 0;
@@ -152,56 +178,79 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                 const uint32_t tph = static_cast<uint32_t>(i & 1);
                 for (int ph = 0; ph < 4; ++ph) {
                     if (p.nch[ph] == 0) continue;
-                    if (ph == 1 || ph == 3) {
-                        mbar_wait_cluster(o_ready, ph == 1 ? 0u : 1u);  // two uses per tile: o complete, y complete
+                    if (ph == 1 && !no_acc) {
+                        mbar_wait_cluster(o_ready, tph);   // both CTAs' o is complete in tensor memory
                         tcgen05_fence_after();
                     }
                     const bool a_tmem = (ph & 1) != 0;
+                    const int kbs = p.kbs[ph];
                     for (int n = 0; n < p.nch[ph]; ++n, ++t) {
                         const int g = static_cast<int>(t & 1);
-                        mbar_wait_cluster(&acc_empty[g], ((t >> 1) & 1) ^ 1);  // both CTAs drained this buffer
-                        tcgen05_fence_after();
-                        const uint32_t acc = tmem_base + DT_ACC_COL0 + g * DT_CHUNK_N;
-                        for (int kb = 0; kb < p.nkb[ph]; ++kb) {
-                            if (n == 0 && ph == 0) mbar_wait(&p_full[kb], tph);
-                            if (n == 0 && ph == 2) mbar_wait_cluster(&p_ready[kb], tph);
-                            mbar_wait(&b_full[s], bph);
+                        if (!no_acc) {
+                            mbar_wait_cluster(&acc_empty[g], ((t >> 1) & 1) ^ 1);  // both CTAs drained this buffer
                             tcgen05_fence_after();
-                            const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(ring + s * DT_B_STAGE));
-                            if (do_mma) {
-                                if (a_tmem) {
-                                    const uint32_t a_t = tmem_base + kb * (BLOCK_K / 2);
+                        }
+                        const uint32_t acc = tmem_base + DT_ACC_COL0 + g * DT_CHUNK_N;
+                        dt_mark(p, 0, 512 + 4 * static_cast<int>(t));
+                        int kb = 0;
+                        for (int st = 0; st < p.nst[ph]; ++st) {
+                            if (!no_tma) {
+                                mbar_wait(&b_full[s], bph);
+                                tcgen05_fence_after();
+                            }
+                            if (st == 0) dt_mark(p, 0, 512 + 4 * static_cast<int>(t) + 1);
+                            const uint32_t b_addr = smem_u32(ring + s * p.stage_bytes);
+                            for (int j = 0; j < kbs; ++j, ++kb) {
+                                if (n == 0 && ph == 0 && !no_tma) { mbar_wait(&p_full[kb], tph); tcgen05_fence_after(); }
+                                if (n == 0 && ph == 2 && !no_acc) { mbar_wait_cluster(&p_ready[kb], tph); tcgen05_fence_after(); }
+                                const uint64_t b_desc = make_kmajor_sw128_desc(b_addr + j * DT_KB_BYTES);
+                                if (do_mma) {
+                                    if (a_tmem) {
+                                        const uint32_t a_t = tmem_base + kb * (BLOCK_K / 2);
 #pragma unroll
-                                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                                        umma_f16_ts_2cta(acc, a_t + k * (UMMA_K / 2), b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                                } else {
-                                    const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(P + kb * A_STAGE_BYTES));
+                                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                            umma_f16_ts_2cta(acc, a_t + k * (UMMA_K / 2), b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                                    } else {
+                                        const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(P + kb * A_STAGE_BYTES));
 #pragma unroll
-                                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                                        umma_f16_ss_2cta(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                            umma_f16_ss_2cta(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                                    }
                                 }
                             }
-                            umma_commit_2cta_mc(&b_empty[s], 3);
+                            if (!no_tma) umma_commit_2cta_mc(&b_empty[s], 3);
                             if (++s == p.stages) { s = 0; bph ^= 1; }
                         }
-                        umma_commit_2cta_mc(&acc_full[g], 3);
+                        if (!no_acc) umma_commit_2cta_mc(&acc_full[g], 3);
+                        dt_mark(p, 0, 512 + 4 * static_cast<int>(t) + 2);
                     }
-                    if (ph == 2) umma_commit_2cta_mc(p_empty, 3);  // P is free for the next tile's t2
+                    if (ph == 2) {
+                        umma_commit_2cta_mc(p_empty, 3);  // P is free for the next tile's t2
+                        // y complete in O and nobody reads o any more: phase 4 may read it — and, phase 4 or not, the NEXT
+                        // tile's phase-1 epilogue may overwrite O (without this wait its arrivals on o_ready would also
+                        // run into a barrier phase nobody consumed: the round-2 "several tiles per pair" bug)
+                        if (!no_acc) {
+                            mbar_wait_cluster(y_ready, tph);
+                            tcgen05_fence_after();
+                        }
+                    }
                 }
             }
         }
         __syncwarp();
     } else {
         // ---------------------------------------------------------------- epilogue (16 warps, both CTAs)
+        // Every warp works on every chunk: warp (q, j) owns TMEM lane quarter q (32 pixel rows) and column quarter j (32 of
+        // the chunk's 128 accumulator columns) — one tcgen05.ld, after which the accumulator goes straight back to the MMA
+        // warp; everything a chunk needs from memory (bias, x) is requested before the wait for the accumulator.
         const int q = warp & 3;
-        const int b = ((warp - 2) >> 2) & 1;
-        const int h = (warp - 2) >> 3;
+        const int jq = (warp - 2) >> 2;
         uint8_t* slab = staging + (warp - 2) * EPI_SLAB_BYTES;
         const uint32_t slab_u = smem_u32(slab);
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-        const uint32_t acc = tmem_base + lane_off + DT_ACC_COL0 + b * DT_CHUNK_N + h * 64;  // this warp's 64 accumulator columns
-        const uint32_t o_base = tmem_base + lane_off;                                      // O, this warp's lanes
-        const uint32_t acc_empty_r = mapa_u32(smem_u32(&acc_empty[b]), 0);
+        const uint32_t acc0 = tmem_base + lane_off + DT_ACC_COL0 + jq * 32;   // + g * 128
+        const uint32_t o_base = tmem_base + lane_off;                         // O, this warp's lanes
+        const uint32_t acc_empty_r = mapa_u32(smem_u32(&acc_empty[0]), 0);     // + g * 8
         const uint32_t o_ready_r = mapa_u32(smem_u32(o_ready), 0);
         const uint32_t p_ready_r = mapa_u32(smem_u32(p_ready), 0);
         const uint32_t P_u = smem_u32(P);
@@ -211,10 +260,10 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
         const uint4 zero4 = make_uint4(0, 0, 0, 0);
         const bool skip_body = (p.dbg & 2) != 0;
 
-        auto hand_back = [&]() {
+        auto hand_back = [&](int g) {
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc_empty_r);
+            if (lane == 0) mbar_arrive_cluster(acc_empty_r + g * 8);
         };
         auto slab_free = [&]() {  // the TMA store that last read this warp's slab has finished reading it
             if (lane == 0) tma_store_wait_read<0>();
@@ -244,10 +293,7 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                 }
             }
         };
-        auto add_bias = [&](const __half* bias, int c0, const uint32_t (&v)[32], float (&tv)[32]) {
-            uint4 cb[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) cb[j] = bias ? __ldg(reinterpret_cast<const uint4*>(bias + c0) + j) : zero4;
+        auto add_bias = [&](const uint4 (&cb)[4], const uint32_t (&v)[32], float (&tv)[32]) {
             const uint32_t* bw = reinterpret_cast<const uint32_t*>(cb);
 #pragma unroll
             for (int e = 0; e < 32; e += 2) {
@@ -275,146 +321,130 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
             }
         };
 
+        const uint32_t y_ready_r = mapa_u32(smem_u32(y_ready), 0);
         uint32_t t = 0;
-        for (int T = pair; T < p.tiles; T += p.num_pairs) {
+        for (int T = (p.dbg & 4) ? p.tiles : pair; T < p.tiles; T += p.num_pairs) {
             const int row_w = T * 256 + rank * BLOCK_M + q * 32;  // first pixel row of this warp
             for (int ph = 0; ph < 4; ++ph) {
-                for (int n = 0; n < p.nch[ph]; ++n, ++t) {
-                    if (static_cast<int>(t & 1) != b) continue;
-                    mbar_wait(&acc_full[b], (t >> 1) & 1);
+                const int rot = p.rot ? pair % (p.nch[ph] > 0 ? p.nch[ph] : 1) : 0;
+                const __half* bias = p.bias[ph];
+                const bool need_x = (ph == 0) || (ph == 2 && p.shortcut);
+                for (int n0 = 0; n0 < p.nch[ph]; ++n0, ++t) {
+                    int n = n0 + rot;   // the chunk this pair works on now (pairs walk the weight matrices in rotated order)
+                    if (n >= p.nch[ph]) n -= p.nch[ph];
+                    const int g = static_cast<int>(t & 1);
+                    const int c0 = n * DT_CHUNK_N + jq * 32;   // GEMM column of this warp's accumulator column 0
+                    const bool tr = warp == 2 && lane == 0;
+                    if (tr) dt_mark(p, 0, 8 * static_cast<int>(t));
+                    // ---- requests that do not depend on the accumulator
+                    uint4 cb[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cb[j] = bias ? __ldg(reinterpret_cast<const uint4*>(bias + c0) + j) : zero4;
+                    if (!skip_body && (need_x || ph >= 2)) slab_free();
+                    if (!skip_body && need_x) fetch_x(row_w, c0);
+                    // ---- the accumulator
+                    if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 5);
+                    mbar_wait(&acc_full[g], (t >> 1) & 1);
                     tcgen05_fence_after();
+                    if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 1);
                     if (skip_body) {
-                        hand_back();
-                        if (ph == 0 || ph == 2) { if (lane == 0) mbar_arrive_cluster(o_ready_r); }
+                        hand_back(g);
+                        if (ph == 0 || ph == 2) { if (lane == 0) mbar_arrive_cluster(ph == 0 ? o_ready_r : y_ready_r); }
                         if (ph == 1) { if (lane == 0) mbar_arrive_cluster(p_ready_r + (n >> 1) * 8); }
                         continue;
                     }
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(acc0 + g * DT_CHUNK_N, v);
+                    uint32_t ov[16];
+                    if (ph == 2) tmem_ld_32x32b_x16(o_base + (c0 >> 1), ov);   // o: the residual of ffn.2
+                    tmem_ld_wait();
+                    hand_back(g);
+                    if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 2);
+                    float tv[32];
+                    add_bias(cb, v, tv);
                     if (ph == 0) {
                         // ---------------- o = acc + b3 + x  ->  O (TMEM, packed fp16)
-#pragma unroll 1
-                        for (int a = 0; a < 2; ++a) {
-                            const int c0 = n * DT_CHUNK_N + h * 64 + a * 32;
-                            uint32_t v[32];
-                            tmem_ld_32x32b_x32(acc + a * 32, v);
-                            slab_free();
-                            fetch_x(row_w, c0);
-                            float tv[32];
-                            tmem_ld_wait();
-                            if (a == 1) hand_back();
-                            add_bias(p.bias[0], c0, v, tv);
-                            cp_async_wait_all();
-                            __syncwarp();
-                            add_slab(tv);
-                            uint32_t w[16];
-                            pack16(tv, w);
-                            tmem_st_32x32b_x16(o_base + (c0 >> 1), w);
-                            __syncwarp();  // every lane has read its slab row before the next LDGSTS overwrites it
-                        }
+                        cp_async_wait_all();
+                        __syncwarp();
+                        add_slab(tv);
+                        uint32_t w[16];
+                        pack16(tv, w);
+                        tmem_st_32x32b_x16(o_base + (c0 >> 1), w);
+                        if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 3);
                         tmem_st_wait();
                         tcgen05_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(o_ready_r);
                     } else if (ph == 1) {
                         // ---------------- t1' = fold4(wsilu(acc + bf0))  ->  P (smem, UMMA K-major SWIZZLE_128B)
-#pragma unroll 1
-                        for (int a = 0; a < 2; ++a) {
-                            const int col0 = n * DT_CHUNK_N + h * 64 + a * 32;  // GEMM column of accumulator column 0
-                            uint32_t v[32];
-                            tmem_ld_32x32b_x32(acc + a * 32, v);
-                            float tv[32];
-                            tmem_ld_wait();
-                            if (a == 1) hand_back();
-                            add_bias(p.bias[1], col0, v, tv);
-                            uint4 o4;
-                            uint32_t* ow = reinterpret_cast<uint32_t*>(&o4);
+                        uint4 o4;
+                        uint32_t* ow = reinterpret_cast<uint32_t*>(&o4);
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                float o2[2];
+                        for (int jj = 0; jj < 4; ++jj) {
+                            float o2[2];
 #pragma unroll
-                                for (int hh = 0; hh < 2; ++hh) {
-                                    const int j = jj * 2 + hh;
-                                    float s4 = wsilu_f(tv[4 * j]);
-                                    s4 += wsilu_f(tv[4 * j + 1]);
-                                    s4 += wsilu_f(tv[4 * j + 2]);
-                                    s4 += wsilu_f(tv[4 * j + 3]);
-                                    o2[hh] = s4;
-                                }
-                                const __half2 h2 = __floats2half2_rn(o2[0], o2[1]);
-                                ow[jj] = *reinterpret_cast<const uint32_t*>(&h2);
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int j = jj * 2 + hh;
+                                float s4 = wsilu_f(tv[4 * j]);
+                                s4 += wsilu_f(tv[4 * j + 1]);
+                                s4 += wsilu_f(tv[4 * j + 2]);
+                                s4 += wsilu_f(tv[4 * j + 3]);
+                                o2[hh] = s4;
                             }
-                            // output channels 32 n + 16 h + 8 a .. + 8: k-block n / 2, 16-byte chunk 4 (n & 1) + 2 h + a of the row
-                            const uint32_t row = static_cast<uint32_t>(q * 32 + lane);
-                            sts128(P_u + (n >> 1) * A_STAGE_BYTES + sw128_offset(row, static_cast<uint32_t>((n & 1) * 4 + h * 2 + a)), o4);
+                            const __half2 h2 = __floats2half2_rn(o2[0], o2[1]);
+                            ow[jj] = *reinterpret_cast<const uint32_t*>(&h2);
                         }
+                        // output channels 32 n + 8 jq .. + 8: k-block n / 2, 16-byte chunk 4 (n & 1) + jq of the row
+                        const uint32_t row = static_cast<uint32_t>(q * 32 + lane);
+                        sts128(P_u + (n >> 1) * A_STAGE_BYTES + sw128_offset(row, static_cast<uint32_t>((n & 1) * 4 + jq)), o4);
+                        if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 3);
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(p_ready_r + (n >> 1) * 8);
                     } else if (ph == 2) {
                         // ---------------- y = (acc + bf2 + o [+ x]) [* q]  ->  O (in place) and global
-#pragma unroll 1
-                        for (int a = 0; a < 2; ++a) {
-                            const int c0 = n * DT_CHUNK_N + h * 64 + a * 32;
-                            uint32_t v[32];
-                            tmem_ld_32x32b_x32(acc + a * 32, v);
-                            uint32_t ov[16];
-                            tmem_ld_32x32b_x16(o_base + (c0 >> 1), ov);
-                            slab_free();
-                            if (p.shortcut) fetch_x(row_w, c0);
-                            float tv[32];
-                            tmem_ld_wait();
-                            if (a == 1) hand_back();
-                            add_bias(p.bias[2], c0, v, tv);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                tv[2 * j] = fma_f32_f16(static_cast<uint16_t>(ov[j] & 0xffffu), ONE, tv[2 * j]);
-                                tv[2 * j + 1] = fma_f32_f16(static_cast<uint16_t>(ov[j] >> 16), ONE, tv[2 * j + 1]);
-                            }
-                            if (p.shortcut) {
-                                cp_async_wait_all();
-                                __syncwarp();
-                                add_slab(tv);
-                                __syncwarp();
-                            }
-                            if (p.qscale) {
-                                uint4 cq[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) cq[j] = __ldg(reinterpret_cast<const uint4*>(p.qscale + c0) + j);
-                                const uint32_t* qw = reinterpret_cast<const uint32_t*>(cq);
-#pragma unroll
-                                for (int e = 0; e < 32; e += 2) {
-                                    const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qw[e >> 1]));
-                                    tv[e] *= qf.x;
-                                    tv[e + 1] *= qf.y;
-                                }
-                            }
-                            uint32_t w[16];
-                            pack16(tv, w);
-                            tmem_st_32x32b_x16(o_base + (c0 >> 1), w);
-                            store_slab(&p.tm_y, w, c0, row_w);
+                        for (int j = 0; j < 16; ++j) {
+                            tv[2 * j] = fma_f32_f16(static_cast<uint16_t>(ov[j] & 0xffffu), ONE, tv[2 * j]);
+                            tv[2 * j + 1] = fma_f32_f16(static_cast<uint16_t>(ov[j] >> 16), ONE, tv[2 * j + 1]);
                         }
+                        if (p.shortcut) {
+                            cp_async_wait_all();
+                            __syncwarp();
+                            add_slab(tv);
+                            __syncwarp();
+                        }
+                        if (p.qscale) {
+                            uint4 cq[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) cq[j] = __ldg(reinterpret_cast<const uint4*>(p.qscale + c0) + j);
+                            const uint32_t* qw = reinterpret_cast<const uint32_t*>(cq);
+#pragma unroll
+                            for (int e = 0; e < 32; e += 2) {
+                                const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qw[e >> 1]));
+                                tv[e] *= qf.x;
+                                tv[e + 1] *= qf.y;
+                            }
+                        }
+                        uint32_t w[16];
+                        pack16(tv, w);
+                        tmem_st_32x32b_x16(o_base + (c0 >> 1), w);
+                        if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 3);
+                        store_slab(&p.tm_y, w, c0, row_w);
                         tmem_st_wait();
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(o_ready_r);
+                        if (lane == 0) mbar_arrive_cluster(y_ready_r);
                     } else {
                         // ---------------- t1n = wsilu(acc + b0n)  ->  global
-#pragma unroll 1
-                        for (int a = 0; a < 2; ++a) {
-                            const int c0 = n * DT_CHUNK_N + h * 64 + a * 32;
-                            uint32_t v[32];
-                            tmem_ld_32x32b_x32(acc + a * 32, v);
-                            float tv[32];
-                            tmem_ld_wait();
-                            if (a == 1) hand_back();
-                            add_bias(p.bias[3], c0, v, tv);
 #pragma unroll
-                            for (int e = 0; e < 32; ++e) tv[e] = wsilu_f(tv[e]);
-                            uint32_t w[16];
-                            pack16(tv, w);
-                            slab_free();
-                            store_slab(&p.tm_t, w, c0, row_w);
-                        }
+                        for (int e = 0; e < 32; ++e) tv[e] = wsilu_f(tv[e]);
+                        uint32_t w[16];
+                        pack16(tv, w);
+                        if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 3);
+                        store_slab(&p.tm_t, w, c0, row_w);
                     }
+                    if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 4);
                 }
             }
         }
@@ -503,10 +533,6 @@ int dcb_tail_plan(DcbTailOp& op)
     DcbTailParams& p = op.p;
     memset(&p, 0, sizeof(p));
     p.p_bytes = inner / 64 * A_STAGE_BYTES;
-    int stages = (SMEM_USABLE - p.p_bytes - DT_STAGING) / DT_B_STAGE;
-    if (stages > 12) stages = 12;
-    if (stages < 4) return 1;
-    p.stages = stages;
     p.M = static_cast<int>(M);
     p.C = C; p.inner = inner; p.inner_next = inner_n;
     p.nkb[0] = inner / 64; p.nch[0] = C / DT_CHUNK_N;
@@ -519,7 +545,11 @@ int dcb_tail_plan(DcbTailOp& op)
     p.x_pitch = op.x.pitch;
     p.shortcut = op.shortcut ? 1 : 0;
     p.tiles = static_cast<int>((M + 255) / 256);
-    const int max_pairs = dt_max_pairs(num_sms);
+    int max_pairs = dt_max_pairs(num_sms);
+    if (const char* e = getenv("DCVC_B200_DT_MAXPAIRS")) {  // debugging: many tiles per pair on small problems
+        const int v = atoi(e);
+        if (v >= 1 && v < max_pairs) max_pairs = v;
+    }
     p.num_pairs = p.tiles < max_pairs ? p.tiles : max_pairs;
     if (p.num_pairs < 1) return 1;
 
@@ -527,15 +557,39 @@ int dcb_tail_plan(DcbTailOp& op)
     const __half* ws[4] = { op.w3, op.wf0, op.wf2, op.w0n ? op.w0n : op.w3 };
     const int Ns[4] = { C, 4 * inner, C, inner_n ? inner_n : C };
     const int Ks[4] = { inner, C, inner, inner_n ? C : inner };
+    int wrep = 1;
+    if (const char* d = getenv("DCVC_B200_DT_WREP")) wrep = atoi(d) > 1 ? atoi(d) : 1;   // tools/dcb_tail_micro.py allocates the copies
+    p.wrep = wrep;
+    int force_kbs = 0;
+    if (const char* e = getenv("DCVC_B200_DT_KBS")) force_kbs = atoi(e);
+    // weight stages: kbs k-blocks of a chunk per ring slot and barrier round trip (measured with one k-block per slot:
+    // ~0.2 us per slot whatever the ring depth — the per-slot protocol, not the bytes, set the pace)
+    int max_kbs = 1;
+    for (int ph = 0; ph < 4; ++ph) {
+        int kbs = 1;
+        for (int c = 4; c >= 1; --c)
+            if (p.nkb[ph] % c == 0 && (!force_kbs || c <= force_kbs)) { kbs = c; break; }
+        p.kbs[ph] = kbs;
+        p.nst[ph] = p.nkb[ph] / kbs;
+        if (p.nch[ph] > 0 && kbs > max_kbs) max_kbs = kbs;
+    }
+    p.stage_bytes = max_kbs * DT_KB_BYTES;
+    int stages = (SMEM_USABLE - p.p_bytes - DT_STAGING) / p.stage_bytes;
+    if (stages > DT_MAX_STAGES) stages = DT_MAX_STAGES;
+    if (stages < 2) return 1;
+    p.stages = stages;
     for (int i = 0; i < 4; ++i) {
-        uint64_t dims[2] = { static_cast<uint64_t>(Ks[i]), static_cast<uint64_t>(Ns[i]) };
-        uint64_t st[1] = { static_cast<uint64_t>(Ks[i]) * 2 };
-        uint32_t box[2] = { 64, DT_CHUNK_N / 2 };
-        if (encode_map(&p.tm_w[i], ws[i], 2, dims, st, box)) return 2;
+        uint64_t d2[2] = { static_cast<uint64_t>(Ks[i]), static_cast<uint64_t>(Ns[i]) * wrep };
+        uint64_t s2[1] = { static_cast<uint64_t>(Ks[i]) * 2 };
+        uint32_t b2[2] = { 64, DT_CHUNK_N / 2 };
+        if (encode_map(&p.tm_w[i], ws[i], 2, d2, s2, b2)) return 2;
     }
     if (encode_act_map(&p.tm_y, op.y, false, true, true, 32, 1, 32)) return 2;
     if (encode_act_map(&p.tm_t, op.t1n.ptr ? op.t1n : op.y, false, true, true, 32, 1, 32)) return 2;
     if (const char* d = getenv("DCVC_B200_GEMM_DBG")) p.dbg = atoi(d);
+    if (const char* d = getenv("DCVC_B200_GEMM_TRACE")) p.trace = reinterpret_cast<unsigned long long*>(strtoull(d, nullptr, 0));
+    p.rot = 1;
+    if (const char* d = getenv("DCVC_B200_DT_ROT")) p.rot = atoi(d) ? 1 : 0;
     op.grid = dim3(2 * p.num_pairs, 1, 1);
     op.planned = true;
     return 0;

@@ -21,7 +21,7 @@ namespace dcvc {
 
 struct alignas(64) DcbTailParams {
     CUtensorMap tm_a;      // t2   [M][inner]    load box {64 ch, 128 rows}, SWIZZLE_128B
-    CUtensorMap tm_w[4];   // W_i  [N_i][K_i]    load box {64 k,  64 rows},  SWIZZLE_128B  (this CTA's half of a 128-column chunk)
+    CUtensorMap tm_w[4];   // W_i  [N_i][K_i]    load box {64 k, 64 rows}, SWIZZLE_128B (this CTA's half of a 128-column chunk)
     CUtensorMap tm_y;      // y    [M][C]        store box {32 ch, 32 rows}, SWIZZLE_64B
     CUtensorMap tm_t;      // t1n  [M][inner_n]  store box {32 ch, 32 rows}, SWIZZLE_64B
     const __half* bias[4]; // per GEMM column (nullptr: none)
@@ -35,9 +35,15 @@ struct alignas(64) DcbTailParams {
     int nch[4];            // 128-column chunks per phase (nch[3] == 0: no phase 4)
     int tiles;             // ceil(M / 256)
     int num_pairs;         // gridDim.x / 2
+    int kbs[4];            // k-blocks per weight stage (one ring slot / barrier round trip, kbs TMA requests), per phase
+    int nst[4];            // stages per chunk = nkb / kbs
+    int stage_bytes;       // ring slot size = max kbs * 8 KB
     int stages;            // weight ring depth
     int p_bytes;           // bytes of the resident activation buffer (inner / 64 * 16 KB)
     int dbg;
+    unsigned long long* trace;   // env DCVC_B200_GEMM_TRACE=<device address of 2048 u64>: timeline of CTA 0 (tools/dcb_tail_trace.py)
+    int rot;               // 1: pair p starts every phase at chunk p % nch (the pairs stream different weight tiles at a time)
+    int wrep;              // timing experiments: the weight matrices are replicated `wrep` times along N, pair p reads copy p % wrep
 };
 
 struct DcbTailOp {

@@ -24,7 +24,7 @@ class _CodecHandle:
             raise RuntimeError("dcvc_create failed: " + self.lib.dcvc_last_error().decode())
 
     def same_device(self, t):
-        if t.device.index != self.device:
+        if t.device.index is not None and t.device.index != self.device:
             raise RuntimeError(f"tensor on cuda:{t.device.index}, but this proxy was created on cuda:{self.device}")
 
     def check(self, rc, what):
@@ -61,7 +61,7 @@ def _push_state_dict(hd: _CodecHandle, state_dict, skip_threshold: float):
                 tt = tt.float()
                 dtype = _lib.DTYPE_F32
             on_dev = 1 if tt.is_cuda else 0
-            if tt.is_cuda and tt.device.index != hd.device:
+            if tt.is_cuda and tt.device.index is not None and tt.device.index != hd.device:
                 raise RuntimeError(f"set_param({name}): tensor lives on cuda:{tt.device.index}, the proxy on cuda:{hd.device}")
         else:
             continue
@@ -131,7 +131,7 @@ class DMCIProxy:
     def profile_get(self):
         """{family: dict(ms, launches, alg_bytes, flops)} accumulated since profile_enable(True)"""
         out = {}
-        for kind, name in enumerate(("pw_gemm", "dw3x3", "elementwise")):
+        for kind, name in enumerate(("pw_gemm", "dw3x3", "elementwise", "dcb_tail")):
             ms, n, b, f = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
             self._hd.lib.dcvc_profile_get(self._hd.h, kind, C.byref(ms), C.byref(n), C.byref(b), C.byref(f))
             out[name] = {"ms": ms.value, "launches": n.value, "alg_bytes": b.value, "flops": f.value}

@@ -77,13 +77,13 @@ def _per_op(d, H, W, C, inner, inner_n, shortcut, qs):
     return y, t1n
 
 
-def _fused(d, H, W, C, inner, inner_n, shortcut, qs, y_out=None, t2_in=None):
+def _fused(d, H, W, C, inner, inner_n, shortcut, qs, y_out=None, t2_in=None, x_is_y=False):
     from dcvc_b200 import ops
     dev = dict(device="cuda", dtype=torch.float16)
     g = lambda k: d[k].half().cuda().reshape(d[k].shape[0], -1).contiguous() if k in d else None  # noqa: E731
     y = y_out if y_out is not None else torch.zeros(H, W, C, **dev)
     t1n = torch.zeros(H, W, inner_n, **dev) if inner_n else None
-    ok = ops.dcb_tail(t2_in if t2_in is not None else _nhwc(d["t2"]), _nhwc(d["x"]), y, g("w3"), g("b3"), g("wf0"), g("bf0"),
+    ok = ops.dcb_tail(t2_in if t2_in is not None else _nhwc(d["t2"]), y if x_is_y else _nhwc(d["x"]), y, g("w3"), g("b3"), g("wf0"), g("bf0"),
                       g("wf2"), g("bf2"), t1n=t1n, w0n=g("w0n"), b0n=g("b0n"),
                       qscale=qs.half().cuda() if qs is not None else None, shortcut=shortcut)
     assert ok, "shape must be eligible for the fused kernel"
@@ -116,6 +116,24 @@ def test_dcb_tail_matches_oracle_and_per_op_kernels(H, W, C, inner, inner_n, sho
         _cmp("t1n vs per-op kernels", t_f, t_p, 2e-3, 2e-3)
     same = (y_f == y_p).float().mean().item()
     print(f"[dcb_tail] {H}x{W} C={C} inner={inner}: y bit-identical to the per-op kernels in {100 * same:.3f} % of the elements")
+
+
+@pytest.mark.parametrize("H,W,C,inner,inner_n,pairs", [(68, 120, 512, 512, 512, 4), (136, 240, 384, 384, 384, 8), (68, 120, 256, 128, 256, 3),
+                                                      (135, 240, 512, 512, 512, 0)])
+def test_dcb_tail_many_tiles_per_pair_in_place(H, W, C, inner, inner_n, pairs, monkeypatch):
+    """several tiles per CTA pair (4K pictures; here forced with the debug cap on the grid) with y overwriting x, the way
+    CodecBase::dcb runs the blocks of a network: bit-identical to the per-op kernels, run after run"""
+    if pairs:
+        monkeypatch.setenv("DCVC_B200_DT_MAXPAIRS", str(pairs))
+    gen = torch.Generator().manual_seed(H + W + C)
+    d = _make(gen, H, W, C, inner, inner_n)
+    y_p, t_p = _per_op(d, H, W, C, inner, inner_n, True, None)
+    torch.cuda.synchronize()
+    for rep in range(3):
+        xy = _nhwc(d["x"]).clone()
+        y_f, t_f = _fused(d, H, W, C, inner, inner_n, True, None, y_out=xy, x_is_y=True)
+        assert torch.equal(y_f, y_p), f"rep {rep}: y differs in {(y_f != y_p).sum().item()} elements"
+        assert torch.equal(t_f, t_p), f"rep {rep}: t1n differs in {(t_f != t_p).sum().item()} elements"
 
 
 def test_dcb_tail_pitched_views_and_in_place_output():
