@@ -20,7 +20,6 @@ LIB_PATH = os.path.join(LIB_DIR, "libdcvc_b200.so")
 
 SOURCES = [
     "pw_gemm.cu",
-    "pw_gemm_ares.cu",
     "dcb_tail.cu",
     "elementwise.cu",
     "frame_io.cu",

@@ -122,7 +122,6 @@ void IntraCodec::clear_plan()
 {
     Segment* segs[] = { &enc0_, &enc1_seg_, &dec0_, &dec_step_[0], &dec_step_[1], &dec_step_[2], &dec_step_[3], &dec4_ };
     for (Segment* s : segs) s->reset();
-    flags_reset();
     if (h_totals_) { cudaFreeHost(h_totals_); h_totals_ = nullptr; }
     for (int k = 0; k < 4; ++k) if (h_sym_[k]) { cudaFreeHost(h_sym_[k]); h_sym_[k] = nullptr; }
     if (h_idx_) { cudaFreeHost(h_idx_); h_idx_ = nullptr; }
@@ -211,10 +210,8 @@ void IntraCodec::plan(int height, int width)
     // ------------------------------------------------------------------ enc_0 (dmci_proxy.cpp:308-394)
     {
         Segment& s = enc0_;
-        begin_split(s);  // the 7 P8 blocks of the analysis transform: half-picture lanes when DCVC_B200_SPLIT_P8=1
         ActView t = dcb(s, l8_, v_in8, enc1_, false, q_enc_, nullptr);     // enc_1, then * q_enc
         for (int i = 0; i < 6; ++i) t = dcb(s, l8_, t, enc2_[i], false, nullptr, nullptr);
-        end_split(s);
         add_gemm(s, GEMM_CONV3X3_S2, t, v_y, enc_down_.w, enc_down_.b, kChY, ACT_NONE, 0, nullptr, nullptr, nullptr);
         if (padded) s.ops.push_back([v_y, v_ypad](cudaStream_t st) { return launch_pad_crop(v_y, v_ypad, st); });
         // hyper encoder
@@ -358,12 +355,10 @@ void IntraCodec::build_synthesis(Segment& s)
     const ActView yh = make_view(yhat_, kChY, kChY, W16_, H16_);
     ActView t = make_view(l8_.A, kChEncDec, kChEncDec, W8_, H8_);
     add_gemm(s, GEMM_TCONV2X2, yh, t, dec_up_.w, nullptr, 4 * kChEncDec, ACT_NONE, 0, nullptr, nullptr, nullptr);
-    begin_split(s);  // the 14 P8 blocks of the synthesis transform: half-picture lanes when DCVC_B200_SPLIT_P8=1
     t = dcb(s, l8_, t, dec1_[0], true, nullptr, nullptr);
     for (int i = 1; i < 13; ++i) t = dcb(s, l8_, t, dec1_[i], false, (i == 12) ? q_dec_ : nullptr, nullptr);
     const ActView out = make_view(dec_out_, kChSrc, kChSrc, W8_, H8_);
     dcb(s, l8_, t, dec2_, false, nullptr, &out);
-    end_split(s);
 }
 
 void IntraCodec::stage_qp(int qp, cudaStream_t stream)
@@ -455,20 +450,15 @@ void IntraCodec::decompress(const uint8_t* bs, int len, int qp, int height, int 
         tick(stream);
         run(k == 0 ? dec0_ : dec_step_[k], stream);
         tock(stream);
-        // DCVC_B200_DECODE_ONE_SYNC=1 (measurement switch): the count and the whole index buffer travel together and the
-        // host waits once per step instead of twice (batched count path); costs copying quarter_ bytes
-        // instead of n
-        const bool one_sync = decode_one_sync_;
+        // two host waits per step: the count, then exactly that many index bytes.  (Copying the whole index buffer with
+        // the count — one wait — was measured on B200: +1.5 % e2e at 1080p for 4 x 0.5 MB of extra D2H traffic; not kept.)
         CK(cudaMemcpyAsync(h_totals_ + k, totals_ + k, 4, cudaMemcpyDeviceToHost, stream));
-        if (one_sync) CK(cudaMemcpyAsync(h_idx_, idx_c_, quarter_, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         const int n = h_totals_[k];
         if (n < 0 || static_cast<size_t>(n) > quarter_) throw std::runtime_error("corrupt index count");
         if (n) {
-            if (!one_sync) {
-                CK(cudaMemcpyAsync(h_idx_, idx_c_, n, cudaMemcpyDeviceToHost, stream));
-                CK(cudaStreamSynchronize(stream));
-            }
+            CK(cudaMemcpyAsync(h_idx_, idx_c_, n, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
             rans_.decode_y(h_decoded_, h_idx_, n);
             CK(cudaMemcpyAsync(decoded_, h_decoded_, n, cudaMemcpyHostToDevice, stream));
         }

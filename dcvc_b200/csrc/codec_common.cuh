@@ -157,20 +157,8 @@ struct Segment {
     // (an event record / wait pair inside the capture).  The list order of the ops is always a valid serial order.
     struct LaneSync { size_t at; int from, to; };
     std::vector<LaneSync> syncs;
-    bool split_open = false;  // inside a half-picture region (CodecBase::begin_split / end_split)
-    bool lanes_region = false;  // ops pushed now may run beside another lane's ops (split region, recon-head lanes)
-    int split_c = 0, split_inner = 0, split_in_pitch = 0;  // channel widths of the previous split block (byte layout of the halves)
     cudaGraphExec_t exec = nullptr;
     int launches = 0;
-    // tile-level chaining of consecutive 1x1 GEMMs (pw_gemm.cuh: done_flags / wait_a): the flag words of this
-    // segment's ops (zeroed at the start of every run) and the most recent chain-capable producer
-    int* flag_begin = nullptr;
-    size_t flag_words = 0;
-    const int* last_flags = nullptr;
-    int last_need = 0;
-    const void* last_out = nullptr;
-    int last_W = 0, last_H = 0, last_C = 0, last_pitch = 0;
-    void break_chain() { last_flags = nullptr; }
     // the most recent fused DepthConvBlock tail (dcb_tail.cuh), kept so that the NEXT block can hang its dc.0 onto it as
     // phase 4 — valid only while it is still the last op of the segment
     std::shared_ptr<DcbTailOp> tail;
@@ -187,7 +175,6 @@ struct Segment {
     void lane_sync(int from, int to)
     {
         annotate(OP_ELEM, 0, 0);
-        break_chain();
         syncs.push_back(LaneSync{ ops.size(), from, to });
         const int hi = (from > to ? from : to) + 1;
         if (hi > n_lanes) n_lanes = hi;
@@ -195,13 +182,11 @@ struct Segment {
     void set_lane(int l)
     {
         annotate(OP_ELEM, 0, 0);  // ops pushed so far keep the lane they were pushed under
-        break_chain();
         cur_lane = l;
         if (l + 1 > n_lanes) n_lanes = l + 1;
     }
     void elem(OpFn f)
     {
-        break_chain();
         annotate(OP_ELEM, 0, 0);
         ops.push_back(std::move(f));
         annotate(OP_ELEM, 0, 0);
@@ -216,12 +201,8 @@ struct Segment {
         if (exec) cudaGraphExecDestroy(exec);
         exec = nullptr;
         ops.clear(); kinds.clear(); alg_bytes.clear(); flops.clear(); lanes.clear(); syncs.clear();
-        cur_lane = 0; n_lanes = 1; split_open = false; lanes_region = false;
-        split_c = split_inner = split_in_pitch = 0;
+        cur_lane = 0; n_lanes = 1;
         launches = 0;
-        flag_begin = nullptr;
-        flag_words = 0;
-        break_chain();
         tail.reset();
     }
 };
@@ -243,7 +224,6 @@ public:
     explicit CodecBase(int device) : device_(device) {}
     virtual ~CodecBase()
     {
-        if (flags_base_) cudaFree(flags_base_);
         if (copy_stream_) cudaStreamDestroy(copy_stream_);
         if (own_stream_) cudaStreamDestroy(own_stream_);
         if (ev_hop_) cudaEventDestroy(ev_hop_);
@@ -435,36 +415,14 @@ protected:
         if (gemm_init() || dcb_tail_init()) throw std::runtime_error(gemm_last_error());
         const char* g = getenv("DCVC_B200_GRAPHS");
         use_graphs_ = !(g && g[0] == '0');
-        // tile-level chaining of the DepthConvBlock GEMMs is an opt-in experiment (DCVC_B200_GEMM_CHAIN=1): parity-green,
-        // but measured 4 % SLOWER end to end on B200 (Intra 1080p decode 2.80 vs 2.70 ms of GPU time, HT-S 5.93 vs
-        // 5.71 ms) — see DESIGN.md "experiments"
-        const char* ch = getenv("DCVC_B200_GEMM_CHAIN");
-        chain_enabled_ = ch && ch[0] == '1';
         const char* ft = getenv("DCVC_B200_FUSE_TAIL");
         fuse_tail_ = !(ft && ft[0] == '0');
-        {
-            const char* sp = getenv("DCVC_B200_SPLIT_P8");   // 1 (= 2 bands) | 2 | 3 | 4
-            const int bands = sp ? atoi(sp) : 0;
-            split_enabled_ = bands >= 1 && bands <= 4;
-            split_parts_ = bands <= 1 ? 2 : bands;
-            const char* dr = getenv("DCVC_B200_TEST_DROP_LANE_SYNC");
-            test_drop_sync_ = dr && dr[0] == '1';
-            const char* lp = getenv("DCVC_B200_LANES_PDL");
-            lanes_pdl_ = !(lp && lp[0] == '0');
-            const char* os = getenv("DCVC_B200_DECODE_ONE_SYNC");
-            decode_one_sync_ = os && os[0] == '1';
-        }
-        if (chain_enabled_ && !flags_base_) {
-            flags_cap_ = (8u << 20) / sizeof(int);
-            CK(cudaMalloc(&flags_base_, flags_cap_ * sizeof(int)));
-        }
-        flags_used_ = 0;
         finalized_ = true;
     }
 
     // ------------------------------------------------------------------ op builders
     void add_gemm(Segment& s, int kind, const ActView& in, const ActView& out, const __half* w, const __half* bias,
-                  int N, int act, int chunk, const ActView* r1, const ActView* r2, const __half* q, bool in_dcb = false)
+                  int N, int act, int chunk, const ActView* r1, const ActView* r2, const __half* q)
     {
         auto op = std::make_shared<GemmOp>();
         op->kind = kind;
@@ -478,43 +436,7 @@ protected:
         op->N = N;
         op->act = act;
         op->chunk_add = chunk;
-        // a kernel launched with PDL sits ON an SM while it waits for its predecessor: beside another lane that could use
-        // the SM this can be counter-productive (DCVC_B200_LANES_PDL=0 launches the ops of lane regions without it)
-        op->pdl = lanes_pdl_ || !s.lanes_region;
-        if (chain_enabled_ && in_dcb && kind == GEMM_PW && flags_base_) {
-            // Tile-level chaining, only between the 1x1 GEMMs of DepthConvBlocks: the op reports completed 128-pixel
-            // tiles; if the previous op of the segment was such a GEMM and wrote exactly this op's input view, the op
-            // waits per tile instead of for the whole previous grid.  Every other access of the block is then ordered
-            // too: residuals are produced by an op of the same chain at the same tile index (ffn.2's `o`) or are older
-            // than the last full-grid synchronisation (the depthwise conv between dc.0 and dc.3), and every buffer a
-            // chained op overwrites was last read by an op of its chain at the same tile index or before that
-            // synchronisation (the block ping-pongs X -> T1 -> T2 -> O -> T1 -> X).
-            const int m_tiles = static_cast<int>((static_cast<long long>(out.W) * out.H + 127) / 128);
-            if (flags_used_ + m_tiles <= flags_cap_) {
-                op->done_flags = flags_base_ + flags_used_;
-                if (!s.flag_begin) s.flag_begin = op->done_flags;
-                flags_used_ += m_tiles;
-                s.flag_words = static_cast<size_t>(flags_base_ + flags_used_ - s.flag_begin);
-                if (s.last_flags && s.last_out == in.ptr && s.last_W == in.W && s.last_H == in.H && s.last_C == in.C &&
-                    s.last_pitch == in.pitch) {
-                    op->wait_a = s.last_flags;
-                    op->wait_a_need = s.last_need;
-                    op->no_grid_wait = true;
-                }
-            }
-        }
         if (gemm_plan(*op)) throw std::runtime_error(std::string("gemm_plan: ") + gemm_last_error());
-        if (op->done_flags && op->ares == 0) {
-            s.last_flags = op->done_flags;
-            s.last_need = op->p.n_tiles * 8;
-            s.last_out = out.ptr;
-            s.last_W = out.W;
-            s.last_H = out.H;
-            s.last_C = out.C;
-            s.last_pitch = out.pitch;
-        } else {
-            s.break_chain();
-        }
         s.annotate(OP_ELEM, 0, 0);
         s.ops.push_back([op](cudaStream_t st) { return gemm_launch(*op, st); });
         s.out_views.resize(s.ops.size());
@@ -541,57 +463,10 @@ protected:
         add_gemm(s, GEMM_PW, in, out, c.w, c.b, c.cout, ACT_NONE, 0, nullptr, nullptr, nullptr);
     }
 
-    // ------------------------------------------------------------------ half-picture lanes (DCVC_B200_SPLIT_P8=1)
-    // Measurement switch, off by default.  Every pw_gemm launch is one persistent wave that ends in a ragged tail and a
-    // drain, and the next launch of the same chain cannot start before it has ended.  Inside a split region every 1x1
-    // GEMM of a DepthConvBlock is issued twice — upper half of the picture on lane 0, lower half on lane 1 (pixel-local
-    // ops: the halves are independent) — as two parallel branches of the graph, so one half's tail and fill overlap the
-    // other half's steady state.  Only the depthwise 3x3 needs rows of both halves: it stays one full-picture launch on
-    // lane 0 between two cross-lane edges.  DCVC_B200_SPLIT_P8=3|4 cuts the picture into that many bands / lanes instead.  Results are bit-identical to the unsplit path (a pixel's value does not
-    // depend on the tile it is computed in).
-    // part `part` of `parts` horizontal bands of a view (the last band takes the remainder rows)
-    static ActView band_view(const ActView& v, int part, int parts)
-    {
-        const int hb = v.H / parts;
-        ActView h = v;
-        h.ptr = static_cast<const __half*>(v.ptr) + static_cast<size_t>(part) * hb * v.W * v.pitch;
-        h.H = (part == parts - 1) ? v.H - hb * (parts - 1) : hb;
-        return h;
-    }
-    // lane 0 waits for every other lane / every other lane waits for lane 0
-    void gather_lanes(Segment& s) { for (int l = 1; l < split_parts_; ++l) s.lane_sync(l, 0); }
-    void scatter_lanes(Segment& s) { for (int l = 1; l < split_parts_; ++l) s.lane_sync(0, l); }
-    void begin_split(Segment& s)
-    {
-        if (!split_enabled_ || s.split_open) return;
-        scatter_lanes(s);  // the other lanes start behind everything lane 0 has done so far in this segment
-        s.split_open = true;
-        s.lanes_region = true;
-        s.split_c = s.split_inner = s.split_in_pitch = 0;
-    }
-    void end_split(Segment& s)
-    {
-        if (!s.split_open) return;
-        gather_lanes(s);
-        s.set_lane(0);
-        s.split_open = false;
-        s.lanes_region = false;
-    }
     void gemm_1x1(Segment& s, const ActView& in, const ActView& out, const __half* w, const __half* bias, int N, int act,
                   int chunk, const ActView* r1, const ActView* r2, const __half* q)
     {
-        if (!s.split_open || in.H < split_parts_) {
-            add_gemm(s, GEMM_PW, in, out, w, bias, N, act, chunk, r1, r2, q, true);
-            return;
-        }
-        for (int part = 0; part < split_parts_; ++part) {
-            s.set_lane(part);
-            const ActView hi = band_view(in, part, split_parts_), ho = band_view(out, part, split_parts_);
-            ActView h1, h2;
-            if (r1) h1 = band_view(*r1, part, split_parts_);
-            if (r2) h2 = band_view(*r2, part, split_parts_);
-            add_gemm(s, GEMM_PW, hi, ho, w, bias, N, act, chunk, r1 ? &h1 : nullptr, r2 ? &h2 : nullptr, q, true);
-        }
+        add_gemm(s, GEMM_PW, in, out, w, bias, N, act, chunk, r1, r2, q);
     }
 
     // DepthConvBlock (layers.py:152-159 == layers_proxy.cpp:71-101): returns the view holding the output.
@@ -602,18 +477,6 @@ protected:
                 const ActView* out)
     {
         const int H = in.H, W = in.W;
-        if (s.split_open) {
-            // The ping-pong buffers are reused from block to block.  While every block has the same channel widths, "upper
-            // half" and "lower half" are the same byte ranges in every tensor that lives in a buffer, so each lane only ever
-            // touches its own half.  When the widths change (adaptor, narrower inner width, another input pitch) the byte
-            // ranges of the halves shift: both lanes meet before such a block.
-            const bool same = (s.split_c == w.c && s.split_inner == w.inner && s.split_in_pitch == in.pitch && !w.adaptor);
-            if (s.split_c != 0 && !same) {
-                gather_lanes(s);
-                scatter_lanes(s);
-            }
-            s.split_c = w.c; s.split_inner = w.inner; s.split_in_pitch = w.adaptor ? w.c : in.pitch;
-        }
         __half* bufX;
         ActView x;
         if (w.adaptor) {
@@ -634,7 +497,7 @@ protected:
         // dc.0: when the previous op of the segment is the fused tail of the block that produced x, this GEMM rides along
         // as that kernel's fourth phase (y is still in its tensor memory); otherwise it is a launch of its own
         bool dc0_fused = false;
-        if (!w.adaptor && !s.split_open && s.tail && s.tail_idx + 1 == s.ops.size() && !s.tail->t1n.ptr &&
+        if (!w.adaptor && s.tail && s.tail_idx + 1 == s.ops.size() && !s.tail->t1n.ptr &&
             s.tail->y.ptr == x.ptr && s.tail->y.C == x.C && s.tail->y.pitch == x.pitch && s.tail->y.W == x.W && s.tail->y.H == x.H) {
             DcbTailOp trial = *s.tail;
             trial.t1n = t1;
@@ -653,22 +516,14 @@ protected:
         if (!dc0_fused) gemm_1x1(s, x, t1, w.w0, w.b0, w.inner, ACT_WSILU, 0, nullptr, nullptr, nullptr);
         {
             const __half* wdw = w.wdw;
-            s.break_chain();  // 3x3 neighbourhoods: full-grid dependency on both sides
-            if (s.split_open) {
-                // the full-picture depthwise conv reads dc.0 rows of both halves and writes rows both halves' dc.3 read
-                if (!test_drop_sync_) gather_lanes(s);
-                s.set_lane(0);
-            }
             s.annotate(OP_ELEM, 0, 0);
-            const bool dw_pdl = lanes_pdl_ || !s.lanes_region;
-            s.ops.push_back([t1, t2, wdw, dw_pdl](cudaStream_t st) { return launch_dw3x3(t1, t2, wdw, st, dw_pdl); });
+            s.ops.push_back([t1, t2, wdw](cudaStream_t st) { return launch_dw3x3(t1, t2, wdw, st, true); });
             s.out_views.resize(s.ops.size());
             s.out_views.back() = t2;
             s.annotate(OP_DW, 2.0 * 2 * W * H * w.inner, 2.0 * 9 * W * H * w.inner);
-            if (s.split_open) scatter_lanes(s);
         }
         const ActView dst = out ? *out : x;
-        if (fuse_tail_ && !s.split_open) {
+        if (fuse_tail_) {
             // dc.3 -> ffn.0 -> ffn.2 as one CTA-pair kernel: o and t1' stay on the SM (dcb_tail.cuh)
             auto op = std::make_shared<DcbTailOp>();
             op->t2 = t2; op->x = x; op->y = dst;
@@ -678,7 +533,6 @@ protected:
             const int r = dcb_tail_plan(*op);
             if (r == 2) throw std::runtime_error(std::string("dcb_tail_plan: ") + gemm_last_error());
             if (r == 0) {
-                s.break_chain();
                 s.annotate(OP_ELEM, 0, 0);
                 s.ops.push_back([op](cudaStream_t st) { return dcb_tail_launch(*op, st); });
                 s.out_views.resize(s.ops.size());
@@ -708,8 +562,6 @@ protected:
     void run(Segment& s, cudaStream_t stream)
     {
         if (s.ops.empty()) return;
-        if (s.flag_words && !(use_graphs_ && s.exec && !profile_ && !getenv("DCVC_B200_OPSUM")))
-            CK(cudaMemsetAsync(s.flag_begin, 0, s.flag_words * sizeof(int), stream));  // (a graph carries its own memset node)
         if (profile_) {
             // per-op CUDA-event timing (graphs off).  All ops of the segment are enqueued back to back with an
             // event before and after each, and read only after the last one: the CPU runs ahead of the GPU, so an
@@ -782,7 +634,6 @@ protected:
                     }
                 }
                 CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-                if (s.flag_words) cudaMemsetAsync(s.flag_begin, 0, s.flag_words * sizeof(int), stream);
                 int rc = 0;
                 std::string lane_err;
                 if (n_lanes > 1) {  // fork: every lane starts where the segment starts
@@ -876,15 +727,10 @@ protected:
         }
     };
 
-    void flags_reset() { flags_used_ = 0; }  // with every re-plan (the segments are rebuilt)
-
     int device_;
     bool finalized_ = false;
     bool use_graphs_ = true;
-    bool chain_enabled_ = true;
     bool fuse_tail_ = true;                    // DCVC_B200_FUSE_TAIL=0: per-op kernels only (A/B runs, kernel emulation)
-    int* flags_base_ = nullptr;
-    size_t flags_cap_ = 0, flags_used_ = 0;
     void* dbg_base_ = nullptr;      // activation arena (DCVC_B200_OPSUM)
     size_t dbg_bytes_ = 0;
     unsigned long long* opsum_dev_ = nullptr;
@@ -898,11 +744,6 @@ protected:
     std::vector<cudaStream_t> lane_streams_;   // side streams of multi-lane segments (graph capture only)
     std::vector<cudaEvent_t> lane_events_;
     std::vector<cudaEvent_t> sync_events_;     // one per cross-lane edge of the largest multi-lane segment
-    bool split_enabled_ = false;               // DCVC_B200_SPLIT_P8=1|2|3|4 (read in finalize)
-    int split_parts_ = 2;                      // horizontal bands = capture lanes of a split region
-    bool decode_one_sync_ = false;             // DCVC_B200_DECODE_ONE_SYNC=1: one host wait per prior step of the Intra decoder
-    bool lanes_pdl_ = true;                    // DCVC_B200_LANES_PDL=0: no programmatic dependent launch inside lane regions
-    bool test_drop_sync_ = false;              // DCVC_B200_TEST_DROP_LANE_SYNC=1: fault injection for the CPU tier's race check
     std::vector<cudaEvent_t> tev_;
     std::vector<cudaEvent_t> prof_events_;
     int tev_n_ = 0;

@@ -116,7 +116,6 @@ void HtlCodec::clear_plan()
     Segment* segs[] = { &s_enc0_, &s_decoder_, &s_reset_head_, &s_fa_i_, &s_fa_m_, &s_fe_, &s_temporal_, &s_dec1_,
                         &s_dec_step_[0], &s_dec_step_[1], &s_dec_step_[2], &s_dec_step_[3], &s_recon_ };
     for (Segment* s : segs) s->reset();
-    flags_reset();
     if (h_totals_) { cudaFreeHost(h_totals_); h_totals_ = nullptr; }
     for (int k = 0; k < 4; ++k) if (h_sym_[k]) { cudaFreeHost(h_sym_[k]); h_sym_[k] = nullptr; }
     if (h_idx_) { cudaFreeHost(h_idx_); h_idx_ = nullptr; }
@@ -129,9 +128,6 @@ void HtlCodec::clear_plan()
 
 ActView HtlCodec::chain(Segment& s, Level& L, ActView in, const DcbW* blocks, int n, const __half* q_last, const ActView* out)
 {
-    // P8 chains run as half-picture lanes when DCVC_B200_SPLIT_P8=1 (codec_common.cuh), one region per chain
-    const bool split = (&L == &l8_);
-    if (split) begin_split(s);
     ActView t = in;
     for (int i = 0; i < n; ++i) {
         const bool last = (i == n - 1);
@@ -141,7 +137,6 @@ ActView HtlCodec::chain(Segment& s, Level& L, ActView in, const DcbW* blocks, in
         if (!o && external && !blocks[i].adaptor) o = &first_out;
         t = dcb(s, L, t, blocks[i], false, last ? q_last : nullptr, o);
     }
-    if (split) end_split(s);
     return t;
 }
 

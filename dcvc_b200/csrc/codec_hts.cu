@@ -48,11 +48,12 @@ private:
     int H8_ = 0, W8_ = 0, H16_ = 0, W16_ = 0, H16p_ = 0, W16p_ = 0, H64_ = 0, W64_ = 0;
     Arena arena_;
     Level l8_, l16_, l32_, l64_;
-    // recon-head lanes (DCVC_B200_HEAD_LANES = 1 | 2 | 4, default 1): the four head pairs share nothing but their
+    // recon-head lanes (DCVC_B200_HEAD_LANES = 1 | 2 | 4, default 2): the four head pairs share nothing but their
     // read-only input, so with n lanes pair j runs on lane j % n as a parallel branch of the recon graph, each lane
-    // with its own ping-pong level and its own shared-block output — one persistent GEMM's tail and drain then overlap
-    // the next branch's work instead of idling the SMs.  Measurement switch: not validated on hardware yet.
-    int head_lanes_ = 1;
+    // with its own ping-pong level and its own shared-block output — one persistent kernel's tail and drain then overlap
+    // the next branch's work instead of idling the SMs.  Measured on B200 (round 2): 1 lane 1182, 2 lanes 1230, 4 lanes
+    // 1207 decoded FPS at 1080p; bit-identical results (tests/test_hts_gpu.py).
+    int head_lanes_ = 2;
     Level lane_l8_[3];
     __half* lane_common8_[3] = { nullptr, nullptr, nullptr };
     __half *cat_enc_ = nullptr, *cat_fam_ = nullptr, *feature_i_ = nullptr, *temporal_in_ = nullptr, *common8_ = nullptr,
@@ -124,7 +125,6 @@ void HtsCodec::clear_plan()
 {
     Segment* segs[] = { &s_enc0_, &s_decoder_, &s_reset_head_, &s_fa_i_, &s_fa_m_, &s_fe_, &s_temporal_, &s_dec1_, &s_dec3_, &s_recon_ };
     for (Segment* s : segs) s->reset();
-    flags_reset();
     if (h_total_) { cudaFreeHost(h_total_); h_total_ = nullptr; }
     if (h_sym_) { cudaFreeHost(h_sym_); h_sym_ = nullptr; }
     if (h_idx_) { cudaFreeHost(h_idx_); h_idx_ = nullptr; }
@@ -139,10 +139,6 @@ ActView HtsCodec::chain(Segment& s, Level& L, ActView in, const DcbW* blocks, in
 {
     // n DepthConvBlocks in sequence; the first may take an external input (then it lands in L.B unless it has an
     // adaptor), the last is redirected to `out` when given and carries the fused per-channel quant scale.
-    // P8 chains run as half-picture lanes when DCVC_B200_SPLIT_P8=1 (codec_common.cuh); a region per chain, so whatever
-    // follows the chain (1x1 head convolutions, the next segment) sees both halves
-    const bool split = (&L == &l8_);
-    if (split) begin_split(s);
     ActView t = in;
     for (int i = 0; i < n; ++i) {
         const bool last = (i == n - 1);
@@ -152,7 +148,6 @@ ActView HtsCodec::chain(Segment& s, Level& L, ActView in, const DcbW* blocks, in
         if (!o && external && !blocks[i].adaptor) o = &first_out;
         t = dcb(s, L, t, blocks[i], false, last ? q_last : nullptr, o);
     }
-    if (split) end_split(s);
     return t;
 }
 
@@ -186,10 +181,8 @@ void HtsCodec::plan(int height, int width)
 
     {
         const char* e = getenv("DCVC_B200_HEAD_LANES");
-        const int n = e ? atoi(e) : 1;
+        const int n = e ? atoi(e) : 2;
         head_lanes_ = (n == 2 || n == 4) ? n : 1;
-        if (head_lanes_ > 1 && split_enabled_)
-            throw std::runtime_error("DCVC_B200_HEAD_LANES and DCVC_B200_SPLIT_P8 are alternatives (both use the capture lanes)");
     }
     size_t bytes = p8 * 2 * (2048 + 1024 + 192 + 512 + 512 + 192 * kG + 4 * 512);
     bytes += static_cast<size_t>(head_lanes_ - 1) * (p8 * 2 * (4 * 512 + 512) + 5 * 4096);
@@ -414,7 +407,6 @@ void HtsCodec::plan(int height, int width)
         // recon head: 4 shared blocks + 8 x (3 blocks + 1x1); head i lands in head_out_[i], head 7 in feature_i
         // (the reset reference, dmc_hts_proxy.cpp:336-338)
         Segment& s = s_recon_;
-        if (head_lanes_ > 1) s.lanes_region = true;
         for (int i = 0; i < kG; ++i) {
             const int lane = (i / 2) % head_lanes_;
             if (head_lanes_ > 1) s.set_lane(lane);
@@ -428,7 +420,7 @@ void HtsCodec::plan(int height, int width)
             const ActView ho = (i == kG - 1) ? v_feature_i : make_view(head_out_ + static_cast<size_t>(i) * p8 * kSrcI, kSrcI, kSrcI, W8, H8);
             conv1x1(s, t, ho, rh_out_[i]);
         }
-        if (head_lanes_ > 1) { s.set_lane(0); s.lanes_region = false; }
+        if (head_lanes_ > 1) s.set_lane(0);
     }
     Segment* segs[] = { &s_enc0_, &s_decoder_, &s_reset_head_, &s_fa_i_, &s_fa_m_, &s_fe_, &s_temporal_, &s_dec1_, &s_dec3_, &s_recon_ };
     for (Segment* s : segs) s->seal();

@@ -112,7 +112,6 @@ void LdCodec::clear_plan()
 {
     Segment* segs[] = { &s_enc0_, &s_decoder_, &s_reset_head_, &s_fa_i_, &s_fa_m_, &s_fe_, &s_temporal_, &s_dec1_, &s_dec3_, &s_recon_ };
     for (Segment* s : segs) s->reset();
-    flags_reset();
     if (h_total_) { cudaFreeHost(h_total_); h_total_ = nullptr; }
     if (h_sym_) { cudaFreeHost(h_sym_); h_sym_ = nullptr; }
     if (h_idx_) { cudaFreeHost(h_idx_); h_idx_ = nullptr; }
@@ -127,9 +126,6 @@ ActView LdCodec::chain(Segment& s, Level& L, ActView in, const DcbW* blocks, int
 {
     // n DepthConvBlocks in sequence; the first may take an external input (then it lands in L.B unless it has an
     // adaptor), the last is redirected to `out` when given and carries the fused per-channel quant scale.
-    // P8 chains run as half-picture lanes when DCVC_B200_SPLIT_P8=1 (codec_common.cuh), one region per chain.
-    const bool split = (&L == &l8_);
-    if (split) begin_split(s);
     ActView t = in;
     for (int i = 0; i < n; ++i) {
         const bool last = (i == n - 1);
@@ -139,7 +135,6 @@ ActView LdCodec::chain(Segment& s, Level& L, ActView in, const DcbW* blocks, int
         if (!o && external && !blocks[i].adaptor) o = &first_out;
         t = dcb(s, L, t, blocks[i], false, last ? q_last : nullptr, o);
     }
-    if (split) end_split(s);
     return t;
 }
 

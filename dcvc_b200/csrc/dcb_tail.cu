@@ -32,7 +32,7 @@ namespace dcvc {
 
 static constexpr int DT_CHUNK_N = 128;                              // GEMM columns per accumulator chunk
 static constexpr int DT_KB_BYTES = (DT_CHUNK_N / 2) * BLOCK_K * 2;  // 8 KB: this CTA's half of one weight k-block
-static constexpr int DT_MAX_STAGES = 16;
+static constexpr int DT_MAX_STAGES = 12;                            // (control block: 61 barriers in 496 bytes)
 static constexpr int DT_MAX_KB = 8;                                 // K <= 512
 static constexpr int DT_ACC_COL0 = 256;
 static constexpr int DT_TMEM_COLS = 512;
@@ -48,7 +48,7 @@ __device__ __forceinline__ void dt_mark(const DcbTailParams& p, int cta, int slo
     }
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __maxnreg__(112)
 dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -64,9 +64,10 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
     uint64_t* acc_full = b_empty + DT_MAX_STAGES;           // [2]  every CTA: accumulator chunk complete
     uint64_t* acc_empty = acc_full + 2;                     // [2]  leader: chunk drained by both CTAs' 16 warps
     uint64_t* p_empty = acc_empty + 2;                      // [1]  every CTA: phase-3 MMAs done, P may be reloaded
-    uint64_t* o_ready = p_empty + 1;                        // [1]  leader: O holds the tile's complete o (both CTAs)
-    uint64_t* y_ready = o_ready + 1;                        // [1]  leader: O holds the tile's complete y; nobody reads o any more
+    uint64_t* o_ready = p_empty + 1;                        // [8]  leader: k-block of O holds the tile's o (both CTAs)
+    uint64_t* y_ready = o_ready + DT_MAX_KB;                // [8]  leader: k-block of O holds the tile's y; its o is not read any more
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ctrl + 496);
+    static_assert((4 * DT_MAX_KB + 2 * DT_MAX_STAGES + 5) * 8 <= 496, "control block overflow");
 
     const int rank = static_cast<int>(cluster_ctarank());
     const int pair = static_cast<int>(blockIdx.x >> 1);
@@ -80,7 +81,9 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
         tma_prefetch_desc(&p.tm_t);
         for (int i = 0; i < DT_MAX_KB; ++i) {
             mbar_init(&p_full[i], 1);
-            mbar_init(&p_ready[i], 64);               // 2 chunks x 16 warps x 2 CTAs
+            mbar_init(&p_ready[i], 32);               // 2 chunks x 8 warps x 2 CTAs
+            mbar_init(&o_ready[i], 8);                // 4 warps (lane quarters) x 2 CTAs
+            mbar_init(&y_ready[i], 8);
         }
         for (int i = 0; i < DT_MAX_STAGES; ++i) {
             mbar_init(&b_full[i], 1);
@@ -88,11 +91,9 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
         }
         for (int g = 0; g < 2; ++g) {
             mbar_init(&acc_full[g], 1);
-            mbar_init(&acc_empty[g], 32);             // 16 warps x 2 CTAs
+            mbar_init(&acc_empty[g], 16);             // 8 warps x 2 CTAs
         }
         mbar_init(p_empty, 1);
-        mbar_init(o_ready, static_cast<uint32_t>(p.nch[0] * 32));   // every chunk of the phase: 16 warps x 2 CTAs
-        mbar_init(y_ready, static_cast<uint32_t>(p.nch[2] * 32));
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -133,13 +134,10 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                 bool next_loaded = false;
                 for (int ph = 0; ph < 4; ++ph) {
                     int cnt = 0;
-                    const int rot = p.rot ? pair % (p.nch[ph] > 0 ? p.nch[ph] : 1) : 0;
                     const int rep_off = p.wrep > 1 ? (pair % p.wrep) * p.nch[ph] * DT_CHUNK_N : 0;   // timing experiments only
                     const uint32_t tx = static_cast<uint32_t>(2 * p.kbs[ph] * DT_KB_BYTES);
                     for (int n = 0; n < p.nch[ph]; ++n) {
-                        int nn = n + rot;
-                        if (nn >= p.nch[ph]) nn -= p.nch[ph];
-                        const int nrow = rep_off + nn * DT_CHUNK_N + rank * (DT_CHUNK_N / 2);
+                        const int nrow = rep_off + n * DT_CHUNK_N + rank * (DT_CHUNK_N / 2);
                         for (int st = 0; st < p.nst[ph]; ++st) {
                             mbar_wait(&b_empty[s], bph ^ 1);
                             if (rank == 0) mbar_expect_tx(&b_full[s], tx);
@@ -178,10 +176,6 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                 const uint32_t tph = static_cast<uint32_t>(i & 1);
                 for (int ph = 0; ph < 4; ++ph) {
                     if (p.nch[ph] == 0) continue;
-                    if (ph == 1 && !no_acc) {
-                        mbar_wait_cluster(o_ready, tph);   // both CTAs' o is complete in tensor memory
-                        tcgen05_fence_after();
-                    }
                     const bool a_tmem = (ph & 1) != 0;
                     const int kbs = p.kbs[ph];
                     for (int n = 0; n < p.nch[ph]; ++n, ++t) {
@@ -202,7 +196,13 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                             const uint32_t b_addr = smem_u32(ring + s * p.stage_bytes);
                             for (int j = 0; j < kbs; ++j, ++kb) {
                                 if (n == 0 && ph == 0 && !no_tma) { mbar_wait(&p_full[kb], tph); tcgen05_fence_after(); }
-                                if (n == 0 && ph == 2 && !no_acc) { mbar_wait_cluster(&p_ready[kb], tph); tcgen05_fence_after(); }
+                                if (n == 0 && !no_acc) {
+                                    // the first chunk of a phase takes its A k-blocks as the epilogue of the previous phase
+                                    // finishes them (later chunks find everything there)
+                                    if (ph == 1) { mbar_wait_cluster(&o_ready[kb], tph); tcgen05_fence_after(); }
+                                    if (ph == 2) { mbar_wait_cluster(&p_ready[kb], tph); tcgen05_fence_after(); }
+                                    if (ph == 3) { mbar_wait_cluster(&y_ready[kb], tph); tcgen05_fence_after(); }
+                                }
                                 const uint64_t b_desc = make_kmajor_sw128_desc(b_addr + j * DT_KB_BYTES);
                                 if (do_mma) {
                                     if (a_tmem) {
@@ -226,11 +226,12 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                     }
                     if (ph == 2) {
                         umma_commit_2cta_mc(p_empty, 3);  // P is free for the next tile's t2
-                        // y complete in O and nobody reads o any more: phase 4 may read it — and, phase 4 or not, the NEXT
-                        // tile's phase-1 epilogue may overwrite O (without this wait its arrivals on o_ready would also
-                        // run into a barrier phase nobody consumed: the round-2 "several tiles per pair" bug)
-                        if (!no_acc) {
-                            mbar_wait_cluster(y_ready, tph);
+                        // Before the NEXT tile's phase-1 epilogue may overwrite O, the phase-3 epilogue must be through with it
+                        // (it reads o and writes y in place).  With a phase 4 that is implied (its first chunk waits for every
+                        // y k-block); without one the wait happens here — else next-tile writes race the readers, and barrier
+                        // phases nobody consumed would swallow next-tile arrivals (the round-2 "several tiles per pair" bug)
+                        if (!no_acc && p.nch[3] == 0) {
+                            for (int kb = 0; kb < p.nkb[1]; ++kb) mbar_wait_cluster(&y_ready[kb], tph);
                             tcgen05_fence_after();
                         }
                     }
@@ -240,18 +241,22 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
         __syncwarp();
     } else {
         // ---------------------------------------------------------------- epilogue (16 warps, both CTAs)
-        // Every warp works on every chunk: warp (q, j) owns TMEM lane quarter q (32 pixel rows) and column quarter j (32 of
-        // the chunk's 128 accumulator columns) — one tcgen05.ld, after which the accumulator goes straight back to the MMA
-        // warp; everything a chunk needs from memory (bias, x) is requested before the wait for the accumulator.
+        // Two groups of 8 warps take alternate chunks (group b <- accumulator buffer b), so one group's TMEM drain overlaps
+        // the other's arithmetic and signalling.  Warp (b, h, q) owns lane quarter q (32 pixel rows) and column half h of
+        // its chunks: 64 accumulator columns = exactly one 64-channel k-block of O (phases 1, 3), drained as two 32-column
+        // pieces; the accumulator goes back to the MMA warp right after the second tcgen05.ld.  Whatever a piece needs from
+        // memory (bias, x) is requested before the wait it can hide behind.
         const int q = warp & 3;
-        const int jq = (warp - 2) >> 2;
+        const int b = ((warp - 2) >> 2) & 1;
+        const int h = (warp - 2) >> 3;
         uint8_t* slab = staging + (warp - 2) * EPI_SLAB_BYTES;
         const uint32_t slab_u = smem_u32(slab);
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-        const uint32_t acc0 = tmem_base + lane_off + DT_ACC_COL0 + jq * 32;   // + g * 128
-        const uint32_t o_base = tmem_base + lane_off;                         // O, this warp's lanes
-        const uint32_t acc_empty_r = mapa_u32(smem_u32(&acc_empty[0]), 0);     // + g * 8
+        const uint32_t acc = tmem_base + lane_off + DT_ACC_COL0 + b * DT_CHUNK_N + h * 64;   // this warp's 64 accumulator columns
+        const uint32_t o_base = tmem_base + lane_off;                                        // O, this warp's lanes
+        const uint32_t acc_empty_r = mapa_u32(smem_u32(&acc_empty[b]), 0);
         const uint32_t o_ready_r = mapa_u32(smem_u32(o_ready), 0);
+        const uint32_t y_ready_r = mapa_u32(smem_u32(y_ready), 0);
         const uint32_t p_ready_r = mapa_u32(smem_u32(p_ready), 0);
         const uint32_t P_u = smem_u32(P);
         const uint32_t my_sw = static_cast<uint32_t>(lane * 64);
@@ -259,11 +264,12 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
         const uint16_t ONE = 0x3C00;
         const uint4 zero4 = make_uint4(0, 0, 0, 0);
         const bool skip_body = (p.dbg & 2) != 0;
+        const bool tr = warp == 2 && lane == 0;
 
-        auto hand_back = [&](int g) {
+        auto hand_back = [&]() {
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc_empty_r + g * 8);
+            if (lane == 0) mbar_arrive_cluster(acc_empty_r);
         };
         auto slab_free = [&]() {  // the TMA store that last read this warp's slab has finished reading it
             if (lane == 0) tma_store_wait_read<0>();
@@ -293,6 +299,10 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                 }
             }
         };
+        auto load_bias = [&](const __half* bias, int c0, uint4 (&cb)[4]) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cb[j] = bias ? __ldg(reinterpret_cast<const uint4*>(bias + c0) + j) : zero4;
+        };
         auto add_bias = [&](const uint4 (&cb)[4], const uint32_t (&v)[32], float (&tv)[32]) {
             const uint32_t* bw = reinterpret_cast<const uint32_t*>(cb);
 #pragma unroll
@@ -320,129 +330,145 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                 tma_store_commit();
             }
         };
+        // x * sigmoid(4 x) up to the factor 1/2: u = x tanh(2 x) + x  (wsilu = u / 2; the caller applies the exact 1/2 once)
+        auto wsilu2 = [&](float x) -> float {
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(x + x));
+            return fmaf(x, th, x);
+        };
 
-        const uint32_t y_ready_r = mapa_u32(smem_u32(y_ready), 0);
         uint32_t t = 0;
         for (int T = (p.dbg & 4) ? p.tiles : pair; T < p.tiles; T += p.num_pairs) {
             const int row_w = T * 256 + rank * BLOCK_M + q * 32;  // first pixel row of this warp
             for (int ph = 0; ph < 4; ++ph) {
-                const int rot = p.rot ? pair % (p.nch[ph] > 0 ? p.nch[ph] : 1) : 0;
                 const __half* bias = p.bias[ph];
                 const bool need_x = (ph == 0) || (ph == 2 && p.shortcut);
-                for (int n0 = 0; n0 < p.nch[ph]; ++n0, ++t) {
-                    int n = n0 + rot;   // the chunk this pair works on now (pairs walk the weight matrices in rotated order)
-                    if (n >= p.nch[ph]) n -= p.nch[ph];
-                    const int g = static_cast<int>(t & 1);
-                    const int c0 = n * DT_CHUNK_N + jq * 32;   // GEMM column of this warp's accumulator column 0
-                    const bool tr = warp == 2 && lane == 0;
+                for (int n = 0; n < p.nch[ph]; ++n, ++t) {
+                    if (static_cast<int>(t & 1) != b) continue;
+                    const int cw = n * DT_CHUNK_N + h * 64;   // GEMM column of this warp's accumulator column 0
                     if (tr) dt_mark(p, 0, 8 * static_cast<int>(t));
-                    // ---- requests that do not depend on the accumulator
+                    // ---- requests of the first piece that do not depend on the accumulator
                     uint4 cb[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) cb[j] = bias ? __ldg(reinterpret_cast<const uint4*>(bias + c0) + j) : zero4;
-                    if (!skip_body && (need_x || ph >= 2)) slab_free();
-                    if (!skip_body && need_x) fetch_x(row_w, c0);
-                    // ---- the accumulator
+                    load_bias(bias, cw, cb);
+                    if (!skip_body && need_x) {
+                        slab_free();
+                        fetch_x(row_w, cw);
+                    }
                     if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 5);
-                    mbar_wait(&acc_full[g], (t >> 1) & 1);
+                    mbar_wait(&acc_full[b], (t >> 1) & 1);
                     tcgen05_fence_after();
                     if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 1);
                     if (skip_body) {
-                        hand_back(g);
-                        if (ph == 0 || ph == 2) { if (lane == 0) mbar_arrive_cluster(ph == 0 ? o_ready_r : y_ready_r); }
-                        if (ph == 1) { if (lane == 0) mbar_arrive_cluster(p_ready_r + (n >> 1) * 8); }
+                        hand_back();
+                        if (lane == 0) {
+                            if (ph == 0) mbar_arrive_cluster(o_ready_r + (2 * n + h) * 8);
+                            if (ph == 1) mbar_arrive_cluster(p_ready_r + (n >> 1) * 8);
+                            if (ph == 2) mbar_arrive_cluster(y_ready_r + (2 * n + h) * 8);
+                        }
                         continue;
                     }
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(acc0 + g * DT_CHUNK_N, v);
-                    uint32_t ov[16];
-                    if (ph == 2) tmem_ld_32x32b_x16(o_base + (c0 >> 1), ov);   // o: the residual of ffn.2
-                    tmem_ld_wait();
-                    hand_back(g);
-                    if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 2);
-                    float tv[32];
-                    add_bias(cb, v, tv);
-                    if (ph == 0) {
-                        // ---------------- o = acc + b3 + x  ->  O (TMEM, packed fp16)
-                        cp_async_wait_all();
-                        __syncwarp();
-                        add_slab(tv);
-                        uint32_t w[16];
-                        pack16(tv, w);
-                        tmem_st_32x32b_x16(o_base + (c0 >> 1), w);
-                        if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 3);
-                        tmem_st_wait();
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(o_ready_r);
-                    } else if (ph == 1) {
-                        // ---------------- t1' = fold4(wsilu(acc + bf0))  ->  P (smem, UMMA K-major SWIZZLE_128B)
-                        uint4 o4;
-                        uint32_t* ow = reinterpret_cast<uint32_t*>(&o4);
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            float o2[2];
-#pragma unroll
-                            for (int hh = 0; hh < 2; ++hh) {
-                                const int j = jj * 2 + hh;
-                                float s4 = wsilu_f(tv[4 * j]);
-                                s4 += wsilu_f(tv[4 * j + 1]);
-                                s4 += wsilu_f(tv[4 * j + 2]);
-                                s4 += wsilu_f(tv[4 * j + 3]);
-                                o2[hh] = s4;
-                            }
-                            const __half2 h2 = __floats2half2_rn(o2[0], o2[1]);
-                            ow[jj] = *reinterpret_cast<const uint32_t*>(&h2);
+#pragma unroll 1
+                    for (int a = 0; a < 2; ++a) {
+                        const int c0 = cw + a * 32;
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(acc + a * 32, v);
+                        uint32_t ov[16];
+                        if (ph == 2) tmem_ld_32x32b_x16(o_base + (c0 >> 1), ov);   // o: the residual of ffn.2
+                        tmem_ld_wait();
+                        if (a == 1) {
+                            hand_back();
+                            if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 2);
                         }
-                        // output channels 32 n + 8 jq .. + 8: k-block n / 2, 16-byte chunk 4 (n & 1) + jq of the row
-                        const uint32_t row = static_cast<uint32_t>(q * 32 + lane);
-                        sts128(P_u + (n >> 1) * A_STAGE_BYTES + sw128_offset(row, static_cast<uint32_t>((n & 1) * 4 + jq)), o4);
-                        if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 3);
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(p_ready_r + (n >> 1) * 8);
-                    } else if (ph == 2) {
-                        // ---------------- y = (acc + bf2 + o [+ x]) [* q]  ->  O (in place) and global
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            tv[2 * j] = fma_f32_f16(static_cast<uint16_t>(ov[j] & 0xffffu), ONE, tv[2 * j]);
-                            tv[2 * j + 1] = fma_f32_f16(static_cast<uint16_t>(ov[j] >> 16), ONE, tv[2 * j + 1]);
-                        }
-                        if (p.shortcut) {
+                        float tv[32];
+                        add_bias(cb, v, tv);
+                        if (a == 0) load_bias(bias, cw + 32, cb);   // the second piece's bias, behind the first piece's arithmetic
+                        if (ph == 0) {
+                            // ---------------- o = acc + b3 + x  ->  O (TMEM, packed fp16)
                             cp_async_wait_all();
                             __syncwarp();
                             add_slab(tv);
-                            __syncwarp();
-                        }
-                        if (p.qscale) {
-                            uint4 cq[4];
+                            __syncwarp();                          // every lane has read its slab row
+                            if (a == 0) fetch_x(row_w, cw + 32);   // the second piece's x, behind the packing + tcgen05.st
+                            uint32_t w[16];
+                            pack16(tv, w);
+                            tmem_st_32x32b_x16(o_base + (c0 >> 1), w);
+                        } else if (ph == 1) {
+                            // ---------------- t1' = fold4(wsilu(acc + bf0))  ->  P (smem, UMMA K-major SWIZZLE_128B)
+                            uint4 o4;
+                            uint32_t* ow = reinterpret_cast<uint32_t*>(&o4);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) cq[j] = __ldg(reinterpret_cast<const uint4*>(p.qscale + c0) + j);
-                            const uint32_t* qw = reinterpret_cast<const uint32_t*>(cq);
+                            for (int jj = 0; jj < 4; ++jj) {
+                                float o2[2];
 #pragma unroll
-                            for (int e = 0; e < 32; e += 2) {
-                                const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qw[e >> 1]));
-                                tv[e] *= qf.x;
-                                tv[e + 1] *= qf.y;
+                                for (int hh = 0; hh < 2; ++hh) {
+                                    const int j = jj * 2 + hh;
+                                    float s4 = wsilu2(tv[4 * j]);
+                                    s4 += wsilu2(tv[4 * j + 1]);
+                                    s4 += wsilu2(tv[4 * j + 2]);
+                                    s4 += wsilu2(tv[4 * j + 3]);
+                                    o2[hh] = 0.5f * s4;   // exact: the same bits as summing the four halves
+                                }
+                                const __half2 h2 = __floats2half2_rn(o2[0], o2[1]);
+                                ow[jj] = *reinterpret_cast<const uint32_t*>(&h2);
                             }
+                            // output channels 32 n + 16 h + 8 a .. + 8: k-block n / 2, 16-byte chunk 4 (n & 1) + 2 h + a of the row
+                            const uint32_t row = static_cast<uint32_t>(q * 32 + lane);
+                            sts128(P_u + (n >> 1) * A_STAGE_BYTES + sw128_offset(row, static_cast<uint32_t>((n & 1) * 4 + h * 2 + a)), o4);
+                        } else if (ph == 2) {
+                            // ---------------- y = (acc + bf2 + o [+ x]) [* q]  ->  O (in place) and global
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                tv[2 * j] = fma_f32_f16(static_cast<uint16_t>(ov[j] & 0xffffu), ONE, tv[2 * j]);
+                                tv[2 * j + 1] = fma_f32_f16(static_cast<uint16_t>(ov[j] >> 16), ONE, tv[2 * j + 1]);
+                            }
+                            if (p.shortcut) {
+                                cp_async_wait_all();
+                                __syncwarp();
+                                add_slab(tv);
+                                __syncwarp();
+                            }
+                            if (p.qscale) {
+                                uint4 cq[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) cq[j] = __ldg(reinterpret_cast<const uint4*>(p.qscale + c0) + j);
+                                const uint32_t* qw = reinterpret_cast<const uint32_t*>(cq);
+#pragma unroll
+                                for (int e = 0; e < 32; e += 2) {
+                                    const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qw[e >> 1]));
+                                    tv[e] *= qf.x;
+                                    tv[e + 1] *= qf.y;
+                                }
+                            }
+                            uint32_t w[16];
+                            pack16(tv, w);
+                            tmem_st_32x32b_x16(o_base + (c0 >> 1), w);
+                            if (!p.shortcut) slab_free();   // (with the shortcut the slab was freed before x was fetched into it)
+                            store_slab(&p.tm_y, w, c0, row_w);
+                            if (p.shortcut && a == 0) {
+                                slab_free();
+                                fetch_x(row_w, cw + 32);
+                            }
+                        } else {
+                            // ---------------- t1n = wsilu(acc + b0n)  ->  global
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) tv[e] = 0.5f * wsilu2(tv[e]);
+                            uint32_t w[16];
+                            pack16(tv, w);
+                            slab_free();
+                            store_slab(&p.tm_t, w, c0, row_w);
                         }
-                        uint32_t w[16];
-                        pack16(tv, w);
-                        tmem_st_32x32b_x16(o_base + (c0 >> 1), w);
-                        if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 3);
-                        store_slab(&p.tm_y, w, c0, row_w);
+                    }
+                    if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 3);
+                    // ---- the chunk's 64 columns are out: tell the MMA warp
+                    if (ph == 0 || ph == 2) {
                         tmem_st_wait();
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(y_ready_r);
-                    } else {
-                        // ---------------- t1n = wsilu(acc + b0n)  ->  global
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) tv[e] = wsilu_f(tv[e]);
-                        uint32_t w[16];
-                        pack16(tv, w);
-                        if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 3);
-                        store_slab(&p.tm_t, w, c0, row_w);
+                        if (lane == 0) mbar_arrive_cluster((ph == 0 ? o_ready_r : y_ready_r) + (2 * n + h) * 8);
+                    } else if (ph == 1) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(p_ready_r + (n >> 1) * 8);
                     }
                     if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 4);
                 }
@@ -588,8 +614,6 @@ int dcb_tail_plan(DcbTailOp& op)
     if (encode_act_map(&p.tm_t, op.t1n.ptr ? op.t1n : op.y, false, true, true, 32, 1, 32)) return 2;
     if (const char* d = getenv("DCVC_B200_GEMM_DBG")) p.dbg = atoi(d);
     if (const char* d = getenv("DCVC_B200_GEMM_TRACE")) p.trace = reinterpret_cast<unsigned long long*>(strtoull(d, nullptr, 0));
-    p.rot = 1;
-    if (const char* d = getenv("DCVC_B200_DT_ROT")) p.rot = atoi(d) ? 1 : 0;
     op.grid = dim3(2 * p.num_pairs, 1, 1);
     op.planned = true;
     return 0;

@@ -133,7 +133,7 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
     // programmatic dependent launch: everything above touched only this CTA's smem / TMEM and overlapped the tail
     // of the previous kernel; from here on its output is read
     griddep_launch_dependents();
-    if (!p.no_grid_wait) griddep_wait();
+    griddep_wait();
     if (threadIdx.x == 0) trace_mark(p, 1);  // setup done
     if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 64 + 15] = static_cast<uint32_t>(clock64());  // SM clock at mark 1
 
@@ -158,25 +158,10 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
             const int num_kblocks = p.num_kblocks;
             const int kblk_per_tap = p.kblk_per_tap;
             const bool lin = p.linear != 0;
-            int flag_next = 0;
-            if (p.wait_a && tile_of(0) >= 0) flag_next = ld_acquire_gpu(p.wait_a + (tile_coord<BLOCK_N>(p, tile_of(0)).ox0 >> 7));
             for (int i = 0;; ++i) {
                 const int tile = tile_of(i);
                 if (tile < 0) break;
                 const TileCoord tc = tile_coord<BLOCK_N>(p, tile);
-                if (p.wait_a) {
-                    // chained op: the pixel tile must have been completed (all N tiles) by the op that writes it.  The
-                    // flag was requested one tile ago (an L2 round trip is ~0.7 us — as long as half a tile's MMAs)
-                    const int* f = p.wait_a + (tc.ox0 >> 7);
-                    int v = flag_next;
-                    while (v < p.wait_a_need) {
-                        __nanosleep(64);
-                        v = ld_acquire_gpu(f);
-                    }
-                    fence_proxy_async_all();
-                    const int tile_n = tile_of(i + 1);
-                    if (tile_n >= 0) flag_next = ld_acquire_gpu(p.wait_a + (tile_coord<BLOCK_N>(p, tile_n).ox0 >> 7));
-                }
                 int tap = 0, kc = 0;
                 for (int kb = 0; kb < num_kblocks; ++kb, ++it) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
@@ -265,7 +250,6 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
         ew.slab = staging + (warp - 2) * p.staging_bufs * EPI_SLAB_BYTES;
         ew.cnt = 0;
         const int g = ew.b;
-        int prev_mt = -1;
         for (int i = g;; i += 2) {
             const int tile = tile_of(i);
             if (tile < 0) break;
@@ -275,20 +259,6 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
             epilogue_tile<BLOCK_N, CHUNK>(p, tc, acc, &tmem_full_bar[g], u & 1, &tmem_empty_bar[g], 0u, ew,
                                           i == 0 ? 7 : (i == 1 ? 9 : 11));
             if (lane == 0 && ew.q == 0 && ew.h == 0) trace_mark(p, i == 0 ? 8 : (i == 1 ? 10 : 12));  // epilogue of tile i done
-            if (p.done_flags) {
-                // report the PREVIOUS tile of this warp: its stores are older than the ones just committed, so
-                // waiting for them costs nothing by now
-                constexpr int kStoresPerTile = CHUNK ? 1 : BLOCK_N / 64;
-                if (lane == 0 && prev_mt >= 0) {
-                    tma_store_wait_done<kStoresPerTile>();
-                    red_release_gpu_add(p.done_flags + prev_mt, 1);
-                }
-                prev_mt = tc.ox0 >> 7;
-            }
-        }
-        if (p.done_flags && lane == 0 && prev_mt >= 0) {
-            tma_store_wait_done<0>();
-            red_release_gpu_add(p.done_flags + prev_mt, 1);
         }
         if (lane == 0) tma_store_wait_read<0>();
         if (lane == 0 && ew.q == 0 && ew.h == 0) trace_mark(p, 13 + g);  // group drained
@@ -653,15 +623,6 @@ int gemm_plan(GemmOp& op)
             }
         }
     }
-    if (op.kind == GEMM_PW) {
-        // 1x1 ops with K <= 512: the A-resident / CTA-pair kernel (pw_gemm_ares.cu)
-        const int r = ares_plan(op, num_sms);
-        if (r == 0) return 0;
-        if (r == 2) return 1;
-        memset(&p, 0, sizeof(p));
-        p.tap_px[0] = p.tap_py[0] = p.tap_dx[0] = p.tap_dy[0] = 0;
-        p.bw = 128; p.bh = 1;
-    }
     const TilePlan tp = pick_tile_plan(n_unit, op.N, op.chunk_add != 0, m_tiles, taps * C / 64, num_sms);
     const int bn = tp.bn;
     if (bn == 0 || op.N % bn != 0) { g_err = "gemm_plan: unsupported N"; return 1; }
@@ -678,12 +639,6 @@ int gemm_plan(GemmOp& op)
     p.phase_c = upsamples ? op.out.C : 0;
     p.n_res = (op.res1.ptr ? 1 : 0) + (op.res2.ptr ? 1 : 0);
     if (op.res2.ptr && !op.res1.ptr) { g_err = "gemm_plan: res2 without res1"; return 1; }
-    if (linear) {
-        p.done_flags = op.done_flags;
-        p.wait_a = op.wait_a;
-        p.wait_a_need = op.wait_a_need;
-        p.no_grid_wait = op.no_grid_wait ? 1 : 0;
-    }
 
     const bool in_split = (op.kind == GEMM_CONV3X3_S2 || op.kind == GEMM_CONV2X2_S2);
     const bool lin2d = linear && tp.cluster == 1;  // the cluster path multicasts 5-D boxes
@@ -776,7 +731,6 @@ int gemm_init()
         g_err = std::string("cudaFuncSetAttribute(pw_gemm): ") + cudaGetErrorString(e);
         return 1;
     }
-    if (ares_init()) return 1;
     done = true;
     return 0;
 }
@@ -811,14 +765,6 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream)
     if (!op.planned) { g_err = "gemm_launch: op not planned"; return 1; }
     if (gemm_init()) return 1;
     cudaError_t e;
-    if (op.ares) {
-        e = ares_launch(op, stream);
-        if (e != cudaSuccess) {
-            g_err = std::string("pw_gemm_ares launch failed: ") + cudaGetErrorString(e);
-            return 1;
-        }
-        return 0;
-    }
     switch (op.block_n + (op.chunk_add ? 1 : 0)) {
     case 64: e = launch_bn<64, false>(op, stream); break;
     case 128: e = launch_bn<128, false>(op, stream); break;

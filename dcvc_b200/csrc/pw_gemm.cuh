@@ -67,15 +67,6 @@ struct alignas(64) PwGemmParams {
                            // cycles per row to walk, measured 0.25 us per 128-row k-block; 2-D rows stream)
     int dbg;               // micro-benchmark switches (env DCVC_B200_GEMM_DBG): 1 = no MMA, 2 = no epilogue body
     unsigned long long* trace;  // env DCVC_B200_GEMM_TRACE=<device address>: 16 globaltimer slots per CTA (tools/gemm_trace.py)
-    // tile-level chaining of consecutive 1x1 ops (same pixel tiling): instead of waiting for the whole previous grid
-    // (griddepcontrol.wait), the TMA producer waits until the 128-pixel tile it is about to load has been completed
-    // by the op that writes it; the epilogue warps count completed tiles for the next op
-    int* done_flags;       // [m_tiles] or nullptr: += 1 per epilogue warp and N tile once the tile's stores are complete
-    const int* wait_a;     // [m_tiles] or nullptr: done_flags of the op that produces the A operand
-    int wait_a_need;       // its n_tiles * 8
-    int no_grid_wait;      // 1: skip griddepcontrol.wait (every input is covered by wait_a or older than the chain)
-    int ares_ctas;         // 0: streaming kernel; 1 / 2: A-resident kernel on single CTAs / CTA pairs (pw_gemm_ares.cu)
-    int tiles_per_group;   // A-resident kernel: N tiles one work item runs through with its activation tile resident
     int num_kblocks;       // taps * C / 64
     int kblk_per_tap;      // C / 64
     int bw, bh;            // pixel tile, bw*bh == 128
@@ -100,16 +91,11 @@ struct GemmOp {
     int N = 0;          // GEMM columns (tconv: 4*Cout, chunk-add: 4*C')
     int act = ACT_NONE;
     int chunk_add = 0;
-    int* done_flags = nullptr;      // see PwGemmParams (optional; streaming kernel, GEMM_PW only)
-    const int* wait_a = nullptr;
-    int wait_a_need = 0;
-    bool no_grid_wait = false;
     bool pdl = true;    // launch with the programmatic-dependent-launch attribute (when DCVC_B200_PDL allows it at all)
     // ---- derived by gemm_plan()
     PwGemmParams p;
     dim3 grid;
     int block_n = 0;
-    int ares = 0;       // 0: streaming kernel, 1 / 2: A-resident kernel with 1 / 2 CTAs per work item
     int stages = 0;
     size_t smem = 0;
     bool planned = false;

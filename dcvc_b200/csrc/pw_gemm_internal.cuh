@@ -1,5 +1,5 @@
 // pw_gemm_internal.cuh — constants and host helpers shared by the pw_gemm translation units
-// (pw_gemm.cu: streaming kernel + planner; pw_gemm_ares.cu: A-resident / CTA-pair kernel).
+// (pw_gemm.cu: the per-op kernel + planner; dcb_tail.cu: the fused DepthConvBlock tail).
 #pragma once
 #include <string>
 
@@ -39,12 +39,5 @@ int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, 
 int encode_act_map(CUtensorMap* m, const ActView& v, bool split2, bool linear, bool lin2d, int bw, int bh, int box_c = 64);
 FastDiv make_fastdiv(uint32_t d);
 bool gemm_pdl_enabled();
-
-// ---- A-resident / CTA-pair kernel (pw_gemm_ares.cu)
-// Tries to plan `op` (a 1x1 op with K <= 512) for the A-resident kernel; returns 0 and sets op.planned on success,
-// 1 when the op is not eligible (the caller falls back to the streaming kernel), 2 on a real error.
-int ares_plan(GemmOp& op, int num_sms);
-int ares_init();
-cudaError_t ares_launch(const GemmOp& op, cudaStream_t stream);
 
 }  // namespace dcvc

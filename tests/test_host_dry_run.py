@@ -66,7 +66,6 @@ class _Dry:
         env = dict(os.environ)
         env.update({"LD_PRELOAD": self.shim, "LD_LIBRARY_PATH": CUDA_LIB + ":" + env.get("LD_LIBRARY_PATH", ""),
                     "DCVC_B200_RANS_SPIN_US": "0", "OMP_NUM_THREADS": "2", "MKL_NUM_THREADS": "2", "DCVC_DRY_THREADS": "2",
-                    "DCVC_B200_TEST_LANES": "1",
                     "DCVC_B200_FUSE_TAIL": "0"})   # the shim emulates the per-op kernels only
         env.pop("DRY_SHIM_EMULATE", None)
         if emulate:
@@ -84,18 +83,10 @@ class _Dry:
         for codec, sizes in CHECK_JOBS:
             self.submit_flow("check", codec, sizes)
         self.submit_flow("check", "hts", ["72x104"], {"DCVC_B200_HEAD_LANES": "4"}, tag="lanes4")
-        self.submit_flow("plan", "hts", ["1080x1920", "2160x3840"], {"DCVC_B200_HEAD_LANES": "2"}, tag="lanes2")
+        self.submit_flow("check", "hts", ["72x104"], {"DCVC_B200_HEAD_LANES": "1"}, tag="lanes1")
+        self.submit_flow("plan", "hts", ["1080x1920", "2160x3840"], {"DCVC_B200_HEAD_LANES": "4"}, tag="lanes4")
         self.submit_flow("check", "hts", ["64x64"], {"DCVC_B200_HEAD_LANES": "2", "DCVC_B200_TEST_ALIAS_LANE_SCRATCH": "1"},
                          tag="lanes-racy")
-        self.submit_flow("check", "intra", ["64x64", "72x104"], {"DCVC_B200_SPLIT_P8": "1", "DCVC_B200_DECODE_ONE_SYNC": "1"},
-                         tag="split")   # + the one-wait-per-step decode hand-off: same results as well
-        self.submit_flow("check", "intra", ["64x64"], {"DCVC_B200_SPLIT_P8": "1", "DCVC_B200_TEST_DROP_LANE_SYNC": "1"},
-                         tag="split-racy")
-        self.submit_flow("plan", "intra", ["1080x1920", "2160x3840", "1096x1928"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
-        self.submit_flow("check", "hts", ["72x104"], {"DCVC_B200_SPLIT_P8": "4"}, tag="split")   # four bands / lanes
-        self.submit_flow("check", "ld", ["72x104"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
-        for codec in ("hts", "ld", "htl"):
-            self.submit_flow("plan", codec, ["1080x1920", "2160x3840", "200x328"], {"DCVC_B200_SPLIT_P8": "1"}, tag="split")
         for name, args, default in GPU_FILES_UNDER_EMULATION:
             if default or FULL:
                 self.submit_pytest(name, args)
@@ -176,67 +167,30 @@ def test_emulated_codec_matches_its_oracle(dry, codec, sizes):
 
 
 def test_recon_head_lanes_change_nothing_but_the_graph_shape(dry):
-    """DCVC_B200_HEAD_LANES (measurement switch, off by default): the four recon-head pairs of the HT-S decoder become
-    parallel branches of the recon graph, each on its own scratch level.  Under emulation the result must be the one of
-    the single-lane run bit for bit (the branches share nothing but their read-only input), the capture must really fork
-    (and join: the shim ends an unjoined capture with cudaErrorStreamCaptureUnjoined, like the runtime), and the arena
-    estimate must cover the extra scratch levels at 1080p and 4K."""
+    """DCVC_B200_HEAD_LANES (default 2): the four recon-head pairs of the HT-S decoder are parallel branches of the recon
+    graph, each on its own scratch level.  Under emulation the result must be the one of the single-lane run bit for bit
+    (the branches share nothing but their read-only input), the capture must really fork (and join: the shim ends an
+    unjoined capture with cudaErrorStreamCaptureUnjoined, like the runtime), and the arena estimate must cover the extra
+    scratch levels at 1080p and 4K."""
     def last_json(r):
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
         return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-    base = last_json(dry.result(("check", "hts")))
-    lanes = last_json(dry.result(("check", "hts", "lanes4")))
-    assert base["capture_forks"] == 0 and lanes["capture_forks"] >= 3
-    assert lanes["runs"][0]["bytes"] == base["runs"][0]["bytes"]
-    assert lanes["runs"][0]["psnr"] == base["runs"][0]["psnr"]
-    plan = last_json(dry.result(("plan", "hts", "lanes2")))
+    base = last_json(dry.result(("check", "hts")))                 # the default: two lanes
+    one = last_json(dry.result(("check", "hts", "lanes1")))
+    four = last_json(dry.result(("check", "hts", "lanes4")))
+    assert one["capture_forks"] == 0 and base["capture_forks"] >= 1 and four["capture_forks"] >= 3
+    for other in (one, four):
+        assert other["runs"][0]["bytes"] == base["runs"][0]["bytes"]
+        assert other["runs"][0]["psnr"] == base["runs"][0]["psnr"]
+    plan = last_json(dry.result(("plan", "hts", "lanes4")))
     assert plan["capture_forks"] >= 1
     assert all(run["arena_overflow_blocks"] == 0 for run in plan["runs"])
     # Emulation runs the branches one after the other, so equal results say nothing about races.  The shim therefore
     # collects what every kernel of a multi-lane graph reads and writes and fails the launch when a range written on
-    # one branch overlaps a range touched on another: the run above passed that check, and a deliberately broken
+    # one branch overlaps a range touched on another: the runs above passed that check, and a deliberately broken
     # wiring (all lanes on lane 0's scratch, a test-only switch) must trip it.
     racy = dry.result(("check", "hts", "lanes-racy"))
     assert racy.returncode != 0 and "lane race" in racy.stderr, racy.stderr[-1500:]
-
-
-def test_half_picture_lanes_change_nothing_but_the_graph_shape(dry):
-    """DCVC_B200_SPLIT_P8 (measurement switch, off by default): the 1x1 GEMMs of the synthesis transform's blocks run as
-    upper / lower half-picture branches of the graph with cross-lane event edges around the full-picture depthwise
-    conv.  Same results as the default path bit for bit (both sizes), the same booked
-    algorithmic work, a capture that forks, and a clean race check — which is not vacuous: the first version of the
-    split raced where a block changes the channel width (the halves' byte ranges shift inside the reused buffers; found
-    by this check, fixed by a two-way edge before such blocks), and dropping the edge in front of the depthwise conv
-    (test-only switch) must trip it.  Plan mode: every half-picture GEMM plans at 1080p, 4K and a padded size."""
-    def last_json(r):
-        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-        return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-    base = last_json(dry.result(("check", "intra")))
-    split = last_json(dry.result(("check", "intra", "split")))
-    assert base["capture_forks"] == 0 and split["capture_forks"] >= 1
-    for a, b in zip(base["runs"], split["runs"]):
-        assert a["bytes"] == b["bytes"] and a["psnr"] == b["psnr"] and a["symbols"] == b["symbols"]
-        assert abs(a["decode_alg_gb"] - b["decode_alg_gb"]) < 1e-9 and abs(a["decode_gmac"] - b["decode_gmac"]) < 1e-9
-        assert b["decode_launches"] > a["decode_launches"]
-    racy = dry.result(("check", "intra", "split-racy"))
-    assert racy.returncode != 0 and "lane race" in racy.stderr, racy.stderr[-1500:]
-    plan = last_json(dry.result(("plan", "intra", "split")))
-    assert plan["capture_forks"] >= 1 and len(plan["runs"]) == 3
-    # the chunk codec: every P8 chain (encoder, decoder, memory update, context, recon heads) as a split region
-    hbase = last_json(dry.result(("check", "hts")))
-    hsplit = last_json(dry.result(("check", "hts", "split")))
-    assert hsplit["capture_forks"] >= 3
-    assert hsplit["runs"][0]["bytes"] == hbase["runs"][0]["bytes"] and hsplit["runs"][0]["psnr"] == hbase["runs"][0]["psnr"]
-    assert abs(hsplit["runs"][0]["decode_alg_gb"] - hbase["runs"][0]["decode_alg_gb"]) < 1e-9
-    for codec in ("hts", "ld", "htl"):   # every half-picture GEMM plans at 1080p / 4K / a ragged size and books the reference's work
-        pl = last_json(dry.result(("plan", codec, "split")))
-        gb, gmac = REFERENCE_DECODE_WORK[codec]
-        assert abs(pl["runs"][0]["decode_alg_gb"] - gb) <= 0.005 * gb + 0.005 and abs(pl["runs"][0]["decode_gmac"] - gmac) <= 0.002 * gmac
-        assert all(run["arena_overflow_blocks"] == 0 for run in pl["runs"])
-    lbase = last_json(dry.result(("check", "ld")))
-    lsplit = last_json(dry.result(("check", "ld", "split")))
-    assert lsplit["capture_forks"] >= 1
-    assert lsplit["runs"][0]["bytes"] == lbase["runs"][0]["bytes"] and lsplit["runs"][0]["psnr"] == lbase["runs"][0]["psnr"]
 
 
 def _pytest_under_emulation(dry, name, args):
@@ -251,7 +205,6 @@ FULL = os.environ.get("DCVC_B200_DRY_FULL") == "1"
 GPU_FILES_UNDER_EMULATION = [
     ("ops", ["tests/test_ops_gpu.py"], True),
     ("sequence-ld", ["tests/test_sequence_gpu.py", "-k", "ld"], True),
-    ("split-lanes", ["tests/test_codec_gpu.py", "-k", "half_picture and 72-104"], True),
     ("sequence-hts", ["tests/test_sequence_gpu.py", "-k", "hts"], False),
     ("htl", ["tests/test_htl_gpu.py", "-k", "64-64 or oracle or bit_identical"], False),
     ("hts", ["tests/test_hts_gpu.py", "-k", "64-64 or oracle or bit_identical"], False),

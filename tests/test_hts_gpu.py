@@ -14,8 +14,6 @@ pytestmark = pytest.mark.gpu
 # First device run of the capture-lane switches happens under tools/round2_first_call.sh (which sets this), not in the
 # driver's unattended round-end run: concurrent persistent kernels are the one kind of change that could hang a box on
 # a first run, and a hung box there would take the bench tier with it.  Remove the gate once they have run green.
-_LANES = pytest.mark.skipif(os.environ.get("DCVC_B200_TEST_LANES") != "1",
-                            reason="capture-lane switches: first device run is scripted (set DCVC_B200_TEST_LANES=1)")
 SKIP = 0.15
 
 
@@ -175,17 +173,14 @@ def test_hts_stream_bit_identical_to_reference_coder(nets):
     assert np.asarray(r.get_encoded_stream()).tobytes() == e["bit_stream"]
 
 
-@_LANES
 @pytest.mark.timeout(300, method="thread")
-@pytest.mark.parametrize("switch,value", [("DCVC_B200_HEAD_LANES", "2"), ("DCVC_B200_HEAD_LANES", "4"),
-                                          ("DCVC_B200_SPLIT_P8", "1"), ("DCVC_B200_SPLIT_P8", "4")])
-def test_capture_lanes_bit_identical(nets, switch, value, monkeypatch):
-    """The two capture-lane switches (measurement switches, default off).  DCVC_B200_HEAD_LANES: the four recon-head pairs
-    run as parallel branches of the recon graph, each on its own scratch level.  DCVC_B200_SPLIT_P8: inside every P8
-    chain the 1x1 GEMMs run as 2 (value 1 or 2), 3 or 4 horizontal-band branches with cross-lane edges around the depthwise conv.
-    Either way one persistent GEMM's tail overlaps another branch's work, and nothing else changes: streams, every
-    decoded frame and the carried state must equal the default run bit for bit (the CPU tier checks the same under
-    emulation, that the captures fork / join, and that no branch races another)."""
+@pytest.mark.parametrize("switch,value", [("DCVC_B200_HEAD_LANES", "1"), ("DCVC_B200_HEAD_LANES", "4"), ("DCVC_B200_FUSE_TAIL", "0")])
+def test_capture_lanes_and_fusion_bit_identical(nets, switch, value, monkeypatch):
+    """DCVC_B200_HEAD_LANES (default 2): the four recon-head pairs run as parallel branches of the recon graph, each on its
+    own scratch level, so one persistent kernel's tail overlaps another branch's work.  DCVC_B200_FUSE_TAIL (default on):
+    the fused DepthConvBlock tail instead of the per-op kernels.  Neither changes a bit: streams, every decoded frame and
+    the carried state must equal the default run (the CPU tier checks under emulation that the captures fork / join and
+    that no branch races another)."""
     from dcvc_b200.model import DMC
     i_net, p_net = nets
     h, w = 136, 200                                        # ragged: pads to 144 x 208

@@ -69,10 +69,13 @@ def test_intra_against_reference_cuda(tmp_path, size, qp):
           f"d_bpp {d_bpp:.2e}, PSNR {p_ours:.4f} vs {p_ref:.4f} dB (d {abs(p_ours - p_ref):.2e}), "
           f"PSNR(ours, ref) {cross:.2f} dB, max|dx| {(ours - ref).abs().max().item():.4f}")
     assert info["intra"]["decode_equals_encode"]
-    # measured on B200 (round 2, profiles/r2_parity_vs_reference_cuda.md) x 2
-    assert abs(p_ours - p_ref) <= 2e-2
-    assert d_bpp <= 4e-3
-    assert cross >= 45.0
+    # The contract (BASELINE.json north_star): 1e-3 dB PSNR, 1e-4 bpp.  Measured on B200 (round 2,
+    # profiles/r2_parity_vs_reference_cuda.md): PSNR within 1.3e-4 dB everywhere — asserted at the contract's 1e-3;
+    # rate within 0.5e-4 .. 2.4e-4 bpp at 1080p (36 .. 62 bytes of 150 .. 440 KB: quantisation ties that flip between fp16-
+    # and fp32-accumulated latents) — asserted at the measured bound x 2; a 256x256 frame has 7.5 KB, 10 bytes are 1.2e-3 bpp.
+    assert abs(p_ours - p_ref) <= 1e-3
+    assert d_bpp <= (5e-4 if h * w >= 1080 * 1920 else 2.5e-3)
+    assert cross >= 35.0   # the flipped ties move single latents by one quantisation step: local, bounded differences
 
 
 @needs_ref
@@ -110,5 +113,6 @@ def test_video_against_reference_cuda(tmp_path, name):
     d_bpp = abs(n_ours - n_ref) * 8 / (h * w * nf)
     print(f"[parity vs reference CUDA] {name} {size} q{qp} unit 0: bytes {n_ours} vs {n_ref}, d_bpp {d_bpp:.2e}, "
           f"PSNR frame0 {p_ours:.4f} vs {p_ref:.4f} dB, PSNR(ours, ref) {psnr(ours, ref):.2f} dB")
-    assert abs(p_ours - p_ref) <= 5e-2
-    assert d_bpp <= 1e-2
+    # measured (round 2): d_bpp 0.8e-4 (HT-S, LD) and 2.2e-4 (HT-L) at 256x384, PSNR within 1e-3 dB
+    assert abs(p_ours - p_ref) <= 2e-3
+    assert d_bpp <= 5e-4
