@@ -443,10 +443,9 @@ protected:
         s.out_views.back() = out;
         {
             char buf[256];
-            snprintf(buf, sizeof(buf), "gemm kind=%d in=%dx%dx%d/%d@%p out=%d/%d@%p N=%d act=%d chunk=%d res=%p,%p bn=%d st=%d resident=%d sb=%d grid=%u",
+            snprintf(buf, sizeof(buf), "gemm kind=%d in=%dx%dx%d/%d@%p out=%d/%d@%p N=%d act=%d chunk=%d res=%p,%p bn=%d st=%d sb=%d grid=%u",
                      kind, in.H, in.W, in.C, in.pitch, in.ptr, out.C, out.pitch, out.ptr, N, act, chunk,
-                     r1 ? r1->ptr : nullptr, r2 ? r2->ptr : nullptr, op->block_n, op->stages, op->p.b_resident,
-                     op->p.staging_bufs, op->grid.x);
+                     r1 ? r1->ptr : nullptr, r2 ? r2->ptr : nullptr, op->block_n, op->stages, op->p.staging_bufs, op->grid.x);
             s.notes.resize(s.ops.size());
             s.notes.back() = buf;
         }

@@ -38,6 +38,11 @@ static constexpr int DT_ACC_COL0 = 256;
 static constexpr int DT_TMEM_COLS = 512;
 static constexpr int DT_STAGING = EPI_WARPS * EPI_SLAB_BYTES;       // one 2 KB slab per epilogue warp
 
+// Cross-CTA signals of the pair.  Default: arrive with CTA-scope release + plain try_wait, as CUTLASS's 2-SM pipelines do;
+// DCVC_B200_GEMM_DBG bit 16 (A/B measurements) switches back to cluster-scope release / acquire.
+#define dt_arrive(addr) do { if (p.dbg & 16) mbar_arrive_cluster(addr); else mbar_arrive_remote(addr); } while (0)
+#define dt_wait(bar, parity) do { if (p.dbg & 16) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity); } while (0)
+
 // timeline marks (tools/dcb_tail_trace.py): globaltimer into p.trace[slot], CTA `cta` only
 __device__ __forceinline__ void dt_mark(const DcbTailParams& p, int cta, int slot)
 {
@@ -48,7 +53,7 @@ __device__ __forceinline__ void dt_mark(const DcbTailParams& p, int cta, int slo
     }
 }
 
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(NUM_THREADS, 1)   // 18 warps are allocated as 20: 96 registers per thread is the ceiling
 dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -181,7 +186,7 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                     for (int n = 0; n < p.nch[ph]; ++n, ++t) {
                         const int g = static_cast<int>(t & 1);
                         if (!no_acc) {
-                            mbar_wait_cluster(&acc_empty[g], ((t >> 1) & 1) ^ 1);  // both CTAs drained this buffer
+                            dt_wait(&acc_empty[g], ((t >> 1) & 1) ^ 1);  // both CTAs drained this buffer
                             tcgen05_fence_after();
                         }
                         const uint32_t acc = tmem_base + DT_ACC_COL0 + g * DT_CHUNK_N;
@@ -199,9 +204,9 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                                 if (n == 0 && !no_acc) {
                                     // the first chunk of a phase takes its A k-blocks as the epilogue of the previous phase
                                     // finishes them (later chunks find everything there)
-                                    if (ph == 1) { mbar_wait_cluster(&o_ready[kb], tph); tcgen05_fence_after(); }
-                                    if (ph == 2) { mbar_wait_cluster(&p_ready[kb], tph); tcgen05_fence_after(); }
-                                    if (ph == 3) { mbar_wait_cluster(&y_ready[kb], tph); tcgen05_fence_after(); }
+                                    if (ph == 1) { dt_wait(&o_ready[kb], tph); tcgen05_fence_after(); }
+                                    if (ph == 2) { dt_wait(&p_ready[kb], tph); tcgen05_fence_after(); }
+                                    if (ph == 3) { dt_wait(&y_ready[kb], tph); tcgen05_fence_after(); }
                                 }
                                 const uint64_t b_desc = make_kmajor_sw128_desc(b_addr + j * DT_KB_BYTES);
                                 if (do_mma) {
@@ -231,7 +236,7 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                         // y k-block); without one the wait happens here — else next-tile writes race the readers, and barrier
                         // phases nobody consumed would swallow next-tile arrivals (the round-2 "several tiles per pair" bug)
                         if (!no_acc && p.nch[3] == 0) {
-                            for (int kb = 0; kb < p.nkb[1]; ++kb) mbar_wait_cluster(&y_ready[kb], tph);
+                            for (int kb = 0; kb < p.nkb[1]; ++kb) dt_wait(&y_ready[kb], tph);
                             tcgen05_fence_after();
                         }
                     }
@@ -269,7 +274,7 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
         auto hand_back = [&]() {
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc_empty_r);
+            if (lane == 0) dt_arrive(acc_empty_r);
         };
         auto slab_free = [&]() {  // the TMA store that last read this warp's slab has finished reading it
             if (lane == 0) tma_store_wait_read<0>();
@@ -361,9 +366,9 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                     if (skip_body) {
                         hand_back();
                         if (lane == 0) {
-                            if (ph == 0) mbar_arrive_cluster(o_ready_r + (2 * n + h) * 8);
-                            if (ph == 1) mbar_arrive_cluster(p_ready_r + (n >> 1) * 8);
-                            if (ph == 2) mbar_arrive_cluster(y_ready_r + (2 * n + h) * 8);
+                            if (ph == 0) dt_arrive(o_ready_r + (2 * n + h) * 8);
+                            if (ph == 1) dt_arrive(p_ready_r + (n >> 1) * 8);
+                            if (ph == 2) dt_arrive(y_ready_r + (2 * n + h) * 8);
                         }
                         continue;
                     }
@@ -464,11 +469,11 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                         tmem_st_wait();
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster((ph == 0 ? o_ready_r : y_ready_r) + (2 * n + h) * 8);
+                        if (lane == 0) dt_arrive((ph == 0 ? o_ready_r : y_ready_r) + (2 * n + h) * 8);
                     } else if (ph == 1) {
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(p_ready_r + (n >> 1) * 8);
+                        if (lane == 0) dt_arrive(p_ready_r + (n >> 1) * 8);
                     }
                     if (tr) dt_mark(p, 0, 8 * static_cast<int>(t) + 4);
                 }

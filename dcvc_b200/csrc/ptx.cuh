@@ -301,6 +301,15 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
+// Same with the default semantics (release at CTA scope), the form CUTLASS uses for its 2-SM pipelines.  The cluster-scope
+// release above costs ~1 us per arrive on B200 (measured in dcb_tail: a cluster-scope fence invalidates L1); what these
+// signals publish lives in tensor memory / shared memory of the signalling CTA and is ordered by tcgen05.fence /
+// fence.proxy.async, not by the generic-proxy release.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
 // wait on a local mbarrier whose arrivals may come from the peer CTA (cluster-scope acquire)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
 {

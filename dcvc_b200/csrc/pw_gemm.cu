@@ -1,17 +1,16 @@
 // pw_gemm.cu — tcgen05 / TMEM / TMA implementation of the dense contractions of the
 // DCVC-UF hot path (see pw_gemm.cuh).  Hand-written for sm_100a.
 //
-// CTA = 128 output pixels x BLOCK_N GEMM columns, 6 warps:
-//   warp 0      TMA producer: per 64-wide k-block one 5-D box of activations (a "tap" of the
-//               2x2-phase-split NHWC tensor; OOB = zero padding) + one 2-D box of weights,
-//               both SWIZZLE_128B, mbarrier complete_tx; afterwards the residual tile.
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BLOCK_N, K=16),
-//               tcgen05.commit releases smem stages / publishes the accumulator.
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns), bias, WSiLU, 4:1 chunk-add,
-//               residual(s), per-channel quant scale, fp16 pack into a swizzled staging tile
-//               (aliased over the drained pipeline stages), TMA store (clips ragged edges).
-// Two CTAs are co-resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's
-// epilogue overlaps the other's main loop.
+// One persistent CTA per SM (grid = min(#tiles, #SMs)), 18 warps, tiles dealt round-robin with the N tile fastest:
+//   warp 0       TMA producer: per 64-wide k-block one box of activations (2-D [pixels][channels] for 1x1 ops; a 5-D
+//                "tap" box of the 2x2-phase-split NHWC tensor for the conv kinds, OOB = zero padding) + one 2-D box of
+//                weights, both SWIZZLE_128B, mbarrier complete_tx, through a ring of num_stages stages.
+//   warp 1       TMEM allocator + single-thread tcgen05.mma issuer (M = 128, N = BLOCK_N, K = 16); tcgen05.commit
+//                releases smem stages / publishes the accumulator; two accumulator buffers in TMEM.
+//   warps 2..17  epilogue (pw_gemm_epilogue.cuh): warp (b, h, q) drains lane quarter q / column half h of the tiles in
+//                accumulator buffer b: tcgen05.ld, bias, WSiLU, 4:1 chunk-add, residual(s), per-channel quant scale,
+//                fp16 pack into its own swizzled slab, its own TMA store (clips ragged edges).
+// The pixel-local runs of DepthConvBlocks do not come through here any more: dcb_tail.cu fuses them.
 #include "pw_gemm.cuh"
 
 #include <stdio.h>
@@ -57,50 +56,27 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
     using Cfg = TileCfg<BLOCK_N>;
     const int STAGES = p.num_stages;
 
-    // run-time carve-up of the 227 KB:
-    //   streaming : [STAGES x (A 16 KB | B BLOCK_N*128 B)] [staging] [control]
-    //   b_resident: [weight slab: num_kblocks x B] [STAGES x A 16 KB] [staging] [control]
+    // run-time carve-up of the 227 KB: [STAGES x (A 16 KB | B BLOCK_N*128 B)] [staging] [control]
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    const int slab_bytes = p.b_resident ? p.num_kblocks * Cfg::B_STAGE_BYTES : 0;
-    const int a_stride = p.b_resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES;
-    uint8_t* a_base = smem + slab_bytes;
+    constexpr int a_stride = Cfg::STAGE_BYTES;
+    uint8_t* a_base = smem;
     uint8_t* staging = a_base + STAGES * a_stride;
     uint8_t* ctrl = smem + SMEM_USABLE;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);   // [MAX_STAGES]
     uint64_t* empty_bar = full_bar + MAX_STAGES;              // [MAX_STAGES]
     uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;         // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;             // [2]
-    uint64_t* slab_bar = tmem_empty_bar + 2;                  // [1]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ctrl + 256);
     uint32_t* stage_clk = reinterpret_cast<uint32_t*>(ctrl + 272);  // [48] SM-clock marks of the first 24 k-blocks (trace)
 
-    // tile schedule: a cluster of CS CTAs owns CS consecutive N tiles of one pixel tile (the activation tile is
-    // TMA-multicast to all of them); work items (pixel tile, N group) are dealt round-robin to the clusters.
-    // With CS == 1 this degenerates to one CTA per (pixel tile, N tile), N fastest.
-    const int CS = p.cluster;
-    const int rank = (CS > 1) ? static_cast<int>(cluster_ctarank()) : 0;
-    const int cid = (CS > 1) ? blockIdx.x / CS : blockIdx.x;
-    const int items = p.m_tiles * p.n_groups;
-    // weight-resident CTAs without a cluster are pinned to N tile (blockIdx % n_tiles) and stride over its pixel tiles
-    const bool pinned = p.b_resident && CS == 1;
-    const int pin_j = static_cast<int>(fdiv(blockIdx.x, p.fd_n_tiles));
-    const int pin_nt = blockIdx.x - pin_j * p.n_tiles;
-    const int pin_ctas = static_cast<int>(fdiv(gridDim.x - pin_nt + p.n_tiles - 1, p.fd_n_tiles));
-    auto tile_of = [&](int i) -> int {  // global tile id (mt * n_tiles + nt) of this CTA's i-th tile, or -1
-        if (pinned) {
-            const int mt = pin_j + i * pin_ctas;
-            return mt < p.m_tiles ? mt * p.n_tiles + pin_nt : -1;
-        }
-        const int w = cid + i * p.num_clusters;
-        if (w >= items) return -1;
-        const int mt = static_cast<int>(fdiv(w, p.fd_n_groups));
-        const int ng = w - mt * p.n_groups;
-        return mt * p.n_tiles + ng * CS + rank;
+    // tile schedule: tile id = pixel tile * n_tiles + N tile, dealt round-robin, so that concurrently running CTAs share
+    // the same activation tile in L2
+    auto tile_of = [&](int i) -> int {
+        const int w = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+        return w < p.total_tiles ? w : -1;
     };
-    const int my_nt = pinned ? pin_nt : rank;  // N tile whose weight slab stays resident
-    const uint16_t mc_mask = static_cast<uint16_t>((1u << CS) - 1u);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -112,9 +88,8 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
         tma_prefetch_desc(&p.tm_c);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], CS);  // every CTA of the cluster releases the (multicast) stage
+            mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(slab_bar, 1);
         for (int g = 0; g < 2; ++g) {
             mbar_init(&tmem_full_bar[g], 1);
             mbar_init(&tmem_empty_bar[g], 8);  // one arrival per epilogue warp serving the buffer
@@ -127,7 +102,6 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (CS > 1) cluster_sync_all();  // barriers of every CTA are initialised before any remote arrive / multicast
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     // programmatic dependent launch: everything above touched only this CTA's smem / TMEM and overlapped the tail
@@ -140,21 +114,13 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
     if (warp == 0) {
         if (elect_one_sync()) {
             // ------------------------------------------------------------ TMA producer
-            if (p.b_resident) {
-                // the weight slab of this CTA's N tile: loaded once, reused by every M tile
-                mbar_expect_tx(slab_bar, slab_bytes);
-                for (int kb = 0; kb < p.num_kblocks; ++kb) {
-                    tma_load_2d(smem + kb * Cfg::B_STAGE_BYTES, &p.tm_b, slab_bar, kb * BLOCK_K, my_nt * BLOCK_N);
-                }
-            }
             // stage / phase / tap counters are kept incrementally: this loop runs on ONE thread and its instruction
             // latency chain bounds how fast k-blocks can be requested (measured 0.32 us per k-block with the
             // straightforward it % STAGES, kb / kblk_per_tap formulation: three integer divisions per iteration)
             uint32_t it = 0;
             int s = 0;
             uint32_t ph = 0;
-            int mc_turn = 0;  // it % CS
-            const uint32_t stage_tx = p.b_resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES;
+            const uint32_t stage_tx = Cfg::STAGE_BYTES;
             const int num_kblocks = p.num_kblocks;
             const int kblk_per_tap = p.kblk_per_tap;
             const bool lin = p.linear != 0;
@@ -169,22 +135,15 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
                     mbar_expect_tx(&full_bar[s], stage_tx);
                     if (lin) {
                         tma_load_2d(a_dst, &p.tm_a, &full_bar[s], kc * BLOCK_K, tc.ox0);
-                    } else if (CS == 1) {
+                    } else {
                         tma_load_5d(a_dst, &p.tm_a, &full_bar[s], kc * BLOCK_K, p.tap_px[tap],
                                     tc.ox0 + p.tap_dx[tap], p.tap_py[tap], tc.oy0 + p.tap_dy[tap]);
-                    } else if (mc_turn == rank) {
-                        // this CTA fetches the k-block for the whole cluster (one L2 read instead of CS)
-                        tma_load_5d_mc(a_dst, &p.tm_a, &full_bar[s], kc * BLOCK_K, p.tap_px[tap],
-                                       tc.ox0 + p.tap_dx[tap], p.tap_py[tap], tc.oy0 + p.tap_dy[tap], mc_mask);
                     }
-                    if (!p.b_resident) {
-                        tma_load_2d(a_dst + A_STAGE_BYTES, &p.tm_b, &full_bar[s], kb * BLOCK_K, tc.n0);
-                    }
+                    tma_load_2d(a_dst + A_STAGE_BYTES, &p.tm_b, &full_bar[s], kb * BLOCK_K, tc.n0);
                     if (it == 0) trace_mark(p, 2);  // first stage requested
                     if (p.trace && it < 24) stage_clk[it] = static_cast<uint32_t>(clock64());
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                     if (++kc == kblk_per_tap) { kc = 0; ++tap; }
-                    if (++mc_turn == CS) mc_turn = 0;
                 }
             }
             trace_mark(p, 3);  // last stage requested
@@ -198,12 +157,7 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
             int s = 0;
             uint32_t ph = 0;
             const int num_kblocks = p.num_kblocks;
-            const bool resident = p.b_resident != 0;
             const bool do_mma = !(p.dbg & 1);
-            if (resident) {
-                mbar_wait(slab_bar, 0);
-                tcgen05_fence_after();
-            }
             int my_tiles = 0;
             while (tile_of(my_tiles) >= 0) ++my_tiles;
             for (int i = 0; i < my_tiles; ++i) {
@@ -218,8 +172,7 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
                     if (it == 0) trace_mark(p, 4);  // first stage landed
                     if (p.trace && it < 24) stage_clk[24 + it] = static_cast<uint32_t>(clock64());
                     const uint32_t a_addr = smem_u32(a_base + s * a_stride);
-                    const uint32_t b_addr = resident ? smem_u32(smem + kb * Cfg::B_STAGE_BYTES)
-                                                     : a_addr + A_STAGE_BYTES;
+                    const uint32_t b_addr = a_addr + A_STAGE_BYTES;
                     const uint64_t a_desc = make_kmajor_sw128_desc(a_addr);
                     const uint64_t b_desc = make_kmajor_sw128_desc(b_addr);
                     if (do_mma) {
@@ -229,8 +182,7 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
                             umma_f16_ss(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                     }
-                    if (CS == 1) umma_commit(&empty_bar[s]);
-                    else umma_commit_mc(&empty_bar[s], mc_mask);
+                    umma_commit(&empty_bar[s]);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&tmem_full_bar[g]);
@@ -267,7 +219,6 @@ pw_gemm_kernel(const __grid_constant__ PwGemmParams p)
 
     __syncthreads();
     if (p.trace && threadIdx.x < 48) p.trace[blockIdx.x * 64 + 16 + threadIdx.x] = stage_clk[threadIdx.x];
-    if (CS > 1) cluster_sync_all();  // no CTA may exit while peers can still multicast into it / arrive on its barriers
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -369,10 +320,8 @@ int encode_act_map(CUtensorMap* m, const ActView& v, bool split2, bool linear, b
 
 struct TilePlan {
     int bn = 0;
-    bool resident = false;
     int stages = 0;
     int staging_bufs = 2;
-    int cluster = 1;
 };
 
 FastDiv make_fastdiv(uint32_t d)
@@ -385,126 +334,45 @@ FastDiv make_fastdiv(uint32_t d)
     return f;
 }
 
-// Chooses the N tile, the cluster size and the smem carve-up.
-// Measured on B200 (tools/gemm_micro.py, DCVC_B200_GEMM_DBG=3): the activation stream out of L2/HBM tops out at
-// ~7 TB/s chip-wide, i.e. every re-read of the activation tensor by another N tile costs as much as reading it
-// from HBM.  So the CTAs that need the same pixel tile form a cluster and share ONE TMA-multicast copy of it
-// (cluster size = N tiles, <= 8); the [bn][K] weight slab stays resident in smem when the CTA is pinned to its
-// N tile and >= 4 activation stages still fit.
+// Chooses the N tile and the pipeline depth.  Every tile streams its activation k-blocks and its weight k-blocks (hot in
+// L2) through the ring; measured on B200 (round 1: tools/gemm_micro.py), weight-resident CTAs and clusters that share one
+// multicast activation tile were both slower on every shape of the codec and are gone.
 static TilePlan pick_tile_plan(int n_unit, int n_total, bool chunk_add, long long m_tiles, int num_kblocks, int num_sms)
 {
     TilePlan best;
     const int cand_all[4] = { 256, 192, 128, 64 };
-    int force_bn = 0, force_sb = 0, force_cs = -1;
-    if (const char* f = getenv("DCVC_B200_GEMM_BN")) force_bn = atoi(f);
-    if (const char* f = getenv("DCVC_B200_GEMM_STAGING")) force_sb = atoi(f);
-    if (const char* f = getenv("DCVC_B200_GEMM_CLUSTER")) force_cs = atoi(f);
-    const char* force_mode = getenv("DCVC_B200_GEMM_MODE");
     double best_cost = 1e30;
     for (int ci = 0; ci < 4; ++ci) {
         const int bn = cand_all[ci];
         if (n_unit % bn) continue;
         if (chunk_add && bn != 256) continue;  // 4->1 fold: 128 accumulator columns per epilogue warp -> one 32-column store box
-        if (force_bn && bn != force_bn) continue;
         const int n_tiles = n_total / bn;
-        const int sub_bytes = SUB_TILE_BYTES;
         const int b_stage = bn * BLOCK_K * 2;
-        const int slab = num_kblocks * b_stage;
-        // cluster size.  Measured (tools/micro.sh, r1): with clusters of 3-6 CTAs the per-k-block cluster-wide
-        // stage release (tcgen05.commit multicast to every CTA) costs more than the multicast saves — 42 us vs
-        // 25 us for M=32640,N=K=384 — and B200's L2 already de-duplicates near-simultaneous unicast reads of a
-        // line.  Clusters therefore stay opt-in (DCVC_B200_GEMM_CLUSTER=n) until the release protocol is reworked.
-        int cs = 1;
-        if (force_cs >= 1 && n_tiles % force_cs == 0 && force_cs <= 8) cs = force_cs;
-        const int n_groups = n_tiles / cs;
-        const long long items = m_tiles * n_groups;
-        const int max_clusters = num_sms / cs;
-        const int clusters = static_cast<int>(items < max_clusters ? items : max_clusters);
-        if (clusters < 1) continue;
-        const long long per_cluster = (items + clusters - 1) / clusters;
-        for (int mode = 0; mode < 2; ++mode) {  // 0 = resident, 1 = streaming
-            TilePlan t;
-            t.bn = bn;
-            t.cluster = cs;
-            if (mode == 0) {
-                // measured slower than streaming on every codec shape (tools/run14.sh: 26.9 vs 24.7 us, 77 vs 53 us):
-                // the smaller N tile it forces re-reads the activations more often.  Kept as an opt-in experiment.
-                if (!force_mode || force_mode[0] != 'r') continue;
-                if (cs > 1 && n_groups != 1) continue;                                   // cluster CTAs: N tile = rank
-                if (cs == 1 && (clusters < n_tiles || m_tiles * n_tiles < 2LL * clusters)) continue;  // pinned + reuse
-                if (cs > 1 && per_cluster < 2) continue;
-                t.resident = true;
-                t.staging_bufs = force_sb ? force_sb : 1;
-                t.stages = (SMEM_USABLE - slab - EPI_GROUPS * t.staging_bufs * sub_bytes) / A_STAGE_BYTES;
-                if (t.stages < 4) continue;
-            } else {
-                if (force_mode && force_mode[0] == 'r') continue;
-                t.resident = false;
-                t.staging_bufs = force_sb ? force_sb : 2;
-                t.stages = (SMEM_USABLE - EPI_GROUPS * t.staging_bufs * sub_bytes) / (A_STAGE_BYTES + b_stage);
-                if (t.stages < 2) continue;
-            }
-            if (t.stages > MAX_STAGES) t.stages = MAX_STAGES;
-            // cost model (arbitrary time units per pixel tile of the whole problem):
-            //   activation stream: one 16 KB k-block per N group (multicast) at the ~7 TB/s chip-wide cap,
-            //   weight stream when not resident (hot in L2, ~3x cheaper per byte), tensor pipe, all scaled by the
-            //   wave quantisation of the persistent grid and a latency penalty for shallow pipelines
-            const double act = static_cast<double>(n_groups) * num_kblocks * A_STAGE_BYTES;
-            const double wgt = t.resident ? 0.0 : static_cast<double>(n_tiles) * num_kblocks * b_stage / 3.0;
-            const double mma = static_cast<double>(n_total) * num_kblocks * 64.0 * 128.0 / 1500.0;  // ~bytes-equivalent
-            const double quant = static_cast<double>(per_cluster) * clusters / static_cast<double>(items);
-            const double depth = 1.0 + 1.5 / t.stages;
-            const double cost = (act + wgt > mma ? act + wgt : mma) * quant * depth * (static_cast<double>(num_sms) / (clusters * cs));
-            if (cost < best_cost) {
-                best_cost = cost;
-                best = t;
-            }
+        const long long items = m_tiles * n_tiles;
+        const int ctas = static_cast<int>(items < num_sms ? items : num_sms);
+        if (ctas < 1) continue;
+        const long long per_cta = (items + ctas - 1) / ctas;
+        TilePlan t;
+        t.bn = bn;
+        t.staging_bufs = 2;
+        t.stages = (SMEM_USABLE - EPI_GROUPS * t.staging_bufs * SUB_TILE_BYTES) / (A_STAGE_BYTES + b_stage);
+        if (t.stages < 2) continue;
+        if (t.stages > MAX_STAGES) t.stages = MAX_STAGES;
+        // cost model (arbitrary time units per pixel tile of the whole problem): activation stream (one 16 KB k-block per
+        // N tile), weight stream (hot in L2, ~3x cheaper per byte), tensor pipe, all scaled by the wave quantisation of the
+        // persistent grid and a latency penalty for shallow pipelines
+        const double act = static_cast<double>(n_tiles) * num_kblocks * A_STAGE_BYTES;
+        const double wgt = static_cast<double>(n_tiles) * num_kblocks * b_stage / 3.0;
+        const double mma = static_cast<double>(n_total) * num_kblocks * 64.0 * 128.0 / 1500.0;  // ~bytes-equivalent
+        const double quant = static_cast<double>(per_cta) * ctas / static_cast<double>(items);
+        const double depth = 1.0 + 1.5 / t.stages;
+        const double cost = (act + wgt > mma ? act + wgt : mma) * quant * depth * (static_cast<double>(num_sms) / ctas);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = t;
         }
     }
     return best;
-}
-
-template <int BN>
-static int max_clusters_for(int cluster)
-{
-    if (gemm_init()) return 0;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(cluster * 64, 1, 1);
-    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = SMEM_TOTAL;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, pw_gemm_kernel<BN, false>, &cfg) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    return n;
-}
-
-// co-resident clusters of `cluster` CTAs (GPC boundaries strand some SMs); cached per (bn, cluster)
-static int max_active_clusters(int bn, int cluster, int num_sms)
-{
-    static int cache[4][9];
-    const int bi = bn == 64 ? 0 : bn == 128 ? 1 : bn == 192 ? 2 : 3;
-    if (cluster <= 1) return num_sms;
-    if (cache[bi][cluster] == 0) {
-        int n = 0;
-        switch (bn) {
-        case 64: n = max_clusters_for<64>(cluster); break;
-        case 128: n = max_clusters_for<128>(cluster); break;
-        case 192: n = max_clusters_for<192>(cluster); break;
-        default: n = max_clusters_for<256>(cluster); break;
-        }
-        cache[bi][cluster] = n > 0 ? n : num_sms / cluster;
-    }
-    return cache[bi][cluster];
 }
 
 int gemm_plan(GemmOp& op)
@@ -641,7 +509,7 @@ int gemm_plan(GemmOp& op)
     if (op.res2.ptr && !op.res1.ptr) { g_err = "gemm_plan: res2 without res1"; return 1; }
 
     const bool in_split = (op.kind == GEMM_CONV3X3_S2 || op.kind == GEMM_CONV2X2_S2);
-    const bool lin2d = linear && tp.cluster == 1;  // the cluster path multicasts 5-D boxes
+    const bool lin2d = linear;
     if (encode_act_map(&p.tm_a, op.in, in_split, linear, lin2d, p.bw, p.bh)) return 1;
     {
         const uint64_t Ktot = static_cast<uint64_t>(taps) * C;
@@ -681,25 +549,15 @@ int gemm_plan(GemmOp& op)
     p.n_tiles = op.N / bn;
     p.tiles_x = tiles_x;
     p.total_tiles = static_cast<int>(m_tiles) * p.n_tiles;
-    p.cluster = tp.cluster;
-    p.n_groups = p.n_tiles / p.cluster;
-    {
-        const long long items = m_tiles * p.n_groups;
-        const int max_clusters = max_active_clusters(bn, p.cluster, num_sms);
-        p.num_clusters = static_cast<int>(items < max_clusters ? items : max_clusters);
-        // pinned weight-resident CTAs: the same number of CTAs for every N tile
-        if (tp.resident && p.cluster == 1) p.num_clusters -= p.num_clusters % p.n_tiles;
-    }
+    const int grid_ctas = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     p.m_tiles = static_cast<int>(m_tiles);
     p.linear = lin2d ? 1 : 0;
     p.fd_n_tiles = make_fastdiv(p.n_tiles);
-    p.fd_n_groups = make_fastdiv(p.n_groups);
     p.fd_tiles_x = make_fastdiv(p.tiles_x);
     p.fd_phase_c = make_fastdiv(p.phase_c > 0 ? p.phase_c : 1);
     p.fd_bw = make_fastdiv(p.bw);
-    op.grid = dim3(p.num_clusters * p.cluster, 1, 1);
+    op.grid = dim3(grid_ctas, 1, 1);
     op.smem = SMEM_TOTAL;
-    p.b_resident = tp.resident ? 1 : 0;
     p.num_stages = tp.stages;
     p.staging_bufs = tp.staging_bufs;
     if (const char* d = getenv("DCVC_B200_GEMM_DBG")) p.dbg = atoi(d);
@@ -748,15 +606,11 @@ static cudaError_t launch_bn(const GemmOp& op, cudaStream_t stream)
     cfg.blockDim = dim3(NUM_THREADS, 1, 1);
     cfg.dynamicSmemBytes = op.smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = op.p.cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (g_pdl && op.pdl) ? 2 : 1;
+    cfg.numAttrs = (g_pdl && op.pdl) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, pw_gemm_kernel<BN, CHUNK>, op.p);
 }
 

@@ -30,7 +30,7 @@ enum GemmKind : int {
     GEMM_CONV2X2_S2 = 2, // pixel_unshuffle(2)+1x1   (reference conv_bias, layers_proxy.cpp:260-266)
     GEMM_TCONV2X2 = 3,   // 1x1 + pixel_shuffle(2)   (reference transposed_conv, layers_proxy.cpp:314-323)
     GEMM_CONV3X3_PS2 = 4, // 3x3, stride 1, pad 1 + pixel_shuffle(2): the HT-L SubpelConv2x (video_model_ht.py:41,
-                          // layers_proxy.cpp:271-275); experimental: not validated on hardware yet
+                          // layers_proxy.cpp:271-275)
 };
 
 // ACT_GDN / ACT_IGDN: out = res1 * rsqrt(acc + bias) resp. res1 * sqrt(acc + bias) — generalised divisive normalisation
@@ -57,12 +57,8 @@ struct alignas(64) PwGemmParams {
     int tiles_x;           // pixel tiles along x
     int total_tiles;       // n_tiles * tiles_x * tiles_y
     int m_tiles;           // tiles_x * tiles_y
-    int b_resident;        // 1: the CTA keeps the whole [BLOCK_N][K] weight slab of its N tile in smem
-    int num_stages;        // pipeline depth (A+B stages when streaming, A-only stages when b_resident)
+    int num_stages;        // pipeline depth (A + B stages)
     int staging_bufs;      // staging slabs per epilogue warp (1 or 2)
-    int cluster;           // CTAs per cluster = N tiles that share one multicast activation tile (1: no cluster)
-    int n_groups;          // n_tiles / cluster
-    int num_clusters;      // gridDim.x / cluster
     int linear;            // 1x1: tm_a / tm_c are plain 2-D [pixels][channels] maps (a 5-D box costs the TMA unit ~4
                            // cycles per row to walk, measured 0.25 us per 128-row k-block; 2-D rows stream)
     int dbg;               // micro-benchmark switches (env DCVC_B200_GEMM_DBG): 1 = no MMA, 2 = no epilogue body
@@ -75,7 +71,7 @@ struct alignas(64) PwGemmParams {
     int chunk_add;         // 1: out[:, j] = sum_{i<4} act(acc[:, 4j+i])
     int n_res;             // 0,1,2 residual operands (same geometry as the output)
     int phase_c;           // tconv: output channels per 2x2 phase (0: not a tconv)
-    FastDiv fd_n_tiles, fd_n_groups, fd_tiles_x, fd_phase_c, fd_bw;
+    FastDiv fd_n_tiles, fd_tiles_x, fd_phase_c, fd_bw;
     int8_t tap_px[9];
     int8_t tap_py[9];
     int8_t tap_dx[9];

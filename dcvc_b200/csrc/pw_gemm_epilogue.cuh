@@ -1,5 +1,5 @@
 // pw_gemm_epilogue.cuh — the TMEM -> registers -> swizzled smem -> TMA-store epilogue shared by the pw_gemm kernels
-// (streaming kernel and A-resident / CTA-pair kernel in pw_gemm.cu): bias, WSiLU, 4:1 chunk-add, up to two
+// (pw_gemm.cu): bias, WSiLU, 4:1 chunk-add, up to two
 // residuals, per-channel quant scale.  One call drains one [128 pixels][BLOCK_N] accumulator tile with the four
 // warps of an epilogue group (one warp per TMEM lane quarter).
 //

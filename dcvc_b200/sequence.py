@@ -60,6 +60,26 @@ def frame_schedule(frame_num: int, frame_delay: int, intra_period: int = -1, res
 Planes = Tuple["object", "object", "object"]      # (y [H,W], u [H/2,W/2], v [H/2,W/2]) uint8 tensors
 
 
+class UnitTimer:
+    """The reference driver's timing of one coded unit (test_video.py:219-221 + 263-267, 284-285 + 321-325): device
+    synchronise, start event, the unit's work (model call + container framing on the host), end event, synchronise."""
+
+    def __init__(self, device=None):
+        import torch
+        self.torch, self.device = torch, device
+        self.e0 = torch.cuda.Event(enable_timing=True)
+        self.e1 = torch.cuda.Event(enable_timing=True)
+
+    def start(self):
+        self.torch.cuda.synchronize(self.device)
+        self.e0.record()
+
+    def stop(self) -> float:
+        self.e1.record()
+        self.torch.cuda.synchronize(self.device)
+        return self.e0.elapsed_time(self.e1)
+
+
 def _device_to_model(planes: Sequence[Planes], frame_delay: int):
     """8-bit planes of 1 .. frame_delay pictures -> fp16 [1, 3*n, H, W] channels_last on the device of the planes"""
     import torch
@@ -90,6 +110,8 @@ class SequenceEncoder:
         self.to_model = to_model or _device_to_model
         self.padding_r, self.padding_b = i_net.get_padding_size(height, width, 16)     # test_video.py:189
         self.bits: List[int] = []          # per picture, like the reference's `bits` list (chunk bits on its first picture)
+        self.timer = None                  # UnitTimer: the reference's per-unit timing protocol (test_video.py:219-267)
+        self.unit_ms: List[float] = []
 
     def encode(self, frames: Iterable[Planes]) -> bytes:
         frames = list(frames)
@@ -101,6 +123,8 @@ class SequenceEncoder:
             if not unit.is_intra:
                 group += [group[-1]] * (self.frame_delay - len(group))      # tail chunk: repeat the last picture
             x = self.to_model(group, self.frame_delay)
+            if self.timer:
+                self.timer.start()
             if unit.is_intra:
                 qp = self.qp_i
                 encoded = self.i_net.compress(x, qp, self.padding_b, self.padding_r)
@@ -117,6 +141,8 @@ class SequenceEncoder:
             n += write_ip(out, unit.is_intra, sps_id, qp, encoded["ec_parallel"], unit.reset_feature_memory,
                           encoded["bit_stream"])
             self.bits += [n * 8] + [0] * (unit.count - 1)
+            if self.timer:
+                self.unit_ms.append(self.timer.stop())
         return out.getvalue()
 
 
@@ -126,6 +152,8 @@ class SequenceDecoder:
         self.i_net, self.p_net = i_net, p_net
         self.frame_delay, self.force_intra = frame_delay, force_intra
         self.from_model = from_model or _device_from_model
+        self.timer = None
+        self.unit_ms: List[float] = []
 
     def decode(self, data: bytes, frame_num: int):
         """yields (y, u, v) uint8 planes of `frame_num` pictures in display order"""
@@ -133,6 +161,8 @@ class SequenceDecoder:
         sps_helper = SPSHelper()
         done = 0
         while done < frame_num:
+            if self.timer:
+                self.timer.start()
             header = read_header(f)
             while header["nal_type"] == NalType.NAL_SPS:
                 sps_helper.add_sps_by_id(read_sps_remaining(f, header["sps_id"]))
@@ -153,6 +183,8 @@ class SequenceDecoder:
             else:
                 raise ValueError("unexpected unit type in a DCVC-UF stream")
             x_hat = decoded["x_hat"]
+            if self.timer:
+                self.unit_ms.append(self.timer.stop())
             for i in range(count):
                 yield self.from_model(x_hat[i] if isinstance(x_hat, (list, tuple)) else x_hat, sps["height"], sps["width"])
             done += count
