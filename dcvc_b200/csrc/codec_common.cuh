@@ -138,7 +138,10 @@ struct Level {  // one pyramid level: two ping-pong buffers + two scratch buffer
 
 using OpFn = std::function<int(cudaStream_t)>;
 
-enum OpKind { OP_GEMM = 0, OP_DW = 1, OP_ELEM = 2, OP_TAIL = 3, OP_KINDS = 4 };  // OP_TAIL: the fused dcb_tail kernel
+// OP_TAIL: the fused dcb_tail kernel.  OP_GEMM_*: the five instantiations of pw_gemm_kernel as kernels of their own (ncu
+// lists them separately too); OP_GEMM stays the family total
+enum OpKind { OP_GEMM = 0, OP_DW = 1, OP_ELEM = 2, OP_TAIL = 3, OP_GEMM_64 = 4, OP_GEMM_128 = 5, OP_GEMM_192 = 6, OP_GEMM_256 = 7,
+              OP_GEMM_256_FOLD = 8, OP_KINDS = 9 };
 
 struct Segment {
     std::vector<OpFn> ops;
@@ -417,6 +420,7 @@ protected:
         use_graphs_ = !(g && g[0] == '0');
         const char* ft = getenv("DCVC_B200_FUSE_TAIL");
         fuse_tail_ = !(ft && ft[0] == '0');
+        if (ft && atoi(ft) > 1) fuse_min_px_ = atoi(ft);   // DCVC_B200_FUSE_TAIL=<pixels>: another threshold (measurements)
         finalized_ = true;
     }
 
@@ -455,7 +459,8 @@ protected:
         if (r1) bytes += px_out * out.C * 2;
         if (r2) bytes += px_out * out.C * 2;
         const double m_px = (kind == GEMM_TCONV2X2 || kind == GEMM_CONV3X3_PS2) ? px_in : px_out;
-        s.annotate(OP_GEMM, bytes, 2.0 * m_px * N * taps * in.C);
+        const int inst = chunk ? OP_GEMM_256_FOLD : (op->block_n == 64 ? OP_GEMM_64 : op->block_n == 128 ? OP_GEMM_128 : op->block_n == 192 ? OP_GEMM_192 : OP_GEMM_256);
+        s.annotate(inst, bytes, 2.0 * m_px * N * taps * in.C);
     }
     void conv1x1(Segment& s, const ActView& in, const ActView& out, const ConvW& c)
     {
@@ -522,7 +527,7 @@ protected:
             s.annotate(OP_DW, 2.0 * 2 * W * H * w.inner, 2.0 * 9 * W * H * w.inner);
         }
         const ActView dst = out ? *out : x;
-        if (fuse_tail_) {
+        if (fuse_tail_ && static_cast<long long>(W) * H >= fuse_min_px_) {
             // dc.3 -> ffn.0 -> ffn.2 as one CTA-pair kernel: o and t1' stay on the SM (dcb_tail.cuh)
             auto op = std::make_shared<DcbTailOp>();
             op->t2 = t2; op->x = x; op->y = dst;
@@ -582,8 +587,11 @@ protected:
             for (size_t i = 0; i < n; ++i) {
                 float ms = 0.f;
                 CK(cudaEventElapsedTime(&ms, prof_events_[2 * i], prof_events_[2 * i + 1]));
-                ProfileAcc& a = prof_[s.kinds[i]];
-                a.ms += ms; a.bytes += s.alg_bytes[i]; a.flops += s.flops[i]; a.launches += 1;
+                for (int pass = 0; pass < 2; ++pass) {   // a pw_gemm instantiation also counts towards the family total
+                    if (pass == 1 && s.kinds[i] < OP_GEMM_64) break;
+                    ProfileAcc& a = prof_[pass == 0 ? s.kinds[i] : OP_GEMM];
+                    a.ms += ms; a.bytes += s.alg_bytes[i]; a.flops += s.flops[i]; a.launches += 1;
+                }
                 if (f) fprintf(f, "%d,%zu,%.3f,%.0f,%.0f\n", s.kinds[i], i, ms * 1e3, s.alg_bytes[i], s.flops[i]);
             }
             if (f) fclose(f);
@@ -730,6 +738,10 @@ protected:
     bool finalized_ = false;
     bool use_graphs_ = true;
     bool fuse_tail_ = true;                    // DCVC_B200_FUSE_TAIL=0: per-op kernels only (A/B runs, kernel emulation)
+    // The fused tail runs 256-pixel tiles on CTA pairs: below ~64 tiles it leaves SMs idle that the per-op kernels (128 x
+    // 64..256 tiles on single CTAs) still fill — measured on B200: P16 of 1080p (8160 px, 32 tiles) 66.6 us fused vs 48.1 us
+    // per-op for a C = 512 block; P8 of 1080p (32640 px) and everything at 4K are above the threshold.
+    long long fuse_min_px_ = 16384;
     void* dbg_base_ = nullptr;      // activation arena (DCVC_B200_OPSUM)
     size_t dbg_bytes_ = 0;
     unsigned long long* opsum_dev_ = nullptr;

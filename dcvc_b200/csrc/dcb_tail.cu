@@ -111,7 +111,9 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     griddep_launch_dependents();
-    griddep_wait();
+    // programmatic dependent launch: everything above overlapped the previous kernel's tail.  The weights do not depend on it
+    // either, so the producer fills the ring first and only then waits (before it touches t2); everybody else waits here
+    if (warp != 0) griddep_wait();
 
     if (warp == 0) {
         if (!(p.dbg & 8) && elect_one_sync()) {
@@ -129,7 +131,8 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
             int i = 0;
             int issued = 0;
             int T = pair;
-            if (T < p.tiles) load_tile(T, 0);
+            bool dep_done = false;   // griddepcontrol.wait + the first tile's t2: after the ring has been filled with weights
+            const int pre_target = p.stages;
             // the next tile's t2 goes out once the ring is full of phase-4 weights: by then phase 3 has been issued
             // completely, so the wait for p_empty is short and phase 4 starts on a full ring
             const int total4 = p.nch[3] * p.nst[3];
@@ -154,6 +157,11 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                                                 (st * p.kbs[ph] + j) * BLOCK_K, nrow);
                             dt_mark(p, 0, 1024 + issued);
                             ++issued;
+                            if (!dep_done && issued == pre_target) {
+                                griddep_wait();
+                                load_tile(T, 0);
+                                dep_done = true;
+                            }
                             if (++s == p.stages) { s = 0; bph ^= 1; }
                             if (ph == 3 && !next_loaded && ++cnt == trigger) {
                                 if (Tn < p.tiles) load_tile(Tn, i + 1);
@@ -162,8 +170,15 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                         }
                     }
                 }
+                if (!dep_done) {   // (a tile with fewer stages than the ring: not a shape the planner accepts, but be safe)
+                    griddep_wait();
+                    load_tile(T, 0);
+                    dep_done = true;
+                }
                 if (!next_loaded && Tn < p.tiles) load_tile(Tn, i + 1);
             }
+        } else if (p.dbg & 8) {
+            griddep_wait();
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -186,6 +201,8 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                     for (int n = 0; n < p.nch[ph]; ++n, ++t) {
                         const int g = static_cast<int>(t & 1);
                         if (!no_acc) {
+                            // (waiting for the NEXT chunk's buffer one stage early was measured: 92.8 -> 103.9 us, the early
+                            // wait blocks the last stage behind an epilogue that has not handed back yet)
                             dt_wait(&acc_empty[g], ((t >> 1) & 1) ^ 1);  // both CTAs drained this buffer
                             tcgen05_fence_after();
                         }

@@ -131,7 +131,8 @@ class DMCIProxy:
     def profile_get(self):
         """{family: dict(ms, launches, alg_bytes, flops)} accumulated since profile_enable(True)"""
         out = {}
-        for kind, name in enumerate(("pw_gemm", "dw3x3", "elementwise", "dcb_tail")):
+        for kind, name in enumerate(("pw_gemm", "dw3x3", "elementwise", "dcb_tail", "pw_gemm<64>", "pw_gemm<128>", "pw_gemm<192>",
+                                     "pw_gemm<256>", "pw_gemm<256,fold>")):
             ms, n, b, f = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
             self._hd.lib.dcvc_profile_get(self._hd.h, kind, C.byref(ms), C.byref(n), C.byref(b), C.byref(f))
             out[name] = {"ms": ms.value, "launches": n.value, "alg_bytes": b.value, "flops": f.value}

@@ -228,7 +228,8 @@ int dcvc_decompress_chunk(dcvc_codec* h, const uint8_t* bit_stream, int32_t len,
 int64_t dcvc_kernel_launches(dcvc_codec* h);
 int dcvc_last_gpu_ms(dcvc_codec* h, float* ms);
 /* per-kernel-family profiling (bench.py roofline): when enabled, segments run un-graphed with a
- * CUDA-event pair around every launch; kind 0 = pw_gemm, 1 = dw3x3, 2 = elementwise/entropy, 3 = dcb_tail (fused).
+ * CUDA-event pair around every launch; kind 0 = pw_gemm, 1 = dw3x3, 2 = elementwise/entropy, 3 = dcb_tail (fused),
+ * 4..8 = the pw_gemm instantiations <64>, <128>, <192>, <256>, <256, fold> on their own (0 is their total).
  * alg_bytes = algorithmic bytes (activation operands in + residuals in + out, fp16). */
 int dcvc_profile_enable(dcvc_codec* h, int32_t on);
 int dcvc_profile_get(dcvc_codec* h, int32_t kind, double* ms, int64_t* launches, double* alg_bytes,

@@ -33,8 +33,12 @@ def build_ref(force: bool = False) -> str | None:
     prebuilt module exists."""
     out = ref_module_path()
     shim = shim_module_path()
-    if os.path.exists(out) and os.path.exists(shim) and not force:
+    shim_src = os.path.join(HERE, "ref_shim.cpp")
+    fresh = os.path.exists(out) and os.path.exists(shim) and os.path.getmtime(shim) >= os.path.getmtime(shim_src)
+    if fresh and not force:
         return out
+    if os.path.exists(out) and os.path.exists(shim) and not os.path.isdir(REF_SRC):
+        return out      # GPU box: no reference tree to rebuild from, the prebuilt files are what there is
     if not os.path.isdir(REF_SRC):
         return None
     import pybind11

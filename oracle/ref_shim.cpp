@@ -10,7 +10,7 @@ namespace py = pybind11;
 
 PYBIND11_MODULE(dcvc_ref_rans, m)
 {
-    py::class_<RansEncoder>(m, "RansEncoder")
+    py::class_<RansEncoder>(m, "RansEncoder", py::module_local())   // module-local: MLCodec_extensions_cpp registers the same C++ types
         .def(py::init<>())
         .def("encode_y", py::overload_cast<const py::array_t<int16_t>&>(&RansEncoder::encode_y))
         .def("encode_z", py::overload_cast<const py::array_t<int8_t>&, const int, const int>(
@@ -23,7 +23,7 @@ PYBIND11_MODULE(dcvc_ref_rans, m)
                  &RansEncoder::set_cdf))
         .def("set_entropy_coder_parallel", &RansEncoder::set_entropy_coder_parallel);
 
-    py::class_<RansDecoder>(m, "RansDecoder")
+    py::class_<RansDecoder>(m, "RansDecoder", py::module_local())
         .def(py::init<>())
         .def("set_stream", py::overload_cast<const py::array_t<uint8_t>&>(&RansDecoder::set_stream))
         .def("decode_y", py::overload_cast<const py::array_t<uint8_t>&>(&RansDecoder::decode_y))

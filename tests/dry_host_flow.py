@@ -76,11 +76,11 @@ class Handle:
 
     def profiled(self, fn):
         """algorithmic bytes / FLOPs the codec books for the launches of fn() (Segment annotations: bench.py's roofline
-        numerators); kinds 0 = pw_gemm, 1 = dw3x3, 2 = elementwise / entropy"""
+        numerators); kinds 0 = pw_gemm (all instantiations), 1 = dw3x3, 2 = elementwise / entropy, 3 = fused dcb_tail"""
         self.lib.dcvc_profile_enable(self.h, 1)
         out = fn()
         acc = {"bytes": 0.0, "flops": 0.0, "launches": 0}
-        for kind in range(3):
+        for kind in range(4):
             ms, n, b, f = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
             self.lib.dcvc_profile_get(self.h, kind, C.byref(ms), C.byref(n), C.byref(b), C.byref(f))
             acc["bytes"] += b.value; acc["flops"] += f.value; acc["launches"] += n.value

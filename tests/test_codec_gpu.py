@@ -67,6 +67,18 @@ def test_all_64_qp_sweep_bit_exact(model):
     assert len(sizes) > 8, "the QP must change the rate"
 
 
+def test_all_64_qp_sweep_1080p(model):
+    """configs[1] as written: DCVC-UF-Intra 1080p single-frame encode / decode on one B200, all 64 q_index values: the decoder
+    reproduces the encoder's reconstruction bit for bit at every rate point; rate grows with q_index overall."""
+    h, w = 1080, 1920
+    sizes = []
+    for qp in range(64):
+        _, enc, a, b = _roundtrip(model, h, w, qp, seed=4321)
+        assert torch.equal(a, b), f"qp {qp}: decoder drifted from the encoder's reconstruction"
+        sizes.append(len(enc["bit_stream"]))
+    assert len(set(sizes)) > 32 and sizes[-1] > sizes[0], "the QP must change the rate"
+
+
 def test_stream_bit_identical_to_reference_coder(model):
     """bit-identical rANS streams given identical quantised latents"""
     from oracle.build_ref import import_ref_shim
@@ -120,6 +132,17 @@ def test_against_cpu_oracle(model, h, w, qp):
     p_gpu = psnr(x_hat_enc.float().cpu()[:, :, :h, :w], xs)
     p_ref = psnr(ref["x_hat"][:, :, :h, :w], xs)
     assert abs(p_gpu - p_ref) <= 0.05, (p_gpu, p_ref)
+    # the reconstructions against EACH OTHER (not only both against the source): where the streams are byte-identical the
+    # quantised latents are identical too and the difference is the synthesis transform's alone — fp16 storage at every op
+    # boundary on both sides, fp32 accumulation in different orders
+    xg, xo = x_hat_enc.float().cpu()[:, :, :h, :w], ref["x_hat"][:, :, :h, :w]
+    cross, dmax = psnr(xg, xo), (xg - xo).abs().max().item()
+    same = enc["bit_stream"] == ref["bit_stream"]
+    print(f"[parity vs oracle] intra {h}x{w} q{qp}: bytes {n_gpu} vs {n_ref} (identical: {same}), PSNR {p_gpu:.4f} vs {p_ref:.4f} dB, "
+          f"PSNR(x_hat_gpu, x_hat_oracle) {cross:.2f} dB, max|dx| {dmax:.4f}")
+    assert cross >= (50.0 if same else 35.0), (cross, same)
+    if same:
+        assert dmax <= 2e-2, dmax
     # symbols: the overwhelming majority of quantised latents agree
     totals = model.proxy.debug_fetch("totals", np.int32)
     for k in range(4):

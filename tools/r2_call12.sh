@@ -1,0 +1,30 @@
+#!/bin/bash
+cd ${GRAFT_REPO_ROOT:-.}
+mkdir -p gpurun_out
+O=gpurun_out
+echo "== dcb_tail tests"
+timeout 600 python -m pytest tests/test_dcb_tail_gpu.py -q -x 2>&1 | tail -4
+echo "== micro"
+timeout 120 python tools/dcb_tail_micro.py 136 240 384 384 384 2>&1 | tail -2
+timeout 120 python tools/dcb_tail_micro.py 270 480 384 384 384 2>&1 | tail -2
+timeout 120 python tools/dcb_tail_micro.py 90 160 384 384 384 2>&1 | tail -2
+timeout 120 python tools/dcb_tail_micro.py 135 240 512 512 512 2>&1 | tail -2
+echo "== trace"
+timeout 200 python tools/dcb_tail_trace.py 136 240 384 384 384 2>&1 | tail -48 | head -26
+echo "== bench fused on / off / fused everywhere"
+for V in "on:1" "off:0" "all:2"; do
+    IFS=: read NAME FT <<< "$V"
+    DCVC_B200_FUSE_TAIL=$FT timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-reference-cuda --no-seq8 --hts-size none > $O/r2c12_bench_$NAME.json 2> $O/r2c12_bench_$NAME.err
+    python - <<PY
+import json
+try:
+    d = json.loads(open("$O/r2c12_bench_$NAME.json").read().strip().splitlines()[-1])
+    h = d["hts"]; r = d["roofline"]
+    print("$NAME: intra dec %.1f e2e %.1f gpu-only %.3f ms enc %.1f launches %d | roofline %s frac %.3f share %.3f whole %.3f | hts dec %.1f gpu-only %.3f enc %.1f | ld %s %s | htl %s %s" %
+          (d["value"], d["e2e"]["value"], d["gpu_only_ms_per_decode"], d["encode_fps"], d["gpu_launches"], r["kernel"], r["frac"], r["share_of_gpu_time"], r["whole_decode_frac"],
+           h["decode_fps"], h["gpu_only_ms_per_chunk_decode"], h["encode_fps"], d["ld"].get("decode_fps"), d["ld"].get("encode_fps"), d["htl"].get("decode_fps"), d["htl"].get("encode_fps")))
+    print("   families:", r.get("families_ms_per_step_isolated"), r.get("families_alg_gbs_in_step"))
+except Exception as e:
+    print("$NAME: no result (%s)" % e); print(open("$O/r2c12_bench_$NAME.err").read()[-1500:])
+PY
+done
