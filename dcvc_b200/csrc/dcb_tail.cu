@@ -32,11 +32,13 @@ namespace dcvc {
 
 static constexpr int DT_CHUNK_N = 128;                              // GEMM columns per accumulator chunk
 static constexpr int DT_KB_BYTES = (DT_CHUNK_N / 2) * BLOCK_K * 2;  // 8 KB: this CTA's half of one weight k-block
-static constexpr int DT_MAX_STAGES = 12;                            // (control block: 61 barriers in 496 bytes)
+static constexpr int DT_MAX_STAGES = 8;                             // (control block: 57 barriers in 496 bytes)
 static constexpr int DT_MAX_KB = 8;                                 // K <= 512
 static constexpr int DT_ACC_COL0 = 256;
 static constexpr int DT_TMEM_COLS = 512;
 static constexpr int DT_STAGING = EPI_WARPS * EPI_SLAB_BYTES;       // one 2 KB slab per epilogue warp
+static constexpr int DT_THREADS = NUM_THREADS + 32;                 // producer + TWO MMA issuers + 16 epilogue warps
+static constexpr int DT_EPI_WARP0 = 3;
 
 // Cross-CTA signals of the pair.  Default: arrive with CTA-scope release + plain try_wait, as CUTLASS's 2-SM pipelines do;
 // DCVC_B200_GEMM_DBG bit 16 (A/B measurements) switches back to cluster-scope release / acquire.
@@ -53,7 +55,7 @@ __device__ __forceinline__ void dt_mark(const DcbTailParams& p, int cta, int slo
     }
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)   // 18 warps are allocated as 20: 96 registers per thread is the ceiling
+__global__ void __launch_bounds__(DT_THREADS, 1)   // 19 warps are allocated as 20: 96 registers per thread is the ceiling
 dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -71,8 +73,9 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
     uint64_t* p_empty = acc_empty + 2;                      // [1]  every CTA: phase-3 MMAs done, P may be reloaded
     uint64_t* o_ready = p_empty + 1;                        // [8]  leader: k-block of O holds the tile's o (both CTAs)
     uint64_t* y_ready = o_ready + DT_MAX_KB;                // [8]  leader: k-block of O holds the tile's y; its o is not read any more
+    uint64_t* xs = y_ready + DT_MAX_KB;                     // [4]  leader: issuer X's MMAs of a phase are complete ([2 X + phase parity])
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ctrl + 496);
-    static_assert((4 * DT_MAX_KB + 2 * DT_MAX_STAGES + 5) * 8 <= 496, "control block overflow");
+    static_assert((4 * DT_MAX_KB + 2 * DT_MAX_STAGES + 9) * 8 <= 496, "control block overflow");
 
     const int rank = static_cast<int>(cluster_ctarank());
     const int pair = static_cast<int>(blockIdx.x >> 1);
@@ -98,7 +101,8 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
             mbar_init(&acc_full[g], 1);
             mbar_init(&acc_empty[g], 16);             // 8 warps x 2 CTAs
         }
-        mbar_init(p_empty, 1);
+        mbar_init(p_empty, 2);                        // both MMA issuers' phase-3 MMAs
+        for (int i = 0; i < 4; ++i) mbar_init(&xs[i], 1);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -181,33 +185,51 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
             griddep_wait();
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 2) {
         if (rank == 0 && elect_one_sync()) {
-            // ------------------------------------------------------------ MMA issuer (leader CTA only)
+            // ------------------------------------------------------------ MMA issuers (leader CTA only)
+            // TWO issuing threads: X = 0 (warp 1) takes the even chunks / accumulator buffer 0, X = 1 (warp 2) the odd ones.
+            // One thread needs ~118 cycles per tcgen05.mma (measured: 1.44 us per 24-MMA chunk, tensor pipe 39 % active in
+            // ncu) while a cta_group::2 N = 128 MMA occupies the pipe for 64: a single issuer is the bottleneck.
+            // Ordering across the two: a tcgen05.commit only covers the MMAs of its own thread, so before a thread issues
+            // the first MMA of a phase it waits until the OTHER thread's MMAs of the previous phase are complete (xs
+            // barriers, two per thread, alternating by phase).  With that, "accumulator of a phase-(p+1) chunk complete"
+            // still implies "every MMA of phase p is done", which the in-place reuse of P and O relies on.
+            const int X = warp - 1;
             constexpr uint32_t idesc = make_idesc_f16_f32(BLOCK_M * 2, DT_CHUNK_N);
             const bool do_mma = !(p.dbg & 1);
             const bool no_acc = (p.dbg & 4) != 0;   // timing experiments: no accumulator hand-off (the epilogue warps idle)
             const bool no_tma = (p.dbg & 8) != 0;   // timing experiments: no loads (operands are whatever smem holds)
+            const bool solo = (p.dbg & 32) != 0;    // timing experiments: one issuer does everything (the second one idles)
             uint32_t t = 0;
             int s = 0;
             uint32_t bph = 0;
             int i = 0;
-            for (int T = pair; T < p.tiles; T += p.num_pairs, ++i) {
+            uint32_t c = 0;                         // global phase counter
+            for (int T = (solo && X == 1) ? p.tiles : pair; T < p.tiles; T += p.num_pairs, ++i) {
                 const uint32_t tph = static_cast<uint32_t>(i & 1);
-                for (int ph = 0; ph < 4; ++ph) {
-                    if (p.nch[ph] == 0) continue;
+                for (int ph = 0; ph < 4; ++ph, ++c) {
+                    if (c > 0 && !solo) {
+                        // the other issuer's MMAs of the previous phase (phase counter c - 1)
+                        mbar_wait(&xs[2 * (1 - X) + ((c - 1) & 1)], ((c - 1) >> 1) & 1);
+                        tcgen05_fence_after();
+                    }
                     const bool a_tmem = (ph & 1) != 0;
                     const int kbs = p.kbs[ph];
                     for (int n = 0; n < p.nch[ph]; ++n, ++t) {
                         const int g = static_cast<int>(t & 1);
+                        if (!solo && g != X) {   // the other issuer's chunk: only keep the ring position in step
+                            for (int st = 0; st < p.nst[ph]; ++st)
+                                if (++s == p.stages) { s = 0; bph ^= 1; }
+                            continue;
+                        }
                         if (!no_acc) {
-                            // (waiting for the NEXT chunk's buffer one stage early was measured: 92.8 -> 103.9 us, the early
-                            // wait blocks the last stage behind an epilogue that has not handed back yet)
                             dt_wait(&acc_empty[g], ((t >> 1) & 1) ^ 1);  // both CTAs drained this buffer
                             tcgen05_fence_after();
                         }
                         const uint32_t acc = tmem_base + DT_ACC_COL0 + g * DT_CHUNK_N;
                         dt_mark(p, 0, 512 + 4 * static_cast<int>(t));
+                        const bool first = solo ? (n == 0) : (n < 2);   // this issuer's first chunk of the phase
                         int kb = 0;
                         for (int st = 0; st < p.nst[ph]; ++st) {
                             if (!no_tma) {
@@ -217,8 +239,8 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                             if (st == 0) dt_mark(p, 0, 512 + 4 * static_cast<int>(t) + 1);
                             const uint32_t b_addr = smem_u32(ring + s * p.stage_bytes);
                             for (int j = 0; j < kbs; ++j, ++kb) {
-                                if (n == 0 && ph == 0 && !no_tma) { mbar_wait(&p_full[kb], tph); tcgen05_fence_after(); }
-                                if (n == 0 && !no_acc) {
+                                if (first && ph == 0 && !no_tma) { mbar_wait(&p_full[kb], tph); tcgen05_fence_after(); }
+                                if (first && !no_acc) {
                                     // the first chunk of a phase takes its A k-blocks as the epilogue of the previous phase
                                     // finishes them (later chunks find everything there)
                                     if (ph == 1) { dt_wait(&o_ready[kb], tph); tcgen05_fence_after(); }
@@ -246,8 +268,11 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                         if (!no_acc) umma_commit_2cta_mc(&acc_full[g], 3);
                         dt_mark(p, 0, 512 + 4 * static_cast<int>(t) + 2);
                     }
+                    // this issuer's MMAs of phase c (possibly none): complete -> xs[2 X + (c & 1)] (leader CTA only)
+                    if (!solo) umma_commit_2cta_mc(&xs[2 * X + (c & 1)], 1);
                     if (ph == 2) {
-                        umma_commit_2cta_mc(p_empty, 3);  // P is free for the next tile's t2
+                        umma_commit_2cta_mc(p_empty, 3);  // (one of two arrivals) P is free for the next tile's t2
+                        if (solo) umma_commit_2cta_mc(p_empty, 3);
                         // Before the NEXT tile's phase-1 epilogue may overwrite O, the phase-3 epilogue must be through with it
                         // (it reads o and writes y in place).  With a phase 4 that is implied (its first chunk waits for every
                         // y k-block); without one the wait happens here — else next-tile writes race the readers, and barrier
@@ -269,9 +294,9 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
         // pieces; the accumulator goes back to the MMA warp right after the second tcgen05.ld.  Whatever a piece needs from
         // memory (bias, x) is requested before the wait it can hide behind.
         const int q = warp & 3;
-        const int b = ((warp - 2) >> 2) & 1;
-        const int h = (warp - 2) >> 3;
-        uint8_t* slab = staging + (warp - 2) * EPI_SLAB_BYTES;
+        const int b = ((warp - DT_EPI_WARP0) >> 2) & 1;
+        const int h = (warp - DT_EPI_WARP0) >> 3;
+        uint8_t* slab = staging + (warp - DT_EPI_WARP0) * EPI_SLAB_BYTES;
         const uint32_t slab_u = smem_u32(slab);
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
         const uint32_t acc = tmem_base + lane_off + DT_ACC_COL0 + b * DT_CHUNK_N + h * 64;   // this warp's 64 accumulator columns
@@ -286,7 +311,7 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
         const uint16_t ONE = 0x3C00;
         const uint4 zero4 = make_uint4(0, 0, 0, 0);
         const bool skip_body = (p.dbg & 2) != 0;
-        const bool tr = warp == 2 && lane == 0;
+        const bool tr = b == 0 && h == 0 && q == 0 && lane == 0;
 
         auto hand_back = [&]() {
             tcgen05_fence_before();
@@ -531,7 +556,7 @@ static int dt_max_pairs(int num_sms)
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * 64, 1, 1);
-    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.blockDim = dim3(DT_THREADS, 1, 1);
     cfg.dynamicSmemBytes = SMEM_TOTAL;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -648,7 +673,7 @@ int dcb_tail_launch(const DcbTailOp& op, cudaStream_t stream)
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = op.grid;
-    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.blockDim = dim3(DT_THREADS, 1, 1);
     cfg.dynamicSmemBytes = SMEM_TOTAL;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
