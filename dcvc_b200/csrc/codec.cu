@@ -12,6 +12,8 @@
 //     captures 64 graphs per segment, dmc_common.cpp:95-106);
 //   * host rANS stays on the CPU (north_star); symbol counts/streams cross PCIe in two small
 //     copies per step; the synthesis transform overlaps the CPU encode.
+#include <chrono>
+#include <cstdio>
 #include "codec_common.cuh"
 
 namespace dcvc {
@@ -442,11 +444,20 @@ void IntraCodec::decompress(const uint8_t* bs, int len, int qp, int height, int 
     const int zh = (height + 63) / 64, zw = (width + 63) / 64;  // dmci_proxy.cpp:432-433
     if (zh != H64_ || zw != W64_) throw std::runtime_error("z geometry mismatch");
     const int nz = kChZ * zh * zw;
+    // DCVC_B200_HOST_TRACE=1: where the host spends a decode (stderr, microseconds) — tools/profile_decode.py
+    static const bool host_trace = getenv("DCVC_B200_HOST_TRACE") != nullptr;
+    using clk = std::chrono::steady_clock;
+    auto us_since = [](clk::time_point t0) { return std::chrono::duration<double, std::micro>(clk::now() - t0).count(); };
+    double tr_wait[4] = {}, tr_copy[4] = {}, tr_rans[4] = {};
+    int tr_n[4] = {};
+    clk::time_point t_all = clk::now(), t0 = t_all;
     rans_.set_stream(bs, len, ec_parallel);
     rans_.decode_z(h_z_, nz, qp * kChZ, kChZ);
+    const double tr_z = us_since(t0);
     tev_n_ = 0;
     CK(cudaMemcpyAsync(z_i8_, h_z_, nz, cudaMemcpyHostToDevice, stream));
     for (int k = 0; k < 4; ++k) {
+        t0 = clk::now();
         tick(stream);
         run(k == 0 ? dec0_ : dec_step_[k], stream);
         tock(stream);
@@ -454,14 +465,26 @@ void IntraCodec::decompress(const uint8_t* bs, int len, int qp, int height, int 
         // the count — one wait — was measured on B200: +1.5 % e2e at 1080p for 4 x 0.5 MB of extra D2H traffic; not kept.)
         CK(cudaMemcpyAsync(h_totals_ + k, totals_ + k, 4, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
+        tr_wait[k] = us_since(t0);
         const int n = h_totals_[k];
         if (n < 0 || static_cast<size_t>(n) > quarter_) throw std::runtime_error("corrupt index count");
+        tr_n[k] = n;
         if (n) {
+            t0 = clk::now();
             CK(cudaMemcpyAsync(h_idx_, idx_c_, n, cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
+            tr_copy[k] = us_since(t0);
+            t0 = clk::now();
             rans_.decode_y(h_decoded_, h_idx_, n);
+            tr_rans[k] = us_since(t0);
             CK(cudaMemcpyAsync(decoded_, h_decoded_, n, cudaMemcpyHostToDevice, stream));
         }
+    }
+    if (host_trace) {
+        fprintf(stderr, "[host trace] intra decode: ec_parallel %d, z %.0f us;", ec_parallel, tr_z);
+        for (int k = 0; k < 4; ++k)
+            fprintf(stderr, " step %d: launch+gpu+count %.0f, idx d2h %.0f, rANS %.0f (n=%d);", k, tr_wait[k], tr_copy[k], tr_rans[k], tr_n[k]);
+        fprintf(stderr, " to last launch %.0f us\n", us_since(t_all));
     }
     tick(stream);
     run(dec4_, stream);

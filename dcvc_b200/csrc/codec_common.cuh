@@ -420,7 +420,7 @@ protected:
         use_graphs_ = !(g && g[0] == '0');
         const char* ft = getenv("DCVC_B200_FUSE_TAIL");
         fuse_tail_ = !(ft && ft[0] == '0');
-        if (ft && atoi(ft) > 1) fuse_min_px_ = atoi(ft);   // DCVC_B200_FUSE_TAIL=<pixels>: another threshold (measurements)
+        if (ft && atoi(ft) > 1) { fuse_min_px_ = atoi(ft); fuse_any_c_ = true; }   // DCVC_B200_FUSE_TAIL=<pixels>: another threshold, any width (measurements, tests)
         finalized_ = true;
     }
 
@@ -527,7 +527,10 @@ protected:
             s.annotate(OP_DW, 2.0 * 2 * W * H * w.inner, 2.0 * 9 * W * H * w.inner);
         }
         const ActView dst = out ? *out : x;
-        if (fuse_tail_ && static_cast<long long>(W) * H >= fuse_min_px_) {
+        // Where the fused kernel is used: measured on B200 (profiles/r2_dcb_tail_timeline.md).  It needs >= 64 pair tiles to fill
+        // the chip (fuse_min_px_), and with C = 512 the resident activation tile (128 KB) leaves each issuer's weight ring half
+        // a chunk: L2-latency-bound, 153-164 us against 131 us per-op at 135x240 — those blocks keep the per-op kernels.
+        if (fuse_tail_ && static_cast<long long>(W) * H >= fuse_min_px_ && (w.c <= 384 || fuse_any_c_)) {
             // dc.3 -> ffn.0 -> ffn.2 as one CTA-pair kernel: o and t1' stay on the SM (dcb_tail.cuh)
             auto op = std::make_shared<DcbTailOp>();
             op->t2 = t2; op->x = x; op->y = dst;
@@ -742,6 +745,7 @@ protected:
     // 64..256 tiles on single CTAs) still fill — measured on B200: P16 of 1080p (8160 px, 32 tiles) 66.6 us fused vs 48.1 us
     // per-op for a C = 512 block; P8 of 1080p (32640 px) and everything at 4K are above the threshold.
     long long fuse_min_px_ = 16384;
+    bool fuse_any_c_ = false;
     void* dbg_base_ = nullptr;      // activation arena (DCVC_B200_OPSUM)
     size_t dbg_bytes_ = 0;
     unsigned long long* opsum_dev_ = nullptr;

@@ -130,13 +130,21 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                     tma_load_2d_2sm(P + kb * A_STAGE_BYTES, &p.tm_a, mapa_u32(smem_u32(&p_full[kb]), 0), kb * BLOCK_K, row0);
                 }
             };
-            int s = 0;
-            uint32_t bph = 0;
+            // Two rings of stages / 2 slots: the chunks alternate between them like they alternate between the two MMA issuers,
+            // so every slot has ONE consumer that sees each of its phases (a consumer that skipped a use of a slot could not tell
+            // the phase it waits for from the one two uses back: mbarrier waits know one parity bit)
+            const int half = p.stages / 2;
+            int sr[2] = { 0, 0 };
+            uint32_t bphr[2] = { 0, 0 };
+            uint32_t tc = 0;   // chunk counter
             int i = 0;
             int issued = 0;
             int T = pair;
-            bool dep_done = false;   // griddepcontrol.wait + the first tile's t2: after the ring has been filled with weights
-            const int pre_target = p.stages;
+            bool dep_done = false;   // griddepcontrol.wait + the first tile's t2: after the weights that need neither
+            // weights that may go out before griddepcontrol.wait: the first chunk of each ring when a ring holds a whole chunk
+            // (no slot is reused, so nothing waits for an MMA that itself waits for t2), else one ring's worth.  (Measured: 1, 2
+            // or 4 stages ahead make no difference behind a warm L2, 92.1-92.3 us; the depth matters for a cold first launch.)
+            const int pre_target = half >= p.nst[0] ? p.nst[0] * (p.nch[0] < 2 ? p.nch[0] : 2) : half;
             // the next tile's t2 goes out once the ring is full of phase-4 weights: by then phase 3 has been issued
             // completely, so the wait for p_empty is short and phase 4 starts on a full ring
             const int total4 = p.nch[3] * p.nst[3];
@@ -148,10 +156,12 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                     int cnt = 0;
                     const int rep_off = p.wrep > 1 ? (pair % p.wrep) * p.nch[ph] * DT_CHUNK_N : 0;   // timing experiments only
                     const uint32_t tx = static_cast<uint32_t>(2 * p.kbs[ph] * DT_KB_BYTES);
-                    for (int n = 0; n < p.nch[ph]; ++n) {
+                    for (int n = 0; n < p.nch[ph]; ++n, ++tc) {
                         const int nrow = rep_off + n * DT_CHUNK_N + rank * (DT_CHUNK_N / 2);
+                        const int r = static_cast<int>(tc & 1);
                         for (int st = 0; st < p.nst[ph]; ++st) {
-                            mbar_wait(&b_empty[s], bph ^ 1);
+                            const int s = r * half + sr[r];
+                            mbar_wait(&b_empty[s], bphr[r] ^ 1);
                             if (rank == 0) mbar_expect_tx(&b_full[s], tx);
                             // a stage = kbs k-blocks of this CTA's 64 weight rows, one 2-D request each (rank-2 boxes stream
                             // through the TMA unit; a rank-3 box {64, 64, kbs} was measured ~25 % slower), ONE barrier round trip
@@ -166,7 +176,7 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                                 load_tile(T, 0);
                                 dep_done = true;
                             }
-                            if (++s == p.stages) { s = 0; bph ^= 1; }
+                            if (++sr[r] == half) { sr[r] = 0; bphr[r] ^= 1; }
                             if (ph == 3 && !next_loaded && ++cnt == trigger) {
                                 if (Tn < p.tiles) load_tile(Tn, i + 1);
                                 next_loaded = true;
@@ -189,8 +199,10 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
         if (rank == 0 && elect_one_sync()) {
             // ------------------------------------------------------------ MMA issuers (leader CTA only)
             // TWO issuing threads: X = 0 (warp 1) takes the even chunks / accumulator buffer 0, X = 1 (warp 2) the odd ones.
-            // One thread needs ~118 cycles per tcgen05.mma (measured: 1.44 us per 24-MMA chunk, tensor pipe 39 % active in
-            // ncu) while a cta_group::2 N = 128 MMA occupies the pipe for 64: a single issuer is the bottleneck.
+            // One thread was measured at 1.44 us per 24-MMA chunk + 0.28 us between chunks (tensor pipe 39 % active in ncu)
+            // while a cta_group::2 N = 128 MMA occupies the pipe for 64 cycles; with two threads the next chunk's MMAs are
+            // queued while the first thread waits for its stage / accumulator barriers: 89.7 -> 86.5 us on the P8 tail
+            // (same box, DCVC_B200_GEMM_DBG bit 32 = one issuer).
             // Ordering across the two: a tcgen05.commit only covers the MMAs of its own thread, so before a thread issues
             // the first MMA of a phase it waits until the OTHER thread's MMAs of the previous phase are complete (xs
             // barriers, two per thread, alternating by phase).  With that, "accumulator of a phase-(p+1) chunk complete"
@@ -202,8 +214,9 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
             const bool no_tma = (p.dbg & 8) != 0;   // timing experiments: no loads (operands are whatever smem holds)
             const bool solo = (p.dbg & 32) != 0;    // timing experiments: one issuer does everything (the second one idles)
             uint32_t t = 0;
-            int s = 0;
-            uint32_t bph = 0;
+            const int half = p.stages / 2;          // two weight rings, one per chunk parity (see the producer)
+            int sr[2] = { 0, 0 };
+            uint32_t bphr[2] = { 0, 0 };
             int i = 0;
             uint32_t c = 0;                         // global phase counter
             for (int T = (solo && X == 1) ? p.tiles : pair; T < p.tiles; T += p.num_pairs, ++i) {
@@ -218,11 +231,7 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                     const int kbs = p.kbs[ph];
                     for (int n = 0; n < p.nch[ph]; ++n, ++t) {
                         const int g = static_cast<int>(t & 1);
-                        if (!solo && g != X) {   // the other issuer's chunk: only keep the ring position in step
-                            for (int st = 0; st < p.nst[ph]; ++st)
-                                if (++s == p.stages) { s = 0; bph ^= 1; }
-                            continue;
-                        }
+                        if (!solo && g != X) continue;   // the other issuer's chunk (and the other ring)
                         if (!no_acc) {
                             dt_wait(&acc_empty[g], ((t >> 1) & 1) ^ 1);  // both CTAs drained this buffer
                             tcgen05_fence_after();
@@ -232,8 +241,9 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                         const bool first = solo ? (n == 0) : (n < 2);   // this issuer's first chunk of the phase
                         int kb = 0;
                         for (int st = 0; st < p.nst[ph]; ++st) {
+                            const int s = g * half + sr[g];
                             if (!no_tma) {
-                                mbar_wait(&b_full[s], bph);
+                                mbar_wait(&b_full[s], bphr[g]);
                                 tcgen05_fence_after();
                             }
                             if (st == 0) dt_mark(p, 0, 512 + 4 * static_cast<int>(t) + 1);
@@ -263,7 +273,7 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                                 }
                             }
                             if (!no_tma) umma_commit_2cta_mc(&b_empty[s], 3);
-                            if (++s == p.stages) { s = 0; bph ^= 1; }
+                            if (++sr[g] == half) { sr[g] = 0; bphr[g] ^= 1; }
                         }
                         if (!no_acc) umma_commit_2cta_mc(&acc_full[g], 3);
                         dt_mark(p, 0, 512 + 4 * static_cast<int>(t) + 2);
@@ -637,18 +647,24 @@ int dcb_tail_plan(DcbTailOp& op)
     if (const char* e = getenv("DCVC_B200_DT_KBS")) force_kbs = atoi(e);
     // weight stages: kbs k-blocks of a chunk per ring slot and barrier round trip (measured with one k-block per slot:
     // ~0.2 us per slot whatever the ring depth — the per-slot protocol, not the bytes, set the pace)
-    int max_kbs = 1;
-    for (int ph = 0; ph < 4; ++ph) {
-        int kbs = 1;
-        for (int c = 4; c >= 1; --c)
-            if (p.nkb[ph] % c == 0 && (!force_kbs || c <= force_kbs)) { kbs = c; break; }
-        p.kbs[ph] = kbs;
-        p.nst[ph] = p.nkb[ph] / kbs;
-        if (p.nch[ph] > 0 && kbs > max_kbs) max_kbs = kbs;
+    // ... as large as leaves four slots: the chunks alternate between two rings (one per MMA issuer) of stages / 2 slots
+    int stages = 0;
+    for (int cap = force_kbs ? force_kbs : 4; cap >= 1; --cap) {
+        int max_kbs = 1;
+        for (int ph = 0; ph < 4; ++ph) {
+            int kbs = 1;
+            for (int c = cap; c >= 1; --c)
+                if (p.nkb[ph] % c == 0) { kbs = c; break; }
+            p.kbs[ph] = kbs;
+            p.nst[ph] = p.nkb[ph] / kbs;
+            if (p.nch[ph] > 0 && kbs > max_kbs) max_kbs = kbs;
+        }
+        p.stage_bytes = max_kbs * DT_KB_BYTES;
+        stages = (SMEM_USABLE - p.p_bytes - DT_STAGING) / p.stage_bytes;
+        if (stages > DT_MAX_STAGES) stages = DT_MAX_STAGES;
+        stages &= ~1;
+        if (stages >= 4) break;
     }
-    p.stage_bytes = max_kbs * DT_KB_BYTES;
-    int stages = (SMEM_USABLE - p.p_bytes - DT_STAGING) / p.stage_bytes;
-    if (stages > DT_MAX_STAGES) stages = DT_MAX_STAGES;
     if (stages < 2) return 1;
     p.stages = stages;
     for (int i = 0; i < 4; ++i) {

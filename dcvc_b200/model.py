@@ -126,9 +126,9 @@ class DMC(DMCI):
         return m
 
     def clear_dpb(self):
-        # the reference forgets ref_feature/memory/ctx; the proxy state is rebuilt by the next
-        # add_ref_feature_from_frame (video_model_ht.py:364-367)
-        pass
+        # the reference forgets ref_feature / memory / ctx (video_model_ht.py:364-367); the proxy's state is rebuilt by the next
+        # add_ref_feature_from_frame.  Coding a P unit in between would silently use the previous GOP's state: refuse it.
+        self._dpb_cleared = True
 
     def _ensure_proxy(self):
         if self.proxy is None:
@@ -139,15 +139,22 @@ class DMC(DMCI):
 
     def add_ref_feature_from_frame(self, frame, apply_feature_adaptor=True):
         self._ensure_proxy()
+        self._dpb_cleared = False
         return self.proxy.add_ref_feature_from_frame(frame, apply_feature_adaptor)
+
+    def _check_dpb(self):
+        if getattr(self, "_dpb_cleared", True):
+            raise RuntimeError("no reference feature: call add_ref_feature_from_frame after clear_dpb / before the first P unit")
 
     def compress(self, x, qp, reset_feature_memory, padding_b, padding_r):
         self._ensure_proxy()
+        self._check_dpb()
         bit_stream, ec_parallel = self.proxy.compress(x, qp, reset_feature_memory, padding_b, padding_r)
         return {"bit_stream": bit_stream.tobytes(), "ec_parallel": ec_parallel}
 
     def decompress(self, bit_stream, sps, qp, ec_part, reset_feature_memory):
         self._ensure_proxy()
+        self._check_dpb()
         x_hat = self.proxy.decompress(np.frombuffer(bit_stream, dtype=np.uint8), qp, sps["height"], sps["width"],
                                       ec_part, reset_feature_memory)
         return {"x_hat": x_hat}

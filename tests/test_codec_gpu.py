@@ -171,3 +171,13 @@ def test_fused_block_tails_change_no_bit(model, h, w, qp, monkeypatch):
     x, enc1, xh1, dec1 = _roundtrip(m2, h, w, qp)
     assert np.array_equal(np.asarray(enc0["bit_stream"]), np.asarray(enc1["bit_stream"]))
     assert torch.equal(xh0, xh1) and torch.equal(dec0, dec1) and torch.equal(xh1, dec1)
+    if h * w >= 2160 * 3840:
+        # by default only blocks up to C = 384 take the fused kernel (the C = 512 ones measured slower, codec_common.cuh dcb());
+        # DCVC_B200_FUSE_TAIL=<pixels> lifts that: the 135x240 C = 512 blocks of a 4K picture run fused as well
+        monkeypatch.setenv("DCVC_B200_FUSE_TAIL", "16384")
+        m3 = DMCI.synthetic(0)
+        m3.update(SKIP)
+        m3 = m3.half().to("cuda")
+        x, enc2, xh2, dec2 = _roundtrip(m3, h, w, qp)
+        assert np.array_equal(np.asarray(enc0["bit_stream"]), np.asarray(enc2["bit_stream"]))
+        assert torch.equal(xh0, xh2) and torch.equal(dec0, dec2)

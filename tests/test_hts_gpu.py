@@ -198,3 +198,19 @@ def test_capture_lanes_and_fusion_bit_identical(nets, switch, value, monkeypatch
     assert np.array_equal(dec0.view(np.uint16), dec1.view(np.uint16))
     # feature_p half of the state: encoder and decoder agree (the memory half is updated lazily on the decoder side)
     assert np.array_equal(enc1.reshape(-1, 1024)[:, 512:].view(np.uint16), dec1.reshape(-1, 1024)[:, 512:].view(np.uint16))
+
+
+def test_p_unit_after_clear_dpb_is_refused(nets):
+    """the reference forgets its reference feature in clear_dpb (video_model_ht.py:364-367) and fails on the next P unit;
+    the mirror must not silently code with the previous GOP's state either"""
+    i_net, p_net = nets
+    h, w = 64, 64
+    pad_r, pad_b = i_net.get_padding_size(h, w, 16)
+    x0 = synth_frame(h, w, 1).half().cuda().contiguous(memory_format=torch.channels_last)
+    x1 = synth_frame(h, w, 2, channels=24).half().cuda().contiguous(memory_format=torch.channels_last)
+    enc = i_net.compress(x0, 30, pad_b, pad_r)
+    p_net.clear_dpb()
+    with pytest.raises(RuntimeError, match="add_ref_feature_from_frame"):
+        p_net.compress(x1, 30, 0, pad_b, pad_r)
+    p_net.add_ref_feature_from_frame(enc["x_hat"])
+    assert len(p_net.compress(x1, 30, 0, pad_b, pad_r)["bit_stream"]) > 8
