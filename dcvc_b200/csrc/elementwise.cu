@@ -715,18 +715,32 @@ int launch_mul_clamp_min(const ActView& in, const ActView& q, const ActView& out
     return 0;
 }
 
-// single-CTA exclusive scan (n <= 1024 * 64)
+// single-CTA exclusive scan (n <= 1024 * 64): every thread owns PER consecutive counts, read once with 128-bit loads (a warp
+// reads PER * 128 contiguous bytes), kept in registers across the block scan, written back as 128-bit stores.  It sits on the
+// critical path of every prior step (count -> scan -> compact -> host), so its latency, not its bandwidth, is what matters.
+template <int PER>
 __global__ void __launch_bounds__(1024)
 scan_counts_kernel(const int32_t* __restrict__ counts, int32_t* __restrict__ offsets,
-                   int32_t* __restrict__ total, int n)
+                   int32_t* __restrict__ total, int n, bool vec)   // vec: both buffers 16-byte aligned
 {
     __shared__ int warp_sums[32];
     const int tid = threadIdx.x;
-    const int per = (n + 1023) / 1024;
-    const int begin = tid * per;
-    const int end = min(begin + per, n);
+    const int begin = tid * PER;
+    int c[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j += 4) {
+        const int i = begin + j;
+        if (vec && i + 3 < n) {
+            const int4 v = *reinterpret_cast<const int4*>(counts + i);
+            c[j] = v.x; c[j + 1] = v.y; c[j + 2] = v.z; c[j + 3] = v.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) c[j + e] = (i + e < n) ? counts[i + e] : 0;
+        }
+    }
     int local = 0;
-    for (int i = begin; i < end; ++i) local += counts[i];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) local += c[j];
     // inclusive warp scan
     int v = local;
     const int lane = tid & 31;
@@ -748,9 +762,22 @@ scan_counts_kernel(const int32_t* __restrict__ counts, int32_t* __restrict__ off
     }
     __syncthreads();
     int run = v - local + ((tid >> 5) > 0 ? warp_sums[(tid >> 5) - 1] : 0);
-    for (int i = begin; i < end; ++i) {
-        offsets[i] = run;
-        run += counts[i];
+#pragma unroll
+    for (int j = 0; j < PER; j += 4) {
+        const int i = begin + j;
+        int4 o;
+        o.x = run; run += c[j];
+        o.y = run; run += c[j + 1];
+        o.z = run; run += c[j + 2];
+        o.w = run; run += c[j + 3];
+        if (vec && i + 3 < n) {
+            *reinterpret_cast<int4*>(offsets + i) = o;
+        } else {
+            if (i < n) offsets[i] = o.x;
+            if (i + 1 < n) offsets[i + 1] = o.y;
+            if (i + 2 < n) offsets[i + 2] = o.z;
+            if (i + 3 < n) offsets[i + 3] = o.w;
+        }
     }
     if (tid == 1023) {
         offsets[n] = warp_sums[31];
@@ -764,7 +791,11 @@ int launch_scan_counts(const int32_t* counts, int32_t* offsets, int32_t* total, 
         fprintf(stderr, "scan_counts: n=%d too large\n", n);
         return 1;
     }
-    scan_counts_kernel<<<1, 1024, 0, s>>>(counts, offsets, total, n);
+    const bool vec = ((reinterpret_cast<uintptr_t>(counts) | reinterpret_cast<uintptr_t>(offsets)) & 15) == 0;
+    if (n <= 1024 * 8) scan_counts_kernel<8><<<1, 1024, 0, s>>>(counts, offsets, total, n, vec);
+    else if (n <= 1024 * 16) scan_counts_kernel<16><<<1, 1024, 0, s>>>(counts, offsets, total, n, vec);
+    else if (n <= 1024 * 32) scan_counts_kernel<32><<<1, 1024, 0, s>>>(counts, offsets, total, n, vec);
+    else scan_counts_kernel<64><<<1, 1024, 0, s>>>(counts, offsets, total, n, vec);
     DCVC_LAUNCH_CHECK();
     return 0;
 }

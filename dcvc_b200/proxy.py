@@ -80,24 +80,29 @@ class DMCIProxy:
 
     def __init__(self):
         self._hd = _CodecHandle(_lib.KIND_INTRA)
-        self._x_hat = None
+        self._x_hat = {}
 
     def set_param(self, state_dict, skip_threshold: float):
         _push_state_dict(self._hd, state_dict, skip_threshold)
 
-    def _out(self, hp, wp, device):
-        if self._x_hat is None or self._x_hat.shape[2] != hp or self._x_hat.shape[3] != wp:
-            self._x_hat = torch.empty((1, 3, hp, wp), dtype=torch.float16, device=device,
-                                      memory_format=torch.channels_last)
-        return self._x_hat
+    def _out(self, side, hp, wp, device):
+        # Reconstructions are written into proxy-owned buffers (no allocation per frame), one for the encoder side and one
+        # for the decoder side: the x_hat of a compress() stays valid through the following decompress() (the usual
+        # encode-then-decode comparison), and is overwritten by the NEXT compress(); clone() what must outlive that.
+        t = self._x_hat.get(side)
+        if t is None or t.shape[2] != hp or t.shape[3] != wp:
+            t = torch.empty((1, 3, hp, wp), dtype=torch.float16, device=device, memory_format=torch.channels_last)
+            self._x_hat[side] = t
+        return t
 
     def compress(self, x: torch.Tensor, qp: int, padding_b: int, padding_r: int):
-        """-> (bit_stream: np.ndarray[uint8], x_hat: fp16 channels_last [1,3,H16p,W16p], ec_parallel)"""
+        """-> (bit_stream: np.ndarray[uint8], x_hat: fp16 channels_last [1,3,H16p,W16p], ec_parallel).
+        x_hat is a proxy-owned buffer, reused by the next compress() call (see _out)."""
         hd = self._hd
         assert x.is_cuda and x.dtype == torch.float16 and x.dim() == 4 and x.shape[0] == 1 and x.shape[1] == 3
         hd.same_device(x)
         _, _, H, W = x.shape
-        out = self._out(H + padding_b, W + padding_r, x.device)
+        out = self._out("enc", H + padding_b, W + padding_r, x.device)
         bs, n, ec = C.c_void_p(), C.c_int32(), C.c_int32()
         stream = C.c_void_p(torch.cuda.current_stream(hd.device).cuda_stream)
         hd.check(hd.lib.dcvc_compress(hd.h, C.c_void_p(x.data_ptr()), H, W, x.stride(1), x.stride(2), x.stride(3),
@@ -107,10 +112,11 @@ class DMCIProxy:
         return stream_np, out, ec.value
 
     def decompress(self, bit_stream: np.ndarray, qp: int, height: int, width: int, ec_parallel: int):
+        """-> x_hat: fp16 channels_last [1,3,H16p,W16p], a proxy-owned buffer reused by the next decompress() call"""
         hd = self._hd
         bs = np.ascontiguousarray(bit_stream, dtype=np.uint8)
         hp, wp = (height + 15) // 16 * 16, (width + 15) // 16 * 16
-        out = self._out(hp, wp, torch.device("cuda", hd.device))
+        out = self._out("dec", hp, wp, torch.device("cuda", hd.device))
         stream = C.c_void_p(torch.cuda.current_stream(hd.device).cuda_stream)
         hd.check(hd.lib.dcvc_decompress(hd.h, C.c_void_p(bs.ctypes.data), bs.size, int(qp), int(height), int(width),
                                         int(ec_parallel), stream, C.c_void_p(out.data_ptr())), "decompress")

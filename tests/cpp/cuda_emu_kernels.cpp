@@ -573,7 +573,7 @@ static const KernelEntry kTable[] = {
     { "mul_clamp_min_kernel", 8, { 8, 4, 8, 4, 8, 4, 8, 4 }, emu_mul_clamp_min },
     { "round_z_kernel", 4, { 8, 8, 8, 8 }, emu_round_z },
     { "int8_to_half_kernel", 3, { 8, 8, 8 }, emu_int8_to_half },
-    { "scan_counts_kernel", 4, { 8, 8, 8, 4 }, emu_scan },
+    { "scan_counts_kernel", 5, { 8, 8, 8, 4, 1 }, emu_scan },
     { "entropy_enc_step_kernel", 1, { static_cast<int>(sizeof(EntropyDev)) }, emu_enc_step },
     { "entropy_dec_index_kernel", 1, { static_cast<int>(sizeof(EntropyDev)) }, emu_dec_index },
     { "compact_kernelIs", 4, { static_cast<int>(sizeof(EntropyDev)), 8, 8, 8 }, emu_compact<int16_t> },

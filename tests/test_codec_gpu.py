@@ -57,6 +57,20 @@ def test_encode_decode_bit_exact(model, h, w, qp):
     assert p > 8.0, f"PSNR {p:.2f} dB: reconstruction unrelated to the input"
 
 
+def test_encoder_reconstruction_stays_valid_through_the_decode(model):
+    """The proxy writes reconstructions into its own buffers, one per side: the x_hat a compress() returned is still the
+    encoder's reconstruction after the following decompress() (the reference allocates a tensor per call, so its callers
+    compare the two without cloning), and it is the NEXT compress() that overwrites it."""
+    h, w, qp = 256, 384, 32
+    x = synth_frame(h, w, 7).half().cuda().contiguous(memory_format=torch.channels_last)
+    enc = model.compress(x, qp, 0, 0)
+    kept = enc["x_hat"].clone()
+    dec = model.decompress(enc["bit_stream"], {"height": h, "width": w}, qp, enc["ec_parallel"])["x_hat"]
+    torch.cuda.synchronize()
+    assert enc["x_hat"].data_ptr() != dec.data_ptr()
+    assert torch.equal(enc["x_hat"], kept) and torch.equal(dec, kept)
+
+
 def test_all_64_qp_sweep_bit_exact(model):
     """configs[1]: the full q_index sweep (small frame to keep the suite fast)"""
     sizes = set()
