@@ -109,10 +109,10 @@ def run_ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    numa = None
-    if os.environ.get("DCVC_B200_NUMA_PIN") == "1":     # opt-in until measured: host threads on the GPU's socket
-        from dcvc_b200.shard import pin_to_gpu_numa_node
-        numa = pin_to_gpu_numa_node(local)
+    # DCVC_B200_PIN=1: host threads of this rank (the rANS pool is created with the first proxy) on the GPU's socket and
+    # on their own cores (opt-in: within the run-to-run spread when measured, dcvc_b200/shard.py)
+    from dcvc_b200.shard import pin_rank
+    numa = pin_rank(local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
     model = make_model(device, world, rank)
     stream = torch.cuda.Stream(device)
     torch.cuda.set_stream(stream)  # a non-default stream, like test_video.py:423-425

@@ -1,6 +1,8 @@
 // rans_host.cpp — see rans_host.h.  Own implementation of the reference bitstream format.
 #include "rans_host.h"
 
+#include <sched.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -229,10 +231,23 @@ ForkJoin::ForkJoin(int workers)
     // busy-waiting only pays when every worker has a hardware thread to itself — counting the sibling processes of a
     // one-process-per-GPU launch (torchrun exports LOCAL_WORLD_SIZE): round 1 measured 0.93 weak-scaling efficiency at 4 and
     // 8 GPUs with unchanged GPU time, i.e. 8 ranks x 8 spinning threads fighting for the cores of two sockets
+    // ... unless this process has been given hardware threads of its own (dcvc_b200/shard.py: pin_rank deals whole cores to
+    // the local ranks before the first proxy exists): then the workers spin on cores nobody else uses
     int local_world = 1;
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) local_world = std::max(1, atoi(e));
-    spin_us_ /= local_world;
-    if (std::thread::hardware_concurrency() < 4u * static_cast<unsigned>(workers + 1) * static_cast<unsigned>(local_world)) spin_us_ = 0;
+    bool own_cores = false;
+#if defined(__linux__)
+    cpu_set_t mask;
+    if (sched_getaffinity(0, sizeof(mask), &mask) == 0) {
+        const int mine = CPU_COUNT(&mask);
+        // (configured processors, not hardware_concurrency(): glibc derives that one from the affinity mask itself)
+        own_cores = mine < static_cast<int>(sysconf(_SC_NPROCESSORS_CONF)) && mine >= workers + 1;
+    }
+#endif
+    if (!own_cores) {
+        spin_us_ /= local_world;
+        if (std::thread::hardware_concurrency() < 4u * static_cast<unsigned>(workers + 1) * static_cast<unsigned>(local_world)) spin_us_ = 0;
+    }
     if (const char* e = getenv("DCVC_B200_RANS_SPIN_US")) spin_us_ = std::max(0, atoi(e));
     for (int i = 0; i < workers; ++i) threads_.emplace_back(&ForkJoin::worker_loop, this, i + 1);
 }

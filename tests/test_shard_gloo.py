@@ -53,7 +53,7 @@ def test_broadcast_and_sharding_world2():
 
 
 def test_gpu_numa_cpu_set_from_a_sysfs_tree(tmp_path):
-    """host placement helper (opt-in in bench.py: DCVC_B200_NUMA_PIN=1): the CPUs of the GPU's NUMA node come from
+    """host placement helper (bench.py: pin_rank): the CPUs of the GPU's NUMA node come from
     sysfs; a platform that does not say (numa_node -1, missing files) changes nothing"""
     from dcvc_b200.shard import _parse_cpulist, gpu_numa_cpus
     assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
@@ -68,3 +68,34 @@ def test_gpu_numa_cpu_set_from_a_sysfs_tree(tmp_path):
     (dev / "numa_node").write_text("-1\n")
     assert gpu_numa_cpus("0000:1b:00.0", str(tmp_path)) is None
     assert gpu_numa_cpus("0000:ff:00.0", str(tmp_path)) is None
+
+
+def test_ranks_get_disjoint_runs_of_whole_cores(tmp_path, monkeypatch):
+    """pin_rank: every local rank gets its own run of whole cores (SMT siblings stay together) inside the CPU set of its
+    GPU's NUMA node — or inside the whole allowed set when the platform names no node; ranks that share a node split it"""
+    import os
+    from dcvc_b200 import shard
+    # a two-package box: cpu c and c + 8 are siblings of core c % 4 of package c // 4 % 2
+    for c in range(16):
+        top = tmp_path / "devices" / "system" / "cpu" / f"cpu{c}" / "topology"
+        top.mkdir(parents=True)
+        (top / "physical_package_id").write_text(f"{(c % 8) // 4}\n")
+        (top / "core_id").write_text(f"{c % 4}\n")
+    sl = shard.core_slices(set(range(16)), 4, str(tmp_path))
+    assert sl == [{0, 8, 1, 9}, {2, 10, 3, 11}, {4, 12, 5, 13}, {6, 14, 7, 15}]
+    assert shard.core_slices({0, 1, 2, 3, 4}, 2, str(tmp_path / "nothing")) == [{0, 1}, {2, 3, 4}]
+
+    applied = {}
+    monkeypatch.setenv("DCVC_B200_PIN", "1")       # opt-in (measured: within the run-to-run spread on a 2-GPU box)
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(16)))
+    monkeypatch.setattr(os, "sched_setaffinity", lambda pid, cpus: applied.__setitem__("cpus", set(cpus)))
+    node = {0: {0, 1, 2, 3, 8, 9, 10, 11}, 1: {0, 1, 2, 3, 8, 9, 10, 11}, 2: {4, 5, 6, 7, 12, 13, 14, 15}, 3: {4, 5, 6, 7, 12, 13, 14, 15}}
+    got = [shard.pin_rank(r, 4, str(tmp_path), node_cpus=lambda d: node[d]) for r in range(4)]
+    assert got == [{0, 8, 1, 9}, {2, 10, 3, 11}, {4, 12, 5, 13}, {6, 14, 7, 15}] and applied["cpus"] == got[3]
+    # no NUMA information: the local ranks split everything that is allowed
+    got = [shard.pin_rank(r, 2, str(tmp_path), node_cpus=lambda d: None) for r in range(2)]
+    assert got == [{0, 1, 2, 3, 8, 9, 10, 11}, {4, 5, 6, 7, 12, 13, 14, 15}]
+    # one rank and no NUMA information, or the switch: nothing changes
+    assert shard.pin_rank(0, 1, str(tmp_path), node_cpus=lambda d: None) is None
+    monkeypatch.delenv("DCVC_B200_PIN")
+    assert shard.pin_rank(0, 2, str(tmp_path), node_cpus=lambda d: None) is None
