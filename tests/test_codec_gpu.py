@@ -168,6 +168,18 @@ def test_against_cpu_oracle(model, h, w, qp):
         h_gpu = np.bincount((s_gpu >> 8).astype(np.int32) + 128, minlength=256)
         h_ref = np.bincount((s_ref >> 8).astype(np.int32) + 128, minlength=256)
         assert np.abs(h_gpu - h_ref).sum() <= 0.03 * len(s_ref) + 8, (k, np.abs(h_gpu - h_ref).sum())
+    # decoder-side isolation — the contract's "identical inputs" without tie flips: the oracle's synthesis transform run
+    # on the GPU's OWN quantised latents (y_hat as the decoder left it), against the GPU's reconstruction.  What is left
+    # is fp16 storage at every op boundary on both sides and fp32 accumulation in different orders through 14 blocks.
+    from oracle import ops_ref
+    H16, W16 = (h + pad_b) // 16, (w + pad_r) // 16
+    yh = model.proxy.debug_fetch("y_hat", np.float16)[: H16 * W16 * 256].reshape(H16, W16, 256)
+    x_iso = ops_ref.shuffle8_clamp(o.decoder(o._nchw32(yh), qp), True)
+    d = (x_hat_enc.float().cpu() - x_iso.float()).abs()
+    iso = psnr(x_hat_enc.float().cpu(), x_iso.float())
+    print(f"[synthesis on identical latents] intra {h}x{w} q{qp}: max|dx| {d.max().item():.5f}, mean|dx| {d.mean().item():.2e}, "
+          f"PSNR(x_hat_gpu, synthesis_oracle(y_hat_gpu)) {iso:.2f} dB")
+    assert d.max().item() <= 1e-2 and iso >= 55.0, (d.max().item(), iso)
 
 
 
