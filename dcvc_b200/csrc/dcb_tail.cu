@@ -154,10 +154,9 @@ dcb_tail_kernel(const __grid_constant__ DcbTailParams p)
                 bool next_loaded = false;
                 for (int ph = 0; ph < 4; ++ph) {
                     int cnt = 0;
-                    const int rep_off = p.wrep > 1 ? (pair % p.wrep) * p.nch[ph] * DT_CHUNK_N : 0;   // timing experiments only
                     const uint32_t tx = static_cast<uint32_t>(2 * p.kbs[ph] * DT_KB_BYTES);
                     for (int n = 0; n < p.nch[ph]; ++n, ++tc) {
-                        const int nrow = rep_off + n * DT_CHUNK_N + rank * (DT_CHUNK_N / 2);
+                        const int nrow = n * DT_CHUNK_N + rank * (DT_CHUNK_N / 2);
                         const int r = static_cast<int>(tc & 1);
                         for (int st = 0; st < p.nst[ph]; ++st) {
                             const int s = r * half + sr[r];
@@ -640,16 +639,11 @@ int dcb_tail_plan(DcbTailOp& op)
     const __half* ws[4] = { op.w3, op.wf0, op.wf2, op.w0n ? op.w0n : op.w3 };
     const int Ns[4] = { C, 4 * inner, C, inner_n ? inner_n : C };
     const int Ks[4] = { inner, C, inner, inner_n ? C : inner };
-    int wrep = 1;
-    if (const char* d = getenv("DCVC_B200_DT_WREP")) wrep = atoi(d) > 1 ? atoi(d) : 1;   // tools/dcb_tail_micro.py allocates the copies
-    p.wrep = wrep;
-    int force_kbs = 0;
-    if (const char* e = getenv("DCVC_B200_DT_KBS")) force_kbs = atoi(e);
     // weight stages: kbs k-blocks of a chunk per ring slot and barrier round trip (measured with one k-block per slot:
     // ~0.2 us per slot whatever the ring depth — the per-slot protocol, not the bytes, set the pace)
     // ... as large as leaves four slots: the chunks alternate between two rings (one per MMA issuer) of stages / 2 slots
     int stages = 0;
-    for (int cap = force_kbs ? force_kbs : 4; cap >= 1; --cap) {
+    for (int cap = 4; cap >= 1; --cap) {
         int max_kbs = 1;
         for (int ph = 0; ph < 4; ++ph) {
             int kbs = 1;
@@ -668,7 +662,7 @@ int dcb_tail_plan(DcbTailOp& op)
     if (stages < 2) return 1;
     p.stages = stages;
     for (int i = 0; i < 4; ++i) {
-        uint64_t d2[2] = { static_cast<uint64_t>(Ks[i]), static_cast<uint64_t>(Ns[i]) * wrep };
+        uint64_t d2[2] = { static_cast<uint64_t>(Ks[i]), static_cast<uint64_t>(Ns[i]) };
         uint64_t s2[1] = { static_cast<uint64_t>(Ks[i]) * 2 };
         uint32_t b2[2] = { 64, DT_CHUNK_N / 2 };
         if (encode_map(&p.tm_w[i], ws[i], 2, d2, s2, b2)) return 2;

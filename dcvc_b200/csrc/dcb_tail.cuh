@@ -42,7 +42,6 @@ struct alignas(64) DcbTailParams {
     int p_bytes;           // bytes of the resident activation buffer (inner / 64 * 16 KB)
     int dbg;
     unsigned long long* trace;   // env DCVC_B200_GEMM_TRACE=<device address of 2048 u64>: timeline of CTA 0 (tools/dcb_tail_trace.py)
-    int wrep;              // timing experiments: the weight matrices are replicated `wrep` times along N, pair p reads copy p % wrep
 };
 
 struct DcbTailOp {

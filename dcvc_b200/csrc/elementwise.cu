@@ -131,11 +131,8 @@ static int launch_dw3x3_ty(const ActView& in, const ActView& out, const __half* 
 
 int launch_dw3x3(const ActView& in, const ActView& out, const __half* w, cudaStream_t s, bool pdl)
 {
-    // rows per thread: DCVC_B200_DW_TY = 2 | 4 | 8 (measurement switch; default 4)
-    static const int ty = []() { const char* e = getenv("DCVC_B200_DW_TY"); return e ? atoi(e) : DW_TY_DEFAULT; }();
-    if (ty == 2) return launch_dw3x3_ty<2>(in, out, w, s, pdl);
-    if (ty == 8) return launch_dw3x3_ty<8>(in, out, w, s, pdl);
-    return launch_dw3x3_ty<4>(in, out, w, s, pdl);
+    // rows per thread: 4 (2 and 8 were measured in round 1 and are gone)
+    return launch_dw3x3_ty<DW_TY_DEFAULT>(in, out, w, s, pdl);
 }
 
 // ------------------------------------------------------------------------------- unshuffle8

@@ -179,7 +179,8 @@ def test_against_cpu_oracle(model, h, w, qp):
     iso = psnr(x_hat_enc.float().cpu(), x_iso.float())
     print(f"[synthesis on identical latents] intra {h}x{w} q{qp}: max|dx| {d.max().item():.5f}, mean|dx| {d.mean().item():.2e}, "
           f"PSNR(x_hat_gpu, synthesis_oracle(y_hat_gpu)) {iso:.2f} dB")
-    assert d.max().item() <= 1e-2 and iso >= 55.0, (d.max().item(), iso)
+    # measured on B200 (round 2): max|dx| 4.9e-4 / 1.2e-3 (one or two fp16 ulps of a value in [0.25, 0.5)), PSNR 80.6 / 72.4 dB
+    assert d.max().item() <= 2.5e-3 and iso >= 66.0, (d.max().item(), iso)
 
 
 

@@ -14,9 +14,8 @@ H, W, C, inner, inner_n = [int(v) for v in sys.argv[1:6]] if len(sys.argv) > 5 e
 g = torch.Generator().manual_seed(0)
 rnd = lambda *s, sc=0.5: (torch.randn(*s, generator=g) * sc).half().cuda()  # noqa: E731
 t2, x = rnd(H, W, inner), rnd(H, W, C)
-R = max(1, int(os.environ.get("DCVC_B200_DT_WREP", "1")))   # timing experiment: R copies of every weight matrix along N
-w3, wf0, wf2 = rnd(R * C, inner, sc=inner ** -0.5), rnd(R * 4 * inner, C, sc=C ** -0.5), rnd(R * C, inner, sc=inner ** -0.5)
-w0n = rnd(R * inner_n, C, sc=C ** -0.5) if inner_n else None
+w3, wf0, wf2 = rnd(C, inner, sc=inner ** -0.5), rnd(4 * inner, C, sc=C ** -0.5), rnd(C, inner, sc=inner ** -0.5)
+w0n = rnd(inner_n, C, sc=C ** -0.5) if inner_n else None
 b3, bf0, bf2 = rnd(C, sc=0.1), rnd(4 * inner, sc=0.1), rnd(C, sc=0.1)
 b0n = rnd(inner_n, sc=0.1) if inner_n else None
 y = torch.zeros(H, W, C, dtype=torch.float16, device="cuda")
@@ -60,8 +59,7 @@ def time_graph(fn, n=10, reps=5):
 
 fl = 2.0 * H * W * (C * inner + 4 * inner * C + C * inner + (inner_n * C if inner_n else 0))
 which = sys.argv[6] if len(sys.argv) > 6 else "both"
-tag = (f"M={H*W} C={C} inner={inner} next={inner_n} dbg={os.environ.get('DCVC_B200_GEMM_DBG', '0')} "
-       f"rot={os.environ.get('DCVC_B200_DT_ROT', '1')} wrep={R}")
+tag = f"M={H*W} C={C} inner={inner} next={inner_n} dbg={os.environ.get('DCVC_B200_GEMM_DBG', '0')}"
 if which in ("both", "fused"):
     us = time_graph(fused)
     print(f"{tag} fused : {us:.1f} us  {fl / us / 1e6:.0f} TFLOP/s")

@@ -21,10 +21,10 @@ VARIANTS = [("per-op", {"DCVC_B200_FUSE_TAIL": "0"}),
             ("fused, no graphs", {"DCVC_B200_GRAPHS": "0"}),
             ("fused, no PDL", {"DCVC_B200_PDL": "0"}),
             ("fused, 8 pairs", {"DCVC_B200_DT_MAXPAIRS": "8"}),
-            ("fused, no rotation", {"DCVC_B200_DT_ROT": "0"})]
+            ("fused, any width", {"DCVC_B200_FUSE_TAIL": "16384"})]
 base = None
 for name, env in VARIANTS:
-    for k in ("DCVC_B200_FUSE_TAIL", "DCVC_B200_GRAPHS", "DCVC_B200_PDL", "DCVC_B200_DT_MAXPAIRS", "DCVC_B200_DT_ROT"):
+    for k in ("DCVC_B200_FUSE_TAIL", "DCVC_B200_GRAPHS", "DCVC_B200_PDL", "DCVC_B200_DT_MAXPAIRS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     m = DMCI.synthetic(0)
