@@ -444,7 +444,7 @@ def bench_seq8(i_net, device, world, rank, args, n_seq=8, n_frames=97, rate_num=
     dec_fps = 8e3 / (sum(j["avg_unit_dec_ms"] for j in alljobs) / len(alljobs))
     total_frames = n_frames * len(alljobs)
     return {"workload": f"{n_seq} synthetic {W}x{H} sequences x {n_frames} frames x {rate_num} rate points (q_index {qps}), HT-S, intra period -1, "
-                        f"reset interval 32; {len(alljobs)} jobs dealt round-robin to {world} rank(s) (configs[3]; test_cfg/runtime_avg.json, test_video.py:527-564)",
+                        f"reset interval 32; {len(alljobs)} jobs dealt in rotated blocks to {world} rank(s) (configs[3]; test_cfg/runtime_avg.json, test_video.py:527-564)",
             "jobs": len(alljobs), "jobs_per_rank": [len(part["jobs"]) for part in gathered],
             "protocol_decode_fps": round(dec_fps, 1), "protocol_encode_fps": round(enc_fps, 1),
             "protocol": "reference per-unit timing: 8 / mean unit time, first 4 units of every job dropped (test_video.py:375-381, test_compress_time.py:48-69)",

@@ -99,3 +99,19 @@ def test_ranks_get_disjoint_runs_of_whole_cores(tmp_path, monkeypatch):
     assert shard.pin_rank(0, 1, str(tmp_path), node_cpus=lambda d: None) is None
     monkeypatch.delenv("DCVC_B200_PIN")
     assert shard.pin_rank(0, 2, str(tmp_path), node_cpus=lambda d: None) is None
+
+
+def test_job_deal_is_a_partition_and_mixes_the_rate_points():
+    """shard_jobs: every job exactly once, equal shares, and with the reference's (sequence, rate) job order every rank
+    sees every rate point when there are at least as many ranks as rate points (8 ranks x 32 jobs: one of each)"""
+    from dcvc_b200.shard import shard_jobs
+    jobs = [(s, r) for s in range(8) for r in range(4)]
+    for world in (1, 2, 3, 4, 8):
+        shares = [shard_jobs(jobs, k, world) for k in range(world)]
+        assert sorted(j for sh in shares for j in sh) == jobs
+        assert max(len(sh) for sh in shares) - min(len(sh) for sh in shares) <= 1
+        if world in (4, 8):
+            for sh in shares:
+                assert sorted({r for _, r in sh}) == [0, 1, 2, 3], (world, sh)
+        if world == 2:   # two rate points per rank would be {0, 2} / {1, 3} with a plain modulo deal
+            assert [sum(r for _, r in sh) for sh in shares] == [24, 24]
