@@ -365,7 +365,7 @@ def run_ours(args):
 def bench_seq8(i_net, device, world, rank, args, n_seq=8, n_frames=97, rate_num=4):
     """BASELINE.json configs[3]: the reference's runtime job — test_cfg/runtime_avg.json has 1080p sequences of 97 frames,
     intra period -1, four rate points each (test_video.py:527-564 submits sequence-major, rate-minor) — here 8 synthetic
-    sequences, dealt round-robin to the ranks (one process per GPU, no cross-GPU dependency), each job coded and decoded
+    sequences, dealt in rotated blocks to the ranks (one process per GPU, no cross-GPU dependency), each job coded and decoded
     through the sequence driver (dcvc_b200/sequence.py = the loop of test_video.py:204-372) with the reference's timing
     protocol per coded unit (first four units dropped, test_video.py:375-381).  Results are gathered on rank 0."""
     import torch.distributed as dist

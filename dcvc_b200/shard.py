@@ -1,7 +1,7 @@
 """Multi-GPU plumbing of the hot path: the path shards by job — (sequence x rate point) or
 independent GOP segments — with NO data-path collective.  One process per GPU; rank 0's checkpoint is
-broadcast once (NCCL over NVLink on the GPU box, gloo in the CPU tests); jobs are dealt round-robin in the
-deterministic order of the reference's job list (test_video.py:527-564)."""
+broadcast once (NCCL over NVLink on the GPU box, gloo in the CPU tests); jobs are dealt in rotated blocks
+(shard_jobs) from the deterministic order of the reference's job list (test_video.py:527-564)."""
 from __future__ import annotations
 
 from collections import OrderedDict
