@@ -2,19 +2,22 @@
 // (see dcb_tail.cuh for the what and why).  Hand-written for sm_100a: TMA, tcgen05.mma cta_group::2 with the A operand
 // from shared memory (phases 1, 3) or from tensor memory (phases 2, 4), tcgen05.ld / tcgen05.st epilogues.
 //
-// Per CTA (one SM), 18 warps:
+// Per CTA (one SM), 19 warps:
 //   warp 0        TMA producer: the tile's t2 k-blocks into the resident buffer P, then the weight k-blocks of all four
-//                 GEMMs, in consumption order, through a ring of 8 KB stages (this CTA's 64 of a chunk's 128 columns)
-//   warp 1        TMEM allocator; in the leader CTA (cluster rank 0) the single thread that issues every tcgen05.mma
-//   warps 2..17   epilogue: warp (b, h, q) drains lane quarter q / column half h of the chunks that land in accumulator
+//                 GEMMs, in consumption order, through two rings of kbs x 8 KB stages (this CTA's 64 of a chunk's 128
+//                 columns; one ring per MMA issuer)
+//   warps 1, 2    warp 1 allocates TMEM; in the leader CTA (cluster rank 0) one thread of each issues the tcgen05.mma
+//                 of the even / odd chunks (accumulator buffer 0 / 1, weight ring 0 / 1)
+//   warps 3..18   epilogue: warp (b, h, q) drains lane quarter q / column half h of the chunks that land in accumulator
 //                 buffer b (chunks alternate between the two 128-column buffers)
 // TMEM (512 columns): [0, C/2) = O: the tile's o, later y, as packed fp16 — the A operand of phases 2 and 4 and the
 //                     residual of phase 3;   [256, 384) and [384, 512) = the two fp32 accumulator buffers.
-// smem: P [inner/64 x 16 KB] (t2, later t1', UMMA K-major SWIZZLE_128B) | weight ring | 16 x 2 KB store slabs | barriers.
+// smem: P [inner/64 x 16 KB] (t2, later t1', UMMA K-major SWIZZLE_128B) | weight rings | 16 x 2 KB store slabs | barriers.
 //
 // Ordering between the phases needs no grid-wide or CTA-wide barrier: every hand-over is an mbarrier, and "all earlier
-// MMAs have completed" is implied by the tcgen05.commit that publishes a later chunk's accumulator (commits complete
-// in issue order), which is what makes the in-place reuse of P and O safe:
+// MMAs have completed" is implied by the tcgen05.commit that publishes a later chunk's accumulator — commits complete in
+// issue order per issuing thread, and each issuer waits for the other's last commit of the previous phase (xs barriers)
+// before its first MMA of a phase — which is what makes the in-place reuse of P and O safe:
 //   P: TMA(t2) -> phase-1 MMAs -> phase-2 epilogue writes t1' -> phase-3 MMAs -> commit(p_empty) -> TMA(next t2)
 //   O: phase-1 epilogue writes o -> phase-2 MMAs -> phase-3 epilogue reads o, writes y -> phase-4 MMAs -> next tile
 #include "dcb_tail.cuh"
